@@ -1,0 +1,103 @@
+"""
+``build(df, component)``: entry point of the DSL (reference ``sakkara/model/utils.py:9-33``).
+
+Same steps as the reference -- copy the frame, add the ``global`` and ``obs`` columns, collect the
+groups the component tree refers to, infer the group graph, build the tree inside a model
+context -- but the context records into :mod:`sakkara_b200.model.sym`, and the recorded model is
+lowered to a flat :class:`~sakkara_b200.plan.model_plan.ModelPlan` that the CUDA evaluator
+consumes.  The returned :class:`B200Model` can be used as a context manager like a ``pm.Model``.
+"""
+from typing import Optional
+
+import numpy as np
+import pandas as pd
+
+from sakkara_b200.model import sym
+from sakkara_b200.model.components import ModelComponent
+from sakkara_b200.plan.lower import lower_model
+from sakkara_b200.plan.model_plan import ModelPlan
+from sakkara_b200.relation.groupset import GroupSet, init
+
+
+class B200Model:
+    """
+    A built model: the recorded variables, the group graph and the lowered plan.
+
+    ``logp_dlogp_function()`` returns the callable PyMC's samplers use per leapfrog step
+    (``ValueGradFunction`` semantics: raveled unconstrained theta in, ``(logp, dlogp)`` out),
+    evaluated by the sm_100a kernels through the C ABI.
+    """
+
+    def __init__(self, recorded: sym.Model, groupset: GroupSet, plan: ModelPlan):
+        self.recorded = recorded
+        self.groupset = groupset
+        self.plan = plan
+
+    # pm.Model-like surface --------------------------------------------------------------------
+    @property
+    def coords(self):
+        return self.recorded.coords
+
+    @property
+    def free_RVs(self):
+        return self.recorded.free_RVs
+
+    @property
+    def observed_RVs(self):
+        return self.recorded.observed_RVs
+
+    @property
+    def named_vars(self):
+        return self.recorded.named_vars
+
+    def __getitem__(self, name: str):
+        return self.recorded.named_vars[name]
+
+    def __enter__(self) -> 'B200Model':
+        self.recorded.__enter__()
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.recorded.__exit__(*exc)
+
+    @property
+    def value_var_names(self):
+        return [b.value_name for b in self.plan.blocks]
+
+    def initial_point(self, dtype='float64') -> np.ndarray:
+        """theta = 0 on the unconstrained scale (PyMC's default start for these families)."""
+        return np.zeros(self.plan.n_params, dtype=dtype)
+
+    def logp_dlogp_function(self, dtype: str = 'float64', max_batch: int = 1, device: Optional[int] = None,
+                            **options):
+        from sakkara_b200.valuegrad import ValueGradFunction
+        return ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
+
+    def to_pymc(self, dtype: str = 'float64', device: Optional[int] = None):
+        """A ``pm.Model`` with the same free variables whose joint logp is one fused-kernel Op
+        (needs PyMC; see sakkara_b200/pytensor_op.py)."""
+        from sakkara_b200.pytensor_op import to_pymc_model
+        return to_pymc_model(self, dtype=dtype, device=device)
+
+
+def build(df: pd.DataFrame, component: ModelComponent) -> B200Model:
+    """
+    Build a model from a single component (typically a ``Likelihood``); all underlying components
+    and their groups are traced from it.
+
+    :param df: frame holding the columns that define the groups used by the components.
+    :param component: component of the lowest hierarchy level.
+    """
+    frame = df.copy()
+    frame['global'] = 'global'
+    frame['obs'] = np.arange(len(df))
+
+    names = set(component.retrieve_groups()) | {'global', 'obs'}
+    missing = names - set(frame.columns)
+    if missing:
+        raise KeyError(f'Group columns {sorted(missing)} are not in the data frame')
+    groupset = init(frame.loc[:, [c for c in frame.columns if c in names]])
+
+    with sym.Model(coords=groupset.coords()) as recorded:
+        component.build(groupset)
+    return B200Model(recorded, groupset, lower_model(recorded))

@@ -1,0 +1,256 @@
+"""
+Lowering of a recorded model (:mod:`sakkara_b200.model.sym`) to a :class:`ModelPlan`.
+
+The symbolic graph the components build contains exactly what the reference hands to PyTensor:
+gathers ``element[index arrays]`` (reference ``sakkara/relation/representation.py:253``) and
+elementwise arithmetic (``sakkara/model/function/base.py:88-92``).  The lowering brings every
+parameter expression into the normal form
+
+    sum_k  coef_k (*) theta_{block_k}[index_k]  +  const
+
+by pushing gathers down to the leaves (index composition) and distributing products over sums.
+Both spellings of a crossed model (``a + b + beta*x`` which builds a dense [A, B] intermediate in
+the reference, and ``beta*x + a + b``) therefore end up as the same per-row
+gathers.  Anything that is not affine in the parameters -- products of two blocks, ``pow``,
+arbitrary ``f_`` callables -- raises ``NotImplementedError``: there is no CPU fallback on this
+path, the caller is told to use the stock PyMC graph.
+"""
+from dataclasses import dataclass
+from typing import Any, List, Optional, Union
+
+import numpy as np
+
+from sakkara_b200.model import sym
+from sakkara_b200.model.dist import FAMILIES
+from sakkara_b200.plan.model_plan import Block, LikelihoodSpec, ModelPlan, PriorParam, Term
+
+
+class UnsupportedModelError(NotImplementedError):
+    """The model has a structure the fused GLM kernel cannot express."""
+
+
+@dataclass
+class Monomial:
+    coef: Union[float, np.ndarray]             # scalar or array broadcastable to the form's shape
+    var: Optional[sym.RandomVar] = None        # free variable, None for the constant part
+    index: Optional[np.ndarray] = None         # int64, flat element of `var` per cell, form-shaped
+
+
+class AffineForm:
+    def __init__(self, shape, monomials: List[Monomial]):
+        self.shape = tuple(shape)
+        self.monomials = monomials
+
+    @property
+    def is_const(self) -> bool:
+        return all(m.var is None for m in self.monomials)
+
+    def const_value(self) -> np.ndarray:
+        total = np.zeros(self.shape, dtype=np.float64)
+        for m in self.monomials:
+            assert m.var is None
+            total = total + m.coef
+        return total
+
+
+def _scale(coef, factor):
+    return coef * factor
+
+
+def _lower(node: Any) -> AffineForm:
+    if isinstance(node, sym.DeterministicVar):
+        return _lower(node.var)
+    if isinstance(node, sym.RandomVar):
+        if node.is_observed:
+            raise UnsupportedModelError('Observed variables cannot be parameters of other variables')
+        index = np.arange(node.size, dtype=np.int64).reshape(node.shape)
+        return AffineForm(node.shape, [Monomial(1.0, node, index)])
+    if isinstance(node, sym.DataVar):
+        return AffineForm(node.shape, [Monomial(np.asarray(node.values, dtype=np.float64))])
+    if isinstance(node, sym.Gather):
+        base = _lower(node.base)
+        out = []
+        for m in base.monomials:
+            coef = m.coef
+            if isinstance(coef, np.ndarray) and coef.ndim > 0:
+                coef = np.broadcast_to(coef, base.shape)[node.indices]
+            index = None if m.var is None else np.broadcast_to(m.index, base.shape)[node.indices]
+            out.append(Monomial(coef, m.var, index))
+        return AffineForm(node.shape, out)
+    if isinstance(node, sym.UnaryOp):
+        if node.op == 'neg':
+            inner = _lower(node.arg)
+            return AffineForm(inner.shape, [Monomial(_scale(m.coef, -1.0), m.var, m.index) for m in inner.monomials])
+        raise UnsupportedModelError(f'{node.op}() may only wrap the whole linear predictor of the likelihood')
+    if isinstance(node, sym.BinOp):
+        left, right = _lower(node.left), _lower(node.right)
+        shape = np.broadcast_shapes(left.shape, right.shape)
+        if node.op in ('add', 'sub'):
+            sign = 1.0 if node.op == 'add' else -1.0
+            monos = [_broadcast(m, left.shape, shape) for m in left.monomials]
+            monos += [_broadcast(Monomial(_scale(m.coef, sign), m.var, m.index), right.shape, shape)
+                      for m in right.monomials]
+            return AffineForm(shape, monos)
+        if node.op == 'mul':
+            if not (left.is_const or right.is_const):
+                raise UnsupportedModelError('Products of two random variables are not affine in theta')
+            const, other, other_shape = (left, right, right.shape) if left.is_const else (right, left, left.shape)
+            factor = const.const_value()
+            factor = float(factor) if factor.ndim == 0 else factor
+            return AffineForm(shape, [_broadcast(Monomial(_scale(m.coef, factor), m.var, m.index), other_shape, shape)
+                                      for m in other.monomials])
+        if node.op == 'truediv':
+            if not right.is_const:
+                raise UnsupportedModelError('Division by a random variable is not affine in theta')
+            factor = 1.0 / right.const_value()
+            factor = float(factor) if factor.ndim == 0 else factor
+            return AffineForm(shape, [_broadcast(Monomial(_scale(m.coef, factor), m.var, m.index), left.shape, shape)
+                                      for m in left.monomials])
+        raise UnsupportedModelError(f'Operator {node.op} cannot be lowered to the fused GLM kernel')
+    if isinstance(node, sym.Var):
+        raise UnsupportedModelError(f'Cannot lower node of type {type(node).__name__}')
+    value = np.asarray(node, dtype=np.float64)
+    return AffineForm(value.shape, [Monomial(float(value) if value.ndim == 0 else value)])
+
+
+def _broadcast(m: Monomial, from_shape, to_shape) -> Monomial:
+    """Bring the index array of a monomial to the (broadcast) shape of the enclosing form."""
+    if m.var is None or tuple(from_shape) == tuple(to_shape):
+        return m
+    return Monomial(m.coef, m.var, np.broadcast_to(m.index, to_shape))
+
+
+def _merge_constants(form: AffineForm) -> Optional[np.ndarray]:
+    consts = [m for m in form.monomials if m.var is None]
+    if not consts:
+        return None
+    total = 0.0
+    for m in consts:
+        total = total + m.coef
+    return total
+
+
+def _prior_param(value: Any, block_of, size: int, what: str) -> PriorParam:
+    form = _lower(value)
+    if form.is_const:
+        const = np.asarray(form.const_value(), dtype=np.float64)
+        if const.size not in (1, size):
+            raise UnsupportedModelError(f'{what}: constant of size {const.size} for a block of size {size}')
+        return PriorParam(const=const.reshape(-1) if const.size > 1 else const.reshape(()))
+    monos = form.monomials
+    if len(monos) != 1 or not np.all(np.asarray(monos[0].coef) == 1.0):
+        raise UnsupportedModelError(f'{what}: prior parameters must be constants or a single gathered variable')
+    m = monos[0]
+    index = np.ascontiguousarray(np.broadcast_to(m.index, form.shape), dtype=np.int64).reshape(-1)
+    if index.size == 1 and size > 1:
+        index = np.repeat(index, size)
+    if index.size != size:
+        raise UnsupportedModelError(f'{what}: parameter of size {index.size} for a block of size {size}')
+    return PriorParam(block=block_of[id(m.var)], index=index)
+
+
+def lower_model(model: sym.Model) -> ModelPlan:
+    """
+    Turn a recorded model into the flat plan.  theta is the concatenation of the free variables in
+    creation order, each on PyMC's unconstrained scale (SURVEY.md §A "theta layouts").
+    """
+    if len(model.observed_RVs) != 1:
+        raise UnsupportedModelError(f'Exactly one observed likelihood is required, found {len(model.observed_RVs)}')
+
+    blocks: List[Block] = []
+    block_of = {}
+    offset = 0
+    for number, rv in enumerate(model.free_RVs):
+        family = FAMILIES[rv.family]
+        if family.discrete:
+            raise UnsupportedModelError(f'{rv.name}: discrete free variables have no gradient')
+        block_of[id(rv)] = number
+        blocks.append(Block(name=rv.name, family=rv.family, offset=offset, size=rv.size, shape=rv.shape,
+                            dims=rv.dims, transform='log' if family.positive else 'identity'))
+        offset += rv.size
+
+    for rv, block in zip(model.free_RVs, blocks):
+        for key, value in rv.params.items():
+            param = _prior_param(value, block_of, block.size, f'{rv.name}.{key}')
+            if not param.is_const:
+                if param.block >= block_of[id(rv)]:
+                    raise UnsupportedModelError(f'{rv.name}.{key}: parameter refers to a later variable')
+                if block.family != 'Normal':
+                    raise UnsupportedModelError(f'{rv.name}.{key}: only Normal blocks may have random parameters')
+                if key == 'sigma' and blocks[param.block].transform != 'log':
+                    raise UnsupportedModelError(f'{rv.name}.sigma must be a positive (HalfNormal/Exponential) variable')
+            block.params[key] = param
+
+    obs = model.observed_RVs[0]
+    y_form = _lower(obs.observed)
+    if not y_form.is_const:
+        raise UnsupportedModelError('Observed data must be constant')
+    y = np.ascontiguousarray(np.broadcast_to(y_form.const_value(), obs.shape), dtype=np.float64).reshape(-1)
+    n_rows = y.size
+
+    spec = LikelihoodSpec(family=obs.family, name=obs.name, y=y)
+    if obs.family == 'Normal':
+        eta_node = obs.params['mu']
+        sigma = _lower(obs.params['sigma'])
+        if sigma.is_const:
+            value = np.unique(np.asarray(sigma.const_value(), dtype=np.float64))
+            if value.size != 1:
+                raise UnsupportedModelError('Row-dependent constant sigma is not supported')
+            spec.sigma_const = float(value[0])
+        else:
+            m = sigma.monomials
+            if len(m) != 1 or not np.all(np.asarray(m[0].coef) == 1.0):
+                raise UnsupportedModelError('Likelihood sigma must be a constant or a single positive variable')
+            element = np.unique(m[0].index)
+            source = block_of[id(m[0].var)]
+            if element.size != 1:
+                raise UnsupportedModelError('Group-dependent likelihood sigma is not supported yet (SURVEY.md §8f.3)')
+            if blocks[source].transform != 'log':
+                raise UnsupportedModelError('Likelihood sigma must be a positive (HalfNormal/Exponential) variable')
+            spec.sigma_block, spec.sigma_index = source, int(element[0])
+    elif obs.family == 'Bernoulli':
+        if 'logit_p' in obs.params:
+            eta_node = obs.params['logit_p']
+        else:
+            eta_node = _unwrap_link(obs.params['p'], 'sigmoid', 'Bernoulli p')
+        if not np.isin(y, (0.0, 1.0)).all():
+            raise ValueError('Bernoulli observations must be 0 or 1')
+    elif obs.family == 'Poisson':
+        eta_node = _unwrap_link(obs.params['mu'], 'exp', 'Poisson mu')
+        if (y < 0).any() or (y != np.floor(y)).any():
+            raise ValueError('Poisson observations must be non-negative integers')
+    else:
+        raise UnsupportedModelError(f'Likelihood family {obs.family} is not supported')
+
+    eta = _lower(eta_node)
+    if np.prod(eta.shape, dtype=np.int64) not in (1, n_rows):
+        raise UnsupportedModelError(f'Linear predictor of shape {eta.shape} for {n_rows} observations')
+    terms: List[Term] = []
+    for m in eta.monomials:
+        if m.var is None:
+            continue
+        index = np.ascontiguousarray(np.broadcast_to(m.index, eta.shape), dtype=np.int64).reshape(-1)
+        if index.size == 1 and n_rows > 1:
+            index = np.repeat(index, n_rows)
+        coef = np.asarray(m.coef, dtype=np.float64)
+        if coef.ndim == 0 and float(coef) == 1.0:
+            x = None
+        else:
+            x = np.ascontiguousarray(np.broadcast_to(coef, eta.shape), dtype=np.float64).reshape(-1)
+            if x.size == 1 and n_rows > 1:
+                x = np.repeat(x, n_rows)
+        terms.append(Term(block=block_of[id(m.var)], index=index, x=x))
+    const = _merge_constants(eta)
+    if const is not None and np.any(np.asarray(const) != 0.0):
+        spec.offset = np.ascontiguousarray(np.broadcast_to(const, (n_rows,)), dtype=np.float64)
+
+    return ModelPlan(blocks=blocks, terms=terms, likelihood=spec, n_rows=n_rows,
+                     coords={k: np.asarray(v) for k, v in model.coords.items()})
+
+
+def _unwrap_link(node: Any, link: str, what: str):
+    while isinstance(node, sym.DeterministicVar):
+        node = node.var
+    if isinstance(node, sym.UnaryOp) and node.op == link:
+        return node.arg
+    raise UnsupportedModelError(f'{what} must be {link}(linear predictor) for the fused kernel')

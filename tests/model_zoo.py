@@ -1,0 +1,149 @@
+"""
+Model definitions shared by the tests, written once against the public DSL so that the same
+function builds the model with ``sakkara_b200.model`` and -- through ``oracle/ref_harness.py`` --
+with the reference's ``sakkara.model``.  Each entry: ``name -> (make_df(), make_likelihood(api, pm, pt))``.
+"""
+import numpy as np
+import pandas as pd
+
+
+# ---------------------------------------------------------------------------------------------
+# C1: README hierarchical linear regression (README.md:18-34; coefficient renamed 'k', quirk D.1)
+# ---------------------------------------------------------------------------------------------
+def readme_df(n_per_group: int = 5, seed: int = 0) -> pd.DataFrame:
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(2 * n_per_group)
+    group = np.repeat([0, 1], n_per_group)
+    k = np.array([1.0, -1.0])
+    y = x * k[group] + 1e-3 * rng.standard_normal(2 * n_per_group)
+    return pd.DataFrame({'x': x, 'y': y, 'group': group})
+
+
+def readme_likelihood(df):
+    def make(api, pm, pt):
+        data = api.data_components(df)
+        coeff = api.DistributionComponent(pm.Normal, name='k', group='group',
+                                          mu=api.DistributionComponent(pm.Normal),
+                                          sigma=api.DistributionComponent(pm.Exponential, lam=1))
+        intercept = api.DistributionComponent(pm.Normal, name='intercept')
+        return api.Likelihood(pm.Normal, name='est', mu=coeff * data['x'] + intercept,
+                              sigma=api.DistributionComponent(pm.Exponential, lam=1), observed=data['y'])
+    return make
+
+
+# ---------------------------------------------------------------------------------------------
+# linear regression with shuffled, string-labelled groups (first-appearance order matters)
+# ---------------------------------------------------------------------------------------------
+def shuffled_linreg_df(n: int = 200, groups: int = 7, seed: int = 1) -> pd.DataFrame:
+    rng = np.random.default_rng(seed)
+    labels = np.array([f'g{j}' for j in rng.permutation(groups)])
+    code = rng.integers(0, groups, n)
+    x = rng.standard_normal(n)
+    k = rng.normal(0.7, 0.5, groups)
+    y = k[code] * x + 0.3 + 0.5 * rng.standard_normal(n)
+    return pd.DataFrame({'x': x, 'y': y, 'group': labels[code]})
+
+
+# ---------------------------------------------------------------------------------------------
+# C3-shaped: nested two-level logistic regression, written like tests/workflows/test_linreg.py:32-57
+# ---------------------------------------------------------------------------------------------
+def nested_df(n: int = 400, g1: int = 4, per_g1: int = 3, seed: int = 2) -> pd.DataFrame:
+    rng = np.random.default_rng(seed)
+    g2 = rng.integers(0, g1 * per_g1, n)
+    x = rng.standard_normal(n)
+    slope = rng.normal(0.5, 0.3, g1)
+    icpt = rng.normal(0.0, 0.5, g1 * per_g1)
+    eta = slope[g2 // per_g1] * x + icpt[g2]
+    y = (rng.random(n) < 1.0 / (1.0 + np.exp(-eta))).astype(np.int64)
+    return pd.DataFrame({'x': x, 'y': y, 'g1': [f'a{v}' for v in g2 // per_g1], 'g2': [f'b{v}' for v in g2]})
+
+
+def nested_logistic_likelihood(df):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        slope = DC(pm.Normal, name='slope', group='g1', mu=DC(pm.Normal), sigma=DC(pm.HalfNormal, sigma=1.0))
+        icpt = DC(pm.Normal, name='icpt', group='g2',
+                  mu=DC(pm.Normal, group='g1', mu=DC(pm.Normal), sigma=DC(pm.HalfNormal, sigma=2.0)),
+                  sigma=DC(pm.HalfNormal, sigma=1.0))
+        return api.Likelihood(pm.Bernoulli, logit_p=slope * data['x'] + icpt, observed=data['y'])
+    return make
+
+
+def nested_normal_likelihood(df, sigma=0.7):
+    """the test_linreg.py model itself: Normal likelihood with a constant sigma"""
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        coeff = DC(pm.Normal, name='coeff', group='g1', mu=DC(pm.Normal), sigma=DC(pm.HalfNormal, sigma=0.5))
+        icpt = DC(pm.Normal, name='intercept', group='g2',
+                  mu=DC(pm.Normal, group='g1', mu=DC(pm.Normal), sigma=DC(pm.HalfNormal, sigma=1.5)),
+                  sigma=DC(pm.HalfNormal, sigma=0.8))
+        return api.Likelihood(pm.Normal, mu=coeff * data['x'] + icpt, sigma=sigma, observed=data['y'])
+    return make
+
+
+# ---------------------------------------------------------------------------------------------
+# C4-shaped: Poisson-log GLM with crossed random effects, both operand orders (quirk D.3)
+# ---------------------------------------------------------------------------------------------
+def crossed_df(n: int = 600, a: int = 6, b: int = 4, seed: int = 3) -> pd.DataFrame:
+    rng = np.random.default_rng(seed)
+    A = rng.integers(0, a, n)
+    B = rng.integers(0, b, n)
+    x = rng.standard_normal(n)
+    eta = 0.2 * x + rng.normal(0, 0.3, a)[A] + rng.normal(0, 0.3, b)[B]
+    return pd.DataFrame({'x': x, 'A': A, 'B': B, 'y': rng.poisson(np.exp(eta))})
+
+
+def crossed_poisson_likelihood(df, obs_term_first: bool = True):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        beta = DC(pm.Normal, name='beta')
+        a = DC(pm.Normal, name='a', group='A', sigma=DC(pm.HalfNormal, sigma=1.0))
+        b = DC(pm.Normal, name='b', group='B', sigma=DC(pm.HalfNormal, sigma=1.0))
+        eta = beta * data['x'] + a + b if obs_term_first else a + b + beta * data['x']
+        return api.Likelihood(pm.Poisson, mu=api.f_(pt.exp)(eta), observed=data['y'])
+    return make
+
+
+# ---------------------------------------------------------------------------------------------
+# tuple groups: parameter defined on (time, sensor), from tests/components/test_distribution_component.py:56-93
+# ---------------------------------------------------------------------------------------------
+def tuple_group_df() -> pd.DataFrame:
+    return pd.DataFrame({
+        'building': np.repeat(list('ab'), 10),
+        'sensor': np.repeat(list('stuv'), 5),
+        'time': np.tile(np.arange(5), 4),
+        'x': np.linspace(-1, 1, 20),
+        'y': np.cos(np.arange(20.0)),
+    })
+
+
+def tuple_group_likelihood(df):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        level = DC(pm.Normal, name='level', group=('time', 'sensor'),
+                   mu=DC(pm.Normal, name='by_time', group='time', mu=DC(pm.Normal, name='top', sigma=3.0)),
+                   sigma=DC(pm.HalfNormal, name='spread', group='building', sigma=1.0))
+        return api.Likelihood(pm.Normal, mu=level - 0.5 * data['x'], sigma=DC(pm.Exponential, lam=2.0),
+                              observed=data['y'])
+    return make
+
+
+def zoo():
+    out = {}
+    df = readme_df()
+    out['readme'] = (df, readme_likelihood(df))
+    df = shuffled_linreg_df()
+    out['shuffled_linreg'] = (df, readme_likelihood(df))
+    df = nested_df()
+    out['nested_logistic'] = (df, nested_logistic_likelihood(df))
+    out['nested_normal'] = (df, nested_normal_likelihood(df))
+    df = crossed_df()
+    out['crossed_poisson'] = (df, crossed_poisson_likelihood(df, True))
+    out['crossed_poisson_dense'] = (df, crossed_poisson_likelihood(df, False))
+    df = tuple_group_df()
+    out['tuple_group'] = (df, tuple_group_likelihood(df))
+    return out
