@@ -1,0 +1,78 @@
+"""
+TEST INFRASTRUCTURE -- independent second opinion on ``oracle/logp_numpy.py``.
+
+Evaluates the *recorded symbolic graph* of a built model (``sakkara_b200.model.sym.Model``: the
+distribution calls with their parameter expressions, exactly what the components handed to the
+backend) with torch fp64 tensors and ``torch.distributions`` log-densities, and differentiates
+with autograd.  It shares no code with the plan lowering nor with the closed-form gradients of
+the NumPy oracle, so agreement between the two pins the lowering (theta layout, gather
+composition, linearisation) and the hand-derived derivatives of SURVEY.md §A at once.
+"""
+import math
+
+import numpy as np
+import torch
+
+from sakkara_b200.model import sym
+
+
+def _evaluate(node, env):
+    if isinstance(node, sym.RandomVar):
+        return env[id(node)]
+    if isinstance(node, sym.DeterministicVar):
+        return _evaluate(node.var, env)
+    if isinstance(node, sym.DataVar):
+        return torch.as_tensor(np.asarray(node.values, dtype=np.float64))
+    if isinstance(node, sym.Gather):
+        base = _evaluate(node.base, env)
+        return base[tuple(torch.as_tensor(np.ascontiguousarray(i), dtype=torch.long) for i in node.indices)]
+    if isinstance(node, sym.BinOp):
+        left, right = _evaluate(node.left, env), _evaluate(node.right, env)
+        return sym.BinOp.OPS[node.op](left, right)
+    if isinstance(node, sym.UnaryOp):
+        arg = _evaluate(node.arg, env)
+        return {'neg': torch.neg, 'exp': torch.exp, 'sigmoid': torch.sigmoid}[node.op](arg)
+    return torch.as_tensor(np.asarray(node, dtype=np.float64))
+
+
+def logp_dlogp_autograd(recorded: sym.Model, theta: np.ndarray):
+    """logp and gradient w.r.t. the raveled unconstrained theta (free variables in creation order)."""
+    theta_t = torch.tensor(np.asarray(theta, dtype=np.float64), requires_grad=True)
+    env = {}
+    offset = 0
+    total = torch.zeros((), dtype=torch.float64)
+    for rv in recorded.free_RVs:
+        raw = theta_t[offset:offset + rv.size].reshape(rv.shape)
+        offset += rv.size
+        params = {k: _evaluate(v, env) for k, v in rv.params.items()}
+        if rv.family == 'Normal':
+            env[id(rv)] = raw
+            total = total + torch.distributions.Normal(params['mu'], params['sigma']).log_prob(raw).sum()
+        elif rv.family == 'HalfNormal':
+            value = torch.exp(raw)
+            env[id(rv)] = value
+            total = total + (torch.distributions.HalfNormal(params['sigma']).log_prob(value) + raw).sum()
+        elif rv.family == 'Exponential':
+            value = torch.exp(raw)
+            env[id(rv)] = value
+            total = total + (torch.distributions.Exponential(params['lam']).log_prob(value) + raw).sum()
+        else:
+            raise NotImplementedError(rv.family)
+    assert offset == theta_t.numel()
+    for rv in recorded.observed_RVs:
+        y = _evaluate(rv.observed, env)
+        params = {k: _evaluate(v, env) for k, v in rv.params.items()}
+        if rv.family == 'Normal':
+            total = total + torch.distributions.Normal(params['mu'], params['sigma']).log_prob(y).sum()
+        elif rv.family == 'Bernoulli':
+            if 'logit_p' in params:
+                d = torch.distributions.Bernoulli(logits=params['logit_p'])
+            else:
+                d = torch.distributions.Bernoulli(probs=params['p'])
+            total = total + d.log_prob(y).sum()
+        elif rv.family == 'Poisson':
+            total = total + torch.distributions.Poisson(params['mu']).log_prob(y).sum()
+        else:
+            raise NotImplementedError(rv.family)
+    total.backward()
+    return float(total.detach()), theta_t.grad.numpy().copy()
