@@ -1,0 +1,48 @@
+"""
+TEST INFRASTRUCTURE -- evaluates logp + dlogp from a *KernelPlan* (sorted rows, segment offsets,
+slot -> theta tables, secondary codes) with plain NumPy.  It shares the formulas of
+``oracle/logp_numpy.py`` but none of the structure decisions of the CUDA path, so comparing it
+with the oracle on the ModelPlan pins ``make_kernel_plan`` (permutation, segments, slot tables,
+uint8/uint16 narrowing, constants) on the CPU, without a GPU.
+"""
+import numpy as np
+
+from oracle.logp_numpy import LOG_SQRT_2PI, sigmoid, softplus
+
+
+def likelihood_from_kernel_plan(kp, theta):
+    """Returns (logp_likelihood incl. constants, grad[P]) in float64."""
+    theta = np.asarray(theta, dtype=np.float64)
+    n = kp.n_rows
+    eta = np.zeros(n) if kp.eta_offset is None else kp.eta_offset.astype(np.float64).copy()
+    slot_rows = []
+    for t in kp.terms:
+        if t.level == 0:
+            slot = np.zeros(n, dtype=np.int64)
+        elif t.level == 1:
+            slot = np.repeat(np.arange(kp.n_primary), np.diff(kp.seg_offsets))
+        else:
+            slot = kp.sec_codes.astype(np.int64)
+        slot_rows.append(slot)
+        x = 1.0 if t.xcol < 0 else kp.xcols[t.xcol].astype(np.float64)
+        eta += theta[t.theta_index.astype(np.int64)[slot]] * x
+    y = kp.y.astype(np.float64)
+    grad = np.zeros(kp.n_params)
+    if kp.family == 0:
+        sigma = np.exp(theta[kp.sigma_theta_index]) if kp.sigma_theta_index >= 0 else kp.sigma_const
+        r = (y - eta) / sigma
+        logp = np.sum(-0.5 * r * r) - n * (LOG_SQRT_2PI + np.log(sigma))
+        d = r / sigma
+        if kp.sigma_theta_index >= 0:
+            grad[kp.sigma_theta_index] += np.sum(r * r - 1.0)
+    elif kp.family == 1:
+        logp = np.sum(y * eta - softplus(eta))
+        d = y - sigmoid(eta)
+    else:
+        mu = np.exp(eta)
+        logp = np.sum(y * eta - mu) + kp.logp_const
+        d = y - mu
+    for t, slot in zip(kp.terms, slot_rows):
+        x = 1.0 if t.xcol < 0 else kp.xcols[t.xcol].astype(np.float64)
+        np.add.at(grad, t.theta_index.astype(np.int64)[slot], d * x)
+    return logp, grad

@@ -1,0 +1,191 @@
+// Shared definitions of the sm_100a kernels: parameter structs, PTX wrappers (mbarrier, TMA bulk
+// copy), warp primitives and the likelihood families.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/skk_b200.h"
+
+namespace skk {
+
+constexpr int kWarp = 32;
+constexpr int kMaxXCols = 6;      // float data columns a plan may stage (besides y / offset)
+constexpr int kMaxTermsPerLevel = 2;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// Parameters of the row kernel (K1).  Passed by value (__grid_constant__).
+//   Row data lives in device columns padded to n_tiles * rows_per_tile rows (zero filled), so a
+//   whole tile can always be fetched with one bulk copy per column.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct RowParams {
+    // row data
+    const T *x[kMaxXCols];
+    const T *y;              // observed column stored as T ...
+    const uint8_t *y8;       // ... or as uint8 (exactly one of y / y8 is non-null)
+    const T *eta_offset;     // optional constant part of eta
+    const void *sec_codes;   // uint16 or int32 per row
+    int32_t n_x;
+    int32_t sec_code_bytes;
+    int64_t n_rows;
+    int32_t n_tiles;
+    int32_t stages;          // smem ring depth per warp
+    // structure
+    const int2 *tile_keys;   // {first, last} primary slot of every tile
+    const int64_t *seg_offsets;  // [n_primary + 1]
+    int32_t n_primary;
+    int32_t n_secondary;
+    int32_t xcol_g[kMaxTermsPerLevel];
+    int32_t xcol_p[kMaxTermsPerLevel];
+    int32_t xcol_s[kMaxTermsPerLevel];
+    // per-evaluation values written by the prepare kernel (K0); b = chain within the batch tile
+    const T *val_g;          // [NG][BT]
+    const T *val_p;          // [NP][n_primary][BT]
+    const T *val_s;          // [NS][n_secondary][BT]
+    // outputs, all fp64
+    double *direct_p;        // [NP][n_primary][BT]   groups that lie inside one tile (zeroed per eval)
+    double *tile_head;       // [n_tiles][NP][BT]     partial of the tile's first group
+    double *tile_tail;       // [n_tiles][NP][BT]     partial of the tile's last group (if != first)
+    double *cta_glob;        // [grid][NG + 1][BT]    global-term partials, last entry = logp partial
+    double *cta_sec;         // [grid][NS][n_secondary][BT]
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+
+// order generic-proxy accesses to shared memory before later async-proxy (TMA) writes
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp primitives (all reductions use a fixed tree => bit-reproducible)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_down_f64(double v, int delta) {
+    return __shfl_down_sync(kFull, v, delta);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(kFull, v, d);
+    return v;  // valid in lane 0
+}
+
+// Among the lanes with `has`, group lanes holding the same key; the lowest lane of each group
+// receives the group's sum (added in ascending lane order).  Returns true on that lane.
+// Must be called by all 32 lanes.
+template <int NV>
+__device__ __forceinline__ bool warp_match_sum(bool has, int key, double (&v)[NV]) {
+    const unsigned active = __ballot_sync(kFull, has);
+    bool leader = false;
+    if (has) {
+        const unsigned peers = __match_any_sync(active, key);
+        const int lane = threadIdx.x & 31;
+        const int first = __ffs(peers) - 1;
+        leader = (lane == first);
+        if (peers & (peers - 1)) {  // more than one lane holds this key
+            double tot[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) tot[k] = 0.0;
+            for (unsigned rest = peers; rest; rest &= rest - 1) {
+                const int src = __ffs(rest) - 1;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) tot[k] += __shfl_sync(peers, v[k], src);
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = tot[k];
+        }
+    }
+    __syncwarp();
+    return leader;
+}
+
+// ---------------------------------------------------------------------------------------------
+// likelihood families: per row, contribution to logp and d logp / d eta
+//   Normal   : the kernel accumulates e = y - eta and e^2; 1/sigma^2 and the constants are applied
+//              once per evaluation in the finalise kernel.
+//   Bernoulli: y*eta - softplus(eta),            d = y - sigmoid(eta)
+//   Poisson  : y*eta - exp(eta) (-lgamma(y+1) is a per-plan constant),  d = y - exp(eta)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Math;
+template <>
+struct Math<float> {
+    static __device__ __forceinline__ float exp(float x) { return expf(x); }
+    static __device__ __forceinline__ float log1p(float x) { return log1pf(x); }
+    static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
+};
+template <>
+struct Math<double> {
+    static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+    static __device__ __forceinline__ double log1p(double x) { return ::log1p(x); }
+    static __device__ __forceinline__ double abs(double x) { return fabs(x); }
+    static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
+};
+
+template <typename T, int FAM>
+__device__ __forceinline__ void family_row(T y, T eta, T &lp, T &d) {
+    if constexpr (FAM == SKK_LIK_NORMAL) {
+        d = y - eta;
+        lp = d * d;
+    } else if constexpr (FAM == SKK_LIK_BERNOULLI_LOGIT) {
+        const T t = Math<T>::exp(-Math<T>::abs(eta));
+        const T inv = T(1) / (T(1) + t);
+        const T sig = eta >= T(0) ? inv : t * inv;
+        lp = y * eta - (Math<T>::max(eta, T(0)) + Math<T>::log1p(t));
+        d = y - sig;
+    } else {
+        const T mu = Math<T>::exp(eta);
+        lp = y * eta - mu;
+        d = y - mu;
+    }
+}
+
+}  // namespace skk

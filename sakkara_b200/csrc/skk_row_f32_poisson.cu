@@ -1,0 +1,8 @@
+// Row-kernel instantiations: float data, poisson likelihood (see skk_row_inst.cuh).
+#include "skk_row_inst.cuh"
+
+namespace skk {
+const void *row_kernel_f32_poisson(int bt, int ng, int np, int ns) {
+    return row_kernel_lookup<float, SKK_LIK_POISSON_LOG>(bt, ng, np, ns);
+}
+}  // namespace skk

@@ -1,0 +1,575 @@
+// K1: the row kernel.  One fused pass over the observation rows computes, for BT parameter
+// vectors at once, the likelihood's logp and the gradient w.r.t. every term of the linear
+// predictor, reduced per group without atomics.
+//
+// Design:
+//  * rows are pre-sorted by the primary grouping level (and by the secondary code inside a primary
+//    segment); a tile = 32*R consecutive rows belongs to one warp; a lane owns R consecutive rows.
+//  * each warp runs its own TMA pipeline: lane 0 issues one cp.async.bulk per data column into the
+//    warp's private shared-memory ring and all lanes wait on the stage's mbarrier -- no
+//    __syncthreads in the main loop, loads of `stages-1` tiles are in flight per warp.
+//  * a lane walks its R rows serially and merges runs of equal keys in registers.  Reductions
+//    across lanes use fixed shuffle trees or __match_any groups summed in lane order, and every
+//    partial lands in a slot with exactly one writer, so results are bit-reproducible:
+//      global terms / logp : per-lane fp64 accumulators over the whole CTA range -> cta_glob[cta]
+//      primary level       : tile inside one segment (the common case) -> one warp sum ->
+//                            tile_head[tile]; tile with segment boundaries -> groups that lie inside
+//                            the tile go to direct_p[group], the first/last group of the tile to
+//                            tile_head/tile_tail.  K4 adds the slots of every group in fixed order.
+//      secondary level     : warp-private accumulator table in shared memory (plain
+//                            read-modify-write: equal codes are contiguous inside a segment, so
+//                            runs that start and end inside a lane are owned by that lane; runs
+//                            shared between lanes are combined with warp_match_sum) -> cta_sec[cta].
+//  * R is odd so that lane-strided shared-memory reads of 4- and 8-byte columns are conflict free.
+#pragma once
+
+#include "skk_common.cuh"
+
+namespace skk {
+
+struct StageLayout {
+    int x_stride;  // x column c starts at c * x_stride
+    int y_off;
+    int off_off;
+    int code_off;
+    int bytes;  // per warp-stage, multiple of 128
+};
+
+template <typename T>
+__host__ __device__ inline StageLayout make_stage_layout(int rows_per_tile, int n_x, bool y_is_u8, bool has_offset,
+                                                         int code_bytes) {
+    StageLayout l{};
+    l.x_stride = rows_per_tile * (int)sizeof(T);
+    int o = n_x * l.x_stride;
+    l.y_off = o;
+    o += rows_per_tile * (y_is_u8 ? 1 : (int)sizeof(T));
+    l.off_off = o;
+    if (has_offset) o += rows_per_tile * (int)sizeof(T);
+    l.code_off = o;
+    o += rows_per_tile * code_bytes;
+    l.bytes = (o + 127) & ~127;
+    return l;
+}
+
+struct CtaLayout {
+    int bars_off;
+    int vals_off;   // secondary value table  [NS][GS][BT] of T
+    int grads_off;  // secondary gradient tables [W][NS][GS][BT] of T
+    int stage_off;
+    int total;
+};
+
+template <typename T>
+__host__ __device__ inline CtaLayout make_cta_layout(int warps, int stages, int stage_bytes, int ns, int gs, int bt) {
+    CtaLayout l{};
+    int o = 0;
+    l.bars_off = o;
+    o += warps * stages * 8;
+    o = (o + 15) & ~15;
+    l.vals_off = o;
+    o += ns * gs * bt * (int)sizeof(T);
+    o = (o + 15) & ~15;
+    l.grads_off = o;
+    o += warps * ns * gs * bt * (int)sizeof(T);
+    o = (o + 127) & ~127;
+    l.stage_off = o;
+    o += warps * stages * stage_bytes;
+    l.total = o;
+    return l;
+}
+
+template <int N>
+struct AtLeast1 {
+    static constexpr int value = N > 0 ? N : 1;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <typename T, int FAM, int BT, int NG, int NP, int NS, int R>
+struct RowKernel {
+    static constexpr int WT = 32 * R;  // rows per tile
+    static constexpr int NGa = AtLeast1<NG>::value;
+    static constexpr int NPa = AtLeast1<NP>::value;
+    static constexpr int NSa = AtLeast1<NS>::value;
+
+    struct Tile {
+        const unsigned char *stage;
+        StageLayout sl;
+        int tile;
+        int kf, kl;
+    };
+
+    // -----------------------------------------------------------------------------------------
+    template <bool FASTP>
+    static __device__ __forceinline__ void process(const RowParams<T> &p, const Tile &tl, const T (&vp_first)[NPa][BT],
+                                                   const T (&vg)[NGa][BT], double (&accG64)[NG + 1][BT],
+                                                   const T *__restrict__ valS, T *__restrict__ gradS, int lane) {
+        const int li = lane * R;
+        const int64_t row0 = (int64_t)tl.tile * WT + li;
+        const int64_t left = p.n_rows - row0;
+        const int nvalid = left >= R ? R : (left > 0 ? (int)left : 0);
+
+        // data columns of the terms (x == 1 when the term has no column)
+        const T *pxg[NGa], *pxp[NPa], *pxs[NSa];
+#pragma unroll
+        for (int t = 0; t < NGa; ++t)
+            pxg[t] = (t < NG && p.xcol_g[t] >= 0)
+                         ? reinterpret_cast<const T *>(tl.stage + p.xcol_g[t] * tl.sl.x_stride) + li : nullptr;
+#pragma unroll
+        for (int t = 0; t < NPa; ++t)
+            pxp[t] = (t < NP && p.xcol_p[t] >= 0)
+                         ? reinterpret_cast<const T *>(tl.stage + p.xcol_p[t] * tl.sl.x_stride) + li : nullptr;
+#pragma unroll
+        for (int t = 0; t < NSa; ++t)
+            pxs[t] = (t < NS && p.xcol_s[t] >= 0)
+                         ? reinterpret_cast<const T *>(tl.stage + p.xcol_s[t] * tl.sl.x_stride) + li : nullptr;
+        const T *sy = reinterpret_cast<const T *>(tl.stage + tl.sl.y_off) + li;
+        const uint8_t *sy8 = reinterpret_cast<const uint8_t *>(tl.stage + tl.sl.y_off) + li;
+        const T *soff = reinterpret_cast<const T *>(tl.stage + tl.sl.off_off) + li;
+        const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(tl.stage + tl.sl.code_off) + li;
+        const int32_t *sc32 = reinterpret_cast<const int32_t *>(tl.stage + tl.sl.code_off) + li;
+        const bool y_u8 = p.y8 != nullptr;
+        const bool has_off = p.eta_offset != nullptr;
+        const bool code16 = p.sec_code_bytes == 2;
+
+        // per-span accumulators in T; folded into fp64 at run / span boundaries
+        T accL[BT], accG[NGa][BT], accP[NPa][BT], accS[NSa][BT];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            accL[b] = T(0);
+#pragma unroll
+            for (int t = 0; t < NGa; ++t) accG[t][b] = T(0);
+#pragma unroll
+            for (int t = 0; t < NPa; ++t) accP[t][b] = T(0);
+#pragma unroll
+            for (int t = 0; t < NSa; ++t) accS[t][b] = T(0);
+        }
+
+        // ---- primary level state ----------------------------------------------------------------
+        T vp[NPa][BT];
+#pragma unroll
+        for (int t = 0; t < NPa; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) vp[t][b] = vp_first[t][b];
+        int kcur = tl.kf;
+        int64_t nextb = INT64_MAX;
+        bool p_changed = false, p_have_head = false, p_inside = false;
+        int p_head_key = 0;
+        double p_head[NPa * BT];
+        if constexpr (NP > 0 && !FASTP) {
+            if (nvalid > 0) {
+                // segment of the lane's first row: largest k in [kf, kl] with seg_offsets[k] <= row0
+                int lo = tl.kf, hi = tl.kl;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (p.seg_offsets[mid] <= row0) lo = mid; else hi = mid - 1;
+                }
+                kcur = lo;
+                nextb = p.seg_offsets[kcur + 1];
+                p_inside = p.seg_offsets[kcur] >= row0;
+#pragma unroll
+                for (int t = 0; t < NP; ++t)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) vp[t][b] = p.val_p[((int64_t)t * p.n_primary + kcur) * BT + b];
+            }
+        }
+
+        // ---- secondary level state --------------------------------------------------------------
+        int scur = 0;
+        bool s_changed = false;
+        int s_head_key = 0;
+        double s_head[NSa * BT];
+        T vs[NSa][BT];
+#pragma unroll
+        for (int t = 0; t < NSa; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) vs[t][b] = T(0);
+        if constexpr (NS > 0) {
+            if (nvalid > 0) {
+                scur = code16 ? (int)sc16[0] : sc32[0];
+#pragma unroll
+                for (int t = 0; t < NS; ++t)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) vs[t][b] = valS[((int64_t)t * p.n_secondary + scur) * BT + b];
+            }
+        }
+
+        // ---- the rows ---------------------------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const bool valid = i < nvalid;
+
+            if constexpr (NP > 0 && !FASTP) {
+                // segment boundaries inside the lane's span (tiles that straddle segments only)
+                while (valid && row0 + i >= nextb) {
+                    if (p_inside) {
+                        // the group started and ended inside this lane: it has no other writer
+#pragma unroll
+                        for (int t = 0; t < NP; ++t)
+#pragma unroll
+                            for (int b = 0; b < BT; ++b)
+                                p.direct_p[((int64_t)t * p.n_primary + kcur) * BT + b] = (double)accP[t][b];
+                    } else {
+                        p_have_head = true;
+                        p_head_key = kcur;
+#pragma unroll
+                        for (int t = 0; t < NP; ++t)
+#pragma unroll
+                            for (int b = 0; b < BT; ++b) p_head[t * BT + b] = (double)accP[t][b];
+                    }
+                    p_changed = true;
+                    p_inside = true;
+                    ++kcur;
+                    nextb = p.seg_offsets[kcur + 1];
+#pragma unroll
+                    for (int t = 0; t < NP; ++t)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) {
+                            accP[t][b] = T(0);
+                            vp[t][b] = p.val_p[((int64_t)t * p.n_primary + kcur) * BT + b];
+                        }
+                }
+                __syncwarp();
+            }
+
+            if constexpr (NS > 0) {
+                const int c = code16 ? (int)sc16[i] : sc32[i];
+                const bool change = valid && (c != scur);
+                if constexpr (FASTP) {
+                    if (change) {
+                        if (s_changed) {
+                            // run started and ended inside this lane; equal codes are contiguous inside
+                            // a primary segment, so no other lane of the warp touches this entry now
+#pragma unroll
+                            for (int t = 0; t < NS; ++t)
+#pragma unroll
+                                for (int b = 0; b < BT; ++b)
+                                    gradS[((int64_t)t * p.n_secondary + scur) * BT + b] += accS[t][b];
+                        } else {
+                            s_head_key = scur;
+#pragma unroll
+                            for (int t = 0; t < NS; ++t)
+#pragma unroll
+                                for (int b = 0; b < BT; ++b) s_head[t * BT + b] = (double)accS[t][b];
+                        }
+                    }
+                } else {
+                    // the tile straddles primary segments: a code may occur in several runs of the
+                    // tile, so lanes flushing the same entry at the same step are combined first
+                    const bool flush = change && s_changed;
+                    double v[NSa * BT];
+#pragma unroll
+                    for (int t = 0; t < NS; ++t)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) v[t * BT + b] = (double)accS[t][b];
+                    if (warp_match_sum<NSa * BT>(flush, scur, v)) {
+#pragma unroll
+                        for (int t = 0; t < NS; ++t)
+#pragma unroll
+                            for (int b = 0; b < BT; ++b)
+                                gradS[((int64_t)t * p.n_secondary + scur) * BT + b] += (T)v[t * BT + b];
+                    }
+                    __syncwarp();
+                    if (change && !s_changed) {
+                        s_head_key = scur;
+#pragma unroll
+                        for (int t = 0; t < NS; ++t)
+#pragma unroll
+                            for (int b = 0; b < BT; ++b) s_head[t * BT + b] = (double)accS[t][b];
+                    }
+                }
+                if (change) {
+                    s_changed = true;
+                    scur = c;
+#pragma unroll
+                    for (int t = 0; t < NS; ++t)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) {
+                            accS[t][b] = T(0);
+                            vs[t][b] = valS[((int64_t)t * p.n_secondary + c) * BT + b];
+                        }
+                }
+            }
+
+            // data of the row
+            const T yv = y_u8 ? (T)sy8[i] : sy[i];
+            T xg[NGa], xp[NPa], xs[NSa];
+#pragma unroll
+            for (int t = 0; t < NG; ++t) xg[t] = pxg[t] ? pxg[t][i] : T(1);
+#pragma unroll
+            for (int t = 0; t < NP; ++t) xp[t] = pxp[t] ? pxp[t][i] : T(1);
+#pragma unroll
+            for (int t = 0; t < NS; ++t) xs[t] = pxs[t] ? pxs[t][i] : T(1);
+            const T off = has_off ? soff[i] : T(0);
+
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                T eta = off;
+#pragma unroll
+                for (int t = 0; t < NG; ++t) eta += vg[t][b] * xg[t];
+#pragma unroll
+                for (int t = 0; t < NP; ++t) eta += vp[t][b] * xp[t];
+#pragma unroll
+                for (int t = 0; t < NS; ++t) eta += vs[t][b] * xs[t];
+                T lp, d;
+                family_row<T, FAM>(yv, eta, lp, d);
+                if (!valid) {
+                    lp = T(0);
+                    d = T(0);
+                }
+                accL[b] += lp;
+#pragma unroll
+                for (int t = 0; t < NG; ++t) accG[t][b] += d * xg[t];
+#pragma unroll
+                for (int t = 0; t < NP; ++t) accP[t][b] += d * xp[t];
+#pragma unroll
+                for (int t = 0; t < NS; ++t) accS[t][b] += d * xs[t];
+            }
+        }
+
+        // ---- global terms and logp: lane-private fp64 accumulators over the CTA's whole range ------
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+#pragma unroll
+            for (int t = 0; t < NG; ++t) accG64[t][b] += (double)accG[t][b];
+            accG64[NG][b] += (double)accL[b];
+        }
+
+        // ---- primary level ------------------------------------------------------------------------
+        if constexpr (NP > 0) {
+            if constexpr (FASTP) {
+#pragma unroll
+                for (int t = 0; t < NP; ++t)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) {
+                        const double s = warp_sum((double)accP[t][b]);
+                        if (lane == 0) p.tile_head[((int64_t)tl.tile * NP + t) * BT + b] = s;
+                    }
+            } else {
+                double *head = p.tile_head + (int64_t)tl.tile * NP * BT;
+                double *tail = p.tile_tail + (int64_t)tl.tile * NP * BT;
+                if (lane < NP * BT) {
+                    head[lane] = 0.0;
+                    tail[lane] = 0.0;
+                }
+                __syncwarp();
+                // round A: the first run of every lane (or its only run); round B: the last run
+                double v[NPa * BT];
+                int key;
+                bool has;
+                for (int round = 0; round < 2; ++round) {
+                    if (round == 0) {
+                        // first run of the lane unless it was a complete group stored directly
+                        has = nvalid > 0 && (p_have_head || !p_changed);
+                        key = p_have_head ? p_head_key : kcur;
+#pragma unroll
+                        for (int k = 0; k < NP * BT; ++k)
+                            v[k] = p_have_head ? p_head[k] : (double)accP[k / BT][k % BT];
+                    } else {
+                        has = p_changed && nvalid > 0;
+                        key = kcur;
+#pragma unroll
+                        for (int k = 0; k < NP * BT; ++k) v[k] = (double)accP[k / BT][k % BT];
+                    }
+                    if (warp_match_sum<NPa * BT>(has, key, v)) {
+                        double *sink = key == tl.kf ? head
+                                       : key == tl.kl ? tail
+                                                      : nullptr;
+#pragma unroll
+                        for (int k = 0; k < NP * BT; ++k) {
+                            double *dst = sink ? sink + k
+                                               : p.direct_p + ((int64_t)(k / BT) * p.n_primary + key) * BT + (k % BT);
+                            *dst = *reinterpret_cast<volatile double *>(dst) + v[k];
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+
+        // ---- secondary level: runs shared between lanes ----------------------------------------------
+        if constexpr (NS > 0) {
+            double v[NSa * BT];
+            for (int round = 0; round < 2; ++round) {
+                bool has;
+                int key;
+                if (round == 0) {
+                    has = nvalid > 0;
+                    key = s_changed ? s_head_key : scur;
+#pragma unroll
+                    for (int k = 0; k < NS * BT; ++k) v[k] = s_changed ? s_head[k] : (double)accS[k / BT][k % BT];
+                } else {
+                    has = s_changed;
+                    key = scur;
+#pragma unroll
+                    for (int k = 0; k < NS * BT; ++k) v[k] = (double)accS[k / BT][k % BT];
+                }
+                if (warp_match_sum<NSa * BT>(has, key, v)) {
+#pragma unroll
+                    for (int k = 0; k < NS * BT; ++k)
+                        gradS[((int64_t)(k / BT) * p.n_secondary + key) * BT + (k % BT)] += (T)v[k];
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    // -----------------------------------------------------------------------------------------
+    static __device__ __forceinline__ void issue_tile(const RowParams<T> &p, int tile, unsigned char *stage,
+                                                      const StageLayout &sl, uint64_t *bar) {
+        const int64_t row = (int64_t)tile * WT;
+        const uint32_t ybytes = p.y8 ? WT : WT * (uint32_t)sizeof(T);
+        uint32_t total = (uint32_t)p.n_x * WT * (uint32_t)sizeof(T) + ybytes;
+        if (p.eta_offset) total += WT * (uint32_t)sizeof(T);
+        if (NS > 0) total += WT * (uint32_t)p.sec_code_bytes;
+        mbar_arrive_expect_tx(bar, total);
+        for (int c = 0; c < p.n_x; ++c)
+            tma_load_1d(stage + c * sl.x_stride, p.x[c] + row, WT * (uint32_t)sizeof(T), bar);
+        if (p.y8)
+            tma_load_1d(stage + sl.y_off, p.y8 + row, ybytes, bar);
+        else
+            tma_load_1d(stage + sl.y_off, p.y + row, ybytes, bar);
+        if (p.eta_offset) tma_load_1d(stage + sl.off_off, p.eta_offset + row, WT * (uint32_t)sizeof(T), bar);
+        if (NS > 0)
+            tma_load_1d(stage + sl.code_off,
+                        reinterpret_cast<const unsigned char *>(p.sec_codes) + row * p.sec_code_bytes,
+                        WT * (uint32_t)p.sec_code_bytes, bar);
+    }
+
+    static __device__ __forceinline__ void load_vp(const RowParams<T> &p, int key, T (&vp)[NPa][BT]) {
+#pragma unroll
+        for (int t = 0; t < NPa; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b)
+                vp[t][b] = (NP > 0) ? p.val_p[((int64_t)t * p.n_primary + key) * BT + b] : T(0);
+    }
+
+    // -----------------------------------------------------------------------------------------
+    static __device__ void run(const RowParams<T> &p) {
+        extern __shared__ __align__(128) unsigned char smem[];
+        const int warps = blockDim.x >> 5;
+        const int warp = threadIdx.x >> 5;
+        const int lane = threadIdx.x & 31;
+        const int stages = p.stages;
+
+        const StageLayout sl =
+            make_stage_layout<T>(WT, p.n_x, p.y8 != nullptr, p.eta_offset != nullptr, NS > 0 ? p.sec_code_bytes : 0);
+        const CtaLayout cl = make_cta_layout<T>(warps, stages, sl.bytes, NS, p.n_secondary, BT);
+        uint64_t *bars = reinterpret_cast<uint64_t *>(smem + cl.bars_off) + warp * stages;
+        T *valS = reinterpret_cast<T *>(smem + cl.vals_off);
+        T *gradS_all = reinterpret_cast<T *>(smem + cl.grads_off);
+        T *gradS = gradS_all + (int64_t)warp * NS * p.n_secondary * BT;
+        unsigned char *stage0 = smem + cl.stage_off + (int64_t)warp * stages * sl.bytes;
+
+        // contiguous, balanced range of tiles for this CTA; its warps interleave inside the range
+        const int64_t nt = p.n_tiles;
+        const int tile_begin = (int)((nt * blockIdx.x) / gridDim.x);
+        const int tile_end = (int)((nt * (blockIdx.x + 1)) / gridDim.x);
+
+        if (lane == 0) {
+            for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        // start the pipeline before touching anything else
+        if (lane == 0) {
+            for (int s = 0; s < stages; ++s) {
+                const int t = tile_begin + warp + s * warps;
+                if (t < tile_end) issue_tile(p, t, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
+            }
+        }
+
+        if constexpr (NS > 0) {
+            const int n = NS * p.n_secondary * BT;
+            for (int k = threadIdx.x; k < n; k += blockDim.x) valS[k] = p.val_s[k];
+            for (int k = threadIdx.x; k < n * warps; k += blockDim.x) gradS_all[k] = T(0);
+            __syncthreads();
+        }
+
+        T vg[NGa][BT];
+#pragma unroll
+        for (int t = 0; t < NGa; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) vg[t][b] = (NG > 0) ? p.val_g[t * BT + b] : T(0);
+
+        double accG64[NG + 1][BT];
+#pragma unroll
+        for (int t = 0; t <= NG; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) accG64[t][b] = 0.0;
+
+        // software prefetch of the tile keys (two tiles ahead) and primary values (one ahead)
+        int tile = tile_begin + warp;
+        int2 k0 = make_int2(0, 0), k1 = make_int2(0, 0);
+        T vp0[NPa][BT];
+        if constexpr (NP > 0) {
+            if (tile < tile_end) k0 = p.tile_keys[tile];
+            if (tile + warps < tile_end) k1 = p.tile_keys[tile + warps];
+        }
+        load_vp(p, k0.x, vp0);
+
+        for (int it = 0; tile < tile_end; tile += warps, ++it) {
+            const int s = it % stages;
+            const uint32_t parity = (uint32_t)(it / stages) & 1u;
+            int2 k2 = make_int2(0, 0);
+            T vp1[NPa][BT];
+            if constexpr (NP > 0) {
+                if (tile + 2 * warps < tile_end) k2 = p.tile_keys[tile + 2 * warps];
+            }
+            load_vp(p, k1.x, vp1);
+
+            mbar_wait(bars + s, parity);
+
+            Tile tl{stage0 + (int64_t)s * sl.bytes, sl, tile, k0.x, k0.y};
+            if (NP == 0 || k0.x == k0.y)
+                process<true>(p, tl, vp0, vg, accG64, valS, gradS, lane);
+            else
+                process<false>(p, tl, vp0, vg, accG64, valS, gradS, lane);
+
+            __syncwarp();
+            const int next = tile + stages * warps;
+            if (lane == 0 && next < tile_end) {
+                fence_proxy_async();
+                issue_tile(p, next, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
+            }
+            k0 = k1;
+            k1 = k2;
+#pragma unroll
+            for (int t = 0; t < NPa; ++t)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) vp0[t][b] = vp1[t][b];
+        }
+
+        // ---- CTA epilogue: fixed-order reductions over lanes, then warps ---------------------------
+        __syncthreads();  // all warps are done with their staging buffers; reuse the first one
+        double *red = reinterpret_cast<double *>(smem + cl.stage_off);  // [warps][(NG+1)*BT]
+        constexpr int NV = (NG + 1) * BT;
+#pragma unroll
+        for (int t = 0; t <= NG; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                const double s = warp_sum(accG64[t][b]);
+                if (lane == 0) red[warp * NV + t * BT + b] = s;
+            }
+        __syncthreads();
+        if (threadIdx.x < NV) {
+            double s = 0.0;
+            for (int w = 0; w < warps; ++w) s += red[w * NV + threadIdx.x];
+            p.cta_glob[(int64_t)blockIdx.x * NV + threadIdx.x] = s;
+        }
+        if constexpr (NS > 0) {
+            const int n = NS * p.n_secondary * BT;
+            for (int k = threadIdx.x; k < n; k += blockDim.x) {
+                double s = 0.0;
+                for (int w = 0; w < warps; ++w) s += (double)gradS_all[(int64_t)w * n + k];
+                p.cta_sec[(int64_t)blockIdx.x * n + k] = s;
+            }
+        }
+    }
+};
+
+template <typename T, int FAM, int BT, int NG, int NP, int NS, int R>
+__global__ void __launch_bounds__(384, 1) skk_row_kernel(const __grid_constant__ RowParams<T> p) {
+    RowKernel<T, FAM, BT, NG, NP, NS, R>::run(p);
+}
+
+}  // namespace skk

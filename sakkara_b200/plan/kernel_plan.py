@@ -1,0 +1,380 @@
+"""
+Kernel plan: what the CUDA library needs, derived from a :class:`ModelPlan` (SURVEY.md §7 step 1/2,
+"index builder").  All integer work here must be exact; it is checked bit-for-bit in
+``tests/test_kernel_plan.py`` (permutation, segment offsets, slot tables).
+
+Decisions taken here:
+
+* **levels** -- every term of the linear predictor indexes its block through a per-row code
+  column.  Constant columns are *global* terms.  The remaining distinct columns are ordered by
+  functional dependence (column c determines column d when every code of c occurs with one code of
+  d -- the reference's parent test, ``sakkara/relation/groupset.py:42-44``).  The finest column
+  becomes the **primary** level: rows are sorted by it, its groups are contiguous segments and the
+  kernel needs no code column for it.  Columns it determines (nested parents) ride on the same
+  segments through a slot -> theta table.  A second, crossed factor becomes the **secondary** level
+  with a per-row code column (uint16 when it fits); rows are sorted by it inside every primary
+  segment so that equal codes are contiguous.
+* **slot order** -- primary groups are numbered so that the groups of one parent are adjacent
+  (lexicographic in coarse-to-fine ancestor codes), which keeps parent-level reductions local.
+* **row order** -- stable sort by (primary slot, secondary slot); LSD radix passes over 16-bit
+  digits (NumPy's stable sort of uint16 is a radix sort), skipped when the rows are already sorted.
+* **storage** -- data columns in the plan's floating type; 0/1 and small-count observations as
+  uint8; identical data columns are stored once.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+from scipy.special import gammaln
+
+from sakkara_b200.plan.lower import UnsupportedModelError
+from sakkara_b200.plan.model_plan import FAMILY_IDS, ModelPlan
+
+LEVEL_GLOBAL, LEVEL_PRIMARY, LEVEL_SECONDARY = 0, 1, 2
+MAX_TERMS_PER_LEVEL = 2
+MAX_SECONDARY_TERMS = 1
+MAX_XCOLS = 6
+
+
+@dataclass
+class KernelTerm:
+    level: int
+    xcol: int                       # -1: no data column
+    theta_index: np.ndarray         # int32[n_slots]
+    block: int = -1                 # for diagnostics
+
+
+@dataclass
+class KernelBlock:
+    family: int
+    offset: int
+    size: int
+    a_const: Optional[np.ndarray] = None    # float64
+    a_index: Optional[np.ndarray] = None    # int32, absolute theta index per element
+    b_const: Optional[np.ndarray] = None
+    b_index: Optional[np.ndarray] = None
+
+
+@dataclass
+class KernelPlan:
+    dtype: np.dtype
+    family: int
+    n_rows: int
+    n_rows_total: int
+    n_params: int
+    perm: Optional[np.ndarray]              # kernel row -> row of the (sharded) input; None = identity
+    xcols: List[np.ndarray]
+    y: np.ndarray
+    y_kind: int                             # 0 float, 1 uint8
+    eta_offset: Optional[np.ndarray]
+    n_primary: int
+    seg_offsets: np.ndarray                 # int64[n_primary + 1]
+    n_secondary: int
+    sec_codes: Optional[np.ndarray]         # uint16 / int32 [n_rows]
+    terms: List[KernelTerm]
+    blocks: List[KernelBlock]
+    sigma_const: float
+    sigma_theta_index: int
+    logp_const: float
+    include_priors: bool = True
+
+    @property
+    def stored_bytes_per_row(self) -> int:
+        s = self.dtype.itemsize
+        n = len(self.xcols) * s + (1 if self.y_kind == 1 else s)
+        if self.eta_offset is not None:
+            n += s
+        if self.sec_codes is not None:
+            n += self.sec_codes.dtype.itemsize
+        return n
+
+    def describe(self) -> str:
+        lv = {0: 'global', 1: 'primary', 2: 'secondary'}
+        lines = [f'KernelPlan: N={self.n_rows} P={self.n_params} dtype={self.dtype} family={self.family} '
+                 f'primary={self.n_primary} secondary={self.n_secondary} bytes/row={self.stored_bytes_per_row}']
+        for t in self.terms:
+            lines.append(f'  term[{lv[t.level]}] block {t.block} xcol {t.xcol} slots {len(t.theta_index)}')
+        return '\n'.join(lines)
+
+
+# ---------------------------------------------------------------------------------------------
+# integer helpers
+# ---------------------------------------------------------------------------------------------
+def dense_codes(index: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """First-appearance factorisation: ``(codes[N] int64, elements[G] int64, first_row[G])``."""
+    codes, elements = pd.factorize(index, sort=False)
+    codes = codes.astype(np.int64, copy=False)
+    first_row = np.flatnonzero(~pd.Series(codes).duplicated(keep='first').values)
+    return codes, np.asarray(elements, dtype=np.int64), first_row
+
+
+def determines(codes_c: np.ndarray, first_row_c: np.ndarray, codes_d: np.ndarray) -> Optional[np.ndarray]:
+    """Lookup ``code of c -> code of d`` if c determines d, else None."""
+    table = codes_d[first_row_c]
+    return table if np.array_equal(table[codes_c], codes_d) else None
+
+
+def stable_argsort_small(keys: np.ndarray, n_keys: int) -> np.ndarray:
+    """Stable argsort of non-negative integer keys < n_keys with 16-bit radix passes."""
+    if n_keys <= 1 << 16:
+        return np.argsort(keys.astype(np.uint16, copy=False), kind='stable')
+    low = (keys & 0xFFFF).astype(np.uint16)
+    order = np.argsort(low, kind='stable')
+    high = (keys >> 16)[order]
+    if n_keys <= 1 << 32:
+        order = order[np.argsort(high.astype(np.uint16), kind='stable')]
+        return order
+    return np.argsort(keys, kind='stable')
+
+
+def sort_rows(primary: Optional[np.ndarray], n_primary: int, secondary: Optional[np.ndarray],
+              n_secondary: int) -> Optional[np.ndarray]:
+    """Permutation that sorts rows by (primary, secondary), stable; None when already sorted."""
+    n = len(primary) if primary is not None else (len(secondary) if secondary is not None else 0)
+    if n == 0 or (primary is None and secondary is None):
+        return None
+
+    def is_sorted() -> bool:
+        if primary is not None and secondary is not None:
+            dp = np.diff(primary)
+            if (dp < 0).any():
+                return False
+            return not ((dp == 0) & (np.diff(secondary) < 0)).any()
+        keys = primary if primary is not None else secondary
+        return not (np.diff(keys) < 0).any()
+
+    if is_sorted():
+        return None
+    perm = None
+    if secondary is not None:
+        perm = stable_argsort_small(secondary, n_secondary)
+    if primary is not None:
+        keys = primary if perm is None else primary[perm]
+        order = stable_argsort_small(keys, n_primary)
+        perm = order if perm is None else perm[order]
+    return perm.astype(np.int64, copy=False)
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class _Column:
+    codes: np.ndarray
+    elements: np.ndarray       # block element (flat index) of every code
+    first_row: np.ndarray
+    terms: List[int] = field(default_factory=list)
+
+    @property
+    def size(self) -> int:
+        return len(self.elements)
+
+
+def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray] = None,
+                     n_rows_total: Optional[int] = None, narrow_y: bool = True,
+                     include_priors: bool = True) -> KernelPlan:
+    """
+    :param rows: optional subset of the rows (this rank's shard); all ranks pass the same ``plan``
+        and disjoint ``rows`` whose union is all rows.
+    :param n_rows_total: number of rows over all ranks (defaults to this plan's rows).
+    """
+    dtype = np.dtype(dtype)
+    if dtype not in (np.dtype('float32'), np.dtype('float64')):
+        raise ValueError('dtype must be float32 or float64')
+    lik = plan.likelihood
+
+    def take(a):
+        if a is None or rows is None:
+            return a
+        return a[rows]
+
+    n = plan.n_rows if rows is None else len(np.arange(plan.n_rows)[rows])
+    total = n if n_rows_total is None else int(n_rows_total)
+
+    # ---- classify the terms ------------------------------------------------------------------------
+    global_terms: Dict[int, int] = {}          # term number -> theta index
+    columns: List[_Column] = []
+    column_of_term: Dict[int, int] = {}
+    elem_of_term: Dict[int, np.ndarray] = {}    # block element per code, per term
+    seen_arrays: Dict[int, int] = {}
+    for number, term in enumerate(plan.terms):
+        block = plan.blocks[term.block]
+        if block.transform != 'identity':
+            raise UnsupportedModelError(f'{block.name}: positive variables cannot enter the linear predictor')
+        index = take(term.index)
+        if n == 0 or block.size == 1 or index.min() == index.max():
+            global_terms[number] = block.offset + (int(index[0]) if n else 0)
+            continue
+        key = id(term.index)
+        if key in seen_arrays:
+            col = seen_arrays[key]
+            column_of_term[number] = col
+            elem_of_term[number] = columns[col].elements
+            columns[col].terms.append(number)
+            continue
+        codes, elements, first_row = dense_codes(index)
+        match = None
+        for c, other in enumerate(columns):
+            if other.size == len(elements) and np.array_equal(other.codes, codes):
+                match = c
+                break
+        if match is None:
+            columns.append(_Column(codes, elements, first_row))
+            match = len(columns) - 1
+        seen_arrays[key] = match
+        column_of_term[number] = match
+        elem_of_term[number] = elements       # same partition, but this term's own block elements
+        columns[match].terms.append(number)
+
+    # ---- order the columns by functional dependence --------------------------------------------------
+    k = len(columns)
+    table: Dict[Tuple[int, int], np.ndarray] = {}
+    for c in range(k):
+        for d in range(k):
+            if c != d and columns[c].size >= columns[d].size:
+                t = determines(columns[c].codes, columns[c].first_row, columns[d].codes)
+                if t is not None:
+                    table[(c, d)] = t
+    finest = [c for c in range(k)
+              if not any((d, c) in table and (c, d) not in table for d in range(k) if d != c)]
+    # twins cannot occur here (identical partitions were merged above)
+    if len(finest) > 2:
+        raise UnsupportedModelError(f'{len(finest)} crossed grouping factors; the fused kernel handles at most two')
+    primary = secondary = None
+    if len(finest) == 1:
+        primary = finest[0]
+    elif len(finest) == 2:
+        a, b = finest
+        # the smaller factor goes to the shared-memory table, the larger one is sorted
+        primary, secondary = (a, b) if columns[a].size >= columns[b].size else (b, a)
+    owner: Dict[int, int] = {}
+    for c in range(k):
+        if c == primary or c == secondary:
+            owner[c] = c
+        elif primary is not None and (primary, c) in table:
+            owner[c] = primary
+        elif secondary is not None and (secondary, c) in table:
+            owner[c] = secondary
+        else:
+            raise UnsupportedModelError('a grouping column is determined by neither sorted level')
+
+    def slot_order(fine: int) -> np.ndarray:
+        """codes of `fine` ordered so that the groups of one ancestor are adjacent"""
+        col = columns[fine]
+        ancestors = sorted((c for c in range(k) if c != fine and owner.get(c) == fine),
+                           key=lambda c: columns[c].size)
+        keys = [np.arange(col.size)] + [table[(fine, a)] for a in reversed(ancestors)]
+        return np.lexsort(tuple(keys)) if ancestors else np.arange(col.size)
+
+    n_primary = n_secondary = 0
+    p_slot_of_row = s_slot_of_row = None
+    p_code_of_slot = s_code_of_slot = None
+    if primary is not None:
+        p_code_of_slot = slot_order(primary)
+        n_primary = len(p_code_of_slot)
+        inv = np.empty(n_primary, dtype=np.int64)
+        inv[p_code_of_slot] = np.arange(n_primary)
+        p_slot_of_row = inv[columns[primary].codes]
+    if secondary is not None:
+        s_code_of_slot = slot_order(secondary)
+        n_secondary = len(s_code_of_slot)
+        inv = np.empty(n_secondary, dtype=np.int64)
+        inv[s_code_of_slot] = np.arange(n_secondary)
+        s_slot_of_row = inv[columns[secondary].codes]
+
+    perm = sort_rows(p_slot_of_row, n_primary, s_slot_of_row, n_secondary)
+
+    def arrange(a):
+        return a if perm is None else a[perm]
+
+    seg_offsets = np.zeros(n_primary + 1, dtype=np.int64)
+    if primary is not None:
+        np.cumsum(np.bincount(p_slot_of_row, minlength=n_primary), out=seg_offsets[1:])
+    sec_codes = None
+    if secondary is not None:
+        sec_codes = arrange(s_slot_of_row).astype(np.uint16 if n_secondary <= 1 << 16 else np.int32)
+
+    # ---- data columns ------------------------------------------------------------------------------------
+    xcols: List[np.ndarray] = []
+    x_sources: List[np.ndarray] = []
+
+    def xcol_of(x: Optional[np.ndarray]) -> int:
+        if x is None:
+            return -1
+        for c, src in enumerate(x_sources):
+            if src is x or (src.shape == x.shape and np.array_equal(src, x)):
+                return c
+        if len(xcols) >= MAX_XCOLS:
+            raise UnsupportedModelError(f'more than {MAX_XCOLS} distinct data columns in the linear predictor')
+        x_sources.append(x)
+        xcols.append(np.ascontiguousarray(arrange(take(x)), dtype=dtype))
+        return len(xcols) - 1
+
+    # ---- terms --------------------------------------------------------------------------------------------------
+    terms: List[KernelTerm] = []
+    counts = {LEVEL_GLOBAL: 0, LEVEL_PRIMARY: 0, LEVEL_SECONDARY: 0}
+    for number, term in enumerate(plan.terms):
+        block = plan.blocks[term.block]
+        xc = xcol_of(term.x)
+        if number in global_terms:
+            level = LEVEL_GLOBAL
+            theta_index = np.array([global_terms[number]], dtype=np.int32)
+        else:
+            c = column_of_term[number]
+            fine = owner[c]
+            level = LEVEL_PRIMARY if fine == primary else LEVEL_SECONDARY
+            code_of_slot = p_code_of_slot if fine == primary else s_code_of_slot
+            own_codes = code_of_slot if c == fine else table[(fine, c)][code_of_slot]
+            theta_index = (block.offset + elem_of_term[number][own_codes]).astype(np.int32)
+        counts[level] += 1
+        terms.append(KernelTerm(level=level, xcol=xc, theta_index=theta_index, block=term.block))
+    if counts[LEVEL_GLOBAL] > MAX_TERMS_PER_LEVEL or counts[LEVEL_PRIMARY] > MAX_TERMS_PER_LEVEL \
+            or counts[LEVEL_SECONDARY] > MAX_SECONDARY_TERMS:
+        raise UnsupportedModelError(
+            f'{counts[LEVEL_GLOBAL]} global / {counts[LEVEL_PRIMARY]} primary / {counts[LEVEL_SECONDARY]} secondary '
+            f'terms; the compiled kernels cover {MAX_TERMS_PER_LEVEL}/{MAX_TERMS_PER_LEVEL}/{MAX_SECONDARY_TERMS}')
+
+    # ---- observed column, offset, constants ---------------------------------------------------------------
+    y_rows = take(lik.y)
+    y_sorted = arrange(y_rows)
+    y_kind = 0
+    if narrow_y and lik.family in ('Bernoulli', 'Poisson') and (n == 0 or y_rows.max() <= 255):
+        y_store = y_sorted.astype(np.uint8)
+        y_kind = 1
+    else:
+        y_store = np.ascontiguousarray(y_sorted, dtype=dtype)
+    eta_offset = None
+    if lik.offset is not None:
+        eta_offset = np.ascontiguousarray(arrange(take(lik.offset)), dtype=dtype)
+    logp_const = 0.0
+    if lik.family == 'Poisson':
+        logp_const = -float(np.sum(gammaln(y_rows + 1.0), dtype=np.float64))
+
+    sigma_const, sigma_theta_index = 1.0, -1
+    if lik.family == 'Normal':
+        if lik.sigma_block is None:
+            sigma_const = float(lik.sigma_const)
+        else:
+            sigma_theta_index = plan.blocks[lik.sigma_block].offset + lik.sigma_index
+
+    # ---- priors ---------------------------------------------------------------------------------------------------
+    blocks: List[KernelBlock] = []
+    for b in plan.blocks:
+        kb = KernelBlock(family=FAMILY_IDS[b.family], offset=b.offset, size=b.size)
+        names = {'Normal': ('mu', 'sigma'), 'HalfNormal': ('sigma', None), 'Exponential': ('lam', None)}[b.family]
+        for slot, pname in zip('ab', names):
+            if pname is None:
+                continue
+            prm = b.params[pname]
+            if prm.is_const:
+                setattr(kb, slot + '_const', np.ascontiguousarray(np.atleast_1d(prm.const), dtype=np.float64))
+            else:
+                src = plan.blocks[prm.block]
+                setattr(kb, slot + '_index', (src.offset + prm.index).astype(np.int32))
+        blocks.append(kb)
+
+    return KernelPlan(dtype=dtype, family=FAMILY_IDS[lik.family], n_rows=n, n_rows_total=total,
+                      n_params=plan.n_params, perm=perm, xcols=xcols, y=np.ascontiguousarray(y_store), y_kind=y_kind,
+                      eta_offset=eta_offset, n_primary=n_primary, seg_offsets=seg_offsets, n_secondary=n_secondary,
+                      sec_codes=None if sec_codes is None else np.ascontiguousarray(sec_codes), terms=terms,
+                      blocks=blocks, sigma_const=sigma_const, sigma_theta_index=sigma_theta_index,
+                      logp_const=logp_const, include_priors=include_priors)
