@@ -44,7 +44,8 @@ def _digest() -> str:
             h.update(path.encode())
             h.update(open(full, 'rb').read())
     h.update(open(os.path.join(INCLUDE, 'skk_b200.h'), 'rb').read())
-    h.update(' '.join(NVCC_FLAGS).encode())
+    # flags without the absolute include paths, so that the stamp survives a move of the tree
+    h.update(' '.join(f for f in NVCC_FLAGS if not os.path.isabs(f)).encode())
     return h.hexdigest()
 
 

@@ -14,8 +14,6 @@ import pandas as pd
 
 from sakkara_b200.model import sym
 from sakkara_b200.model.components import ModelComponent
-from sakkara_b200.plan.lower import lower_model
-from sakkara_b200.plan.model_plan import ModelPlan
 from sakkara_b200.relation.groupset import GroupSet, init
 
 
@@ -28,7 +26,7 @@ class B200Model:
     evaluated by the sm_100a kernels through the C ABI.
     """
 
-    def __init__(self, recorded: sym.Model, groupset: GroupSet, plan: ModelPlan):
+    def __init__(self, recorded: sym.Model, groupset: GroupSet, plan: 'ModelPlan'):
         self.recorded = recorded
         self.groupset = groupset
         self.plan = plan
@@ -88,6 +86,8 @@ def build(df: pd.DataFrame, component: ModelComponent) -> B200Model:
     :param df: frame holding the columns that define the groups used by the components.
     :param component: component of the lowest hierarchy level.
     """
+    from sakkara_b200.plan.lower import lower_model    # late import: plan.lower needs model.sym
+
     frame = df.copy()
     frame['global'] = 'global'
     frame['obs'] = np.arange(len(df))

@@ -1,0 +1,35 @@
+"""
+Generates the golden fixtures of tests/golden/*.npz by running the REFERENCE's own
+``sakkara.model.build()`` (from /root/reference, through the recording fake PyMC of
+``oracle/ref_harness.py``) on the models of tests/model_zoo.py and lowering the recorded graph.
+The fixtures pin: theta layout (free-variable creation order, names, shapes, dims, transforms),
+every gather index the reference computes (int64, bit-exact) and the data columns.
+
+    python tests/golden/make_golden.py         # only works where /root/reference exists
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, 'tests'), HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from model_zoo import zoo  # noqa: E402
+from oracle.ref_harness import reference_plan  # noqa: E402
+from plan_io import plan_to_arrays  # noqa: E402
+
+
+def main():
+    for name, (df, make) in zoo().items():
+        plan = reference_plan(make, df)
+        path = os.path.join(HERE, f'{name}.npz')
+        np.savez_compressed(path, **plan_to_arrays(plan))
+        print(f'{name}: P={plan.n_params} N={plan.n_rows} -> {os.path.relpath(path, ROOT)}')
+
+
+if __name__ == '__main__':
+    main()
