@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""
+bench.py -- logp+dlogp throughput of the B200 evaluator on the BASELINE.json configurations.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--impl b200|reference]
+
+One JSON line on stdout (rank 0).  A *step* is one logp+dlogp evaluation of the whole batch of
+parameter vectors over all rows of the workload.
+
+  value      row-evaluations / s (= rows_total * batch / step time), inputs resident in HBM; step time
+             from CUDA events on the library's stream, L2 flushed between steps, max over ranks
+  e2e        the same metric through the public call with HOST buffers (theta H2D, logp+dlogp D2H
+             and the stream synchronisation inside the timed region)
+  roofline   stored bytes the row kernel reads per launch / its event-timed duration, against the
+             measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the fused OpenMP C restatement (oracle/logp_c.c) on a bounded sample, all host cores
+
+Default workload c4: Poisson-log GLM with crossed random effects, 100M rows, 10k x 1k groups, fp32 --
+the configuration BASELINE.json quotes at 1/2/4/8 GPUs; rows are sharded contiguously by the sorted
+primary factor and every evaluation ends in one all-reduce of [dlogp, logp] (strong scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: rows, dtype, batch (total), description
+    'c2': dict(rows=1_000_000, dtype='float64', batch=4, shard='rows',
+               workload='hierarchical linear regression: 1M rows, 1,000 groups, fp64, 4 chains'),
+    'c3': dict(rows=10_000_000, dtype='float32', batch=1, shard='rows',
+               workload='hierarchical logistic regression (Bernoulli-logit): 10M rows, nested 100x100 groups, fp32'),
+    'c4': dict(rows=100_000_000, dtype='float32', batch=1, shard='rows',
+               workload='Poisson-log GLM with crossed random effects: 100M rows, 10k+1k groups, fp32, row-sharded'),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_plan(config: str, rows: int, rank: int, world: int, seed: int = 1):
+    """This rank's rows of the synthetic workload as a ModelPlan (plus the total row count)."""
+    from sakkara_b200 import synth
+    share = rows // world + (1 if rank < rows % world else 0)
+    if config == 'c2':
+        cols, _ = synth.linreg_columns(rows, 1000, seed=seed)
+        lo = sum(rows // world + (1 if r < rows % world else 0) for r in range(rank))
+        cols = {k: v[lo:lo + share] for k, v in cols.items()}
+        return synth.linreg_plan(cols)
+    if config == 'c3':
+        g1, per = 100, 100
+        span = (g1 * per) // world
+        cols, _ = synth.logistic_columns(share, g1, per, seed=seed, block=rank,
+                                         g2_range=(rank * span, (rank + 1) * span if rank < world - 1 else g1 * per))
+        return synth.logistic_plan(cols)
+    if config == 'c4':
+        a, b = 10_000, 1_000
+        span = a // world
+        parts = []
+        chunk = 12_500_000
+        for start in range(0, share, chunk):
+            c, _ = synth.poisson_columns(min(chunk, share - start), a, b, seed=seed, block=rank * 1000 + start // chunk,
+                                         a_range=(rank * span, (rank + 1) * span if rank < world - 1 else a))
+            parts.append(c)
+        cols = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+        return synth.poisson_plan(cols)
+    raise ValueError(config)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.device}', f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def cpu_baseline(config: str, dtype: str, seconds: float = 10.0, sample_rows: int = 4_000_000):
+    """Fused OpenMP C restatement on a bounded sample of the same workload, all host cores."""
+    from oracle.logp_c import COracle
+    from sakkara_b200 import synth
+    rows = min(CONFIGS[config]['rows'], sample_rows)
+    plan = make_plan(config, rows, 0, 1)
+    theta = synth.start_point(plan, 1, dtype=dtype)[0]
+    cores = os.cpu_count() or 1
+    f = COracle(plan, dtype=dtype, threads=cores)
+    f(theta)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        f(theta)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds or n >= 200:
+            break
+    return {'value': rows * n / dt, 'unit': 'row-evals/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{rows} rows of the {config} workload, {n} evaluations of oracle/logp_c.c (fused OpenMP loop, '
+                      f'{dtype}) in {dt:.1f} s'}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port on the host cores (PyMC/PyTensor are not installable here)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    from oracle.logp_c import COracle
+    from sakkara_b200 import synth
+    rows = min(cfg['rows'], args.ref_rows)
+    plan = make_plan(args.config, rows, 0, 1)
+    theta = synth.start_point(plan, cfg['batch'], dtype=cfg['dtype'])
+    cores = os.cpu_count() or 1
+    f = COracle(plan, dtype=cfg['dtype'], threads=cores)
+    for _ in range(args.warmup):
+        for th in theta:
+            f(th)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for th in theta:
+            f(th)
+    dt = time.perf_counter() - t0
+    value = rows * cfg['batch'] * args.steps / dt
+    sample = (f'{rows} rows of the {args.config} workload per step (bounded sample; the metric is per row), '
+              f'oracle/logp_c.c fused OpenMP loop, {cfg["dtype"]}')
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'logp_dlogp_row_evals_per_s', 'value': value, 'unit': 'row-evals/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f64' if cfg['dtype'] == 'float64' else 'f32', 'data': 'synthetic',
+        'config': {'workload': cfg['workload'], 'rows_per_step': rows, 'batch': cfg['batch']},
+        'cpu_baseline': {'value': value, 'unit': 'row-evals/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'row-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--config', default=os.environ.get('SKK_BENCH_CONFIG', 'c4'), choices=sorted(CONFIGS))
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--rows', type=int, default=0, help='override the number of rows (testing)')
+    ap.add_argument('--ref-rows', type=int, default=8_000_000)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--check', action='store_true', help='verify one evaluation against the oracle (small --rows)')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from sakkara_b200 import synth
+    from sakkara_b200.valuegrad import ValueGradFunction
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    cfg = CONFIGS[args.config]
+    rows_total = args.rows or cfg['rows']
+    dtype, batch = cfg['dtype'], cfg['batch']
+    t0 = time.time()
+    plan = make_plan(args.config, rows_total, rank, world)
+    t_gen = time.time() - t0
+    f = ValueGradFunction(plan, dtype=dtype, max_batch=batch, device=local, n_rows_total=rows_total)
+    t0 = time.time()
+    kp = f.kernel_plan
+    t_plan = time.time() - t0
+    t0 = time.time()
+    skk = f.skk
+    t_upload = time.time() - t0
+    st0 = skk.stats()
+    if rank == 0:
+        log(f'[bench] {args.config}: rows/rank={plan.n_rows} P={plan.n_params} gen {t_gen:.1f}s plan {t_plan:.1f}s '
+            f'upload {t_upload:.1f}s grid={st0["grid"]}x{st0["block"]} smem={st0["smem_bytes"]} '
+            f'bytes/row={st0["stored_bytes_per_row"]}')
+        log(kp.describe())
+
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(skk.unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(uid, 0)
+        skk.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    theta = synth.start_point(plan, batch, dtype=dtype)
+    P = plan.n_params
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    th_dev = torch.from_numpy(theta).to(dev)
+    logp_dev = torch.empty(batch, dtype=tdt, device=dev)
+    grad_dev = torch.empty(batch, P, dtype=tdt, device=dev)
+    stream = torch.cuda.ExternalStream(skk.stream, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    if args.check:
+        from oracle.logp_numpy import parity_error
+        lp, g = f(theta)
+        for b in range(batch):
+            el, eg = parity_error(lp[b], g[b], plan, theta[b].astype(np.float64))
+            log(f'[check] chain {b}: err_logp={el:.2e} err_grad={eg:.2e}')
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_steps(n, timed):
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        with torch.cuda.stream(stream):
+            for i in range(n):
+                flush.zero_()                                   # evict the row data from L2
+                starts[i].record(stream)
+                skk.eval_device(th_dev.data_ptr(), batch, logp_dev.data_ptr(), grad_dev.data_ptr(), sync=False)
+                ends[i].record(stream)
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in zip(starts, ends)] if timed else None
+
+    # ---- device-resident timing: W warm-up steps, then exactly K timed steps -------------------------
+    device_steps(args.warmup, False)
+    sampler = ClockSampler(local)
+    launches0 = skk.stats()['launches']
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    step_ms = device_steps(args.steps, True)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = skk.stats()['launches'] - launches0
+    ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    ms_per_step = total_ms / args.steps
+    value = rows_total * batch / (ms_per_step * 1e-3)
+
+    # ---- the row kernel alone (events inside the library, around the launch) -------------------------
+    kern = []
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, min(args.steps, 10))):
+            flush.zero_()
+            torch.cuda.synchronize()
+            skk.eval_device(th_dev.data_ptr(), batch, logp_dev.data_ptr(), grad_dev.data_ptr(), sync=True,
+                            time_kernels=True)
+            kern.append(skk.stats()['last_row_kernel_ms'])
+    kern_ms = float(np.mean(kern))
+    esize = 8 if dtype == 'float64' else 4
+    bt = 4 if batch >= 2 else 1
+    launches_per_eval = (batch + bt - 1) // bt if batch >= 2 else 1
+    alg_bytes = plan.n_rows * st0['stored_bytes_per_row'] + bt * (2 * P * esize + esize)
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'kernel': 'skk_row_kernel', 'kernel_ms': kern_ms, 'bytes_per_launch': alg_bytes,
+                'launches_per_step': launches_per_eval, 'peak_source': peak_src}
+
+    # ---- end to end through the public call with host buffers ---------------------------------------------
+    for _ in range(args.warmup):
+        f(theta)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        f(theta)
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = rows_total * batch * args.steps / float(t_e2e.item())
+    e2e = {'value': e2e_value, 'unit': 'row-evals/s', 'h2d_bytes_per_step': batch * P * esize,
+           'd2h_bytes_per_step': batch * (P + 1) * esize, 'ms_per_step': 1e3 * float(t_e2e.item()) / args.steps}
+
+    out = {
+        'metric': 'logp_dlogp_row_evals_per_s', 'value': value, 'unit': 'row-evals/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64' if dtype == 'float64' else 'f32',
+        'data': 'synthetic',
+        'config': {'workload': cfg['workload'], 'rows_total': rows_total, 'rows_per_gpu': plan.n_rows,
+                   'n_params': P, 'batch': batch, 'l2': 'flushed between steps (256 MiB memset)',
+                   'parallelism': f'rows x{world}' if world > 1 else 'single GPU',
+                   'grid': st0['grid'], 'block': st0['block'], 'smem_bytes': st0['smem_bytes']},
+        'evals_per_s': batch / (ms_per_step * 1e-3), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+        'roofline': roofline, 'wall_s_timed_region': wall,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline(args.config, dtype)
+    elif rank == 0:
+        out['cpu_baseline'] = None
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    f.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
