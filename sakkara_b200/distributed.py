@@ -1,0 +1,60 @@
+"""
+Multi-GPU plumbing (one process per GPU, ``torch.distributed``): row sharding and the exchange of
+the NCCL unique id.  The data path itself -- one all-reduce(sum) of ``[dlogp, logp]`` per
+evaluation -- runs inside libskk_b200.so on the plan's stream (``skk_comm_init``); nothing here
+touches the per-evaluation path.  The reference has no counterpart.
+"""
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def rank_world() -> Tuple[int, int, int]:
+    return (int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')),
+            int(os.environ.get('LOCAL_RANK', '0')))
+
+
+def shard_bounds(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced row range of a rank: sizes differ by at most one."""
+    base, extra = divmod(n_rows, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sorted_shard(plan, rank: int, world: int) -> np.ndarray:
+    """
+    Rows of this rank when the rows are sorted by the finest grouping level first and then cut
+    into contiguous ranges: groups stay (almost) whole on one rank, so every rank
+    sees long segments.  Returns row numbers of the unsharded plan, ascending within the shard.
+    """
+    from sakkara_b200.plan.kernel_plan import make_kernel_plan
+    if world == 1:
+        return np.arange(plan.n_rows)
+    full = make_kernel_plan(plan, dtype='float64', structure_only=True)
+    lo, hi = shard_bounds(plan.n_rows, rank, world)
+    perm = np.arange(plan.n_rows) if full.perm is None else full.perm
+    return np.sort(perm[lo:hi])
+
+
+def exchange_unique_id(skk_plan, group=None) -> bytes:
+    """Rank 0 creates the NCCL unique id; everybody receives it through torch.distributed."""
+    import torch.distributed as dist
+    box = [skk_plan.unique_id() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
+def sharded_valuegrad(plan, dtype='float64', max_batch: int = 1, device: Optional[int] = None, group=None):
+    """
+    ValueGradFunction over this rank's rows with the all-reduce enabled: every rank passes the same
+    (full) ``plan`` and receives the full ``(logp, dlogp)`` from each call.
+    """
+    import torch.distributed as dist
+    from sakkara_b200.valuegrad import ValueGradFunction
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rows = sorted_shard(plan, rank, world)
+    f = ValueGradFunction(plan, dtype=dtype, max_batch=max_batch, device=device, rows=rows, n_rows_total=plan.n_rows)
+    if world > 1:
+        f.skk.comm_init(exchange_unique_id(f.skk, group), rank, world)
+    return f

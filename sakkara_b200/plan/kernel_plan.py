@@ -171,11 +171,13 @@ class _Column:
 
 def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray] = None,
                      n_rows_total: Optional[int] = None, narrow_y: bool = True,
-                     include_priors: bool = True) -> KernelPlan:
+                     include_priors: bool = True, structure_only: bool = False) -> KernelPlan:
     """
     :param rows: optional subset of the rows (this rank's shard); all ranks pass the same ``plan``
         and disjoint ``rows`` whose union is all rows.
     :param n_rows_total: number of rows over all ranks (defaults to this plan's rows).
+    :param structure_only: compute levels, permutation and segments only (no data columns); used to
+        cut sorted rows into per-rank shards.
     """
     dtype = np.dtype(dtype)
     if dtype not in (np.dtype('float32'), np.dtype('float64')):
@@ -187,7 +189,12 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
             return a
         return a[rows]
 
-    n = plan.n_rows if rows is None else len(np.arange(plan.n_rows)[rows])
+    if rows is None:
+        n = plan.n_rows
+    elif isinstance(rows, slice):
+        n = len(range(*rows.indices(plan.n_rows)))
+    else:
+        n = len(rows)
     total = n if n_rows_total is None else int(n_rows_total)
 
     # ---- classify the terms ------------------------------------------------------------------------
@@ -292,6 +299,12 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     sec_codes = None
     if secondary is not None:
         sec_codes = arrange(s_slot_of_row).astype(np.uint16 if n_secondary <= 1 << 16 else np.int32)
+
+    if structure_only:
+        return KernelPlan(dtype=dtype, family=FAMILY_IDS[lik.family], n_rows=n, n_rows_total=total,
+                          n_params=plan.n_params, perm=perm, xcols=[], y=np.empty(0), y_kind=0, eta_offset=None,
+                          n_primary=n_primary, seg_offsets=seg_offsets, n_secondary=n_secondary, sec_codes=sec_codes,
+                          terms=[], blocks=[], sigma_const=1.0, sigma_theta_index=-1, logp_const=0.0)
 
     # ---- data columns ------------------------------------------------------------------------------------
     xcols: List[np.ndarray] = []
