@@ -36,16 +36,38 @@ def _sources() -> List[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
 
 
+def _includes(path: str, seen=None) -> List[str]:
+    """Transitive closure of the quoted #include files of a source (dependency tracking)."""
+    seen = seen if seen is not None else []
+    for line in open(path):
+        line = line.strip()
+        if line.startswith('#include "'):
+            name = line.split('"')[1]
+            full = os.path.normpath(os.path.join(os.path.dirname(path), name))
+            if os.path.exists(full) and full not in seen:
+                seen.append(full)
+                _includes(full, seen)
+    return seen
+
+
+def _flags_digest() -> str:
+    # flags without the absolute include paths, so that stamps survive a move of the tree
+    return ' '.join(f for f in NVCC_FLAGS if not os.path.isabs(f))
+
+
+def _source_digest(src: str) -> str:
+    h = hashlib.sha256()
+    for path in [src] + sorted(_includes(src)):
+        h.update(os.path.basename(path).encode())
+        h.update(open(path, 'rb').read())
+    h.update(_flags_digest().encode())
+    return h.hexdigest()
+
+
 def _digest() -> str:
     h = hashlib.sha256()
-    for path in sorted(os.listdir(CSRC)):
-        full = os.path.join(CSRC, path)
-        if os.path.isfile(full) and path.endswith(('.cu', '.cuh', '.h')):
-            h.update(path.encode())
-            h.update(open(full, 'rb').read())
-    h.update(open(os.path.join(INCLUDE, 'skk_b200.h'), 'rb').read())
-    # flags without the absolute include paths, so that the stamp survives a move of the tree
-    h.update(' '.join(f for f in NVCC_FLAGS if not os.path.isabs(f)).encode())
+    for src in _sources():
+        h.update(_source_digest(src).encode())
     return h.hexdigest()
 
 
@@ -56,12 +78,17 @@ def is_current() -> bool:
 
 def _compile(nvcc: str, src: str) -> str:
     obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + '.o')
+    digest = _source_digest(src)
+    if os.path.exists(obj) and os.path.exists(obj + '.sha256') and open(obj + '.sha256').read() == digest:
+        return obj
     cmd = [nvcc] + NVCC_FLAGS + ['-c', src, '-o', obj]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     with open(obj + '.log', 'w') as f:
         f.write(' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError(f'nvcc failed on {src}:\n{proc.stdout}\n{proc.stderr}')
+    with open(obj + '.sha256', 'w') as f:
+        f.write(digest)
     return obj
 
 

@@ -21,12 +21,18 @@
 #include "skk_row_inst.cuh"
 
 namespace skk {
-const void *row_kernel_f32_normal(int, int, int, int);
-const void *row_kernel_f32_bernoulli(int, int, int, int);
-const void *row_kernel_f32_poisson(int, int, int, int);
-const void *row_kernel_f64_normal(int, int, int, int);
-const void *row_kernel_f64_bernoulli(int, int, int, int);
-const void *row_kernel_f64_poisson(int, int, int, int);
+const void *row_kernel_f32_normal_bt1(int, int, int);
+const void *row_kernel_f32_normal_bt4(int, int, int);
+const void *row_kernel_f32_bernoulli_bt1(int, int, int);
+const void *row_kernel_f32_bernoulli_bt4(int, int, int);
+const void *row_kernel_f32_poisson_bt1(int, int, int);
+const void *row_kernel_f32_poisson_bt4(int, int, int);
+const void *row_kernel_f64_normal_bt1(int, int, int);
+const void *row_kernel_f64_normal_bt4(int, int, int);
+const void *row_kernel_f64_bernoulli_bt1(int, int, int);
+const void *row_kernel_f64_bernoulli_bt4(int, int, int);
+const void *row_kernel_f64_poisson_bt1(int, int, int);
+const void *row_kernel_f64_poisson_bt4(int, int, int);
 }  // namespace skk
 
 using namespace skk;
@@ -137,7 +143,8 @@ struct skk_plan {
 
     void *theta_dev = nullptr, *val_g = nullptr, *val_p = nullptr, *val_s = nullptr;
     double *direct_p = nullptr, *tile_head = nullptr, *tile_tail = nullptr, *cta_glob = nullptr, *cta_sec = nullptr;
-    double *lik_vec = nullptr, *prior_grad = nullptr, *prior_lp = nullptr;
+    double *lik_vec = nullptr, *prior_grad = nullptr, *prior_lp = nullptr, *to_mu = nullptr, *to_sigma = nullptr;
+    double *glob_tot = nullptr, *sec_tot = nullptr;
     void *out_dev = nullptr;  // [B*P grad | B logp]
 
     PriorParams prior{};
@@ -182,16 +189,16 @@ static int upload_bytes(skk_plan *pl, void **out, const void *host, size_t bytes
 }
 
 static const void *lookup_kernel(int dtype, int family, int bt, int ng, int np, int ns) {
-    if (dtype == SKK_F32) {
-        if (family == SKK_LIK_NORMAL) return row_kernel_f32_normal(bt, ng, np, ns);
-        if (family == SKK_LIK_BERNOULLI_LOGIT) return row_kernel_f32_bernoulli(bt, ng, np, ns);
-        if (family == SKK_LIK_POISSON_LOG) return row_kernel_f32_poisson(bt, ng, np, ns);
-    } else {
-        if (family == SKK_LIK_NORMAL) return row_kernel_f64_normal(bt, ng, np, ns);
-        if (family == SKK_LIK_BERNOULLI_LOGIT) return row_kernel_f64_bernoulli(bt, ng, np, ns);
-        if (family == SKK_LIK_POISSON_LOG) return row_kernel_f64_poisson(bt, ng, np, ns);
-    }
-    return nullptr;
+    typedef const void *(*Lookup)(int, int, int);
+    static const Lookup table[2][3][2] = {
+        {{row_kernel_f32_normal_bt1, row_kernel_f32_normal_bt4},
+         {row_kernel_f32_bernoulli_bt1, row_kernel_f32_bernoulli_bt4},
+         {row_kernel_f32_poisson_bt1, row_kernel_f32_poisson_bt4}},
+        {{row_kernel_f64_normal_bt1, row_kernel_f64_normal_bt4},
+         {row_kernel_f64_bernoulli_bt1, row_kernel_f64_bernoulli_bt4},
+         {row_kernel_f64_poisson_bt1, row_kernel_f64_poisson_bt4}}};
+    if (family < 0 || family > 2 || (bt != 1 && bt != 4)) return nullptr;
+    return table[dtype == SKK_F64 ? 1 : 0][family][bt == 4 ? 1 : 0](ng, np, ns);
 }
 
 static int env_int(const char *name, int fallback) {
@@ -382,25 +389,50 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     for (const Link &l : links)
         if (l.parent < 0 || l.parent >= d->n_params) return fail(SKK_ERR_INVALID, "prior link outside theta");
     std::stable_sort(links.begin(), links.end(), [](const Link &a, const Link &b) { return a.parent < b.parent; });
-    std::vector<int64_t> link_ptr(d->n_params + 1, 0);
-    std::vector<int32_t> link_child(links.size());
-    std::vector<int8_t> link_kind(links.size());
-    for (size_t k = 0; k < links.size(); ++k) {
-        link_ptr[links[k].parent + 1]++;
-        link_child[k] = links[k].child;
-        link_kind[k] = links[k].kind;
+    // parents = elements with children; those with long lists first (a whole CTA each)
+    struct Parent {
+        int32_t element;
+        int64_t lo, hi;
+    };
+    std::vector<Parent> parents;
+    for (size_t k = 0; k < links.size();) {
+        size_t e = k;
+        while (e < links.size() && links[e].parent == links[k].parent) ++e;
+        parents.push_back(Parent{(int32_t)links[k].parent, (int64_t)k, (int64_t)e});
+        k = e;
     }
-    for (int64_t j = 0; j < d->n_params; ++j) link_ptr[j + 1] += link_ptr[j];
+    std::stable_sort(parents.begin(), parents.end(), [](const Parent &a, const Parent &b) {
+        return (a.hi - a.lo > 1024) > (b.hi - b.lo > 1024);
+    });
+    int n_heavy = 0;
+    std::vector<int32_t> parent_el(parents.size()), link_child(links.size());
+    std::vector<int64_t> link_ptr(parents.size() + 1, 0);
+    std::vector<int8_t> link_kind(links.size());
+    {
+        size_t w = 0;
+        for (size_t q = 0; q < parents.size(); ++q) {
+            if (parents[q].hi - parents[q].lo > 1024) ++n_heavy;
+            parent_el[q] = parents[q].element;
+            link_ptr[q] = (int64_t)w;
+            for (int64_t e = parents[q].lo; e < parents[q].hi; ++e, ++w) {
+                link_child[w] = links[e].child;
+                link_kind[w] = links[e].kind;
+            }
+        }
+        link_ptr[parents.size()] = (int64_t)w;
+    }
     DevBlock *blocks_dev = nullptr;
-    int32_t *block_of_dev = nullptr, *link_child_dev = nullptr;
+    int32_t *block_of_dev = nullptr, *link_child_dev = nullptr, *parent_dev = nullptr;
     int64_t *link_ptr_dev = nullptr;
     int8_t *link_kind_dev = nullptr;
     if (int rc = dev_upload(pl, &blocks_dev, blocks.data(), blocks.size())) return rc;
     if (int rc = dev_upload(pl, &block_of_dev, block_of.data(), block_of.size())) return rc;
+    if (int rc = dev_upload(pl, &parent_dev, parent_el.data(), parent_el.size())) return rc;
     if (int rc = dev_upload(pl, &link_ptr_dev, link_ptr.data(), link_ptr.size())) return rc;
     if (int rc = dev_upload(pl, &link_child_dev, link_child.data(), link_child.size())) return rc;
     if (int rc = dev_upload(pl, &link_kind_dev, link_kind.data(), link_kind.size())) return rc;
-    pl->prior = PriorParams{blocks_dev, block_of_dev, link_ptr_dev, link_child_dev, link_kind_dev, d->n_params, 0};
+    pl->prior = PriorParams{blocks_dev, block_of_dev, parent_dev, link_ptr_dev, link_child_dev, link_kind_dev,
+                            (int32_t)parents.size(), n_heavy, d->n_params, 0};
 
     // ---- launch geometry -------------------------------------------------------------------------------------
     cudaDeviceProp prop;
@@ -441,14 +473,40 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     if (int rc = dev_alloc(pl, &pl->lik_vec, B * (P + 2), true)) return rc;
     if (int rc = dev_alloc(pl, &pl->prior_grad, B * P, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->prior_lp, B * P, true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->to_mu, B * P, true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->to_sigma, B * P, true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->glob_tot, (size_t)(kMaxTermsPerLevel + 1) * bt, true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->sec_tot, std::max<size_t>(1, pl->ns) * std::max<int64_t>(1, d->n_secondary) * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &tmp, B * P + B, true)) return rc;
     pl->out_dev = tmp;
     CUDA_TRY(cudaMallocHost(&pl->h_in, std::max<size_t>(16, B * P * sizeof(T))));
     CUDA_TRY(cudaMallocHost(&pl->h_out, std::max<size_t>(16, (B * P + B) * sizeof(T))));
 
-    pl->reduce = ReduceParams{csr_dev, lvl_dev, t_dev, slot_dev, pl->tile_keys, pl->seg_off, pl->direct_p, pl->tile_head,
-                              pl->tile_tail, pl->cta_glob, pl->cta_sec, pl->lik_vec, d->n_params, d->n_primary,
-                              d->n_secondary, pl->ng, pl->np, pl->ns, 1, 0, 1, 0, WT, d->logp_const};
+    pl->reduce = ReduceParams{};
+    pl->reduce.csr_ptr = csr_dev;
+    pl->reduce.entry_level = lvl_dev;
+    pl->reduce.entry_t = t_dev;
+    pl->reduce.entry_slot = slot_dev;
+    pl->reduce.tile_keys = pl->tile_keys;
+    pl->reduce.seg_offsets = pl->seg_off;
+    pl->reduce.direct_p = pl->direct_p;
+    pl->reduce.tile_head = pl->tile_head;
+    pl->reduce.tile_tail = pl->tile_tail;
+    pl->reduce.cta_glob = pl->cta_glob;
+    pl->reduce.cta_sec = pl->cta_sec;
+    pl->reduce.glob_tot = pl->glob_tot;
+    pl->reduce.sec_tot = pl->sec_tot;
+    pl->reduce.lik_vec = pl->lik_vec;
+    pl->reduce.n_params = d->n_params;
+    pl->reduce.n_primary = d->n_primary;
+    pl->reduce.n_secondary = d->n_secondary;
+    pl->reduce.ng = pl->ng;
+    pl->reduce.np = pl->np;
+    pl->reduce.ns = pl->ns;
+    pl->reduce.rows_per_tile = WT;
+    pl->reduce.blocks_p = pl->np > 0 ? (int)((d->n_primary + 255) / 256) : 0;
+    pl->reduce.blocks_s = pl->ns > 0 ? (int)((d->n_secondary + 31) / 32) : 0;
+    pl->reduce.logp_const = d->logp_const;
     return SKK_OK;
 }
 
@@ -515,8 +573,14 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
     if (pl->include_priors && P > 0) {
         PriorParams pp = pl->prior;
         pp.batch = batch;
-        skk_prior_kernel<T><<<(unsigned)((P + 127) / 128), 128, 0, st>>>(pp, th, pl->prior_grad, pl->prior_lp);
+        skk_prior_kernel<T><<<(unsigned)((P + 127) / 128), 128, 0, st>>>(pp, th, pl->prior_grad, pl->prior_lp, pl->to_mu,
+                                                                      pl->to_sigma);
         pl->stats.launches++;
+        if (pp.n_parents > 0) {
+            const unsigned blocks = (unsigned)(pp.n_heavy + (pp.n_parents - pp.n_heavy + 7) / 8);
+            skk_prior_link_kernel<<<blocks, 256, 0, st>>>(pp, pl->prior_grad, pl->to_mu, pl->to_sigma);
+            pl->stats.launches++;
+        }
     }
 
     for (int b0 = 0; b0 < batch;) {
@@ -544,19 +608,22 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
         // K1: the rows
         if (int rc = launch_rows<T>(pl, cfg, timed)) return rc;
 
-        // K4a: fixed-order reduction of the partial slots per theta element
+        // K4a: totals per slot, then per theta element, all in fixed order
         ReduceParams rp = pl->reduce;
         rp.bt = bt;
         rp.b0 = b0;
         rp.b_valid = b_valid;
         rp.grid = cfg.grid;
-        const unsigned warps_needed = (unsigned)(P + 1);
-        const unsigned blocks = (warps_needed * 32 + 255) / 256;
-        if (bt == 4)
-            skk_reduce_kernel<4><<<blocks, 256, 0, st>>>(rp);
-        else
-            skk_reduce_kernel<1><<<blocks, 256, 0, st>>>(rp);
-        pl->stats.launches++;
+        const unsigned slot_blocks = (unsigned)(rp.blocks_p + rp.blocks_s + 1);
+        const unsigned theta_blocks = (unsigned)std::max<size_t>(1, (P + 255) / 256);
+        if (bt == 4) {
+            skk_slot_total_kernel<4><<<slot_blocks, 256, 0, st>>>(rp);
+            skk_theta_reduce_kernel<4><<<theta_blocks, 256, 0, st>>>(rp);
+        } else {
+            skk_slot_total_kernel<1><<<slot_blocks, 256, 0, st>>>(rp);
+            skk_theta_reduce_kernel<1><<<theta_blocks, 256, 0, st>>>(rp);
+        }
+        pl->stats.launches += 2;
         b0 += b_valid;
     }
 

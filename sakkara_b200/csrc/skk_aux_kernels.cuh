@@ -1,8 +1,13 @@
-// Small per-evaluation kernels around the row kernel (all O(P) or O(#partials), fp64 inside):
-//   K0 prepare : gather theta into the value tables the row kernel reads (slot order)
-//   K3 priors  : logp term and gradient of every parameter block, incl. hyper-parameter links
-//   K4a reduce : add the row kernel's partial slots per theta element in fixed order
-//   K4b final  : likelihood scale (Normal), + priors, + constants -> logp[B], dlogp[B, P]
+// Small per-evaluation kernels around the row kernel.  All are O(P) or O(#partial slots), use fp64
+// internally and add in a fixed order (serial per thread, or lane-strided + fixed shuffle tree), so
+// the whole evaluation is bit-reproducible.
+//   K0  prepare      : gather theta into the value tables the row kernel reads (slot order)
+//   K3a prior terms  : per theta element, its own prior logp term and gradient, and what it
+//                      contributes to the gradient of its prior's mu / sigma hyper-parameters
+//   K3b prior links  : per hyper-parameter element, the sum over its children (CSR, built at plan time)
+//   K4a slot totals  : per (term, slot): direct_p + tile partials | sum over CTA partials
+//   K4t theta reduce : per theta element, the sum over the slots that map to it  -> lik_vec
+//   K4b final        : likelihood scale (Normal), + priors, + constants -> logp[B], dlogp[B, P]
 #pragma once
 
 #include "skk_common.cuh"
@@ -11,6 +16,34 @@ namespace skk {
 
 constexpr double kLogSqrt2Pi = 0.91893853320467274178032973640562;
 constexpr double kLogSqrt2OverPi = -0.22579135264472743236309761494744;
+constexpr int kSerialLimit = 48;  // longer partial lists are summed by a whole warp
+
+// Runs body(first, last, item) for every lane of the warp whose list [first, last) is long, with
+// all 32 lanes cooperating on one list at a time: lane-strided partial sums + fixed shuffle tree.
+// `value(e, b)` returns the e-th addend of chain b; `store(item, b, sum)` is called on lane 0.
+template <int BT, typename Value, typename Store>
+__device__ __forceinline__ void warp_cooperative_lists(bool heavy, int64_t first, int64_t last, int64_t item,
+                                                       Value value, Store store) {
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(kFull, heavy);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t lo = __shfl_sync(kFull, first, src), hi = __shfl_sync(kFull, last, src);
+        const int64_t it = __shfl_sync(kFull, item, src);
+        double acc[BT];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+        for (int64_t e = lo + lane; e < hi; e += 32)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) acc[b] += value(it, e, b);
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            const double s = warp_sum(acc[b]);
+            if (lane == 0) store(it, b, s);
+        }
+    }
+}
 
 // ---- K0 -------------------------------------------------------------------------------------
 struct PrepTerm {
@@ -60,74 +93,105 @@ struct DevBlock {
 struct PriorParams {
     const DevBlock *blocks;
     const int32_t *block_of;    // [P]
-    const int64_t *link_ptr;    // [P+1] CSR: hyper-parameter element -> child elements
+    // hyper-parameter elements ("parents") and their children, heavy parents first
+    const int32_t *parent;      // [n_parents] theta element
+    const int64_t *link_ptr;    // [n_parents + 1]
     const int32_t *link_child;  // child theta element
-    const int8_t *link_kind;    // 0: parent is the child's a (mu), 1: the child's b (sigma)
+    const int8_t *link_kind;    // 0: parent is the child's mu, 1: the child's (log) sigma
+    int32_t n_parents;
+    int32_t n_heavy;            // parents handled by a whole CTA
     int64_t n_params;
     int32_t batch;
 };
 
-// standardised residual and scale of a Normal-prior element
-template <typename T>
-__device__ __forceinline__ void normal_prior(const DevBlock &blk, int64_t j, const T *__restrict__ th, double &z,
-                                             double &sd) {
-    const int64_t g = j - blk.offset;
-    const double mu = blk.a_index ? (double)th[blk.a_index[g]] : blk.a_const[blk.a_const_len == 1 ? 0 : g];
-    sd = blk.b_index ? exp((double)th[blk.b_index[g]]) : blk.b_const[blk.b_const_len == 1 ? 0 : g];
-    z = ((double)th[j] - mu) / sd;
-}
-
 template <typename T>
 __global__ void skk_prior_kernel(const __grid_constant__ PriorParams pp, const T *__restrict__ theta,
-                                 double *__restrict__ prior_grad, double *__restrict__ prior_lp) {
+                                 double *__restrict__ prior_grad, double *__restrict__ prior_lp,
+                                 double *__restrict__ to_mu, double *__restrict__ to_sigma) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j >= pp.n_params) return;
     const DevBlock blk = pp.blocks[pp.block_of[j]];
+    const int64_t g = j - blk.offset;
     for (int b = 0; b < pp.batch; ++b) {
         const T *th = theta + (int64_t)b * pp.n_params;
-        double lp, g;
         const double v = (double)th[j];
+        double lp, grad, cm = 0.0, cs = 0.0;
         if (blk.family == SKK_PRIOR_NORMAL) {
-            double z, sd;
-            normal_prior(blk, j, th, z, sd);
+            const double mu = blk.a_index ? (double)th[blk.a_index[g]] : blk.a_const[blk.a_const_len == 1 ? 0 : g];
+            const double sd = blk.b_index ? exp((double)th[blk.b_index[g]]) : blk.b_const[blk.b_const_len == 1 ? 0 : g];
+            const double z = (v - mu) / sd;
             lp = -0.5 * z * z - kLogSqrt2Pi - log(sd);
-            g = -z / sd;
+            grad = -z / sd;
+            cm = z / sd;          // d/d mu
+            cs = z * z - 1.0;     // d/d log(sigma)
         } else if (blk.family == SKK_PRIOR_HALFNORMAL) {
-            const double tau = blk.a_const[blk.a_const_len == 1 ? 0 : j - blk.offset];
+            const double tau = blk.a_const[blk.a_const_len == 1 ? 0 : g];
             const double q = exp(v) / tau;
             lp = -0.5 * q * q + kLogSqrt2OverPi - log(tau) + v;
-            g = -q * q + 1.0;
+            grad = -q * q + 1.0;
         } else {  // SKK_PRIOR_EXPONENTIAL
-            const double lam = blk.a_const[blk.a_const_len == 1 ? 0 : j - blk.offset];
+            const double lam = blk.a_const[blk.a_const_len == 1 ? 0 : g];
             const double s = exp(v);
             lp = log(lam) - lam * s + v;
-            g = -lam * s + 1.0;
+            grad = -lam * s + 1.0;
         }
-        // children whose prior has this element as mu or (log) sigma, in fixed order
-        for (int64_t e = pp.link_ptr[j]; e < pp.link_ptr[j + 1]; ++e) {
+        const int64_t o = (int64_t)b * pp.n_params + j;
+        prior_grad[o] = grad;
+        prior_lp[o] = lp;
+        to_mu[o] = cm;
+        to_sigma[o] = cs;
+    }
+}
+
+// One CTA per heavy parent (blockIdx.x < n_heavy), one warp per light parent afterwards.
+__global__ void skk_prior_link_kernel(const __grid_constant__ PriorParams pp, double *__restrict__ prior_grad,
+                                      const double *__restrict__ to_mu, const double *__restrict__ to_sigma) {
+    __shared__ double part[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const bool heavy = (int)blockIdx.x < pp.n_heavy;
+    const int64_t p = heavy ? blockIdx.x : pp.n_heavy + ((int64_t)blockIdx.x - pp.n_heavy) * warps + warp;
+    if (p >= pp.n_parents) return;
+    const int64_t lo = pp.link_ptr[p], hi = pp.link_ptr[p + 1];
+    const int64_t first = heavy ? lo + threadIdx.x : lo + lane;
+    const int64_t step = heavy ? blockDim.x : 32;
+    for (int b = 0; b < pp.batch; ++b) {
+        const double *cm = to_mu + (int64_t)b * pp.n_params, *cs = to_sigma + (int64_t)b * pp.n_params;
+        double acc = 0.0;
+        for (int64_t e = first; e < hi; e += step) {
             const int64_t c = pp.link_child[e];
-            double z, sd;
-            normal_prior(pp.blocks[pp.block_of[c]], c, th, z, sd);
-            g += pp.link_kind[e] == 0 ? z / sd : z * z - 1.0;
+            acc += pp.link_kind[e] == 0 ? cm[c] : cs[c];
         }
-        prior_grad[(int64_t)b * pp.n_params + j] = g;
-        prior_lp[(int64_t)b * pp.n_params + j] = lp;
+        acc = warp_sum(acc);
+        if (heavy) {
+            if (lane == 0) part[warp] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double s = 0.0;
+                for (int w = 0; w < warps; ++w) s += part[w];
+                prior_grad[(int64_t)b * pp.n_params + pp.parent[p]] += s;
+            }
+            __syncthreads();
+        } else if (lane == 0) {
+            prior_grad[(int64_t)b * pp.n_params + pp.parent[p]] += acc;
+        }
     }
 }
 
 // ---- K4a ------------------------------------------------------------------------------------
 struct ReduceParams {
-    const int64_t *csr_ptr;     // [P+2]: entries of theta element j; element P = the logp partial
+    const int64_t *csr_ptr;     // [P+1]: slots of theta element j
     const int8_t *entry_level;
     const int8_t *entry_t;      // term number within its level
     const int32_t *entry_slot;
     const int2 *tile_keys;
     const int64_t *seg_offsets;
-    const double *direct_p;     // [NP][GP][BT]
+    double *direct_p;           // [NP][GP][BT]  in: groups inside one tile; out: total per primary slot
     const double *tile_head;    // [tiles][NP][BT]
     const double *tile_tail;
     const double *cta_glob;     // [grid][NG+1][BT]
     const double *cta_sec;      // [grid][NS][GS][BT]
+    double *glob_tot;           // [NG+1][BT]
+    double *sec_tot;            // [NS][GS][BT]
     double *lik_vec;            // [B][P+2]
     int64_t n_params;
     int64_t n_primary, n_secondary;
@@ -135,62 +199,116 @@ struct ReduceParams {
     int32_t bt, b0, b_valid;
     int32_t grid;               // CTAs of the row kernel
     int32_t rows_per_tile;
+    int32_t blocks_p, blocks_s; // CTAs of the slot-total kernel working on the primary / secondary level
     double logp_const;
 };
 
+// blockIdx.x in [0, blocks_p): primary slots, one per thread;  [blocks_p, blocks_p + blocks_s):
+// secondary slots, 32 per CTA x 8 ranges of row-kernel CTAs;  last CTA: global terms and logp.
 template <int BT>
-__global__ void skk_reduce_kernel(const __grid_constant__ ReduceParams rp) {
+__global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_constant__ ReduceParams rp) {
     const int lane = threadIdx.x & 31;
-    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;  // one warp per element
-    if (j > rp.n_params) return;
-    double acc[BT];
-#pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b] = 0.0;
-
-    if (j == rp.n_params) {
-        // likelihood logp partial: last entry of every CTA's global block
-        for (int c = lane; c < rp.grid; c += 32)
-#pragma unroll
-            for (int b = 0; b < BT; ++b) acc[b] += rp.cta_glob[((int64_t)c * (rp.ng + 1) + rp.ng) * BT + b];
-    } else {
-        for (int64_t e = rp.csr_ptr[j]; e < rp.csr_ptr[j + 1]; ++e) {
-            const int level = rp.entry_level[e], t = rp.entry_t[e];
-            const int64_t slot = rp.entry_slot[e];
-            if (level == SKK_LEVEL_GLOBAL) {
-                for (int c = lane; c < rp.grid; c += 32)
-#pragma unroll
-                    for (int b = 0; b < BT; ++b) acc[b] += rp.cta_glob[((int64_t)c * (rp.ng + 1) + t) * BT + b];
-            } else if (level == SKK_LEVEL_SECONDARY) {
-                for (int c = lane; c < rp.grid; c += 32)
-#pragma unroll
-                    for (int b = 0; b < BT; ++b)
-                        acc[b] += rp.cta_sec[(((int64_t)c * rp.ns + t) * rp.n_secondary + slot) * BT + b];
-            } else {
-                const int64_t r0 = rp.seg_offsets[slot], r1 = rp.seg_offsets[slot + 1];
-                if (r1 > r0) {
-                    if (lane == 0)
-#pragma unroll
-                        for (int b = 0; b < BT; ++b) acc[b] += rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b];
-                    const int64_t t_lo = r0 / rp.rows_per_tile, t_hi = (r1 - 1) / rp.rows_per_tile;
-                    for (int64_t tile = t_lo + lane; tile <= t_hi; tile += 32) {
-                        const int2 k = rp.tile_keys[tile];
-                        const double *src = k.x == slot ? rp.tile_head : (k.y == slot ? rp.tile_tail : nullptr);
-                        if (src)
-#pragma unroll
-                            for (int b = 0; b < BT; ++b) acc[b] += src[((int64_t)tile * rp.np + t) * BT + b];
-                    }
-                }
+    if ((int)blockIdx.x < rp.blocks_p) {
+        const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        const bool valid = slot < rp.n_primary;
+        int64_t t_lo = 0, t_hi = -1;
+        if (valid) {
+            const int64_t r0 = rp.seg_offsets[slot], r1 = rp.seg_offsets[slot + 1];
+            if (r1 > r0) {
+                t_lo = r0 / rp.rows_per_tile;
+                t_hi = (r1 - 1) / rp.rows_per_tile;
             }
         }
-    }
+        auto addend = [&](int64_t s, int64_t tile, int t, int b) -> double {
+            const int2 k = rp.tile_keys[tile];
+            const double *src = k.x == s ? rp.tile_head : (k.y == s ? rp.tile_tail : nullptr);
+            return src ? src[(tile * rp.np + t) * BT + b] : 0.0;
+        };
+        const bool heavy = valid && (t_hi - t_lo + 1 > kSerialLimit);
+        for (int t = 0; t < rp.np; ++t) {
+            if (valid && !heavy && t_hi >= t_lo) {
+                double acc[BT];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) {
-        const double s = warp_sum(acc[b]);
-        if (lane == 0 && b < rp.b_valid) rp.lik_vec[(int64_t)(rp.b0 + b) * (rp.n_params + 2) + j] = s;
+                for (int b = 0; b < BT; ++b) acc[b] = rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b];
+                for (int64_t tile = t_lo; tile <= t_hi; ++tile)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) acc[b] += addend(slot, tile, t, b);
+#pragma unroll
+                for (int b = 0; b < BT; ++b) rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b] = acc[b];
+            }
+            warp_cooperative_lists<BT>(
+                heavy, t_lo, t_hi + 1, slot, [&](int64_t s, int64_t tile, int b) { return addend(s, tile, t, b); },
+                [&](int64_t s, int b, double sum) { rp.direct_p[((int64_t)t * rp.n_primary + s) * BT + b] += sum; });
+        }
+    } else if ((int)blockIdx.x < rp.blocks_p + rp.blocks_s) {
+        // 32 consecutive slots (coalesced) x 8 sub-ranges of CTAs, combined in fixed order
+        __shared__ double part[8][32];
+        const int sub = threadIdx.x >> 5;
+        const int64_t slot = ((int64_t)blockIdx.x - rp.blocks_p) * 32 + lane;
+        const int per = (rp.grid + 7) / 8;
+        const int c0 = sub * per, c1 = min(rp.grid, c0 + per);
+        for (int t = 0; t < rp.ns; ++t)
+            for (int b = 0; b < BT; ++b) {
+                double acc = 0.0;
+                if (slot < rp.n_secondary)
+                    for (int c = c0; c < c1; ++c)
+                        acc += rp.cta_sec[(((int64_t)c * rp.ns + t) * rp.n_secondary + slot) * BT + b];
+                part[sub][lane] = acc;
+                __syncthreads();
+                if (sub == 0 && slot < rp.n_secondary) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) s += part[k][lane];
+                    rp.sec_tot[((int64_t)t * rp.n_secondary + slot) * BT + b] = s;
+                }
+                __syncthreads();
+            }
+    } else {
+        // global terms and the logp partial: one warp per (term, chain)
+        const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+        for (int item = warp; item < (rp.ng + 1) * BT; item += warps) {
+            double acc = 0.0;
+            for (int c = lane; c < rp.grid; c += 32) acc += rp.cta_glob[(int64_t)c * (rp.ng + 1) * BT + item];
+            acc = warp_sum(acc);
+            if (lane == 0) rp.glob_tot[item] = acc;
+        }
     }
-    if (j == rp.n_params && lane == 0)
-        for (int b = 0; b < rp.b_valid; ++b)
-            rp.lik_vec[(int64_t)(rp.b0 + b) * (rp.n_params + 2) + rp.n_params + 1] = rp.logp_const;
+}
+
+// per theta element: sum of the totals of the slots that map to it
+template <int BT>
+__global__ void __launch_bounds__(256) skk_theta_reduce_kernel(const __grid_constant__ ReduceParams rp) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool valid = j < rp.n_params;
+    const int64_t lo = valid ? rp.csr_ptr[j] : 0, hi = valid ? rp.csr_ptr[j + 1] : 0;
+    auto addend = [&](int64_t, int64_t e, int b) -> double {
+        const int level = rp.entry_level[e], t = rp.entry_t[e];
+        const int64_t slot = rp.entry_slot[e];
+        if (level == SKK_LEVEL_GLOBAL) return rp.glob_tot[t * BT + b];
+        if (level == SKK_LEVEL_PRIMARY) return rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b];
+        return rp.sec_tot[((int64_t)t * rp.n_secondary + slot) * BT + b];
+    };
+    auto store = [&](int64_t el, int b, double sum) {
+        if (b < rp.b_valid) rp.lik_vec[(int64_t)(rp.b0 + b) * (rp.n_params + 2) + el] = sum;
+    };
+    const bool heavy = hi - lo > kSerialLimit;
+    if (valid && !heavy) {
+        double acc[BT];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+        for (int64_t e = lo; e < hi; ++e)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) acc[b] += addend(j, e, b);
+#pragma unroll
+        for (int b = 0; b < BT; ++b) store(j, b, acc[b]);
+    }
+    warp_cooperative_lists<BT>(heavy, lo, hi, j, addend, store);
+    if (j == 0)
+        for (int b = 0; b < rp.b_valid; ++b) {
+            double *row = rp.lik_vec + (int64_t)(rp.b0 + b) * (rp.n_params + 2);
+            row[rp.n_params] = rp.glob_tot[rp.ng * BT + b];  // likelihood logp partial
+            row[rp.n_params + 1] = rp.logp_const;
+        }
 }
 
 // ---- K4b ------------------------------------------------------------------------------------

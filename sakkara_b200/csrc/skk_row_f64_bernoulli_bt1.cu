@@ -1,0 +1,6 @@
+// Row-kernel instantiations: double data, bernoulli likelihood, batch tile 1 (see skk_row_inst.cuh).
+#include "skk_row_inst.cuh"
+
+namespace skk {
+const void *row_kernel_f64_bernoulli_bt1(int ng, int np, int ns) { return row_kernel_lookup<double, SKK_LIK_BERNOULLI_LOGIT, 1>(ng, np, ns); }
+}  // namespace skk

@@ -1,0 +1,6 @@
+// Row-kernel instantiations: double data, normal likelihood, batch tile 1 (see skk_row_inst.cuh).
+#include "skk_row_inst.cuh"
+
+namespace skk {
+const void *row_kernel_f64_normal_bt1(int ng, int np, int ns) { return row_kernel_lookup<double, SKK_LIK_NORMAL, 1>(ng, np, ns); }
+}  // namespace skk
