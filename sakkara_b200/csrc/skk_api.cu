@@ -158,6 +158,8 @@ struct skk_plan {
     skk_stats_t stats{};
 };
 
+static const int64_t kHeavyLinks = 512;  // hyper-parameters with more children get a whole CTA
+
 static size_t elt_size(int dtype) { return dtype == SKK_F64 ? 8 : 4; }
 
 template <typename U>
@@ -402,7 +404,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
         k = e;
     }
     std::stable_sort(parents.begin(), parents.end(), [](const Parent &a, const Parent &b) {
-        return (a.hi - a.lo > 1024) > (b.hi - b.lo > 1024);
+        return (a.hi - a.lo > kHeavyLinks) > (b.hi - b.lo > kHeavyLinks);
     });
     int n_heavy = 0;
     std::vector<int32_t> parent_el(parents.size()), link_child(links.size());
@@ -411,7 +413,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     {
         size_t w = 0;
         for (size_t q = 0; q < parents.size(); ++q) {
-            if (parents[q].hi - parents[q].lo > 1024) ++n_heavy;
+            if (parents[q].hi - parents[q].lo > kHeavyLinks) ++n_heavy;
             parent_el[q] = parents[q].element;
             link_ptr[q] = (int64_t)w;
             for (int64_t e = parents[q].lo; e < parents[q].hi; ++e, ++w) {
@@ -472,7 +474,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     if (int rc = dev_alloc(pl, &pl->cta_sec, (size_t)grid_max * std::max(1, pl->ns) * std::max<int64_t>(1, d->n_secondary) * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->lik_vec, B * (P + 2), true)) return rc;
     if (int rc = dev_alloc(pl, &pl->prior_grad, B * P, true)) return rc;
-    if (int rc = dev_alloc(pl, &pl->prior_lp, B * P, true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->prior_lp, B * ((P + kPriorThreads - 1) / kPriorThreads + 1), true)) return rc;
     if (int rc = dev_alloc(pl, &pl->to_mu, B * P, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->to_sigma, B * P, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->glob_tot, (size_t)(kMaxTermsPerLevel + 1) * bt, true)) return rc;
@@ -573,12 +575,13 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
     if (pl->include_priors && P > 0) {
         PriorParams pp = pl->prior;
         pp.batch = batch;
-        skk_prior_kernel<T><<<(unsigned)((P + 127) / 128), 128, 0, st>>>(pp, th, pl->prior_grad, pl->prior_lp, pl->to_mu,
-                                                                      pl->to_sigma);
+        skk_prior_kernel<T><<<(unsigned)((P + kPriorThreads - 1) / kPriorThreads), kPriorThreads, 0, st>>>(
+            pp, th, pl->prior_grad, pl->prior_lp, pl->to_mu, pl->to_sigma);
         pl->stats.launches++;
         if (pp.n_parents > 0) {
-            const unsigned blocks = (unsigned)(pp.n_heavy + (pp.n_parents - pp.n_heavy + 7) / 8);
-            skk_prior_link_kernel<<<blocks, 256, 0, st>>>(pp, pl->prior_grad, pl->to_mu, pl->to_sigma);
+            const int per_cta = pp.n_heavy > 0 ? 32 : 8;  // light parents: one warp each
+            const unsigned blocks = (unsigned)(pp.n_heavy + (pp.n_parents - pp.n_heavy + per_cta - 1) / per_cta);
+            skk_prior_link_kernel<<<blocks, pp.n_heavy > 0 ? 1024 : 256, 0, st>>>(pp, pl->prior_grad, pl->to_mu, pl->to_sigma);
             pl->stats.launches++;
         }
     }
@@ -615,7 +618,7 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
         rp.b_valid = b_valid;
         rp.grid = cfg.grid;
         const unsigned slot_blocks = (unsigned)(rp.blocks_p + rp.blocks_s + 1);
-        const unsigned theta_blocks = (unsigned)std::max<size_t>(1, (P + 255) / 256);
+        const unsigned theta_blocks = (unsigned)std::max<size_t>(1, (P * 32 + 255) / 256);
         if (bt == 4) {
             skk_slot_total_kernel<4><<<slot_blocks, 256, 0, st>>>(rp);
             skk_theta_reduce_kernel<4><<<theta_blocks, 256, 0, st>>>(rp);
@@ -642,8 +645,8 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
         out_logp = static_cast<T *>(logp_out);
     }
     {
-        FinalParams fp{pl->lik_vec, pl->prior_grad, pl->prior_lp, pl->n_params, pl->n_rows_total, pl->sigma_idx,
-                       pl->sigma_const, pl->family, pl->include_priors};
+        FinalParams fp{pl->lik_vec, pl->prior_grad, pl->prior_lp, (int32_t)((P + kPriorThreads - 1) / kPriorThreads),
+                       pl->n_params, pl->n_rows_total, pl->sigma_idx, pl->sigma_const, pl->family, pl->include_priors};
         dim3 grid((unsigned)std::max<size_t>(1, (P + 255) / 256), (unsigned)batch);
         skk_final_kernel<T><<<grid, 256, 0, st>>>(fp, th, out_logp, out_grad);
         pl->stats.launches++;

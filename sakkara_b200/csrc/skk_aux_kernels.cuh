@@ -104,42 +104,63 @@ struct PriorParams {
     int32_t batch;
 };
 
+constexpr int kPriorThreads = 128;
+
 template <typename T>
-__global__ void skk_prior_kernel(const __grid_constant__ PriorParams pp, const T *__restrict__ theta,
-                                 double *__restrict__ prior_grad, double *__restrict__ prior_lp,
-                                 double *__restrict__ to_mu, double *__restrict__ to_sigma) {
+__global__ void __launch_bounds__(kPriorThreads)
+skk_prior_kernel(const __grid_constant__ PriorParams pp, const T *__restrict__ theta, double *__restrict__ prior_grad,
+                 double *__restrict__ prior_lp_part, double *__restrict__ to_mu, double *__restrict__ to_sigma) {
+    __shared__ double part[kPriorThreads / 32];
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j >= pp.n_params) return;
-    const DevBlock blk = pp.blocks[pp.block_of[j]];
-    const int64_t g = j - blk.offset;
+    const bool valid = j < pp.n_params;
+    DevBlock blk{};
+    int64_t g = 0;
+    if (valid) {
+        blk = pp.blocks[pp.block_of[j]];
+        g = j - blk.offset;
+    }
     for (int b = 0; b < pp.batch; ++b) {
         const T *th = theta + (int64_t)b * pp.n_params;
-        const double v = (double)th[j];
-        double lp, grad, cm = 0.0, cs = 0.0;
-        if (blk.family == SKK_PRIOR_NORMAL) {
-            const double mu = blk.a_index ? (double)th[blk.a_index[g]] : blk.a_const[blk.a_const_len == 1 ? 0 : g];
-            const double sd = blk.b_index ? exp((double)th[blk.b_index[g]]) : blk.b_const[blk.b_const_len == 1 ? 0 : g];
-            const double z = (v - mu) / sd;
-            lp = -0.5 * z * z - kLogSqrt2Pi - log(sd);
-            grad = -z / sd;
-            cm = z / sd;          // d/d mu
-            cs = z * z - 1.0;     // d/d log(sigma)
-        } else if (blk.family == SKK_PRIOR_HALFNORMAL) {
-            const double tau = blk.a_const[blk.a_const_len == 1 ? 0 : g];
-            const double q = exp(v) / tau;
-            lp = -0.5 * q * q + kLogSqrt2OverPi - log(tau) + v;
-            grad = -q * q + 1.0;
-        } else {  // SKK_PRIOR_EXPONENTIAL
-            const double lam = blk.a_const[blk.a_const_len == 1 ? 0 : g];
-            const double s = exp(v);
-            lp = log(lam) - lam * s + v;
-            grad = -lam * s + 1.0;
+        double lp = 0.0;
+        if (valid) {
+            const double v = (double)th[j];
+            double grad, cm = 0.0, cs = 0.0;
+            if (blk.family == SKK_PRIOR_NORMAL) {
+                const double mu = blk.a_index ? (double)th[blk.a_index[g]] : blk.a_const[blk.a_const_len == 1 ? 0 : g];
+                const double sd =
+                    blk.b_index ? exp((double)th[blk.b_index[g]]) : blk.b_const[blk.b_const_len == 1 ? 0 : g];
+                const double z = (v - mu) / sd;
+                lp = -0.5 * z * z - kLogSqrt2Pi - log(sd);
+                grad = -z / sd;
+                cm = z / sd;       // d/d mu
+                cs = z * z - 1.0;  // d/d log(sigma)
+            } else if (blk.family == SKK_PRIOR_HALFNORMAL) {
+                const double tau = blk.a_const[blk.a_const_len == 1 ? 0 : g];
+                const double q = exp(v) / tau;
+                lp = -0.5 * q * q + kLogSqrt2OverPi - log(tau) + v;
+                grad = -q * q + 1.0;
+            } else {  // SKK_PRIOR_EXPONENTIAL
+                const double lam = blk.a_const[blk.a_const_len == 1 ? 0 : g];
+                const double sv = exp(v);
+                lp = log(lam) - lam * sv + v;
+                grad = -lam * sv + 1.0;
+            }
+            const int64_t o = (int64_t)b * pp.n_params + j;
+            prior_grad[o] = grad;
+            to_mu[o] = cm;
+            to_sigma[o] = cs;
         }
-        const int64_t o = (int64_t)b * pp.n_params + j;
-        prior_grad[o] = grad;
-        prior_lp[o] = lp;
-        to_mu[o] = cm;
-        to_sigma[o] = cs;
+        // logp of the priors: fixed tree per CTA, the CTA partials are added in order by the final kernel
+        const double s = warp_sum(lp);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kPriorThreads / 32; ++w) tot += part[w];
+            prior_lp_part[(int64_t)b * gridDim.x + blockIdx.x] = tot;
+        }
+        __syncthreads();
     }
 }
 
@@ -157,7 +178,20 @@ __global__ void skk_prior_link_kernel(const __grid_constant__ PriorParams pp, do
     for (int b = 0; b < pp.batch; ++b) {
         const double *cm = to_mu + (int64_t)b * pp.n_params, *cs = to_sigma + (int64_t)b * pp.n_params;
         double acc = 0.0;
-        for (int64_t e = first; e < hi; e += step) {
+        int64_t e = first;
+        for (; e + 3 * step < hi; e += 4 * step) {  // four independent gathers in flight
+            const int64_t c0 = pp.link_child[e], c1 = pp.link_child[e + step], c2 = pp.link_child[e + 2 * step],
+                          c3 = pp.link_child[e + 3 * step];
+            const int8_t k0 = pp.link_kind[e], k1 = pp.link_kind[e + step], k2 = pp.link_kind[e + 2 * step],
+                         k3 = pp.link_kind[e + 3 * step];
+            const double v0 = k0 == 0 ? cm[c0] : cs[c0], v1 = k1 == 0 ? cm[c1] : cs[c1];
+            const double v2 = k2 == 0 ? cm[c2] : cs[c2], v3 = k3 == 0 ? cm[c3] : cs[c3];
+            acc += v0;
+            acc += v1;
+            acc += v2;
+            acc += v3;
+        }
+        for (; e < hi; e += step) {
             const int64_t c = pp.link_child[e];
             acc += pp.link_kind[e] == 0 ? cm[c] : cs[c];
         }
@@ -203,6 +237,13 @@ struct ReduceParams {
     double logp_const;
 };
 
+__device__ __forceinline__ int64_t t_lo_of(const ReduceParams &rp, int64_t slot) {
+    return rp.seg_offsets[slot] / rp.rows_per_tile;
+}
+__device__ __forceinline__ int64_t t_hi_of(const ReduceParams &rp, int64_t slot) {
+    return (rp.seg_offsets[slot + 1] - 1) / rp.rows_per_tile;
+}
+
 // blockIdx.x in [0, blocks_p): primary slots, one per thread;  [blocks_p, blocks_p + blocks_s):
 // secondary slots, 32 per CTA x 8 ranges of row-kernel CTAs;  last CTA: global terms and logp.
 template <int BT>
@@ -219,9 +260,14 @@ __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_consta
                 t_hi = (r1 - 1) / rp.rows_per_tile;
             }
         }
+        // a tile strictly inside the slot's row range lies wholly in the slot: its head partial is
+        // the slot's; only the first and the last tile need the key check
         auto addend = [&](int64_t s, int64_t tile, int t, int b) -> double {
-            const int2 k = rp.tile_keys[tile];
-            const double *src = k.x == s ? rp.tile_head : (k.y == s ? rp.tile_tail : nullptr);
+            const double *src = rp.tile_head;
+            if (tile == t_lo_of(rp, s) || tile == t_hi_of(rp, s)) {
+                const int2 k = rp.tile_keys[tile];
+                src = k.x == s ? rp.tile_head : (k.y == s ? rp.tile_tail : nullptr);
+            }
             return src ? src[(tile * rp.np + t) * BT + b] : 0.0;
         };
         const bool heavy = valid && (t_hi - t_lo + 1 > kSerialLimit);
@@ -230,9 +276,19 @@ __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_consta
                 double acc[BT];
 #pragma unroll
                 for (int b = 0; b < BT; ++b) acc[b] = rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b];
-                for (int64_t tile = t_lo; tile <= t_hi; ++tile)
+                const int2 k_lo = rp.tile_keys[t_lo], k_hi = rp.tile_keys[t_hi];
+                const double *s_lo = k_lo.x == slot ? rp.tile_head : (k_lo.y == slot ? rp.tile_tail : nullptr);
+                const double *s_hi = k_hi.x == slot ? rp.tile_head : (k_hi.y == slot ? rp.tile_tail : nullptr);
+                if (s_lo)
 #pragma unroll
-                    for (int b = 0; b < BT; ++b) acc[b] += addend(slot, tile, t, b);
+                    for (int b = 0; b < BT; ++b) acc[b] += s_lo[(t_lo * rp.np + t) * BT + b];
+#pragma unroll 4
+                for (int64_t tile = t_lo + 1; tile < t_hi; ++tile)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) acc[b] += rp.tile_head[(tile * rp.np + t) * BT + b];
+                if (s_hi && t_hi > t_lo)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) acc[b] += s_hi[(t_hi * rp.np + t) * BT + b];
 #pragma unroll
                 for (int b = 0; b < BT; ++b) rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b] = acc[b];
             }
@@ -275,35 +331,32 @@ __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_consta
     }
 }
 
-// per theta element: sum of the totals of the slots that map to it
+// per theta element: sum of the totals of the slots that map to it; one warp per element, lanes
+// strided over the element's slots, fixed shuffle tree
 template <int BT>
 __global__ void __launch_bounds__(256) skk_theta_reduce_kernel(const __grid_constant__ ReduceParams rp) {
-    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool valid = j < rp.n_params;
-    const int64_t lo = valid ? rp.csr_ptr[j] : 0, hi = valid ? rp.csr_ptr[j + 1] : 0;
-    auto addend = [&](int64_t, int64_t e, int b) -> double {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (j >= rp.n_params) return;
+    const int64_t lo = rp.csr_ptr[j], hi = rp.csr_ptr[j + 1];
+    double acc[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+    for (int64_t e = lo + lane; e < hi; e += 32) {
         const int level = rp.entry_level[e], t = rp.entry_t[e];
         const int64_t slot = rp.entry_slot[e];
-        if (level == SKK_LEVEL_GLOBAL) return rp.glob_tot[t * BT + b];
-        if (level == SKK_LEVEL_PRIMARY) return rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b];
-        return rp.sec_tot[((int64_t)t * rp.n_secondary + slot) * BT + b];
-    };
-    auto store = [&](int64_t el, int b, double sum) {
-        if (b < rp.b_valid) rp.lik_vec[(int64_t)(rp.b0 + b) * (rp.n_params + 2) + el] = sum;
-    };
-    const bool heavy = hi - lo > kSerialLimit;
-    if (valid && !heavy) {
-        double acc[BT];
+        const double *src = level == SKK_LEVEL_GLOBAL    ? rp.glob_tot + (int64_t)t * BT
+                            : level == SKK_LEVEL_PRIMARY ? rp.direct_p + ((int64_t)t * rp.n_primary + slot) * BT
+                                                         : rp.sec_tot + ((int64_t)t * rp.n_secondary + slot) * BT;
 #pragma unroll
-        for (int b = 0; b < BT; ++b) acc[b] = 0.0;
-        for (int64_t e = lo; e < hi; ++e)
-#pragma unroll
-            for (int b = 0; b < BT; ++b) acc[b] += addend(j, e, b);
-#pragma unroll
-        for (int b = 0; b < BT; ++b) store(j, b, acc[b]);
+        for (int b = 0; b < BT; ++b) acc[b] += src[b];
     }
-    warp_cooperative_lists<BT>(heavy, lo, hi, j, addend, store);
-    if (j == 0)
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+        const double sum = (hi - lo > 1) ? warp_sum(acc[b]) : acc[b];
+        if (lane == 0 && b < rp.b_valid) rp.lik_vec[(int64_t)(rp.b0 + b) * (rp.n_params + 2) + j] = sum;
+    }
+    if (j == 0 && lane == 0)
         for (int b = 0; b < rp.b_valid; ++b) {
             double *row = rp.lik_vec + (int64_t)(rp.b0 + b) * (rp.n_params + 2);
             row[rp.n_params] = rp.glob_tot[rp.ng * BT + b];  // likelihood logp partial
@@ -315,7 +368,8 @@ __global__ void __launch_bounds__(256) skk_theta_reduce_kernel(const __grid_cons
 struct FinalParams {
     const double *lik_vec;      // [B][P+2] (all-reduced over ranks when sharded)
     const double *prior_grad;   // [B][P]
-    const double *prior_lp;     // [B][P]
+    const double *prior_lp_part; // [B][prior_ctas] per-CTA partial sums of the prior logp terms
+    int32_t prior_ctas;
     int64_t n_params;
     int64_t n_rows_total;
     int64_t sigma_theta_index;  // -1: constant sigma
@@ -344,11 +398,12 @@ __global__ void skk_final_kernel(const __grid_constant__ FinalParams fp, const T
         out_grad[(int64_t)b * P + j] = (T)g;
     }
     if (blockIdx.x == 0) {
-        // logp: priors summed in fixed order (strided per thread, then a fixed tree)
+        // logp: CTA partials of the prior kernel, added in fixed order (strided per thread, fixed tree)
         __shared__ double part[32];
         double s = 0.0;
         if (fp.include_priors)
-            for (int64_t k = threadIdx.x; k < P; k += blockDim.x) s += fp.prior_lp[(int64_t)b * P + k];
+            for (int k = threadIdx.x; k < fp.prior_ctas; k += blockDim.x)
+                s += fp.prior_lp_part[(int64_t)b * fp.prior_ctas + k];
         s = warp_sum(s);
         if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
         __syncthreads();

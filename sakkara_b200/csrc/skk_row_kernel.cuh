@@ -99,14 +99,14 @@ struct RowKernel {
     };
 
     // -----------------------------------------------------------------------------------------
-    template <bool FASTP>
+    template <bool FASTP, bool FULL>
     static __device__ __forceinline__ void process(const RowParams<T> &p, const Tile &tl, const T (&vp_first)[NPa][BT],
                                                    const T (&vg)[NGa][BT], double (&accG64)[NG + 1][BT],
                                                    const T *__restrict__ valS, T *__restrict__ gradS, int lane) {
         const int li = lane * R;
         const int64_t row0 = (int64_t)tl.tile * WT + li;
         const int64_t left = p.n_rows - row0;
-        const int nvalid = left >= R ? R : (left > 0 ? (int)left : 0);
+        const int nvalid = FULL ? R : (left >= R ? R : (left > 0 ? (int)left : 0));
 
         // data columns of the terms (x == 1 when the term has no column)
         const T *pxg[NGa], *pxp[NPa], *pxs[NSa];
@@ -196,7 +196,7 @@ struct RowKernel {
         // ---- the rows ---------------------------------------------------------------------------
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-            const bool valid = i < nvalid;
+            const bool valid = FULL || i < nvalid;
 
             if constexpr (NP > 0 && !FASTP) {
                 // segment boundaries inside the lane's span (tiles that straddle segments only)
@@ -520,10 +520,15 @@ struct RowKernel {
             mbar_wait(bars + s, parity);
 
             Tile tl{stage0 + (int64_t)s * sl.bytes, sl, tile, k0.x, k0.y};
-            if (NP == 0 || k0.x == k0.y)
-                process<true>(p, tl, vp0, vg, accG64, valS, gradS, lane);
-            else
-                process<false>(p, tl, vp0, vg, accG64, valS, gradS, lane);
+            const bool full = (int64_t)(tile + 1) * WT <= p.n_rows;
+            if (NP == 0 || k0.x == k0.y) {
+                if (full)
+                    process<true, true>(p, tl, vp0, vg, accG64, valS, gradS, lane);
+                else
+                    process<true, false>(p, tl, vp0, vg, accG64, valS, gradS, lane);
+            } else {
+                process<false, false>(p, tl, vp0, vg, accG64, valS, gradS, lane);
+            }
 
             __syncwarp();
             const int next = tile + stages * warps;

@@ -1,0 +1,113 @@
+"""
+The CPU oracle (oracle/logp_numpy.py, oracle/logp_c.c) against independent evidence -- the
+floating-point values of this path are unpinned by the reference, so the oracle is
+anchored on: torch autograd over the recorded graph with torch.distributions densities,
+scipy.stats log-densities, central finite differences, and hand-computed values on the README model.
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+from helpers import build_model, theta_points
+from model_zoo import zoo
+from oracle.autograd_check import logp_dlogp_autograd
+from oracle.logp_c import COracle
+from oracle.logp_numpy import logp_dlogp, parity_error
+
+ZOO = zoo()
+
+
+@pytest.mark.parametrize('name', sorted(ZOO))
+def test_numpy_oracle_equals_autograd_on_recorded_graph(name):
+    model = build_model(ZOO[name])
+    for theta in theta_points(model.plan, 4, seed=1):
+        logp, grad = logp_dlogp_autograd(model.recorded, theta)
+        err_l, err_g = parity_error(logp, grad, model.plan, theta)
+        assert err_l < 1e-13 and err_g < 1e-13
+
+
+@pytest.mark.parametrize('dtype,tol', [('float64', 1e-13), ('float32', 2e-6)])
+@pytest.mark.parametrize('name', sorted(ZOO))
+def test_c_oracle_equals_numpy_oracle(name, dtype, tol):
+    model = build_model(ZOO[name])
+    f = COracle(model.plan, dtype, threads=3)
+    for theta in theta_points(model.plan, 3, seed=2):
+        theta = theta.astype(dtype)
+        logp, grad = f(theta)
+        err_l, err_g = parity_error(logp, grad, model.plan, theta.astype(np.float64))
+        assert err_l < tol and err_g < tol
+
+
+def test_readme_model_against_scipy():
+    """logp of the README model written out with scipy.stats, term by term."""
+    df, _ = ZOO['readme']
+    model = build_model(ZOO['readme'])
+    theta = np.array([0.3, -0.2, 0.9, -1.1, 0.05, -0.4])     # [mu_k, log s_k, k0, k1, intercept, log s_est]
+    mu_k, s_k, k, icpt, s_est = theta[0], np.exp(theta[1]), theta[2:4], theta[4], np.exp(theta[5])
+    expected = stats.norm.logpdf(mu_k, 0, 1)
+    expected += stats.expon.logpdf(s_k, scale=1.0) + theta[1]                     # Exponential(lam=1) + log-Jacobian
+    expected += stats.norm.logpdf(k, mu_k, s_k).sum()
+    expected += stats.norm.logpdf(icpt, 0, 1)
+    expected += stats.expon.logpdf(s_est, scale=1.0) + theta[5]
+    eta = k[df['group'].values] * df['x'].values + icpt
+    expected += stats.norm.logpdf(df['y'].values, eta, s_est).sum()
+    logp, _ = logp_dlogp(model.plan, theta)
+    assert abs(logp - expected) < 1e-12 * abs(expected)
+
+
+def test_halfnormal_bernoulli_poisson_against_scipy():
+    model = build_model(ZOO['nested_logistic'])
+    plan = model.plan
+    theta = theta_points(plan, 2, seed=9)[1]
+    sl = plan.block_slices()
+    v = {name: theta[s] for name, s in sl.items()}
+    par = plan.blocks[7].params['mu'].index
+    expected = stats.norm.logpdf(v['mu_slope'], 0, 1).sum()
+    expected += (stats.halfnorm.logpdf(np.exp(v['sigma_slope']), scale=1.0) + v['sigma_slope']).sum()
+    expected += stats.norm.logpdf(v['slope'], v['mu_slope'], np.exp(v['sigma_slope'])).sum()
+    expected += stats.norm.logpdf(v['mu_mu_icpt'], 0, 1).sum()
+    expected += (stats.halfnorm.logpdf(np.exp(v['sigma_mu_icpt']), scale=2.0) + v['sigma_mu_icpt']).sum()
+    expected += stats.norm.logpdf(v['mu_icpt'], v['mu_mu_icpt'], np.exp(v['sigma_mu_icpt'])).sum()
+    expected += (stats.halfnorm.logpdf(np.exp(v['sigma_icpt']), scale=1.0) + v['sigma_icpt']).sum()
+    expected += stats.norm.logpdf(v['icpt'], v['mu_icpt'][par], np.exp(v['sigma_icpt'])).sum()
+    eta = v['slope'][plan.terms[0].index] * plan.terms[0].x + v['icpt'][plan.terms[1].index]
+    p = 1 / (1 + np.exp(-eta))
+    expected += stats.bernoulli.logpmf(plan.likelihood.y.astype(int), p).sum()
+    assert abs(logp_dlogp(plan, theta)[0] - expected) < 1e-11 * abs(expected)
+
+    model = build_model(ZOO['crossed_poisson'])
+    plan = model.plan
+    theta = theta_points(plan, 2, seed=9)[1]
+    eta = sum(theta[plan.blocks[t.block].offset + t.index] * (1.0 if t.x is None else t.x) for t in plan.terms)
+    lik = stats.poisson.logpmf(plan.likelihood.y.astype(int), np.exp(eta)).sum()
+    from oracle.logp_c import priors_only
+    assert abs(logp_dlogp(plan, theta)[0] - (logp_dlogp(priors_only(plan), theta)[0] + lik)) < 1e-10 * abs(lik)
+
+
+@pytest.mark.parametrize('name', ['readme', 'nested_logistic', 'crossed_poisson', 'tuple_group'])
+def test_gradient_against_finite_differences(name):
+    plan = build_model(ZOO[name]).plan
+    theta = theta_points(plan, 2, seed=4, scale=0.3)[1]
+    _, grad = logp_dlogp(plan, theta)
+    h = 1e-6
+    for j in range(plan.n_params):
+        e = np.zeros_like(theta)
+        e[j] = h
+        fd = (logp_dlogp(plan, theta + e)[0] - logp_dlogp(plan, theta - e)[0]) / (2 * h)
+        assert abs(fd - grad[j]) <= 1e-5 * max(1.0, abs(grad[j])), (j, fd, grad[j])
+
+
+def test_float32_mode_accumulates_sums_in_float64():
+    plan = build_model(ZOO['shuffled_linreg']).plan
+    theta = theta_points(plan, 2, seed=1)[1].astype(np.float32)
+    logp, grad = logp_dlogp(plan, theta, np.float32)
+    assert logp.dtype == np.float32 and grad.dtype == np.float32
+    err_l, err_g = parity_error(logp, grad, plan, theta.astype(np.float64))
+    assert err_l < 1e-6 and err_g < 1e-5
+
+
+def test_error_metric_uses_the_l1_mass_of_the_reduction():
+    plan = build_model(ZOO['readme']).plan
+    theta = np.zeros(plan.n_params)
+    logp, grad, mass_l, mass_g = logp_dlogp(plan, theta, np.float64, True)
+    assert (mass_g >= np.abs(grad) - 1e-12).all() and mass_l >= abs(logp) - 1e-12
