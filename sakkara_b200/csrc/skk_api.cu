@@ -212,7 +212,7 @@ template <typename T>
 static int cta_smem(const skk_plan *pl, int warps, int stages, int bt) {
     const StageLayout sl = make_stage_layout<T>(pl->rows_per_tile, pl->n_x, pl->y_u8, pl->has_off,
                                                 pl->ns > 0 ? pl->sec_code_bytes : 0);
-    return make_cta_layout<T>(warps, stages, sl.bytes, pl->ns, (int)pl->n_secondary, bt).total;
+    return make_cta_layout<T>(warps, stages, sl.bytes, pl->ns, (int)pl->n_secondary, bt, pl->np).total;
 }
 
 template <typename T>
@@ -441,7 +441,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, pl->device));
     pl->n_sms = prop.multiProcessorCount;
     const int smem_limit = (int)prop.sharedMemPerBlockOptin;
-    pl->warps = std::max(1, std::min(12, env_int("SKK_WARPS", 8)));
+    pl->warps = std::max(1, std::min(8, env_int("SKK_WARPS", 8)));  // kernels are compiled for <= 256 threads
     pl->stages = std::max(2, std::min(8, env_int("SKK_STAGES", 3)));
     const int bt_max = d->max_batch > 1 ? 4 : 1;
     while (cta_smem<T>(pl, pl->warps, pl->stages, bt_max) > smem_limit) {

@@ -159,9 +159,25 @@ struct Math;
 // magnitude inside the 1e-4 tolerance stated for fp32; double: the accurate library functions.
 template <>
 struct Math<float> {
-    static __device__ __forceinline__ float exp(float x) { return __expf(x); }
-    static __device__ __forceinline__ float log1p_of_exp_neg(float t) { return __logf(1.0f + t); }  // t in (0, 1]
-    static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
+    static __device__ __forceinline__ float ex2(float x) {
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float lg2(float x) {
+        float r;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float exp(float x) { return ex2(x * 1.4426950408889634f); }
+    static __device__ __forceinline__ float log1p_of_exp_neg(float t) {  // t in (0, 1]
+        return lg2(1.0f + t) * 0.6931471805599453f;
+    }
+    static __device__ __forceinline__ float rcp(float x) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
     static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
     static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
 };

@@ -53,14 +53,27 @@ __host__ __device__ inline StageLayout make_stage_layout(int rows_per_tile, int 
 
 struct CtaLayout {
     int bars_off;
-    int vals_off;   // secondary value table  [NS][GS][BT] of T
-    int grads_off;  // secondary gradient tables [W][NS][GS][BT] of T
+    int vals_off;     // secondary value table  [NS][GS][BT] of T
+    int grads_off;    // secondary gradient tables [W][NS][GS][BT] of T
+    int scratch_off;  // per-warp scratch of the straddling-tile path
+    int scratch_bytes;
     int stage_off;
     int total;
 };
 
+constexpr int kStagedGroups = 32;  // straddling tiles with up to this many segments are handled on chip
+
+// scratch of one warp: segment offsets [33] | values [32][NP][BT] T | accumulators [32][NP][BT] f64 | touched [32]
 template <typename T>
-__host__ __device__ inline CtaLayout make_cta_layout(int warps, int stages, int stage_bytes, int ns, int gs, int bt) {
+__host__ __device__ inline int warp_scratch_bytes(int np, int bt) {
+    if (np == 0) return 0;
+    const int vals = (kStagedGroups * np * bt * (int)sizeof(T) + 7) & ~7;
+    return ((kStagedGroups + 1) * 8 + vals + kStagedGroups * np * bt * 8 + kStagedGroups + 15) & ~15;
+}
+
+template <typename T>
+__host__ __device__ inline CtaLayout make_cta_layout(int warps, int stages, int stage_bytes, int ns, int gs, int bt,
+                                                     int np) {
     CtaLayout l{};
     int o = 0;
     l.bars_off = o;
@@ -71,6 +84,10 @@ __host__ __device__ inline CtaLayout make_cta_layout(int warps, int stages, int 
     o = (o + 15) & ~15;
     l.grads_off = o;
     o += warps * ns * gs * bt * (int)sizeof(T);
+    o = (o + 15) & ~15;
+    l.scratch_off = o;
+    l.scratch_bytes = warp_scratch_bytes<T>(np, bt);
+    o += warps * l.scratch_bytes;
     o = (o + 127) & ~127;
     l.stage_off = o;
     o += warps * stages * stage_bytes;
@@ -102,7 +119,8 @@ struct RowKernel {
     template <bool FASTP, bool FULL>
     static __device__ __forceinline__ void process(const RowParams<T> &p, const Tile &tl, const T (&vp_first)[NPa][BT],
                                                    const T (&vg)[NGa][BT], double (&accG64)[NG + 1][BT],
-                                                   const T *__restrict__ valS, T *__restrict__ gradS, int lane) {
+                                                   const T *__restrict__ valS, T *__restrict__ gradS,
+                                                   unsigned char *scratch, int lane) {
         const int li = lane * R;
         const int64_t row0 = (int64_t)tl.tile * WT + li;
         const int64_t left = p.n_rows - row0;
@@ -155,21 +173,51 @@ struct RowKernel {
         bool p_changed = false, p_have_head = false, p_inside = false;
         int p_head_key = 0;
         double p_head[NPa * BT];
+        // Straddling tiles: the tile's segment offsets, values and accumulators are staged in the warp's
+        // shared-memory scratch (one coalesced global load each) so that the per-lane search, the value
+        // reloads at boundaries and the cross-lane combine never wait on global memory.
+        const int ng = tl.kl - tl.kf + 1;
+        const bool staged = ng <= kStagedGroups;
+        int64_t *s_off = reinterpret_cast<int64_t *>(scratch);
+        T *s_val = reinterpret_cast<T *>(scratch + (kStagedGroups + 1) * 8);
+        double *s_acc = reinterpret_cast<double *>(scratch + (kStagedGroups + 1) * 8 +
+                                                   ((kStagedGroups * NP * BT * (int)sizeof(T) + 7) & ~7));
+        unsigned char *s_touch = reinterpret_cast<unsigned char *>(s_acc + kStagedGroups * NP * BT);
+        auto seg_off = [&](int k) -> int64_t { return staged ? s_off[k - tl.kf] : p.seg_offsets[k]; };
+        auto load_vals = [&](int k) {
+#pragma unroll
+            for (int t = 0; t < NP; ++t)
+#pragma unroll
+                for (int b = 0; b < BT; ++b)
+                    vp[t][b] = staged ? s_val[((k - tl.kf) * NP + t) * BT + b]
+                                      : p.val_p[((int64_t)t * p.n_primary + k) * BT + b];
+        };
         if constexpr (NP > 0 && !FASTP) {
+            if (staged) {
+                for (int j = lane; j <= ng; j += 32) s_off[j] = p.seg_offsets[tl.kf + j];
+                if (lane < ng) {
+#pragma unroll
+                    for (int t = 0; t < NP; ++t)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) {
+                            s_val[(lane * NP + t) * BT + b] = p.val_p[((int64_t)t * p.n_primary + tl.kf + lane) * BT + b];
+                            s_acc[(lane * NP + t) * BT + b] = 0.0;
+                        }
+                    s_touch[lane] = 0;
+                }
+                __syncwarp();
+            }
             if (nvalid > 0) {
-                // segment of the lane's first row: largest k in [kf, kl] with seg_offsets[k] <= row0
+                // segment of the lane's first row: largest k in [kf, kl] with seg_off(k) <= row0
                 int lo = tl.kf, hi = tl.kl;
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (p.seg_offsets[mid] <= row0) lo = mid; else hi = mid - 1;
+                    if (seg_off(mid) <= row0) lo = mid; else hi = mid - 1;
                 }
                 kcur = lo;
-                nextb = p.seg_offsets[kcur + 1];
-                p_inside = p.seg_offsets[kcur] >= row0;
-#pragma unroll
-                for (int t = 0; t < NP; ++t)
-#pragma unroll
-                    for (int b = 0; b < BT; ++b) vp[t][b] = p.val_p[((int64_t)t * p.n_primary + kcur) * BT + b];
+                nextb = seg_off(kcur + 1);
+                p_inside = seg_off(kcur) >= row0;
+                load_vals(kcur);
             }
         }
 
@@ -219,14 +267,12 @@ struct RowKernel {
                     p_changed = true;
                     p_inside = true;
                     ++kcur;
-                    nextb = p.seg_offsets[kcur + 1];
+                    nextb = seg_off(kcur + 1);
 #pragma unroll
                     for (int t = 0; t < NP; ++t)
 #pragma unroll
-                        for (int b = 0; b < BT; ++b) {
-                            accP[t][b] = T(0);
-                            vp[t][b] = p.val_p[((int64_t)t * p.n_primary + kcur) * BT + b];
-                        }
+                        for (int b = 0; b < BT; ++b) accP[t][b] = T(0);
+                    load_vals(kcur);
                 }
                 __syncwarp();
             }
@@ -347,11 +393,13 @@ struct RowKernel {
             } else {
                 double *head = p.tile_head + (int64_t)tl.tile * NP * BT;
                 double *tail = p.tile_tail + (int64_t)tl.tile * NP * BT;
-                if (lane < NP * BT) {
-                    head[lane] = 0.0;
-                    tail[lane] = 0.0;
+                if (!staged) {
+                    if (lane < NP * BT) {
+                        head[lane] = 0.0;
+                        tail[lane] = 0.0;
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 // round A: the first run of every lane (or its only run); round B: the last run
                 double v[NPa * BT];
                 int key;
@@ -371,18 +419,41 @@ struct RowKernel {
                         for (int k = 0; k < NP * BT; ++k) v[k] = (double)accP[k / BT][k % BT];
                     }
                     if (warp_match_sum<NPa * BT>(has, key, v)) {
-                        double *sink = key == tl.kf ? head
-                                       : key == tl.kl ? tail
-                                                      : nullptr;
+                        if (staged) {
 #pragma unroll
-                        for (int k = 0; k < NP * BT; ++k) {
-                            double *dst = sink ? sink + k
-                                               : p.direct_p + ((int64_t)(k / BT) * p.n_primary + key) * BT + (k % BT);
-                            *dst = *reinterpret_cast<volatile double *>(dst) + v[k];
+                            for (int k = 0; k < NP * BT; ++k) s_acc[(key - tl.kf) * NP * BT + k] += v[k];
+                            s_touch[key - tl.kf] = 1;
+                        } else {
+                            double *sink = key == tl.kf ? head : key == tl.kl ? tail : nullptr;
+#pragma unroll
+                            for (int k = 0; k < NP * BT; ++k) {
+                                double *dst =
+                                    sink ? sink + k
+                                         : p.direct_p + ((int64_t)(k / BT) * p.n_primary + key) * BT + (k % BT);
+                                *dst = *reinterpret_cast<volatile double *>(dst) + v[k];
+                            }
                         }
                     }
                     __syncwarp();
                 }
+                if (staged && lane < ng) {
+                    // one plain store per group: first -> tile_head, last -> tile_tail, groups in between
+                    // (not stored by a single lane already) -> direct_p
+                    const int gkey = tl.kf + lane;
+                    if (lane == 0 || lane == ng - 1 || s_touch[lane]) {
+#pragma unroll
+                        for (int k = 0; k < NP * BT; ++k) {
+                            const double tot = s_acc[lane * NP * BT + k];
+                            if (lane == 0)
+                                head[k] = tot;
+                            else if (lane == ng - 1)
+                                tail[k] = tot;
+                            else
+                                p.direct_p[((int64_t)(k / BT) * p.n_primary + gkey) * BT + (k % BT)] = tot;
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
 
@@ -453,12 +524,13 @@ struct RowKernel {
 
         const StageLayout sl =
             make_stage_layout<T>(WT, p.n_x, p.y8 != nullptr, p.eta_offset != nullptr, NS > 0 ? p.sec_code_bytes : 0);
-        const CtaLayout cl = make_cta_layout<T>(warps, stages, sl.bytes, NS, p.n_secondary, BT);
+        const CtaLayout cl = make_cta_layout<T>(warps, stages, sl.bytes, NS, p.n_secondary, BT, NP);
         uint64_t *bars = reinterpret_cast<uint64_t *>(smem + cl.bars_off) + warp * stages;
         T *valS = reinterpret_cast<T *>(smem + cl.vals_off);
         T *gradS_all = reinterpret_cast<T *>(smem + cl.grads_off);
         T *gradS = gradS_all + (int64_t)warp * NS * p.n_secondary * BT;
         unsigned char *stage0 = smem + cl.stage_off + (int64_t)warp * stages * sl.bytes;
+        unsigned char *scratch = smem + cl.scratch_off + warp * cl.scratch_bytes;
 
         // contiguous, balanced range of tiles for this CTA; its warps interleave inside the range
         const int64_t nt = p.n_tiles;
@@ -523,11 +595,11 @@ struct RowKernel {
             const bool full = (int64_t)(tile + 1) * WT <= p.n_rows;
             if (NP == 0 || k0.x == k0.y) {
                 if (full)
-                    process<true, true>(p, tl, vp0, vg, accG64, valS, gradS, lane);
+                    process<true, true>(p, tl, vp0, vg, accG64, valS, gradS, scratch, lane);
                 else
-                    process<true, false>(p, tl, vp0, vg, accG64, valS, gradS, lane);
+                    process<true, false>(p, tl, vp0, vg, accG64, valS, gradS, scratch, lane);
             } else {
-                process<false, false>(p, tl, vp0, vg, accG64, valS, gradS, lane);
+                process<false, false>(p, tl, vp0, vg, accG64, valS, gradS, scratch, lane);
             }
 
             __syncwarp();
@@ -573,7 +645,7 @@ struct RowKernel {
 };
 
 template <typename T, int FAM, int BT, int NG, int NP, int NS, int R>
-__global__ void __launch_bounds__(384, 1) skk_row_kernel(const __grid_constant__ RowParams<T> p) {
+__global__ void __launch_bounds__(256, (BT == 1 ? 2 : 1)) skk_row_kernel(const __grid_constant__ RowParams<T> p) {
     RowKernel<T, FAM, BT, NG, NP, NS, R>::run(p);
 }
 
