@@ -451,6 +451,13 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             return fail(SKK_ERR_UNSUPPORTED, "secondary level with %lld members does not fit in shared memory",
                         (long long)pl->n_secondary);
     }
+    // two resident CTAs per SM hide more latency than a third pipeline stage
+    if (!getenv("SKK_STAGES") && pl->stages > 2) {
+        const int per_sm = (int)prop.sharedMemPerMultiprocessor;
+        if (2 * (cta_smem<T>(pl, pl->warps, pl->stages, 1) + 1024) > per_sm &&
+            2 * (cta_smem<T>(pl, pl->warps, 2, 1) + 1024) <= per_sm)
+            pl->stages = 2;
+    }
     if (int rc = configure_launch<T>(pl, 1, &pl->cfg1)) return rc;
     if (bt_max == 4)
         if (int rc = configure_launch<T>(pl, 4, &pl->cfg4)) return rc;

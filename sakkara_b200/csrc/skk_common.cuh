@@ -119,7 +119,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Among the lanes with `has`, group lanes holding the same key; the lowest lane of each group
 // receives the group's sum (added in ascending lane order).  Returns true on that lane.
-// Must be called by all 32 lanes.
+// Works for any arrangement of keys.  Must be called by all 32 lanes.
 template <int NV>
 __device__ __forceinline__ bool warp_match_sum(bool has, int key, double (&v)[NV]) {
     const unsigned active = __ballot_sync(kFull, has);
@@ -144,6 +144,26 @@ __device__ __forceinline__ bool warp_match_sum(bool has, int key, double (&v)[NV
     }
     __syncwarp();
     return leader;
+}
+
+// Same contract for keys that are non-decreasing along the participating lanes (equal keys occupy
+// consecutive lanes): a fixed five-step shuffle tree, no loops and no divergence.
+template <int NV>
+__device__ __forceinline__ bool warp_sorted_run_sum(bool has, int key, double (&v)[NV]) {
+    const int lane = threadIdx.x & 31;
+    const int k = has ? key : -1 - lane;  // lanes without a value never merge with a neighbour
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int other = __shfl_down_sync(kFull, k, d);
+        const bool take = (lane + d < 32) && (other == k);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const double w = __shfl_down_sync(kFull, v[q], d);
+            if (take) v[q] += w;
+        }
+    }
+    const int before = __shfl_up_sync(kFull, k, 1);
+    return has && (lane == 0 || before != k);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -232,17 +232,13 @@ struct RowKernel {
 #pragma unroll
             for (int b = 0; b < BT; ++b) vs[t][b] = T(0);
         if constexpr (NS > 0) {
-            if (nvalid > 0) {
-                scur = code16 ? (int)sc16[0] : sc32[0];
-#pragma unroll
-                for (int t = 0; t < NS; ++t)
-#pragma unroll
-                    for (int b = 0; b < BT; ++b) vs[t][b] = valS[((int64_t)t * p.n_secondary + scur) * BT + b];
-            }
+            if (nvalid > 0) scur = code16 ? (int)sc16[0] : sc32[0];
         }
 
         // ---- the rows ---------------------------------------------------------------------------
-#pragma unroll
+        // Only the common path (tile inside one segment, all rows valid) is unrolled; the other
+        // variants stay rolled to keep the kernel inside the instruction cache.
+#pragma unroll(FASTP && FULL ? R : 1)
         for (int i = 0; i < R; ++i) {
             const bool valid = FULL || i < nvalid;
 
@@ -274,7 +270,7 @@ struct RowKernel {
                         for (int b = 0; b < BT; ++b) accP[t][b] = T(0);
                     load_vals(kcur);
                 }
-                __syncwarp();
+                if constexpr (NS > 0) __syncwarp();
             }
 
             if constexpr (NS > 0) {
@@ -329,11 +325,13 @@ struct RowKernel {
 #pragma unroll
                     for (int t = 0; t < NS; ++t)
 #pragma unroll
-                        for (int b = 0; b < BT; ++b) {
-                            accS[t][b] = T(0);
-                            vs[t][b] = valS[((int64_t)t * p.n_secondary + c) * BT + b];
-                        }
+                        for (int b = 0; b < BT; ++b) accS[t][b] = T(0);
                 }
+                // the value of the row's own code: independent of the run bookkeeping above
+#pragma unroll
+                for (int t = 0; t < NS; ++t)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) vs[t][b] = valS[((int64_t)t * p.n_secondary + c) * BT + b];
             }
 
             // data of the row
@@ -418,7 +416,10 @@ struct RowKernel {
 #pragma unroll
                         for (int k = 0; k < NP * BT; ++k) v[k] = (double)accP[k / BT][k % BT];
                     }
-                    if (warp_match_sum<NPa * BT>(has, key, v)) {
+                    // first-run keys ascend with the lane and equal keys sit in consecutive lanes; a last
+                    // run that began inside its lane is the only pending piece of its group in this round
+                    const bool leader = round == 0 ? warp_sorted_run_sum<NPa * BT>(has, key, v) : has;
+                    if (leader) {
                         if (staged) {
 #pragma unroll
                             for (int k = 0; k < NP * BT; ++k) s_acc[(key - tl.kf) * NP * BT + k] += v[k];
@@ -474,7 +475,11 @@ struct RowKernel {
 #pragma unroll
                     for (int k = 0; k < NS * BT; ++k) v[k] = (double)accS[k / BT][k % BT];
                 }
-                if (warp_match_sum<NSa * BT>(has, key, v)) {
+                // inside one segment the codes ascend with the lane (same argument as above); a tile
+                // that straddles segments may repeat a code anywhere, so it takes the general grouping
+                const bool leader = FASTP ? (round == 0 ? warp_sorted_run_sum<NSa * BT>(has, key, v) : has)
+                                          : warp_match_sum<NSa * BT>(has, key, v);
+                if (leader) {
 #pragma unroll
                     for (int k = 0; k < NS * BT; ++k)
                         gradS[((int64_t)(k / BT) * p.n_secondary + key) * BT + (k % BT)] += (T)v[k];
