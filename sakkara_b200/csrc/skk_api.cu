@@ -114,6 +114,13 @@ struct LaunchCfg {
     int smem = 0;
 };
 
+struct GraphEntry {
+    int batch = 0;
+    unsigned flags = 0;
+    const void *theta = nullptr, *logp = nullptr, *grad = nullptr;
+    cudaGraphExec_t exec = nullptr;
+};
+
 struct skk_plan {
     int dtype = 0, family = 0, device = 0;
     int64_t n_rows = 0, n_params = 0, n_rows_total = 0;
@@ -130,10 +137,12 @@ struct skk_plan {
     int rows_per_tile = 0, n_tiles = 0, warps = 8, stages = 3, n_sms = 0;
     LaunchCfg cfg1, cfg4;  // batch tile 1 and 4
 
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;  // side: the prior kernels run next to the row kernel
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::vector<void *> allocs;
     size_t device_bytes = 0;
+    bool use_graphs = true;
+    std::vector<GraphEntry> graphs;
 
     void *x[kMaxXCols] = {nullptr};
     void *y = nullptr, *off = nullptr, *codes = nullptr;
@@ -142,13 +151,14 @@ struct skk_plan {
     PrepParams prep{};
 
     void *theta_dev = nullptr, *val_g = nullptr, *val_p = nullptr, *val_s = nullptr;
-    double *direct_p = nullptr, *tile_head = nullptr, *tile_tail = nullptr, *cta_glob = nullptr, *cta_sec = nullptr;
-    double *lik_vec = nullptr, *prior_grad = nullptr, *prior_lp = nullptr, *to_mu = nullptr, *to_sigma = nullptr;
-    double *glob_tot = nullptr, *sec_tot = nullptr;
+    double *totals = nullptr, *direct_p = nullptr;  // direct_p = totals + (ng + 1) * bt (per launch)
+    double *tile_head = nullptr, *tile_tail = nullptr, *cta_glob = nullptr, *cta_sec = nullptr;
+    double *lik_vec = nullptr, *prior_grad = nullptr, *prior_lp = nullptr, *link_val = nullptr;
     void *out_dev = nullptr;  // [B*P grad | B logp]
 
     PriorParams prior{};
     ReduceParams reduce{};
+    int prior_ctas = 0;
 
     void *h_in = nullptr, *h_out = nullptr;  // pinned staging
 
@@ -313,29 +323,54 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             entries.push_back(Entry{td.theta_index[s], (int8_t)td.level, (int8_t)t, (int32_t)s});
         }
     }
+    // theta element -> units of the `totals` buffer ([NG+1 global | NP*GP primary | NS*GS secondary])
     std::stable_sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) { return a.theta < b.theta; });
-    std::vector<int64_t> csr_ptr(d->n_params + 2, 0);
-    std::vector<int8_t> e_level(entries.size()), e_t(entries.size());
-    std::vector<int32_t> e_slot(entries.size());
-    for (size_t k = 0; k < entries.size(); ++k) {
-        csr_ptr[entries[k].theta + 1]++;
-        e_level[k] = entries[k].level;
-        e_t[k] = entries[k].t;
-        e_slot[k] = entries[k].slot;
+    auto unit_of = [&](const Entry &e) -> int64_t {
+        if (e.level == SKK_LEVEL_GLOBAL) return e.t;
+        if (e.level == SKK_LEVEL_PRIMARY) return (pl->ng + 1) + (int64_t)e.t * d->n_primary + e.slot;
+        return (pl->ng + 1) + (int64_t)pl->np * d->n_primary + (int64_t)e.t * d->n_secondary + e.slot;
+    };
+    if ((pl->ng + 1) + (int64_t)pl->np * d->n_primary + (int64_t)pl->ns * d->n_secondary >= INT32_MAX)
+        return fail(SKK_ERR_UNSUPPORTED, "too many group slots");
+    std::vector<int32_t> single_unit(d->n_params, -1), multi_elem, multi_unit;
+    std::vector<int64_t> multi_ptr(1, 0);
+    for (size_t k = 0; k < entries.size();) {
+        size_t e = k;
+        while (e < entries.size() && entries[e].theta == entries[k].theta) ++e;
+        if (e - k == 1) {
+            single_unit[entries[k].theta] = (int32_t)unit_of(entries[k]);
+        } else {
+            single_unit[entries[k].theta] = -2;
+            multi_elem.push_back((int32_t)entries[k].theta);
+            for (size_t q = k; q < e; ++q) multi_unit.push_back((int32_t)unit_of(entries[q]));
+            multi_ptr.push_back((int64_t)multi_unit.size());
+        }
+        k = e;
     }
-    for (int64_t j = 0; j < d->n_params; ++j) csr_ptr[j + 1] += csr_ptr[j];
-    csr_ptr[d->n_params + 1] = csr_ptr[d->n_params];
-    int64_t *csr_dev = nullptr;
-    int8_t *lvl_dev = nullptr, *t_dev = nullptr;
-    int32_t *slot_dev = nullptr;
-    if (int rc = dev_upload(pl, &csr_dev, csr_ptr.data(), csr_ptr.size())) return rc;
-    if (int rc = dev_upload(pl, &lvl_dev, e_level.data(), e_level.size())) return rc;
-    if (int rc = dev_upload(pl, &t_dev, e_t.data(), e_t.size())) return rc;
-    if (int rc = dev_upload(pl, &slot_dev, e_slot.data(), e_slot.size())) return rc;
+    int32_t *single_dev = nullptr, *multi_elem_dev = nullptr, *multi_unit_dev = nullptr;
+    int64_t *multi_ptr_dev = nullptr;
+    if (int rc = dev_upload(pl, &single_dev, single_unit.data(), single_unit.size())) return rc;
+    if (int rc = dev_upload(pl, &multi_elem_dev, multi_elem.data(), multi_elem.size())) return rc;
+    if (int rc = dev_upload(pl, &multi_unit_dev, multi_unit.data(), multi_unit.size())) return rc;
+    if (int rc = dev_upload(pl, &multi_ptr_dev, multi_ptr.data(), multi_ptr.size())) return rc;
 
-    // ---- priors: block table and hyper-parameter link CSR -----------------------------------------------
-    std::vector<DevBlock> blocks(d->n_blocks);
-    std::vector<int32_t> block_of(d->n_params, -1);
+    // primary slots: tile range, and which partial of the first / last tile belongs to the slot
+    std::vector<int4> slot_desc(std::max<int64_t>(1, d->n_primary), make_int4(0, -1, 0, 0));
+    for (int64_t sl = 0; sl < d->n_primary; ++sl) {
+        const int64_t r0 = seg[sl], r1 = seg[sl + 1];
+        if (r1 <= r0) continue;
+        const int t_lo = (int)(r0 / WT), t_hi = (int)((r1 - 1) / WT);
+        auto kind = [&](int tile) { return keys[tile].x == sl ? 1 : (keys[tile].y == sl ? 2 : 0); };
+        slot_desc[sl] = make_int4(t_lo, t_hi, kind(t_lo), kind(t_hi));
+    }
+    int4 *slot_desc_dev = nullptr;
+    if (int rc = dev_upload(pl, &slot_desc_dev, slot_desc.data(), slot_desc.size())) return rc;
+
+    // ---- priors, flattened per theta element; hyper-parameter links as contiguous ranges -----------------
+    const size_t Pn = (size_t)d->n_params;
+    std::vector<int8_t> fam(Pn, -1);
+    std::vector<int32_t> a_src(Pn, -1), b_src(Pn, -1), e_mu(Pn, -1), e_sigma(Pn, -1);
+    std::vector<double> a_const(Pn, 0.0), b_const(Pn, 1.0);
     struct Link {
         int64_t parent;
         int32_t child;
@@ -348,46 +383,35 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             return fail(SKK_ERR_INVALID, "block %d outside theta", k);
         if (bd.family != SKK_PRIOR_NORMAL && bd.family != SKK_PRIOR_HALFNORMAL && bd.family != SKK_PRIOR_EXPONENTIAL)
             return fail(SKK_ERR_UNSUPPORTED, "block %d: unknown prior family %d", k, bd.family);
-        DevBlock &db = blocks[k];
-        db.family = bd.family;
-        db.offset = bd.offset;
-        db.size = bd.size;
-        db.a_const_len = bd.a_const_len;
-        db.b_const_len = bd.b_const_len;
-        db.a_const = db.b_const = nullptr;
-        db.a_index = db.b_index = nullptr;
-        if (bd.a_index) {
-            if (bd.family != SKK_PRIOR_NORMAL) return fail(SKK_ERR_UNSUPPORTED, "block %d: only Normal priors take random parameters", k);
-            int32_t *p = nullptr;
-            if (int rc = dev_upload(pl, &p, bd.a_index, (size_t)bd.size)) return rc;
-            db.a_index = p;
-        } else {
-            if (bd.a_const_len != 1 && bd.a_const_len != bd.size) return fail(SKK_ERR_INVALID, "block %d: bad a_const_len", k);
-            double *p = nullptr;
-            if (int rc = dev_upload(pl, &p, bd.a_const, (size_t)bd.a_const_len)) return rc;
-            db.a_const = p;
-        }
-        if (bd.family == SKK_PRIOR_NORMAL) {
-            if (bd.b_index) {
-                int32_t *p = nullptr;
-                if (int rc = dev_upload(pl, &p, bd.b_index, (size_t)bd.size)) return rc;
-                db.b_index = p;
+        const bool normal = bd.family == SKK_PRIOR_NORMAL;
+        if (!normal && (bd.a_index || bd.b_index))
+            return fail(SKK_ERR_UNSUPPORTED, "block %d: only Normal priors take random parameters", k);
+        if (!bd.a_index && bd.a_const_len != 1 && bd.a_const_len != bd.size)
+            return fail(SKK_ERR_INVALID, "block %d: bad a_const_len", k);
+        if (normal && !bd.b_index && bd.b_const_len != 1 && bd.b_const_len != bd.size)
+            return fail(SKK_ERR_INVALID, "block %d: bad b_const_len", k);
+        for (int64_t g = 0; g < bd.size; ++g) {
+            const int64_t j = bd.offset + g;
+            if (fam[j] != -1) return fail(SKK_ERR_INVALID, "blocks overlap at theta[%lld]", (long long)j);
+            fam[j] = (int8_t)bd.family;
+            if (bd.a_index) {
+                a_src[j] = bd.a_index[g];
+                links.push_back(Link{bd.a_index[g], (int32_t)j, 0});
             } else {
-                if (bd.b_const_len != 1 && bd.b_const_len != bd.size) return fail(SKK_ERR_INVALID, "block %d: bad b_const_len", k);
-                double *p = nullptr;
-                if (int rc = dev_upload(pl, &p, bd.b_const, (size_t)bd.b_const_len)) return rc;
-                db.b_const = p;
+                a_const[j] = bd.a_const[bd.a_const_len == 1 ? 0 : g];
+            }
+            if (normal) {
+                if (bd.b_index) {
+                    b_src[j] = bd.b_index[g];
+                    links.push_back(Link{bd.b_index[g], (int32_t)j, 1});
+                } else {
+                    b_const[j] = bd.b_const[bd.b_const_len == 1 ? 0 : g];
+                }
             }
         }
-        for (int64_t g = 0; g < bd.size; ++g) {
-            if (block_of[bd.offset + g] != -1) return fail(SKK_ERR_INVALID, "blocks overlap at theta[%lld]", (long long)(bd.offset + g));
-            block_of[bd.offset + g] = k;
-            if (bd.a_index) links.push_back(Link{bd.a_index[g], (int32_t)(bd.offset + g), 0});
-            if (bd.family == SKK_PRIOR_NORMAL && bd.b_index) links.push_back(Link{bd.b_index[g], (int32_t)(bd.offset + g), 1});
-        }
     }
-    for (int64_t j = 0; j < d->n_params; ++j)
-        if (block_of[j] < 0) return fail(SKK_ERR_INVALID, "theta[%lld] belongs to no block", (long long)j);
+    for (size_t j = 0; j < Pn; ++j)
+        if (fam[j] < 0) return fail(SKK_ERR_INVALID, "theta[%lld] belongs to no block", (long long)j);
     for (const Link &l : links)
         if (l.parent < 0 || l.parent >= d->n_params) return fail(SKK_ERR_INVALID, "prior link outside theta");
     std::stable_sort(links.begin(), links.end(), [](const Link &a, const Link &b) { return a.parent < b.parent; });
@@ -407,34 +431,36 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
         return (a.hi - a.lo > kHeavyLinks) > (b.hi - b.lo > kHeavyLinks);
     });
     int n_heavy = 0;
-    std::vector<int32_t> parent_el(parents.size()), link_child(links.size());
+    std::vector<int32_t> parent_el(parents.size());
     std::vector<int64_t> link_ptr(parents.size() + 1, 0);
-    std::vector<int8_t> link_kind(links.size());
     {
-        size_t w = 0;
+        int64_t w = 0;
         for (size_t q = 0; q < parents.size(); ++q) {
             if (parents[q].hi - parents[q].lo > kHeavyLinks) ++n_heavy;
             parent_el[q] = parents[q].element;
-            link_ptr[q] = (int64_t)w;
-            for (int64_t e = parents[q].lo; e < parents[q].hi; ++e, ++w) {
-                link_child[w] = links[e].child;
-                link_kind[w] = links[e].kind;
-            }
+            link_ptr[q] = w;
+            for (int64_t e = parents[q].lo; e < parents[q].hi; ++e, ++w)
+                (links[e].kind == 0 ? e_mu : e_sigma)[links[e].child] = (int32_t)w;
         }
-        link_ptr[parents.size()] = (int64_t)w;
+        link_ptr[parents.size()] = w;
     }
-    DevBlock *blocks_dev = nullptr;
-    int32_t *block_of_dev = nullptr, *link_child_dev = nullptr, *parent_dev = nullptr;
+    int8_t *fam_dev = nullptr;
+    int32_t *a_src_dev = nullptr, *b_src_dev = nullptr, *e_mu_dev = nullptr, *e_sigma_dev = nullptr, *parent_dev = nullptr;
+    double *a_const_dev = nullptr, *b_const_dev = nullptr;
     int64_t *link_ptr_dev = nullptr;
-    int8_t *link_kind_dev = nullptr;
-    if (int rc = dev_upload(pl, &blocks_dev, blocks.data(), blocks.size())) return rc;
-    if (int rc = dev_upload(pl, &block_of_dev, block_of.data(), block_of.size())) return rc;
+    if (int rc = dev_upload(pl, &fam_dev, fam.data(), fam.size())) return rc;
+    if (int rc = dev_upload(pl, &a_src_dev, a_src.data(), a_src.size())) return rc;
+    if (int rc = dev_upload(pl, &b_src_dev, b_src.data(), b_src.size())) return rc;
+    if (int rc = dev_upload(pl, &a_const_dev, a_const.data(), a_const.size())) return rc;
+    if (int rc = dev_upload(pl, &b_const_dev, b_const.data(), b_const.size())) return rc;
+    if (int rc = dev_upload(pl, &e_mu_dev, e_mu.data(), e_mu.size())) return rc;
+    if (int rc = dev_upload(pl, &e_sigma_dev, e_sigma.data(), e_sigma.size())) return rc;
     if (int rc = dev_upload(pl, &parent_dev, parent_el.data(), parent_el.size())) return rc;
     if (int rc = dev_upload(pl, &link_ptr_dev, link_ptr.data(), link_ptr.size())) return rc;
-    if (int rc = dev_upload(pl, &link_child_dev, link_child.data(), link_child.size())) return rc;
-    if (int rc = dev_upload(pl, &link_kind_dev, link_kind.data(), link_kind.size())) return rc;
-    pl->prior = PriorParams{blocks_dev, block_of_dev, parent_dev, link_ptr_dev, link_child_dev, link_kind_dev,
-                            (int32_t)parents.size(), n_heavy, d->n_params, 0};
+    pl->prior = PriorParams{fam_dev,    a_src_dev,    b_src_dev, a_const_dev, b_const_dev, e_mu_dev, e_sigma_dev,
+                            parent_dev, link_ptr_dev, (int32_t)parents.size(), n_heavy, d->n_params,
+                            (int64_t)links.size(), 0};
+    pl->prior_ctas = (int)((Pn + kPriorThreads - 1) / kPriorThreads);
 
     // ---- launch geometry -------------------------------------------------------------------------------------
     cudaDeviceProp prop;
@@ -474,48 +500,54 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     pl->val_p = tmp;
     if (int rc = dev_alloc(pl, &tmp, std::max<size_t>(1, pl->ns) * std::max<int64_t>(1, d->n_secondary) * bt, true)) return rc;
     pl->val_s = tmp;
-    if (int rc = dev_alloc(pl, &pl->direct_p, std::max<size_t>(1, pl->np) * std::max<int64_t>(1, d->n_primary) * bt, true)) return rc;
+    const size_t units = (size_t)(pl->ng + 1) + (size_t)pl->np * d->n_primary + (size_t)pl->ns * d->n_secondary;
+    if (int rc = dev_alloc(pl, &pl->totals, units * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->tile_head, (size_t)pl->n_tiles * std::max(1, pl->np) * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->tile_tail, (size_t)pl->n_tiles * std::max(1, pl->np) * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->cta_glob, (size_t)grid_max * (pl->ng + 1) * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->cta_sec, (size_t)grid_max * std::max(1, pl->ns) * std::max<int64_t>(1, d->n_secondary) * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->lik_vec, B * (P + 2), true)) return rc;
     if (int rc = dev_alloc(pl, &pl->prior_grad, B * P, true)) return rc;
-    if (int rc = dev_alloc(pl, &pl->prior_lp, B * ((P + kPriorThreads - 1) / kPriorThreads + 1), true)) return rc;
-    if (int rc = dev_alloc(pl, &pl->to_mu, B * P, true)) return rc;
-    if (int rc = dev_alloc(pl, &pl->to_sigma, B * P, true)) return rc;
-    if (int rc = dev_alloc(pl, &pl->glob_tot, (size_t)(kMaxTermsPerLevel + 1) * bt, true)) return rc;
-    if (int rc = dev_alloc(pl, &pl->sec_tot, std::max<size_t>(1, pl->ns) * std::max<int64_t>(1, d->n_secondary) * bt, true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->prior_lp, B * (size_t)(pl->prior_ctas + 1), true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->link_val, B * std::max<size_t>(1, links.size()), true)) return rc;
     if (int rc = dev_alloc(pl, &tmp, B * P + B, true)) return rc;
     pl->out_dev = tmp;
     CUDA_TRY(cudaMallocHost(&pl->h_in, std::max<size_t>(16, B * P * sizeof(T))));
     CUDA_TRY(cudaMallocHost(&pl->h_out, std::max<size_t>(16, (B * P + B) * sizeof(T))));
 
-    pl->reduce = ReduceParams{};
-    pl->reduce.csr_ptr = csr_dev;
-    pl->reduce.entry_level = lvl_dev;
-    pl->reduce.entry_t = t_dev;
-    pl->reduce.entry_slot = slot_dev;
-    pl->reduce.tile_keys = pl->tile_keys;
-    pl->reduce.seg_offsets = pl->seg_off;
-    pl->reduce.direct_p = pl->direct_p;
-    pl->reduce.tile_head = pl->tile_head;
-    pl->reduce.tile_tail = pl->tile_tail;
-    pl->reduce.cta_glob = pl->cta_glob;
-    pl->reduce.cta_sec = pl->cta_sec;
-    pl->reduce.glob_tot = pl->glob_tot;
-    pl->reduce.sec_tot = pl->sec_tot;
-    pl->reduce.lik_vec = pl->lik_vec;
-    pl->reduce.n_params = d->n_params;
-    pl->reduce.n_primary = d->n_primary;
-    pl->reduce.n_secondary = d->n_secondary;
-    pl->reduce.ng = pl->ng;
-    pl->reduce.np = pl->np;
-    pl->reduce.ns = pl->ns;
-    pl->reduce.rows_per_tile = WT;
-    pl->reduce.blocks_p = pl->np > 0 ? (int)((d->n_primary + 255) / 256) : 0;
-    pl->reduce.blocks_s = pl->ns > 0 ? (int)((d->n_secondary + 31) / 32) : 0;
-    pl->reduce.logp_const = d->logp_const;
+    ReduceParams &rp = pl->reduce;
+    rp = ReduceParams{};
+    rp.slot_desc = slot_desc_dev;
+    rp.tile_head = pl->tile_head;
+    rp.tile_tail = pl->tile_tail;
+    rp.cta_glob = pl->cta_glob;
+    rp.cta_sec = pl->cta_sec;
+    rp.totals = pl->totals;
+    rp.single_unit = single_dev;
+    rp.multi_elem = multi_elem_dev;
+    rp.multi_ptr = multi_ptr_dev;
+    rp.multi_unit = multi_unit_dev;
+    rp.n_multi = (int32_t)multi_elem.size();
+    rp.theta_blocks = (int32_t)std::max<size_t>(1, (P + 255) / 256);
+    rp.lik_vec = pl->lik_vec;
+    rp.n_params = d->n_params;
+    rp.n_primary = d->n_primary;
+    rp.n_secondary = d->n_secondary;
+    rp.ng = pl->ng;
+    rp.np = pl->np;
+    rp.ns = pl->ns;
+    rp.blocks_p = pl->np > 0 ? (int)((d->n_primary + 255) / 256) : 0;
+    rp.blocks_s = pl->ns > 0 ? (int)((d->n_secondary + 31) / 32) : 0;
+    rp.logp_const = d->logp_const;
+    rp.prior_grad = pl->prior_grad;
+    rp.prior_lp_part = pl->prior_lp;
+    rp.prior_ctas = pl->prior_ctas;
+    rp.include_priors = pl->include_priors;
+    rp.n_rows_total = pl->n_rows_total;
+    rp.sigma_theta_index = pl->sigma_idx;
+    rp.sigma_const = pl->sigma_const;
+    rp.family = pl->family;
+    pl->use_graphs = env_int("SKK_NO_GRAPH", 0) == 0;
     return SKK_OK;
 }
 
@@ -523,7 +555,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
 // evaluation
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed) {
+static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, int bt) {
     RowParams<T> rp{};
     for (int c = 0; c < pl->n_x; ++c) rp.x[c] = static_cast<const T *>(pl->x[c]);
     rp.y = pl->y_u8 ? nullptr : static_cast<const T *>(pl->y);
@@ -547,7 +579,7 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed) {
     rp.val_g = static_cast<const T *>(pl->val_g);
     rp.val_p = static_cast<const T *>(pl->val_p);
     rp.val_s = static_cast<const T *>(pl->val_s);
-    rp.direct_p = pl->direct_p;
+    rp.direct_p = pl->totals + (size_t)(pl->ng + 1) * bt;
     rp.tile_head = pl->tile_head;
     rp.tile_tail = pl->tile_tail;
     rp.cta_glob = pl->cta_glob;
@@ -556,8 +588,115 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed) {
     if (timed) CUDA_TRY(cudaEventRecord(pl->evk0, pl->stream));
     CUDA_TRY(cudaLaunchKernel(cfg.fn, dim3(cfg.grid), dim3(pl->warps * 32), args, cfg.smem, pl->stream));
     if (timed) CUDA_TRY(cudaEventRecord(pl->evk1, pl->stream));
-    pl->stats.launches++;
-    pl->stats.row_kernel_launches++;
+    return SKK_OK;
+}
+
+// Enqueues one evaluation on pl->stream (+ the prior kernels on pl->side, forked and joined with
+// events).  Used directly, or recorded once into a CUDA graph and replayed.
+//   theta_in/out pointers are device pointers here; returns the number of kernels enqueued.
+template <typename T>
+static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *out_grad, bool timed, int *n_launch) {
+    const size_t P = (size_t)pl->n_params;
+    cudaStream_t st = pl->stream;
+    int launches = 0;
+    const bool sharded = pl->comm != nullptr;
+
+    // K3: priors for the whole batch, next to the row kernel
+    const bool priors = pl->include_priors && P > 0;
+    if (priors) {
+        CUDA_TRY(cudaEventRecord(pl->ev_fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
+        PriorParams pp = pl->prior;
+        pp.batch = batch;
+        skk_prior_kernel<T><<<(unsigned)pl->prior_ctas, kPriorThreads, 0, pl->side>>>(pp, th, pl->prior_grad, pl->prior_lp,
+                                                                                    pl->link_val);
+        ++launches;
+        if (pp.n_parents > 0) {
+            const int per_cta = pp.n_heavy > 0 ? 32 : 8;  // light parents: one warp each
+            const unsigned blocks = (unsigned)(pp.n_heavy + (pp.n_parents - pp.n_heavy + per_cta - 1) / per_cta);
+            skk_prior_link_kernel<<<blocks, pp.n_heavy > 0 ? 1024 : 256, 0, pl->side>>>(pp, pl->prior_grad, pl->link_val);
+            ++launches;
+        }
+        CUDA_TRY(cudaEventRecord(pl->ev_join, pl->side));
+    }
+
+    bool joined = false;
+    for (int b0 = 0; b0 < batch;) {
+        const int remaining = batch - b0;
+        const bool wide = remaining >= 2 && pl->cfg4.fn != nullptr;
+        const int bt = wide ? 4 : 1;
+        const int b_valid = std::min(bt, remaining);
+        const LaunchCfg &cfg = wide ? pl->cfg4 : pl->cfg1;
+        double *direct_p = pl->totals + (size_t)(pl->ng + 1) * bt;
+
+        // K0: value tables in slot order (+ clears the primary accumulators)
+        if (pl->prep.n_terms > 0) {
+            PrepParams pp = pl->prep;
+            pp.bt = bt;
+            pp.b_valid = b_valid;
+            int64_t most = 1;
+            for (int i = 0; i < pp.n_terms; ++i) most = std::max(most, pp.term[i].n_slots);
+            dim3 grid((unsigned)std::min<int64_t>((most + 255) / 256, 1024), (unsigned)pp.n_terms);
+            skk_prepare_kernel<T><<<grid, 256, 0, st>>>(pp, th + (size_t)b0 * P, static_cast<T *>(pl->val_g),
+                                                        static_cast<T *>(pl->val_p), static_cast<T *>(pl->val_s), direct_p);
+            ++launches;
+        }
+
+        // K1: the rows
+        if (int rc = launch_rows<T>(pl, cfg, timed, bt)) return rc;
+        ++launches;
+        pl->stats.row_kernel_launches++;
+
+        // K4a: totals per slot
+        ReduceParams rp = pl->reduce;
+        rp.bt = bt;
+        rp.b0 = b0;
+        rp.b_valid = b_valid;
+        rp.grid = cfg.grid;
+        const unsigned slot_blocks = (unsigned)(rp.blocks_p + rp.blocks_s + 1);
+        const unsigned theta_blocks = (unsigned)(rp.theta_blocks + (rp.n_multi + 7) / 8);
+        if (bt == 4)
+            skk_slot_total_kernel<4><<<slot_blocks, 256, 0, st>>>(rp);
+        else
+            skk_slot_total_kernel<1><<<slot_blocks, 256, 0, st>>>(rp);
+        ++launches;
+
+        // K4f: per theta element; single GPU: straight to the outputs (needs the priors)
+        if (!sharded && priors && !joined) {
+            CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+            joined = true;
+        }
+        if (sharded) {
+            if (bt == 4)
+                skk_theta_kernel<T, 4, false><<<theta_blocks, 256, 0, st>>>(rp, th, out_logp, out_grad);
+            else
+                skk_theta_kernel<T, 1, false><<<theta_blocks, 256, 0, st>>>(rp, th, out_logp, out_grad);
+        } else {
+            if (bt == 4)
+                skk_theta_kernel<T, 4, true><<<theta_blocks, 256, 0, st>>>(rp, th, out_logp, out_grad);
+            else
+                skk_theta_kernel<T, 1, true><<<theta_blocks, 256, 0, st>>>(rp, th, out_logp, out_grad);
+        }
+        ++launches;
+        b0 += b_valid;
+    }
+
+    if (sharded) {
+        // one all-reduce of [dlogp, logp partial, constant] per evaluation, then the final combination
+        NCCL_TRY(g_nccl.AllReduce(pl->lik_vec, pl->lik_vec, (size_t)batch * (P + 2), /*ncclDouble*/ 8, /*ncclSum*/ 0,
+                                  pl->comm, st));
+        ++launches;
+        if (priors) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+        FinalParams fp{pl->lik_vec, pl->prior_grad, pl->prior_lp, pl->prior_ctas, pl->n_params, pl->n_rows_total,
+                       pl->sigma_idx, pl->sigma_const, pl->family, pl->include_priors};
+        dim3 grid((unsigned)std::max<size_t>(1, (P + 255) / 256), (unsigned)batch);
+        skk_final_kernel<T><<<grid, 256, 0, st>>>(fp, th, out_logp, out_grad);
+        ++launches;
+    } else if (priors && !joined) {
+        CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+    }
+    CUDA_TRY(cudaGetLastError());
+    *n_launch = launches;
     return SKK_OK;
 }
 
@@ -568,105 +707,65 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
     const bool timed = flags & SKK_EVAL_TIME_KERNELS;
     cudaStream_t st = pl->stream;
     CUDA_TRY(cudaSetDevice(pl->device));
+
+    const T *th = dev_io ? static_cast<const T *>(theta) : static_cast<const T *>(pl->theta_dev);
+    T *out_grad = dev_io ? static_cast<T *>(grad_out) : static_cast<T *>(pl->out_dev);
+    T *out_logp = dev_io ? static_cast<T *>(logp_out) : static_cast<T *>(pl->out_dev) + (size_t)batch * P;
+    if (!dev_io) std::memcpy(pl->h_in, theta, (size_t)batch * P * sizeof(T));
+
+    // Graph replay: the sequence is fixed for (batch, buffers); NCCL and event timing stay on the direct path.
+    const bool graphable = pl->use_graphs && !timed && pl->comm == nullptr;
+    GraphEntry *hit = nullptr;
+    if (graphable)
+        for (GraphEntry &g : pl->graphs)
+            if (g.batch == batch && (g.flags & 0xffu) == (flags & SKK_EVAL_DEVICE_IO) && g.theta == th && g.logp == out_logp &&
+                g.grad == out_grad)
+                hit = &g;
+
+    int launches = 0;
+    auto enqueue_all = [&]() -> int {
+        if (!dev_io)
+            CUDA_TRY(cudaMemcpyAsync(pl->theta_dev, pl->h_in, (size_t)batch * P * sizeof(T), cudaMemcpyHostToDevice, st));
+        if (int rc = enqueue_eval<T>(pl, th, batch, out_logp, out_grad, timed, &launches)) return rc;
+        if (!dev_io)  // gradient rows and logp are contiguous in out_dev for this batch size
+            CUDA_TRY(cudaMemcpyAsync(pl->h_out, pl->out_dev, ((size_t)batch * P + batch) * sizeof(T),
+                                     cudaMemcpyDeviceToHost, st));
+        return SKK_OK;
+    };
+
     CUDA_TRY(cudaEventRecord(pl->ev0, st));
-
-    const T *th = static_cast<const T *>(pl->theta_dev);
-    if (dev_io) {
-        th = static_cast<const T *>(theta);
+    if (graphable && !hit && pl->graphs.size() < 16) {
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_all();
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc != SKK_OK || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            if (rc == SKK_OK) return fail(SKK_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            return rc;
+        }
+        GraphEntry g;
+        g.batch = batch;
+        g.flags = flags & SKK_EVAL_DEVICE_IO;
+        g.theta = th;
+        g.logp = out_logp;
+        g.grad = out_grad;
+        ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(SKK_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+        pl->graphs.push_back(g);
+        hit = &pl->graphs.back();
+        hit->flags |= (unsigned)launches << 8;  // remember the kernel count of this graph
+    }
+    if (hit) {
+        CUDA_TRY(cudaGraphLaunch(hit->exec, st));
+        launches = (int)(hit->flags >> 8);
     } else {
-        std::memcpy(pl->h_in, theta, (size_t)batch * P * sizeof(T));
-        CUDA_TRY(cudaMemcpyAsync(pl->theta_dev, pl->h_in, (size_t)batch * P * sizeof(T), cudaMemcpyHostToDevice, st));
+        if (int rc = enqueue_all()) return rc;
     }
-
-    // K3: priors for the whole batch
-    if (pl->include_priors && P > 0) {
-        PriorParams pp = pl->prior;
-        pp.batch = batch;
-        skk_prior_kernel<T><<<(unsigned)((P + kPriorThreads - 1) / kPriorThreads), kPriorThreads, 0, st>>>(
-            pp, th, pl->prior_grad, pl->prior_lp, pl->to_mu, pl->to_sigma);
-        pl->stats.launches++;
-        if (pp.n_parents > 0) {
-            const int per_cta = pp.n_heavy > 0 ? 32 : 8;  // light parents: one warp each
-            const unsigned blocks = (unsigned)(pp.n_heavy + (pp.n_parents - pp.n_heavy + per_cta - 1) / per_cta);
-            skk_prior_link_kernel<<<blocks, pp.n_heavy > 0 ? 1024 : 256, 0, st>>>(pp, pl->prior_grad, pl->to_mu, pl->to_sigma);
-            pl->stats.launches++;
-        }
-    }
-
-    for (int b0 = 0; b0 < batch;) {
-        const int remaining = batch - b0;
-        const bool wide = remaining >= 2 && pl->cfg4.fn != nullptr;
-        const int bt = wide ? 4 : 1;
-        const int b_valid = std::min(bt, remaining);
-        const LaunchCfg &cfg = wide ? pl->cfg4 : pl->cfg1;
-
-        // K0: value tables in slot order
-        if (pl->prep.n_terms > 0) {
-            PrepParams pp = pl->prep;
-            pp.bt = bt;
-            pp.b_valid = b_valid;
-            int64_t most = 1;
-            for (int i = 0; i < pp.n_terms; ++i) most = std::max(most, pp.term[i].n_slots);
-            dim3 grid((unsigned)std::min<int64_t>((most + 255) / 256, 1024), (unsigned)pp.n_terms);
-            skk_prepare_kernel<T><<<grid, 256, 0, st>>>(pp, th + (size_t)b0 * P, static_cast<T *>(pl->val_g),
-                                                        static_cast<T *>(pl->val_p), static_cast<T *>(pl->val_s));
-            pl->stats.launches++;
-        }
-        if (pl->np > 0)
-            CUDA_TRY(cudaMemsetAsync(pl->direct_p, 0, (size_t)pl->np * pl->n_primary * bt * sizeof(double), st));
-
-        // K1: the rows
-        if (int rc = launch_rows<T>(pl, cfg, timed)) return rc;
-
-        // K4a: totals per slot, then per theta element, all in fixed order
-        ReduceParams rp = pl->reduce;
-        rp.bt = bt;
-        rp.b0 = b0;
-        rp.b_valid = b_valid;
-        rp.grid = cfg.grid;
-        const unsigned slot_blocks = (unsigned)(rp.blocks_p + rp.blocks_s + 1);
-        const unsigned theta_blocks = (unsigned)std::max<size_t>(1, (P * 32 + 255) / 256);
-        if (bt == 4) {
-            skk_slot_total_kernel<4><<<slot_blocks, 256, 0, st>>>(rp);
-            skk_theta_reduce_kernel<4><<<theta_blocks, 256, 0, st>>>(rp);
-        } else {
-            skk_slot_total_kernel<1><<<slot_blocks, 256, 0, st>>>(rp);
-            skk_theta_reduce_kernel<1><<<theta_blocks, 256, 0, st>>>(rp);
-        }
-        pl->stats.launches += 2;
-        b0 += b_valid;
-    }
-
-    // row-sharded: one all-reduce of [dlogp, logp partial, constant] per evaluation
-    if (pl->comm) {
-        NCCL_TRY(g_nccl.AllReduce(pl->lik_vec, pl->lik_vec, (size_t)batch * (P + 2), /*ncclDouble*/ 8, /*ncclSum*/ 0,
-                                  pl->comm, st));
-        pl->stats.launches++;
-    }
-
-    // K4b
-    T *out_grad = static_cast<T *>(pl->out_dev);
-    T *out_logp = out_grad + (size_t)pl->max_batch * P;
-    if (dev_io) {
-        out_grad = static_cast<T *>(grad_out);
-        out_logp = static_cast<T *>(logp_out);
-    }
-    {
-        FinalParams fp{pl->lik_vec, pl->prior_grad, pl->prior_lp, (int32_t)((P + kPriorThreads - 1) / kPriorThreads),
-                       pl->n_params, pl->n_rows_total, pl->sigma_idx, pl->sigma_const, pl->family, pl->include_priors};
-        dim3 grid((unsigned)std::max<size_t>(1, (P + 255) / 256), (unsigned)batch);
-        skk_final_kernel<T><<<grid, 256, 0, st>>>(fp, th, out_logp, out_grad);
-        pl->stats.launches++;
-    }
-    CUDA_TRY(cudaGetLastError());
-
-    if (!dev_io) {
-        // grad rows are contiguous for `batch` chains; logp sits after max_batch rows
-        CUDA_TRY(cudaMemcpyAsync(pl->h_out, out_grad, (size_t)batch * P * sizeof(T), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(static_cast<T *>(pl->h_out) + (size_t)batch * P, out_logp, (size_t)batch * sizeof(T),
-                                 cudaMemcpyDeviceToHost, st));
-    }
+    pl->stats.launches += launches;
     CUDA_TRY(cudaEventRecord(pl->ev1, st));
+
     if (dev_io && (flags & SKK_EVAL_NO_SYNC)) {
         pl->stats.evals++;
         return SKK_OK;
@@ -704,8 +803,11 @@ static void free_plan(skk_plan *pl) {
     for (void *p : pl->allocs) cudaFree(p);
     if (pl->h_in) cudaFreeHost(pl->h_in);
     if (pl->h_out) cudaFreeHost(pl->h_out);
-    for (cudaEvent_t e : {pl->ev0, pl->ev1, pl->evk0, pl->evk1})
+    for (GraphEntry &g : pl->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (cudaEvent_t e : {pl->ev0, pl->ev1, pl->evk0, pl->evk1, pl->ev_fork, pl->ev_join})
         if (e) cudaEventDestroy(e);
+    if (pl->side) cudaStreamDestroy(pl->side);
     if (pl->stream) cudaStreamDestroy(pl->stream);
     delete pl;
 }
@@ -782,8 +884,14 @@ int skk_plan_create(const skk_plan_desc *d, skk_plan **out) {
     if (ce != cudaSuccess) return guard(fail(SKK_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(ce)));
     ce = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) return guard(fail(SKK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)));
+    ce = cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) return guard(fail(SKK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)));
     for (cudaEvent_t *e : {&pl->ev0, &pl->ev1, &pl->evk0, &pl->evk1}) {
         ce = cudaEventCreate(e);
+        if (ce != cudaSuccess) return guard(fail(SKK_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce)));
+    }
+    for (cudaEvent_t *e : {&pl->ev_fork, &pl->ev_join}) {
+        ce = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
         if (ce != cudaSuccess) return guard(fail(SKK_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce)));
     }
     rc = d->dtype == SKK_F64 ? create_impl<double>(d, pl) : create_impl<float>(d, pl);
@@ -834,6 +942,9 @@ int skk_comm_init(skk_plan *pl, const void *unique_id128, int32_t rank, int32_t 
     NcclId id;
     std::memcpy(id.bytes, unique_id128, 128);
     NCCL_TRY(g_nccl.CommInitRank(&pl->comm, nranks, id, rank));
+    for (GraphEntry &g : pl->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    pl->graphs.clear();
     pl->nranks = nranks;
     pl->rank = rank;
     return SKK_OK;
