@@ -48,20 +48,24 @@ def log(*a):
 
 
 def make_plan(config: str, rows: int, rank: int, world: int, seed: int = 1):
-    """This rank's rows of the synthetic workload as a ModelPlan (plus the total row count)."""
+    """
+    This rank's rows of the synthetic workload as a ModelPlan.  Group members carry their global
+    numbers, so every rank of a sharded run has the same theta layout (P is the same everywhere) and
+    the all-reduced gradient means the same thing on all ranks.
+    """
     from sakkara_b200 import synth
     share = rows // world + (1 if rank < rows % world else 0)
     if config == 'c2':
         cols, _ = synth.linreg_columns(rows, 1000, seed=seed)
         lo = sum(rows // world + (1 if r < rows % world else 0) for r in range(rank))
         cols = {k: v[lo:lo + share] for k, v in cols.items()}
-        return synth.linreg_plan(cols)
+        return synth.linreg_plan(cols, groups=1000)
     if config == 'c3':
         g1, per = 100, 100
         span = (g1 * per) // world
         cols, _ = synth.logistic_columns(share, g1, per, seed=seed, block=rank,
                                          g2_range=(rank * span, (rank + 1) * span if rank < world - 1 else g1 * per))
-        return synth.logistic_plan(cols)
+        return synth.logistic_plan(cols, groups=(g1, per))
     if config == 'c4':
         a, b = 10_000, 1_000
         span = a // world
@@ -72,7 +76,7 @@ def make_plan(config: str, rows: int, rank: int, world: int, seed: int = 1):
                                          a_range=(rank * span, (rank + 1) * span if rank < world - 1 else a))
             parts.append(c)
         cols = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
-        return synth.poisson_plan(cols)
+        return synth.poisson_plan(cols, groups=(a, b))
     raise ValueError(config)
 
 
@@ -146,7 +150,7 @@ def cpu_baseline(config: str, dtype: str, seconds: float = 10.0, sample_rows: in
         f(theta)
         n += 1
         dt = time.perf_counter() - t0
-        if dt > seconds or n >= 200:
+        if dt > seconds or n >= 5000:
             break
     return {'value': rows * n / dt, 'unit': 'row-evals/s', 'cores': cores, 'kind': 'port',
             'sample': f'{rows} rows of the {config} workload, {n} evaluations of oracle/logp_c.c (fused OpenMP loop, '
@@ -255,11 +259,35 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     if args.check:
-        from oracle.logp_numpy import parity_error
+        # the GPU result against the CPU oracle: per-shard likelihood by the C oracle, summed over the
+        # ranks, plus the priors; error in the metric of SURVEY.md §8d (relative to the L1 mass)
+        from oracle.logp_c import COracle, priors_only
+        from oracle.logp_numpy import logp_dlogp
         lp, g = f(theta)
+        shard = COracle(plan, dtype='float64', threads=max(1, (os.cpu_count() or 1) // world))
+        shard.prior_plan = None
         for b in range(batch):
-            el, eg = parity_error(lp[b], g[b], plan, theta[b].astype(np.float64))
-            log(f'[check] chain {b}: err_logp={el:.2e} err_grad={eg:.2e}')
+            th64 = theta[b].astype(np.float64)
+            grad = np.zeros(P)
+            d = shard.desc
+            if plan.likelihood.family == 'Normal':
+                d.sigma = float(np.exp(th64[d.sigma_theta_index])) if d.sigma_theta_index >= 0 \
+                    else plan.likelihood.sigma_const
+            import ctypes
+            lik = shard.fn(ctypes.byref(d), th64.ctypes.data, grad.ctypes.data, shard.threads) + shard.const
+            absg = np.zeros(P)
+            vec = torch.from_numpy(np.concatenate([grad, [lik]])).to(dev)
+            if world > 1:
+                dist.all_reduce(vec)
+            vec = vec.cpu().numpy()
+            pl_, pg_ = logp_dlogp(priors_only(plan), th64)
+            ref_l, ref_g = vec[-1] + pl_, vec[:-1] + pg_
+            err_l = abs(float(lp[b]) - ref_l) / max(abs(ref_l), 1.0)
+            scale = np.maximum(np.abs(ref_g), np.abs(ref_g).max() * 1e-3 + 1e-300)
+            err_g = float(np.max(np.abs(np.asarray(g[b], dtype=np.float64) - ref_g) / scale))
+            if rank == 0:
+                log(f'[check] chain {b}: logp={float(lp[b]):.6e} rel.err logp={err_l:.2e} grad={err_g:.2e} '
+                    f'(vs oracle/logp_c.c summed over {world} rank(s))')
 
     def barrier():
         torch.cuda.synchronize()

@@ -713,8 +713,9 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
     T *out_logp = dev_io ? static_cast<T *>(logp_out) : static_cast<T *>(pl->out_dev) + (size_t)batch * P;
     if (!dev_io) std::memcpy(pl->h_in, theta, (size_t)batch * P * sizeof(T));
 
-    // Graph replay: the sequence is fixed for (batch, buffers); NCCL and event timing stay on the direct path.
-    const bool graphable = pl->use_graphs && !timed && pl->comm == nullptr;
+    // Graph replay: the sequence (including the NCCL all-reduce of sharded runs) is fixed for
+    // (batch, buffers); evaluations with event timing of the row kernel stay on the direct path.
+    const bool graphable = pl->use_graphs && !timed;
     GraphEntry *hit = nullptr;
     if (graphable)
         for (GraphEntry &g : pl->graphs)
@@ -740,9 +741,12 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
         int rc = enqueue_all();
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc != SKK_OK || ce != cudaSuccess) {
+            // not capturable in this environment (e.g. an NCCL build without graph support): run directly
             if (graph) cudaGraphDestroy(graph);
-            if (rc == SKK_OK) return fail(SKK_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-            return rc;
+            (void)cudaGetLastError();
+            pl->use_graphs = false;
+            if (int rc2 = enqueue_all()) return rc2;
+            goto enqueued;
         }
         GraphEntry g;
         g.batch = batch;
@@ -763,6 +767,7 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
     } else {
         if (int rc = enqueue_all()) return rc;
     }
+enqueued:
     pl->stats.launches += launches;
     CUDA_TRY(cudaEventRecord(pl->ev1, st));
 

@@ -27,8 +27,15 @@ def _zeros_index(n: int) -> np.ndarray:
     return np.broadcast_to(np.zeros(1, dtype=np.int64), (n,))
 
 
-def _first_appearance(codes: np.ndarray) -> Tuple[np.ndarray, int, np.ndarray]:
-    """codes relabelled in first-appearance order (what Group / pd.factorize produce) + first rows"""
+def _first_appearance(codes: np.ndarray, fixed: Optional[int] = None) -> Tuple[np.ndarray, int, np.ndarray]:
+    """
+    codes relabelled in first-appearance order (what Group / pd.factorize produce) + first rows.
+    ``fixed``: keep the raw codes as member numbers of a group with that many members -- the
+    labelling every rank of a row-sharded run must share (a rank sees only some members).
+    """
+    if fixed is not None:
+        codes = np.asarray(codes, dtype=np.int64)
+        return codes, int(fixed), None
     dense, members = pd.factorize(codes, sort=False)
     first = np.flatnonzero(~pd.Series(dense).duplicated(keep='first').values)
     return dense.astype(np.int64, copy=False), len(members), first
@@ -55,10 +62,10 @@ def linreg_columns(n: int, groups: int, seed: int = 1):
     return {'x': x, 'y': y, 'group': codes}, {'k': k}
 
 
-def linreg_plan(cols) -> ModelPlan:
+def linreg_plan(cols, groups: Optional[int] = None) -> ModelPlan:
     """README-shaped hierarchical linear regression; theta = [mu_k, log s_k, k(G), intercept, log s_est]."""
     n = len(cols['y'])
-    g, G, _ = _first_appearance(cols['group'])
+    g, G, _ = _first_appearance(cols['group'], groups)
     zg = np.zeros(G, dtype=np.int64)
     blocks = _blocks([
         ('mu_k', 'Normal', 1, ('global',), {'mu': _const(0), 'sigma': _const(1)}),
@@ -87,12 +94,20 @@ def logistic_columns(n: int, g1: int, per_g1: int, seed: int = 1, block: int = 0
     return {'x': x, 'y': y, 'g1': g2 // per_g1, 'g2': g2}, {'slope': slope, 'icpt': icpt}
 
 
-def logistic_plan(cols) -> ModelPlan:
-    """theta = [mu_slope, ls_slope, slope(G1), mu_mu_icpt, ls_mu_icpt, mu_icpt(G1), ls_icpt, icpt(G2)]"""
+def logistic_plan(cols, groups: Optional[Tuple[int, int]] = None) -> ModelPlan:
+    """
+    theta = [mu_slope, ls_slope, slope(G1), mu_mu_icpt, ls_mu_icpt, mu_icpt(G1), ls_icpt, icpt(G2)].
+    ``groups=(g1, per_g1)``: fixed labelling g2 = g1 * per_g1 + j (sharded runs).
+    """
     n = len(cols['y'])
-    c1, G1, _ = _first_appearance(cols['g1'])
-    c2, G2, first2 = _first_appearance(cols['g2'])
-    parent = c1[first2]                                  # g1 code of each g2 member
+    if groups is None:
+        c1, G1, _ = _first_appearance(cols['g1'])
+        c2, G2, first2 = _first_appearance(cols['g2'])
+        parent = c1[first2]                              # g1 code of each g2 member
+    else:
+        G1, G2 = groups[0], groups[0] * groups[1]
+        c1, c2 = np.asarray(cols['g1'], dtype=np.int64), np.asarray(cols['g2'], dtype=np.int64)
+        parent = np.arange(G2, dtype=np.int64) // groups[1]
     z1, z2 = np.zeros(G1, dtype=np.int64), np.zeros(G2, dtype=np.int64)
     blocks = _blocks([
         ('mu_slope', 'Normal', 1, ('global',), {'mu': _const(0), 'sigma': _const(1)}),
@@ -125,11 +140,11 @@ def poisson_columns(n: int, a: int, b: int, seed: int = 1, block: int = 0, a_ran
     return {'x': x.astype(np.float64), 'y': y, 'A': A, 'B': B}, {'a': ea, 'b': eb}
 
 
-def poisson_plan(cols) -> ModelPlan:
+def poisson_plan(cols, groups: Optional[Tuple[int, int]] = None) -> ModelPlan:
     """theta = [beta, ls_a, a(A), ls_b, b(B)] (model written obs-term first: beta*x + a + b)"""
     n = len(cols['y'])
-    ca, GA, _ = _first_appearance(cols['A'])
-    cb, GB, _ = _first_appearance(cols['B'])
+    ca, GA, _ = _first_appearance(cols['A'], None if groups is None else groups[0])
+    cb, GB, _ = _first_appearance(cols['B'], None if groups is None else groups[1])
     za, zb = np.zeros(GA, dtype=np.int64), np.zeros(GB, dtype=np.int64)
     blocks = _blocks([
         ('beta', 'Normal', 1, ('global',), {'mu': _const(0), 'sigma': _const(1)}),
