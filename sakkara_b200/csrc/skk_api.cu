@@ -804,6 +804,10 @@ static void free_plan(skk_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
     if (pl->stream) cudaStreamSynchronize(pl->stream);
+    // graphs that captured the all-reduce hold the communicator: release them before destroying it
+    for (GraphEntry &g : pl->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    pl->graphs.clear();
     if (pl->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(pl->comm);
     for (void *p : pl->allocs) cudaFree(p);
     if (pl->h_in) cudaFreeHost(pl->h_in);
@@ -959,6 +963,9 @@ int skk_comm_destroy(skk_plan *pl) {
     if (!pl) return fail(SKK_ERR_INVALID, "null plan");
     if (pl->comm) {
         CUDA_TRY(cudaStreamSynchronize(pl->stream));
+        for (GraphEntry &g : pl->graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        pl->graphs.clear();
         NCCL_TRY(g_nccl.CommDestroy(pl->comm));
         pl->comm = nullptr;
     }
