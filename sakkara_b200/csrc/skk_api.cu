@@ -21,18 +21,18 @@
 #include "skk_row_inst.cuh"
 
 namespace skk {
-const void *row_kernel_f32_normal_bt1(int, int, int);
-const void *row_kernel_f32_normal_bt4(int, int, int);
-const void *row_kernel_f32_bernoulli_bt1(int, int, int);
-const void *row_kernel_f32_bernoulli_bt4(int, int, int);
-const void *row_kernel_f32_poisson_bt1(int, int, int);
-const void *row_kernel_f32_poisson_bt4(int, int, int);
-const void *row_kernel_f64_normal_bt1(int, int, int);
-const void *row_kernel_f64_normal_bt4(int, int, int);
-const void *row_kernel_f64_bernoulli_bt1(int, int, int);
-const void *row_kernel_f64_bernoulli_bt4(int, int, int);
-const void *row_kernel_f64_poisson_bt1(int, int, int);
-const void *row_kernel_f64_poisson_bt4(int, int, int);
+const void *row_kernel_f32_normal_bt1(int, int, int, int);
+const void *row_kernel_f32_normal_bt4(int, int, int, int);
+const void *row_kernel_f32_bernoulli_bt1(int, int, int, int);
+const void *row_kernel_f32_bernoulli_bt4(int, int, int, int);
+const void *row_kernel_f32_poisson_bt1(int, int, int, int);
+const void *row_kernel_f32_poisson_bt4(int, int, int, int);
+const void *row_kernel_f64_normal_bt1(int, int, int, int);
+const void *row_kernel_f64_normal_bt4(int, int, int, int);
+const void *row_kernel_f64_bernoulli_bt1(int, int, int, int);
+const void *row_kernel_f64_bernoulli_bt4(int, int, int, int);
+const void *row_kernel_f64_poisson_bt1(int, int, int, int);
+const void *row_kernel_f64_poisson_bt4(int, int, int, int);
 }  // namespace skk
 
 using namespace skk;
@@ -200,8 +200,8 @@ static int upload_bytes(skk_plan *pl, void **out, const void *host, size_t bytes
     return rc;
 }
 
-static const void *lookup_kernel(int dtype, int family, int bt, int ng, int np, int ns) {
-    typedef const void *(*Lookup)(int, int, int);
+static const void *lookup_kernel(int dtype, int family, int bt, int ng, int np, int ns, int spec) {
+    typedef const void *(*Lookup)(int, int, int, int);
     static const Lookup table[2][3][2] = {
         {{row_kernel_f32_normal_bt1, row_kernel_f32_normal_bt4},
          {row_kernel_f32_bernoulli_bt1, row_kernel_f32_bernoulli_bt4},
@@ -210,7 +210,7 @@ static const void *lookup_kernel(int dtype, int family, int bt, int ng, int np, 
          {row_kernel_f64_bernoulli_bt1, row_kernel_f64_bernoulli_bt4},
          {row_kernel_f64_poisson_bt1, row_kernel_f64_poisson_bt4}}};
     if (family < 0 || family > 2 || (bt != 1 && bt != 4)) return nullptr;
-    return table[dtype == SKK_F64 ? 1 : 0][family][bt == 4 ? 1 : 0](ng, np, ns);
+    return table[dtype == SKK_F64 ? 1 : 0][family][bt == 4 ? 1 : 0](ng, np, ns, spec);
 }
 
 static int env_int(const char *name, int fallback) {
@@ -227,7 +227,16 @@ static int cta_smem(const skk_plan *pl, int warps, int stages, int bt) {
 
 template <typename T>
 static int configure_launch(skk_plan *pl, int bt, LaunchCfg *cfg) {
-    cfg->fn = lookup_kernel(pl->dtype, pl->family, bt, pl->ng, pl->np, pl->ns);
+    // which terms carry a data column, how y and the codes are stored (RowSpec bits)
+    int spec = 0;
+    for (int t = 0; t < pl->ng; ++t) spec |= (pl->xcol_g[t] >= 0) << t;
+    for (int t = 0; t < pl->np; ++t) spec |= (pl->xcol_p[t] >= 0) << (2 + t);
+    for (int t = 0; t < pl->ns; ++t) spec |= (pl->xcol_s[t] >= 0) << (4 + t);
+    if (pl->y_u8) spec |= 64;
+    if (pl->has_off) spec |= 128;
+    if (pl->ns > 0 && pl->sec_code_bytes == 2) spec |= 256;
+    if (env_int("SKK_GENERIC", 0)) spec = -2;  // force the run-time kernels (testing)
+    cfg->fn = lookup_kernel(pl->dtype, pl->family, bt, pl->ng, pl->np, pl->ns, spec);
     if (!cfg->fn)
         return fail(SKK_ERR_UNSUPPORTED, "no row kernel for %d global / %d primary / %d secondary terms", pl->ng,
                     pl->np, pl->ns);

@@ -2,5 +2,5 @@
 #include "skk_row_inst.cuh"
 
 namespace skk {
-const void *row_kernel_f64_bernoulli_bt4(int ng, int np, int ns) { return row_kernel_lookup<double, SKK_LIK_BERNOULLI_LOGIT, 4>(ng, np, ns); }
+const void *row_kernel_f64_bernoulli_bt4(int ng, int np, int ns, int spec) { return row_kernel_lookup<double, SKK_LIK_BERNOULLI_LOGIT, 4>(ng, np, ns, spec); }
 }  // namespace skk

@@ -100,9 +100,33 @@ struct AtLeast1 {
     static constexpr int value = N > 0 ? N : 1;
 };
 
+// Compile-time description of which terms carry a data column and how y / codes are stored.
+// SPEC < 0: everything is read from the kernel parameters at run time (generic kernels, one per
+// term-count shape).  SPEC >= 0: bit t (global term t), bit 2+t (primary), bit 4+t (secondary) = the
+// term has an x column; bit 6 = y stored as uint8; bit 7 = constant offset column; bit 8 = 16-bit
+// secondary codes.  The hot shapes of the BASELINE configurations are compiled with a fixed SPEC,
+// which removes the predicated loads and the multiplications by one from the row loop.
+template <int SPEC>
+struct RowSpec {
+    static constexpr bool fixed = SPEC >= 0;
+    template <typename P>
+    static __device__ __forceinline__ bool xg(const P &p, int t) { return fixed ? ((SPEC >> t) & 1) : p.xcol_g[t] >= 0; }
+    template <typename P>
+    static __device__ __forceinline__ bool xp(const P &p, int t) { return fixed ? ((SPEC >> (2 + t)) & 1) : p.xcol_p[t] >= 0; }
+    template <typename P>
+    static __device__ __forceinline__ bool xs(const P &p, int t) { return fixed ? ((SPEC >> (4 + t)) & 1) : p.xcol_s[t] >= 0; }
+    template <typename P>
+    static __device__ __forceinline__ bool y_u8(const P &p) { return fixed ? ((SPEC >> 6) & 1) : p.y8 != nullptr; }
+    template <typename P>
+    static __device__ __forceinline__ bool has_off(const P &p) { return fixed ? ((SPEC >> 7) & 1) : p.eta_offset != nullptr; }
+    template <typename P>
+    static __device__ __forceinline__ bool code16(const P &p) { return fixed ? ((SPEC >> 8) & 1) : p.sec_code_bytes == 2; }
+};
+
 // ---------------------------------------------------------------------------------------------
-template <typename T, int FAM, int BT, int NG, int NP, int NS, int R>
+template <typename T, int FAM, int BT, int NG, int NP, int NS, int R, int SPEC = -1>
 struct RowKernel {
+    using Spec = RowSpec<SPEC>;
     static constexpr int WT = 32 * R;  // rows per tile
     static constexpr int NGa = AtLeast1<NG>::value;
     static constexpr int NPa = AtLeast1<NP>::value;
@@ -130,24 +154,24 @@ struct RowKernel {
         const T *pxg[NGa], *pxp[NPa], *pxs[NSa];
 #pragma unroll
         for (int t = 0; t < NGa; ++t)
-            pxg[t] = (t < NG && p.xcol_g[t] >= 0)
+            pxg[t] = (t < NG && Spec::xg(p, t))
                          ? reinterpret_cast<const T *>(tl.stage + p.xcol_g[t] * tl.sl.x_stride) + li : nullptr;
 #pragma unroll
         for (int t = 0; t < NPa; ++t)
-            pxp[t] = (t < NP && p.xcol_p[t] >= 0)
+            pxp[t] = (t < NP && Spec::xp(p, t))
                          ? reinterpret_cast<const T *>(tl.stage + p.xcol_p[t] * tl.sl.x_stride) + li : nullptr;
 #pragma unroll
         for (int t = 0; t < NSa; ++t)
-            pxs[t] = (t < NS && p.xcol_s[t] >= 0)
+            pxs[t] = (t < NS && Spec::xs(p, t))
                          ? reinterpret_cast<const T *>(tl.stage + p.xcol_s[t] * tl.sl.x_stride) + li : nullptr;
         const T *sy = reinterpret_cast<const T *>(tl.stage + tl.sl.y_off) + li;
         const uint8_t *sy8 = reinterpret_cast<const uint8_t *>(tl.stage + tl.sl.y_off) + li;
         const T *soff = reinterpret_cast<const T *>(tl.stage + tl.sl.off_off) + li;
         const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(tl.stage + tl.sl.code_off) + li;
         const int32_t *sc32 = reinterpret_cast<const int32_t *>(tl.stage + tl.sl.code_off) + li;
-        const bool y_u8 = p.y8 != nullptr;
-        const bool has_off = p.eta_offset != nullptr;
-        const bool code16 = p.sec_code_bytes == 2;
+        const bool y_u8 = Spec::y_u8(p);
+        const bool has_off = Spec::has_off(p);
+        const bool code16 = Spec::code16(p);
 
         // per-span accumulators in T; folded into fp64 at run / span boundaries
         T accL[BT], accG[NGa][BT], accP[NPa][BT], accS[NSa][BT];
@@ -338,11 +362,11 @@ struct RowKernel {
             const T yv = y_u8 ? (T)sy8[i] : sy[i];
             T xg[NGa], xp[NPa], xs[NSa];
 #pragma unroll
-            for (int t = 0; t < NG; ++t) xg[t] = pxg[t] ? pxg[t][i] : T(1);
+            for (int t = 0; t < NG; ++t) xg[t] = Spec::xg(p, t) ? pxg[t][i] : T(1);
 #pragma unroll
-            for (int t = 0; t < NP; ++t) xp[t] = pxp[t] ? pxp[t][i] : T(1);
+            for (int t = 0; t < NP; ++t) xp[t] = Spec::xp(p, t) ? pxp[t][i] : T(1);
 #pragma unroll
-            for (int t = 0; t < NS; ++t) xs[t] = pxs[t] ? pxs[t][i] : T(1);
+            for (int t = 0; t < NS; ++t) xs[t] = Spec::xs(p, t) ? pxs[t][i] : T(1);
             const T off = has_off ? soff[i] : T(0);
 
 #pragma unroll
@@ -649,9 +673,9 @@ struct RowKernel {
     }
 };
 
-template <typename T, int FAM, int BT, int NG, int NP, int NS, int R>
+template <typename T, int FAM, int BT, int NG, int NP, int NS, int R, int SPEC = -1>
 __global__ void __launch_bounds__(256, (BT == 1 ? 2 : 1)) skk_row_kernel(const __grid_constant__ RowParams<T> p) {
-    RowKernel<T, FAM, BT, NG, NP, NS, R>::run(p);
+    RowKernel<T, FAM, BT, NG, NP, NS, R, SPEC>::run(p);
 }
 
 }  // namespace skk
