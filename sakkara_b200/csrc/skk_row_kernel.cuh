@@ -301,23 +301,18 @@ struct RowKernel {
                 const int c = code16 ? (int)sc16[i] : sc32[i];
                 const bool change = valid && (c != scur);
                 if constexpr (FASTP) {
-                    if (change) {
-                        if (s_changed) {
-                            // run started and ended inside this lane; equal codes are contiguous inside
-                            // a primary segment, so no other lane of the warp touches this entry now
+                    // Inside one segment equal codes are contiguous, so the run that ends here ends in
+                    // this lane only: its sum goes to the table with a plain read-modify-write (lanes
+                    // that hold the same code in their *last* run add theirs after the loop).  Written
+                    // without branches -- load and add always, store under the predicate.
 #pragma unroll
-                            for (int t = 0; t < NS; ++t)
+                    for (int t = 0; t < NS; ++t)
 #pragma unroll
-                                for (int b = 0; b < BT; ++b)
-                                    gradS[((int64_t)t * p.n_secondary + scur) * BT + b] += accS[t][b];
-                        } else {
-                            s_head_key = scur;
-#pragma unroll
-                            for (int t = 0; t < NS; ++t)
-#pragma unroll
-                                for (int b = 0; b < BT; ++b) s_head[t * BT + b] = (double)accS[t][b];
+                        for (int b = 0; b < BT; ++b) {
+                            T *slot = gradS + ((int64_t)t * p.n_secondary + scur) * BT + b;
+                            const T updated = *slot + accS[t][b];
+                            if (change) *slot = updated;
                         }
-                    }
                 } else {
                     // the tile straddles primary segments: a code may occur in several runs of the
                     // tile, so lanes flushing the same entry at the same step are combined first
@@ -482,33 +477,44 @@ struct RowKernel {
             }
         }
 
-        // ---- secondary level: runs shared between lanes ----------------------------------------------
+        // ---- secondary level: the runs still open at the end of the lanes' spans ------------------------
         if constexpr (NS > 0) {
             double v[NSa * BT];
-            for (int round = 0; round < 2; ++round) {
-                bool has;
-                int key;
-                if (round == 0) {
-                    has = nvalid > 0;
-                    key = s_changed ? s_head_key : scur;
+            if constexpr (FASTP) {
+                // codes ascend with the lane: one sorted-run sum, the first lane of each run updates the table
+                __syncwarp();
 #pragma unroll
-                    for (int k = 0; k < NS * BT; ++k) v[k] = s_changed ? s_head[k] : (double)accS[k / BT][k % BT];
-                } else {
-                    has = s_changed;
-                    key = scur;
-#pragma unroll
-                    for (int k = 0; k < NS * BT; ++k) v[k] = (double)accS[k / BT][k % BT];
-                }
-                // inside one segment the codes ascend with the lane (same argument as above); a tile
-                // that straddles segments may repeat a code anywhere, so it takes the general grouping
-                const bool leader = FASTP ? (round == 0 ? warp_sorted_run_sum<NSa * BT>(has, key, v) : has)
-                                          : warp_match_sum<NSa * BT>(has, key, v);
-                if (leader) {
+                for (int k = 0; k < NS * BT; ++k) v[k] = (double)accS[k / BT][k % BT];
+                if (warp_sorted_run_sum<NSa * BT>(nvalid > 0, scur, v)) {
 #pragma unroll
                     for (int k = 0; k < NS * BT; ++k)
-                        gradS[((int64_t)(k / BT) * p.n_secondary + key) * BT + (k % BT)] += (T)v[k];
+                        gradS[((int64_t)(k / BT) * p.n_secondary + scur) * BT + (k % BT)] += (T)v[k];
                 }
                 __syncwarp();
+            } else {
+                // a tile that straddles segments may repeat a code anywhere: general grouping, first
+                // runs (or only runs) in round A, last runs in round B
+                for (int round = 0; round < 2; ++round) {
+                    bool has;
+                    int key;
+                    if (round == 0) {
+                        has = nvalid > 0;
+                        key = s_changed ? s_head_key : scur;
+#pragma unroll
+                        for (int k = 0; k < NS * BT; ++k) v[k] = s_changed ? s_head[k] : (double)accS[k / BT][k % BT];
+                    } else {
+                        has = s_changed;
+                        key = scur;
+#pragma unroll
+                        for (int k = 0; k < NS * BT; ++k) v[k] = (double)accS[k / BT][k % BT];
+                    }
+                    if (warp_match_sum<NSa * BT>(has, key, v)) {
+#pragma unroll
+                        for (int k = 0; k < NS * BT; ++k)
+                            gradS[((int64_t)(k / BT) * p.n_secondary + key) * BT + (k % BT)] += (T)v[k];
+                    }
+                    __syncwarp();
+                }
             }
         }
     }
