@@ -202,6 +202,7 @@ def main():
     ap.add_argument('--rows', type=int, default=0, help='override the number of rows (testing)')
     ap.add_argument('--ref-rows', type=int, default=8_000_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--collective', default='auto', choices=['auto', 'peer', 'nccl'])
     ap.add_argument('--check', action='store_true', help='verify one evaluation against the oracle (small --rows)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -242,12 +243,8 @@ def main():
             f'bytes/row={st0["stored_bytes_per_row"]}')
         log(kp.describe())
 
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(skk.unique_id()), dtype=torch.uint8).to(dev)
-        dist.broadcast(uid, 0)
-        skk.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    from sakkara_b200.distributed import connect
+    collective = connect(skk, rank, world, args.collective)
 
     theta = synth.start_point(plan, batch, dtype=dtype)
     P = plan.n_params
@@ -367,7 +364,7 @@ def main():
         'data': 'synthetic',
         'config': {'workload': cfg['workload'], 'rows_total': rows_total, 'rows_per_gpu': plan.n_rows,
                    'n_params': P, 'batch': batch, 'l2': 'flushed between steps (256 MiB memset)',
-                   'parallelism': f'rows x{world}' if world > 1 else 'single GPU',
+                   'parallelism': f'rows x{world}' if world > 1 else 'single GPU', 'collective': collective,
                    'grid': st0['grid'], 'block': st0['block'], 'smem_bytes': st0['smem_bytes']},
         'evals_per_s': batch / (ms_per_step * 1e-3), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
         'roofline': roofline, 'wall_s_timed_region': wall,

@@ -186,6 +186,18 @@ int skk_comm_unique_id(void *out128);
 int skk_comm_init(skk_plan *plan, const void *unique_id128, int32_t rank, int32_t nranks);
 int skk_comm_destroy(skk_plan *plan);
 
+/*
+ * One-shot all-reduce over NVLink peer memory, the default collective of row-sharded runs on one
+ * box (<= 8 ranks): instead of ncclAllReduce, every rank stores its [dlogp, logp] vector into a
+ * buffer of every peer (CUDA IPC mapping) and the final kernel adds the R vectors in rank order.
+ *   skk_peer_alloc : allocates this rank's receive buffer for nranks peers, returns its 64-byte
+ *                    cudaIpcMemHandle_t for the caller to all-gather;
+ *   skk_peer_init  : handles = nranks x 64 bytes in rank order (own entry ignored).
+ * After skk_peer_init every skk_eval ends with the peer exchange (takes precedence over NCCL).
+ */
+int skk_peer_alloc(skk_plan *plan, int32_t nranks, void *handle_out64);
+int skk_peer_init(skk_plan *plan, const void *handles, int32_t rank, int32_t nranks);
+
 int skk_stats(skk_plan *plan, skk_stats_t *out);
 
 /* cudaStream_t the plan launches on (so that callers can record their own events on it). */

@@ -164,6 +164,13 @@ struct skk_plan {
 
     void *comm = nullptr;
     int nranks = 1, rank = 0;
+    // one-shot all-reduce over peer memory
+    PeerParams peer{};
+    bool peer_ready = false;
+    void *peer_local = nullptr;            // this rank's receive buffer
+    void *peer_opened[kMaxPeers] = {nullptr};
+    int *peer_status = nullptr;            // mapped host memory
+    int peer_nranks = 0;
 
     skk_stats_t stats{};
 };
@@ -608,7 +615,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
     const size_t P = (size_t)pl->n_params;
     cudaStream_t st = pl->stream;
     int launches = 0;
-    const bool sharded = pl->comm != nullptr;
+    const bool sharded = pl->comm != nullptr || pl->peer_ready;
 
     // K3: priors for the whole batch, next to the row kernel
     const bool priors = pl->include_priors && P > 0;
@@ -692,14 +699,21 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
 
     if (sharded) {
         // one all-reduce of [dlogp, logp partial, constant] per evaluation, then the final combination
-        NCCL_TRY(g_nccl.AllReduce(pl->lik_vec, pl->lik_vec, (size_t)batch * (P + 2), /*ncclDouble*/ 8, /*ncclSum*/ 0,
-                                  pl->comm, st));
-        ++launches;
-        if (priors) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
         FinalParams fp{pl->lik_vec, pl->prior_grad, pl->prior_lp, pl->prior_ctas, pl->n_params, pl->n_rows_total,
                        pl->sigma_idx, pl->sigma_const, pl->family, pl->include_priors};
         dim3 grid((unsigned)std::max<size_t>(1, (P + 255) / 256), (unsigned)batch);
-        skk_final_kernel<T><<<grid, 256, 0, st>>>(fp, th, out_logp, out_grad);
+        if (pl->peer_ready) {
+            skk_peer_push_kernel<<<1, 1024, 0, st>>>(pl->peer, pl->lik_vec, (int64_t)batch * (int64_t)(P + 2));
+            ++launches;
+            if (priors) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+            skk_final_kernel<T, true><<<grid, 256, 0, st>>>(fp, pl->peer, th, out_logp, out_grad);
+        } else {
+            NCCL_TRY(g_nccl.AllReduce(pl->lik_vec, pl->lik_vec, (size_t)batch * (P + 2), /*ncclDouble*/ 8,
+                                      /*ncclSum*/ 0, pl->comm, st));
+            ++launches;
+            if (priors) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+            skk_final_kernel<T, false><<<grid, 256, 0, st>>>(fp, pl->peer, th, out_logp, out_grad);
+        }
         ++launches;
     } else if (priors && !joined) {
         CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
@@ -785,6 +799,10 @@ enqueued:
         return SKK_OK;
     }
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (pl->peer_status && *pl->peer_status) {
+        *pl->peer_status = 0;
+        return fail(SKK_ERR_NCCL, "peer all-reduce timed out waiting for another rank");
+    }
     if (!dev_io) {
         std::memcpy(grad_out, pl->h_out, (size_t)batch * P * sizeof(T));
         std::memcpy(logp_out, static_cast<T *>(pl->h_out) + (size_t)batch * P, (size_t)batch * sizeof(T));
@@ -818,6 +836,9 @@ static void free_plan(skk_plan *pl) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
     pl->graphs.clear();
     if (pl->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(pl->comm);
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (pl->peer_opened[r]) cudaIpcCloseMemHandle(pl->peer_opened[r]);
+    if (pl->peer_status) cudaFreeHost(pl->peer_status);
     for (void *p : pl->allocs) cudaFree(p);
     if (pl->h_in) cudaFreeHost(pl->h_in);
     if (pl->h_out) cudaFreeHost(pl->h_out);
@@ -978,6 +999,69 @@ int skk_comm_destroy(skk_plan *pl) {
         NCCL_TRY(g_nccl.CommDestroy(pl->comm));
         pl->comm = nullptr;
     }
+    return SKK_OK;
+}
+
+static int64_t peer_stride(const skk_plan *pl) {
+    const int64_t n = (int64_t)pl->max_batch * (pl->n_params + 2);
+    return (n + 1) & ~(int64_t)1;  // even: slots stay 16-byte aligned
+}
+
+int skk_peer_alloc(skk_plan *pl, int32_t nranks, void *handle_out64) {
+    if (!pl || !handle_out64) return fail(SKK_ERR_INVALID, "null argument");
+    if (nranks < 1 || nranks > kMaxPeers) return fail(SKK_ERR_UNSUPPORTED, "peer all-reduce handles up to %d ranks", kMaxPeers);
+    if (pl->peer_local) return fail(SKK_ERR_INVALID, "peer buffer already allocated");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    const size_t bytes = (size_t)2 * nranks * peer_stride(pl) * sizeof(double) + (size_t)nranks * sizeof(unsigned long long);
+    CUDA_TRY(cudaMalloc(&pl->peer_local, bytes));
+    pl->allocs.push_back(pl->peer_local);
+    pl->device_bytes += bytes;
+    CUDA_TRY(cudaMemset(pl->peer_local, 0, bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, pl->peer_local));
+    std::memcpy(handle_out64, &h, 64);
+    pl->peer_nranks = nranks;
+    return SKK_OK;
+}
+
+int skk_peer_init(skk_plan *pl, const void *handles, int32_t rank, int32_t nranks) {
+    if (!pl || !handles) return fail(SKK_ERR_INVALID, "null argument");
+    if (!pl->peer_local || nranks != pl->peer_nranks) return fail(SKK_ERR_INVALID, "call skk_peer_alloc with the same nranks first");
+    if (rank < 0 || rank >= nranks) return fail(SKK_ERR_INVALID, "rank %d of %d", rank, nranks);
+    if (pl->peer_ready) return fail(SKK_ERR_INVALID, "peer all-reduce already initialised");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    const int64_t stride = peer_stride(pl);
+    PeerParams pp{};
+    pp.stride = stride;
+    pp.rank = rank;
+    pp.nranks = nranks;
+    for (int r = 0; r < nranks; ++r) {
+        void *base = pl->peer_local;
+        if (r != rank) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const char *>(handles) + (size_t)r * 64, 64);
+            CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            pl->peer_opened[r] = base;
+        }
+        pp.peer_buf[r] = static_cast<double *>(base);
+        pp.peer_flag[r] = reinterpret_cast<unsigned long long *>(static_cast<double *>(base) + (size_t)2 * nranks * stride);
+    }
+    unsigned long long *words = nullptr;
+    if (int rc = dev_alloc(pl, &words, 2, true)) return rc;
+    pp.seq = words;
+    pp.done = reinterpret_cast<unsigned int *>(words + 1);
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&pl->peer_status), sizeof(int), cudaHostAllocMapped));
+    *pl->peer_status = 0;
+    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&pp.status), pl->peer_status, 0));
+    pl->peer = pp;
+    for (GraphEntry &g : pl->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    pl->graphs.clear();
+    pl->peer_ready = true;
+    pl->nranks = nranks;
+    pl->rank = rank;
     return SKK_OK;
 }
 

@@ -420,6 +420,65 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const T *__restrict__ 
     }
 }
 
+// ---- one-shot all-reduce over NVLink peer memory ----------------------------------------------
+// Every rank owns a buffer of 2 (parity) x R slots of `stride` doubles plus R flags, mapped into
+// all peers with CUDA IPC.  Evaluation number seq (1, 2, ...):
+//   push : the rank stores its vector into slot [seq & 1][rank] of EVERY peer (plain stores over
+//          NVLink), fences, then stores flag[rank] = seq on every peer;
+//   final: every rank waits until all R flags of its own buffer reach seq and adds the R slots in
+//          rank order -- the same order everywhere, so all ranks obtain bit-identical results.
+// A rank can be at most one evaluation ahead of a peer (it needs that peer's flag to finish), hence
+// two parities suffice.  Spins are bounded: on timeout a status word in mapped host memory is set
+// and the kernel carries on, so a lost peer can never hang the GPU.
+constexpr int kMaxPeers = 8;
+struct PeerParams {
+    double *peer_buf[kMaxPeers];              // peer_buf[r]: rank r's buffer as seen from this rank
+    unsigned long long *peer_flag[kMaxPeers]; // rank r's flags
+    unsigned long long *seq;                  // this rank's evaluation counter (device)
+    unsigned int *done;                       // CTAs of the final kernel that have read their slots
+    int *status;                              // mapped host word, != 0 after a timeout
+    int64_t stride;                           // doubles per slot
+    int32_t rank, nranks;
+};
+
+__global__ void __launch_bounds__(1024) skk_peer_push_kernel(const __grid_constant__ PeerParams pp,
+                                                             const double *__restrict__ vec, int64_t n) {
+    const unsigned long long seq = *pp.seq + 1;
+    const int64_t slot = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride;
+    const int64_t n2 = n >> 1;
+    const double2 *src2 = reinterpret_cast<const double2 *>(vec);
+    for (int r = 0; r < pp.nranks; ++r) {
+        double *dst = pp.peer_buf[r] + slot;
+        double2 *dst2 = reinterpret_cast<double2 *>(dst);
+        for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) dst2[i] = src2[i];
+        if ((n & 1) && threadIdx.x == 0) dst[n - 1] = vec[n - 1];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pp.nranks) {
+        volatile unsigned long long *flag = pp.peer_flag[threadIdx.x] + pp.rank;
+        *flag = seq;
+    }
+}
+
+// waits until every peer's vector of this evaluation has arrived (called by all threads of a CTA)
+__device__ __forceinline__ unsigned long long peer_wait(const PeerParams &pp) {
+    const unsigned long long seq = *pp.seq + 1;
+    if (threadIdx.x < pp.nranks) {
+        volatile unsigned long long *flag = pp.peer_flag[pp.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        while (*flag < seq) {
+            if (clock64() - t0 > (1ll << 32)) {  // ~2 s: report and go on
+                *pp.status = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    return seq;
+}
+
 // ---- K4b (sharded runs: after the all-reduce) ------------------------------------------------
 struct FinalParams {
     const double *lik_vec;      // [B][P+2], all-reduced over ranks
@@ -434,12 +493,28 @@ struct FinalParams {
     int32_t include_priors;
 };
 
-template <typename T>
-__global__ void skk_final_kernel(const __grid_constant__ FinalParams fp, const T *__restrict__ theta,
-                                 T *__restrict__ out_logp, T *__restrict__ out_grad) {
+// PEER: the likelihood vector is the rank-ordered sum of the peers' slots (one-shot all-reduce
+// above); otherwise it is read from lik_vec (single rank, or after ncclAllReduce).
+template <typename T, bool PEER>
+__global__ void skk_final_kernel(const __grid_constant__ FinalParams fp, const __grid_constant__ PeerParams pp,
+                                 const T *__restrict__ theta, T *__restrict__ out_logp, T *__restrict__ out_grad) {
     const int b = blockIdx.y;
     const int64_t P = fp.n_params;
-    const double *lik = fp.lik_vec + (int64_t)b * (P + 2);
+    const double *lik_in = fp.lik_vec + (int64_t)b * (P + 2);
+    const double *mine = nullptr;
+    if constexpr (PEER) {
+        const unsigned long long seq = peer_wait(pp);
+        mine = pp.peer_buf[pp.rank] + (int64_t)(seq & 1) * pp.nranks * pp.stride + (int64_t)b * (P + 2);
+    }
+    auto lik_at = [&](int64_t k) -> double {
+        if constexpr (PEER) {
+            double s = 0.0;
+            for (int r = 0; r < pp.nranks; ++r) s += mine[(int64_t)r * pp.stride + k];
+            return s;
+        } else {
+            return lik_in[k];
+        }
+    };
     double scale = 1.0, sigma = 1.0;
     if (fp.family == SKK_LIK_NORMAL) {
         sigma = fp.sigma_theta_index >= 0 ? exp((double)theta[(int64_t)b * P + fp.sigma_theta_index]) : fp.sigma_const;
@@ -447,9 +522,9 @@ __global__ void skk_final_kernel(const __grid_constant__ FinalParams fp, const T
     }
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j < P) {
-        double g = lik[j] * scale;
+        double g = lik_at(j) * scale;
         if (fp.family == SKK_LIK_NORMAL && j == fp.sigma_theta_index)
-            g += lik[P] * scale - (double)fp.n_rows_total;  // sum(r^2 - 1), r = e / sigma
+            g += lik_at(P) * scale - (double)fp.n_rows_total;  // sum(r^2 - 1), r = e / sigma
         if (fp.include_priors) g += fp.prior_grad[(int64_t)b * P + j];
         out_grad[(int64_t)b * P + j] = (T)g;
     }
@@ -467,12 +542,26 @@ __global__ void skk_final_kernel(const __grid_constant__ FinalParams fp, const T
             for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
             double ll;
             if (fp.family == SKK_LIK_NORMAL)
-                ll = -0.5 * lik[P] * scale - (double)fp.n_rows_total * (kLogSqrt2Pi + log(sigma));
+                ll = -0.5 * lik_at(P) * scale - (double)fp.n_rows_total * (kLogSqrt2Pi + log(sigma));
             else
-                ll = lik[P];
-            out_logp[b] = (T)(tot + ll + lik[P + 1]);
+                ll = lik_at(P);
+            out_logp[b] = (T)(tot + ll + lik_at(P + 1));
+        }
+    }
+    if constexpr (PEER) {
+        // the last CTA to finish closes the evaluation (the slots of this parity may be reused two
+        // evaluations later, the flags only grow)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int total = gridDim.x * gridDim.y;
+            if (atomicAdd(pp.done, 1u) == total - 1) {
+                *pp.done = 0;
+                *pp.seq = *pp.seq + 1;
+            }
         }
     }
 }
+
 
 }  // namespace skk

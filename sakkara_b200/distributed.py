@@ -45,7 +45,31 @@ def exchange_unique_id(skk_plan, group=None) -> bytes:
     return box[0]
 
 
-def sharded_valuegrad(plan, dtype='float64', max_batch: int = 1, device: Optional[int] = None, group=None):
+def connect(skk_plan, rank: int, world: int, collective: str = 'auto', group=None) -> str:
+    """
+    Enable the per-evaluation all-reduce on a plan.  ``'peer'``: one-shot exchange over NVLink peer
+    memory written by our own kernels (ranks of one box, <= 8); ``'nccl'``: ncclAllReduce;
+    ``'auto'``: peer when possible.  Returns the collective in use.
+    """
+    import torch.distributed as dist
+    if world == 1:
+        return 'none'
+    if collective == 'auto':
+        collective = 'peer' if world <= 8 else 'nccl'
+    if collective == 'peer':
+        handles = [None] * world
+        dist.all_gather_object(handles, skk_plan.peer_alloc(world), group=group)
+        skk_plan.peer_init(handles, rank, world)
+        dist.barrier(group=group)           # every rank has mapped every buffer before the first push
+    elif collective == 'nccl':
+        skk_plan.comm_init(exchange_unique_id(skk_plan, group), rank, world)
+    else:
+        raise ValueError(collective)
+    return collective
+
+
+def sharded_valuegrad(plan, dtype='float64', max_batch: int = 1, device: Optional[int] = None, group=None,
+                      collective: str = 'auto'):
     """
     ValueGradFunction over this rank's rows with the all-reduce enabled: every rank passes the same
     (full) ``plan`` and receives the full ``(logp, dlogp)`` from each call.
@@ -55,6 +79,5 @@ def sharded_valuegrad(plan, dtype='float64', max_batch: int = 1, device: Optiona
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     rows = sorted_shard(plan, rank, world)
     f = ValueGradFunction(plan, dtype=dtype, max_batch=max_batch, device=device, rows=rows, n_rows_total=plan.n_rows)
-    if world > 1:
-        f.skk.comm_init(exchange_unique_id(f.skk, group), rank, world)
+    connect(f.skk, rank, world, collective, group)
     return f

@@ -54,7 +54,8 @@ class Stats(C.Structure):
 
 
 EXPORTS = ('skk_plan_create', 'skk_eval', 'skk_plan_destroy', 'skk_last_error', 'skk_comm_unique_id',
-           'skk_comm_init', 'skk_comm_destroy', 'skk_stats', 'skk_stream', 'skk_abi_version')
+           'skk_comm_init', 'skk_comm_destroy', 'skk_peer_alloc', 'skk_peer_init', 'skk_stats', 'skk_stream',
+           'skk_abi_version')
 
 _lib = None
 
@@ -83,6 +84,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.skk_comm_init.restype = C.c_int
     lib.skk_comm_destroy.argtypes = [C.c_void_p]
     lib.skk_comm_destroy.restype = C.c_int
+    lib.skk_peer_alloc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.skk_peer_alloc.restype = C.c_int
+    lib.skk_peer_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.skk_peer_init.restype = C.c_int
     lib.skk_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.skk_stats.restype = C.c_int
     lib.skk_stream.argtypes = [C.c_void_p]
@@ -197,6 +202,21 @@ class SkkPlan:
             raise ValueError('unique_id must be 128 bytes')
         buf = C.create_string_buffer(unique_id, 128)
         _check(self.lib, self.lib.skk_comm_init(self._handle, buf, rank, nranks))
+
+    def peer_alloc(self, nranks: int) -> bytes:
+        """Allocate the receive buffer of the peer-memory all-reduce; returns its 64-byte IPC handle."""
+        self._guard()
+        buf = C.create_string_buffer(64)
+        _check(self.lib, self.lib.skk_peer_alloc(self._handle, nranks, buf))
+        return buf.raw
+
+    def peer_init(self, handles, rank: int, nranks: int) -> None:
+        """``handles``: the IPC handles of all ranks in rank order (from an all-gather)."""
+        self._guard()
+        blob = b''.join(handles)
+        if len(blob) != 64 * nranks:
+            raise ValueError('need one 64-byte handle per rank')
+        _check(self.lib, self.lib.skk_peer_init(self._handle, C.create_string_buffer(blob, len(blob)), rank, nranks))
 
     def comm_destroy(self) -> None:
         self._guard()

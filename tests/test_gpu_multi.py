@@ -11,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, dtype, out):
+def _worker(rank, world, port, dtype, collective, out):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
@@ -26,22 +26,24 @@ def _worker(rank, world, port, dtype, out):
         for plan in (synth.poisson_plan(synth.poisson_columns(200_000, 400, 30, seed=5)[0]),
                      synth.linreg_plan(synth.linreg_columns(150_000, 300, seed=5)[0]),
                      synth.logistic_plan(synth.logistic_columns(120_000, 20, 30, seed=5)[0])):
-            f = sharded_valuegrad(plan, dtype=dtype, max_batch=4, device=rank)
+            f = sharded_valuegrad(plan, dtype=dtype, max_batch=4, device=rank, collective=collective)
             assert f.kernel_plan.n_rows < plan.n_rows
             theta = synth.start_point(plan, 3, seed=1, scale=0.3, dtype=dtype)
             logp, grad = f(theta)
             for b in range(3):
                 results.append(assert_parity(logp[b], grad[b], plan, theta[b], dtype))
-            again = f(theta)
-            assert np.array_equal(again[1], grad)
+            for _ in range(3):                  # repeated calls reuse both parities of the peer buffers
+                again = f(theta)
+                assert np.array_equal(again[1], grad) and np.array_equal(again[0], logp)
             f.close()
         out[rank] = max(max(e) for e in results)
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('collective', ['peer', 'nccl'])
 @pytest.mark.parametrize('dtype', ['float64', 'float32'])
-def test_row_sharded_parity(dtype):
+def test_row_sharded_parity(dtype, collective):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -49,5 +51,5 @@ def test_row_sharded_parity(dtype):
         pytest.skip('needs at least two GPUs')
     with mp.Manager() as manager:
         out = manager.dict()
-        mp.spawn(_worker, args=(world, 29650 + os.getpid() % 300, dtype, out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, 29650 + os.getpid() % 300, dtype, collective, out), nprocs=world, join=True)
         assert sorted(out.keys()) == list(range(world))
