@@ -40,6 +40,8 @@ CONFIGS = {
                workload='hierarchical logistic regression (Bernoulli-logit): 10M rows, nested 100x100 groups, fp32'),
     'c4': dict(rows=100_000_000, dtype='float32', batch=1, shard='rows',
                workload='Poisson-log GLM with crossed random effects: 100M rows, 10k+1k groups, fp32, row-sharded'),
+    'c5': dict(rows=1_000_000, dtype='float64', batch=1024, shard='chains',
+               workload='batched multi-chain evaluation: 1,024 chains x 1M rows x 1k groups, fp64, chains sharded'),
 }
 
 
@@ -54,6 +56,9 @@ def make_plan(config: str, rows: int, rank: int, world: int, seed: int = 1):
     the all-reduced gradient means the same thing on all ranks.
     """
     from sakkara_b200 import synth
+    if config == 'c5':                      # every rank holds all rows; the chains are sharded
+        cols, _ = synth.linreg_columns(rows, 1000, seed=seed)
+        return synth.linreg_plan(cols, groups=1000)
     share = rows // world + (1 if rank < rows % world else 0)
     if config == 'c2':
         cols, _ = synth.linreg_columns(rows, 1000, seed=seed)
@@ -239,10 +244,15 @@ def main():
     cfg = CONFIGS[args.config]
     rows_total = args.rows or cfg['rows']
     dtype, batch = cfg['dtype'], cfg['batch']
+    chains_sharded = cfg['shard'] == 'chains'
+    batch_total = batch
+    if chains_sharded:
+        batch = batch_total // world + (1 if rank < batch_total % world else 0)
     t0 = time.time()
     plan = make_plan(args.config, rows_total, rank, world)
     t_gen = time.time() - t0
-    f = ValueGradFunction(plan, dtype=dtype, max_batch=batch, device=local, n_rows_total=rows_total)
+    f = ValueGradFunction(plan, dtype=dtype, max_batch=batch, device=local,
+                          n_rows_total=plan.n_rows if chains_sharded else rows_total)
     t0 = time.time()
     kp = f.kernel_plan
     t_plan = time.time() - t0
@@ -257,9 +267,9 @@ def main():
         log(kp.describe())
 
     from sakkara_b200.distributed import connect
-    collective = connect(skk, rank, world, args.collective)
+    collective = 'none (chains are independent)' if chains_sharded else connect(skk, rank, world, args.collective)
 
-    theta = synth.start_point(plan, batch, dtype=dtype)
+    theta = synth.start_point(plan, batch, seed=rank if chains_sharded else 0, dtype=dtype)
     P = plan.n_params
     tdt = torch.float64 if dtype == 'float64' else torch.float32
     th_dev = torch.from_numpy(theta).to(dev)
@@ -334,7 +344,8 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     ms_per_step = total_ms / args.steps
-    value = rows_total * batch / (ms_per_step * 1e-3)
+    work = rows_total * (batch_total if chains_sharded else batch)      # row-evaluations per step, all ranks
+    value = work / (ms_per_step * 1e-3)
 
     # ---- the row kernel alone (events inside the library, around the launch) -------------------------
     kern = []
@@ -347,8 +358,9 @@ def main():
             kern.append(skk.stats()['last_row_kernel_ms'])
     kern_ms = float(np.mean(kern))
     esize = 8 if dtype == 'float64' else 4
-    bt = 4 if batch >= 2 else 1
-    launches_per_eval = (batch + bt - 1) // bt if batch >= 2 else 1
+    chain_path = skk.stats()['row_kernel_launches'] and batch >= 32 and kp.n_secondary == 0
+    bt = batch if chain_path else (4 if batch >= 2 else 1)
+    launches_per_eval = 1 if chain_path else ((batch + 3) // 4 if batch >= 2 else 1)
     alg_bytes = plan.n_rows * st0['stored_bytes_per_row'] + bt * (2 * P * esize + esize)
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -360,6 +372,12 @@ def main():
                               'frac': canonical / peak,
                               'note': 'SURVEY 8d canonical layout (floatX y, int32 codes); the plan stores fewer bytes'}}
 
+    if chain_path:
+        # K2 is ALU-bound: 11 flop per row-evaluation for the Normal/identity model
+        roofline['alu'] = {'flop_per_row_eval': 11, 'achieved_tflops': 11 * plan.n_rows * batch / (kern_ms * 1e-3) / 1e12,
+                           'nominal_fp64_tflops': 37.0, 'note': 'chain-per-lane kernel; no fp64 peak in MEASURED_PEAKS.json'}
+        roofline['kernel'] = 'skk_chain_kernel'
+
     # ---- end to end through the public call with host buffers ---------------------------------------------
     for _ in range(args.warmup):
         f(theta)
@@ -370,7 +388,7 @@ def main():
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = rows_total * batch * args.steps / float(t_e2e.item())
+    e2e_value = work * args.steps / float(t_e2e.item())
     e2e = {'value': e2e_value, 'unit': 'row-evals/s', 'h2d_bytes_per_step': batch * P * esize,
            'd2h_bytes_per_step': batch * (P + 1) * esize, 'ms_per_step': 1e3 * float(t_e2e.item()) / args.steps}
 
@@ -380,10 +398,10 @@ def main():
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64' if dtype == 'float64' else 'f32',
         'data': 'synthetic',
         'config': {'workload': cfg['workload'], 'rows_total': rows_total, 'rows_per_gpu': plan.n_rows,
-                   'n_params': P, 'batch': batch, 'l2': 'flushed between steps (256 MiB memset)',
+                   'n_params': P, 'batch': batch_total if chains_sharded else batch, 'batch_per_gpu': batch, 'l2': 'flushed between steps (256 MiB memset)',
                    'parallelism': f'rows x{world}' if world > 1 else 'single GPU', 'collective': collective,
                    'grid': st0['grid'], 'block': st0['block'], 'smem_bytes': st0['smem_bytes']},
-        'evals_per_s': batch / (ms_per_step * 1e-3), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+        'evals_per_s': (batch_total if chains_sharded else batch) / (ms_per_step * 1e-3), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
         'roofline': roofline, 'wall_s_timed_region': wall,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

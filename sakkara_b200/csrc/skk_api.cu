@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "skk_aux_kernels.cuh"
+#include "skk_chain_kernel.cuh"
 #include "skk_row_inst.cuh"
 
 namespace skk {
@@ -33,6 +34,8 @@ const void *row_kernel_f64_bernoulli_bt1(int, int, int, int);
 const void *row_kernel_f64_bernoulli_bt4(int, int, int, int);
 const void *row_kernel_f64_poisson_bt1(int, int, int, int);
 const void *row_kernel_f64_poisson_bt4(int, int, int, int);
+const void *chain_kernel_f32(int, int, int);
+const void *chain_kernel_f64(int, int, int);
 }  // namespace skk
 
 using namespace skk;
@@ -164,6 +167,15 @@ struct skk_plan {
 
     void *comm = nullptr;
     int nranks = 1, rank = 0;
+    // chain-per-lane path (K2) for large batches
+    bool chain_ready = false;
+    const void *chain_fn = nullptr;
+    int chain_ranges = 0, chain_tiles = 0, chain_smem = 0, chain_bp = 0;
+    int2 *chain_keys = nullptr;
+    double *chain_totals = nullptr, *chain_head = nullptr, *chain_tail = nullptr, *chain_glob = nullptr;
+    ChainReduceParams chain_reduce{};
+    int32_t *theta_index_dev[kMaxTerms] = {nullptr};
+    int term_level[kMaxTerms] = {0}, term_slot_in_level[kMaxTerms] = {0};
     // one-shot all-reduce over peer memory
     PeerParams peer{};
     bool peer_ready = false;
@@ -175,6 +187,7 @@ struct skk_plan {
     skk_stats_t stats{};
 };
 
+static const int kChainMinBatch = 32;     // batches from this size on use the chain-per-lane kernels
 static const int64_t kHeavyLinks = 512;  // hyper-parameters with more children get a whole CTA
 
 static size_t elt_size(int dtype) { return dtype == SKK_F64 ? 8 : 4; }
@@ -264,7 +277,9 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     pl->rows_per_tile = WT;
     pl->n_tiles = (int)((d->n_rows + WT - 1) / WT);
     if (pl->n_tiles < 1) pl->n_tiles = 1;
-    const size_t padded = (size_t)pl->n_tiles * WT;
+    // whole tiles of the row kernel (544 rows) and of the chain kernel (512 rows)
+    const size_t padded = std::max((size_t)pl->n_tiles * WT,
+                                   (size_t)((d->n_rows + kChainTileRows - 1) / kChainTileRows) * kChainTileRows);
     const size_t n = (size_t)d->n_rows;
 
     // ---- row columns, padded to whole tiles ------------------------------------------------------
@@ -332,6 +347,9 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
         if (rc) return rc;
         const int64_t slots = td.level == SKK_LEVEL_GLOBAL ? 1 : td.level == SKK_LEVEL_PRIMARY ? d->n_primary : d->n_secondary;
         pl->prep.term[i] = PrepTerm{ti, td.n_slots, (int64_t)t * slots, td.level};
+        pl->theta_index_dev[i] = ti;
+        pl->term_level[i] = td.level;
+        pl->term_slot_in_level[i] = t;
         (td.level == SKK_LEVEL_GLOBAL ? pl->xcol_g : td.level == SKK_LEVEL_PRIMARY ? pl->xcol_p : pl->xcol_s)[t] = td.xcol;
         for (int64_t s = 0; s < td.n_slots; ++s) {
             if (td.theta_index[s] < 0 || td.theta_index[s] >= d->n_params)
@@ -564,6 +582,83 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     rp.sigma_const = pl->sigma_const;
     rp.family = pl->family;
     pl->use_graphs = env_int("SKK_NO_GRAPH", 0) == 0;
+
+    // ---- chain-per-lane path: batches of >= kChainMinBatch vectors, models without a secondary level ----------
+    if (pl->ns == 0 && pl->max_batch >= kChainMinBatch && env_int("SKK_NO_CHAIN", 0) == 0) {
+        pl->chain_fn = pl->dtype == SKK_F64 ? chain_kernel_f64(pl->family, pl->ng, pl->np)
+                                            : chain_kernel_f32(pl->family, pl->ng, pl->np);
+        if (!pl->chain_fn) return fail(SKK_ERR_UNSUPPORTED, "no chain kernel for this shape");
+        const int TR = kChainTileRows;
+        pl->chain_tiles = (int)std::max<int64_t>(1, (d->n_rows + TR - 1) / TR);
+        pl->chain_bp = (pl->max_batch + 31) & ~31;
+        const int gy = (pl->chain_bp / 32 + kChainWarps - 1) / kChainWarps;
+        pl->chain_ranges = std::max(1, std::min(pl->chain_tiles, std::max(1, pl->n_sms * 4 / gy)));
+        const int RR = pl->chain_ranges;
+        const size_t es = sizeof(T);
+        const int stage = (int)(((size_t)pl->n_x * TR * es + (pl->y_u8 ? TR : TR * es) + (pl->has_off ? TR * es : 0) + 127) & ~(size_t)127);
+        pl->chain_smem = 128 + 2 * stage;
+        CUDA_TRY(cudaFuncSetAttribute(pl->chain_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->chain_smem));
+        std::vector<int2> rk(RR, make_int2(0, 0));
+        std::vector<int64_t> rstart(RR + 1, 0);
+        for (int c = 0; c <= RR; ++c) rstart[c] = std::min<int64_t>(d->n_rows, ((int64_t)pl->chain_tiles * c / RR) * TR);
+        if (d->n_primary > 0)
+            for (int c = 0; c < RR; ++c) {
+                if (rstart[c] >= rstart[c + 1]) continue;
+                const int kf = (int)(std::upper_bound(seg.begin(), seg.end(), rstart[c]) - seg.begin()) - 1;
+                const int kl = (int)(std::upper_bound(seg.begin(), seg.end(), rstart[c + 1] - 1) - seg.begin()) - 1;
+                rk[c] = make_int2(std::min<int>(kf, (int)d->n_primary - 1), std::min<int>(kl, (int)d->n_primary - 1));
+            }
+        std::vector<int4> cdesc(std::max<int64_t>(1, d->n_primary), make_int4(0, -1, 0, 0));
+        for (int64_t sl = 0; sl < d->n_primary; ++sl) {
+            const int64_t q0 = seg[sl], q1 = seg[sl + 1];
+            if (q1 <= q0) continue;
+            const int c_lo = (int)(std::upper_bound(rstart.begin(), rstart.end(), q0) - rstart.begin()) - 1;
+            const int c_hi = (int)(std::upper_bound(rstart.begin(), rstart.end(), q1 - 1) - rstart.begin()) - 1;
+            auto kind = [&](int c) { return rk[c].x == sl ? 1 : (rk[c].y == sl ? 2 : 0); };
+            cdesc[sl] = make_int4(c_lo, c_hi, kind(c_lo), kind(c_hi));
+        }
+        std::vector<int32_t> multi_of(P, -1);
+        for (size_t m = 0; m < multi_elem.size(); ++m) multi_of[multi_elem[m]] = (int32_t)m;
+        int4 *cdesc_dev = nullptr;
+        int32_t *multi_of_dev = nullptr;
+        if (int rc = dev_upload(pl, &pl->chain_keys, rk.data(), rk.size())) return rc;
+        if (int rc = dev_upload(pl, &cdesc_dev, cdesc.data(), cdesc.size())) return rc;
+        if (int rc = dev_upload(pl, &multi_of_dev, multi_of.data(), multi_of.size())) return rc;
+        const size_t bp = (size_t)pl->chain_bp;
+        const size_t cunits = (size_t)(pl->ng + 1) + (size_t)pl->np * d->n_primary;
+        if (int rc = dev_alloc(pl, &pl->chain_totals, cunits * bp, true)) return rc;
+        if (int rc = dev_alloc(pl, &pl->chain_head, (size_t)RR * std::max(1, pl->np) * bp, true)) return rc;
+        if (int rc = dev_alloc(pl, &pl->chain_tail, (size_t)RR * std::max(1, pl->np) * bp, true)) return rc;
+        if (int rc = dev_alloc(pl, &pl->chain_glob, (size_t)RR * (pl->ng + 1) * bp, true)) return rc;
+        ChainReduceParams &cr = pl->chain_reduce;
+        cr = ChainReduceParams{};
+        cr.slot_desc = cdesc_dev;
+        cr.totals = pl->chain_totals;
+        cr.head = pl->chain_head;
+        cr.tail = pl->chain_tail;
+        cr.glob = pl->chain_glob;
+        cr.single_unit = single_dev;
+        cr.multi_elem = multi_elem_dev;
+        cr.multi_ptr = multi_ptr_dev;
+        cr.multi_unit = multi_unit_dev;
+        cr.multi_of = multi_of_dev;
+        cr.ranges = RR;
+        cr.ng = pl->ng;
+        cr.np = pl->np;
+        cr.bp = pl->chain_bp;
+        cr.n_primary = d->n_primary;
+        cr.n_params = d->n_params;
+        cr.prior_grad = pl->prior_grad;
+        cr.prior_lp_part = pl->prior_lp;
+        cr.prior_ctas = pl->prior_ctas;
+        cr.include_priors = pl->include_priors;
+        cr.family = pl->family;
+        cr.n_rows_total = pl->n_rows_total;
+        cr.sigma_theta_index = pl->sigma_idx;
+        cr.sigma_const = pl->sigma_const;
+        cr.logp_const = d->logp_const;
+        pl->chain_ready = true;
+    }
     return SKK_OK;
 }
 
@@ -634,6 +729,60 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             ++launches;
         }
         CUDA_TRY(cudaEventRecord(pl->ev_join, pl->side));
+    }
+
+    if (pl->chain_ready && batch >= kChainMinBatch && !sharded) {
+        // K2: lane = chain; one pass over the rows for the whole batch
+        ChainParams<T> cp{};
+        for (int c = 0; c < pl->n_x; ++c) cp.x[c] = static_cast<const T *>(pl->x[c]);
+        cp.y = pl->y_u8 ? nullptr : static_cast<const T *>(pl->y);
+        cp.y8 = pl->y_u8 ? static_cast<const uint8_t *>(pl->y) : nullptr;
+        cp.eta_offset = static_cast<const T *>(pl->off);
+        cp.n_x = pl->n_x;
+        cp.n_rows = pl->n_rows;
+        cp.n_tiles = pl->chain_tiles;
+        cp.range_keys = pl->chain_keys;
+        cp.seg_offsets = pl->seg_off;
+        cp.n_primary = (int32_t)pl->n_primary;
+        for (int i = 0; i < pl->prep.n_terms; ++i) {
+            const int t = pl->term_slot_in_level[i];
+            if (pl->term_level[i] == SKK_LEVEL_GLOBAL) {
+                cp.xcol_g[t] = pl->xcol_g[t];
+                cp.theta_index_g[t] = pl->theta_index_dev[i];
+            } else {
+                cp.xcol_p[t] = pl->xcol_p[t];
+                cp.theta_index_p[t] = pl->theta_index_dev[i];
+            }
+        }
+        cp.theta = th;
+        cp.n_params = pl->n_params;
+        cp.batch = batch;
+        cp.bp = pl->chain_bp;
+        cp.direct = pl->chain_totals + (size_t)(pl->ng + 1) * pl->chain_bp;
+        cp.head = pl->chain_head;
+        cp.tail = pl->chain_tail;
+        cp.glob = pl->chain_glob;
+        if (pl->np > 0)
+            CUDA_TRY(cudaMemsetAsync(cp.direct, 0, (size_t)pl->np * pl->n_primary * pl->chain_bp * sizeof(double), st));
+        const int gy = ((batch + 31) / 32 + kChainWarps - 1) / kChainWarps;
+        void *args[] = {&cp};
+        if (timed) CUDA_TRY(cudaEventRecord(pl->evk0, st));
+        CUDA_TRY(cudaLaunchKernel(pl->chain_fn, dim3(pl->chain_ranges, gy), dim3(kChainWarps * 32), args, pl->chain_smem, st));
+        if (timed) CUDA_TRY(cudaEventRecord(pl->evk1, st));
+        ++launches;
+        pl->stats.row_kernel_launches++;
+        ChainReduceParams cr = pl->chain_reduce;
+        cr.batch = batch;
+        const int threads = std::min(256, (batch + 31) & ~31);
+        skk_chain_slot_kernel<<<dim3((unsigned)std::max<int64_t>(pl->ng + 1, std::min<int64_t>(std::max<int64_t>(1, pl->n_primary), 2048)), 2),
+                                threads, 0, st>>>(cr);
+        ++launches;
+        if (priors) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+        skk_chain_final_kernel<T><<<(unsigned)std::min<size_t>(std::max<size_t>(1, P), 2048), threads, 0, st>>>(cr, th, out_logp, out_grad);
+        ++launches;
+        CUDA_TRY(cudaGetLastError());
+        *n_launch = launches;
+        return SKK_OK;
     }
 
     bool joined = false;

@@ -161,7 +161,7 @@ skk_prior_kernel(const __grid_constant__ PriorParams pp, const T *__restrict__ t
 
 // One CTA per heavy parent (blockIdx.x < n_heavy), one warp per light parent afterwards.  The
 // children's contributions are contiguous in link_val.
-__global__ void skk_prior_link_kernel(const __grid_constant__ PriorParams pp, double *__restrict__ prior_grad,
+static __global__ void skk_prior_link_kernel(const __grid_constant__ PriorParams pp, double *__restrict__ prior_grad,
                                       const double *__restrict__ link_val) {
     __shared__ double part[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -441,7 +441,7 @@ struct PeerParams {
     int32_t rank, nranks;
 };
 
-__global__ void __launch_bounds__(1024) skk_peer_push_kernel(const __grid_constant__ PeerParams pp,
+static __global__ void __launch_bounds__(1024) skk_peer_push_kernel(const __grid_constant__ PeerParams pp,
                                                              const double *__restrict__ vec, int64_t n) {
     const unsigned long long seq = *pp.seq + 1;
     const int64_t slot = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride;

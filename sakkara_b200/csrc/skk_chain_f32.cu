@@ -1,0 +1,11 @@
+// Chain-per-lane kernel instantiations (float), see skk_chain_kernel.cuh.
+#include "skk_chain_kernel.cuh"
+
+namespace skk {
+const void *chain_kernel_f32(int family, int ng, int np) {
+    if (family == SKK_LIK_NORMAL) return chain_kernel_lookup<float, SKK_LIK_NORMAL>(ng, np);
+    if (family == SKK_LIK_BERNOULLI_LOGIT) return chain_kernel_lookup<float, SKK_LIK_BERNOULLI_LOGIT>(ng, np);
+    if (family == SKK_LIK_POISSON_LOG) return chain_kernel_lookup<float, SKK_LIK_POISSON_LOG>(ng, np);
+    return nullptr;
+}
+}  // namespace skk

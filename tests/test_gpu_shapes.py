@@ -97,3 +97,51 @@ def test_secondary_level_too_large_is_rejected():
     f = ValueGradFunction(synth.poisson_plan(cols), dtype='float64')
     with pytest.raises(SkkError, match='shared memory'):
         f.skk
+
+
+# ---- chain-per-lane path (K2): batches of >= 32 parameter vectors, models without a secondary level ----
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+@pytest.mark.parametrize('batch', [32, 45, 128])
+def test_chain_per_lane_linreg(batch, dtype):
+    cols, _ = synth.linreg_columns(60_000, 300, seed=batch)
+    plan = synth.linreg_plan(cols)
+    f = ValueGradFunction(plan, dtype=dtype, max_batch=batch)
+    theta = synth.start_point(plan, batch, seed=2, scale=0.3, dtype=dtype)
+    logp, grad = f(theta)
+    assert f.stats()['row_kernel_launches'] == 1          # one pass over the rows for the whole batch
+    for b in (0, 1, batch // 2, batch - 1):
+        assert_parity(logp[b], grad[b], plan, theta[b], dtype)
+    again = f(theta)
+    assert np.array_equal(again[0], logp) and np.array_equal(again[1], grad)
+    # the same points through the row-parallel kernels (batch tiles of 4) agree
+    g = ValueGradFunction(plan, dtype=dtype, max_batch=8)
+    lp4, gr4 = g(theta[:8])
+    tol = 1e-12 if dtype == 'float64' else 2e-5
+    assert np.allclose(lp4, logp[:8], rtol=tol) and np.allclose(gr4, grad[:8], rtol=tol, atol=tol * np.abs(grad[:8]).max())
+    f.close()
+    g.close()
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+@pytest.mark.parametrize('n,groups', [(1, 1), (513, 2), (5000, 5000), (40_000, 7), (100_000, 1)])
+def test_chain_per_lane_group_sizes(n, groups, dtype):
+    cols, _ = synth.linreg_columns(n, groups, seed=n)
+    plan = synth.linreg_plan(cols)
+    f = ValueGradFunction(plan, dtype=dtype, max_batch=40)
+    theta = synth.start_point(plan, 40, seed=3, scale=0.3, dtype=dtype)
+    logp, grad = f(theta)
+    for b in (0, 17, 39):
+        assert_parity(logp[b], grad[b], plan, theta[b], dtype)
+    f.close()
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+def test_chain_per_lane_nested_logistic(dtype):
+    cols, _ = synth.logistic_columns(80_000, 10, 20, seed=4)
+    plan = synth.logistic_plan(cols)
+    f = ValueGradFunction(plan, dtype=dtype, max_batch=64)
+    theta = synth.start_point(plan, 64, seed=4, scale=0.3, dtype=dtype)
+    logp, grad = f(theta)
+    for b in (0, 31, 32, 63):
+        assert_parity(logp[b], grad[b], plan, theta[b], dtype)
+    f.close()
