@@ -719,13 +719,13 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
         PriorParams pp = pl->prior;
         pp.batch = batch;
-        skk_prior_kernel<T><<<(unsigned)pl->prior_ctas, kPriorThreads, 0, pl->side>>>(pp, th, pl->prior_grad, pl->prior_lp,
+        skk_prior_kernel<T><<<dim3((unsigned)pl->prior_ctas, (unsigned)batch), kPriorThreads, 0, pl->side>>>(pp, th, pl->prior_grad, pl->prior_lp,
                                                                                     pl->link_val);
         ++launches;
         if (pp.n_parents > 0) {
             const int per_cta = pp.n_heavy > 0 ? 32 : 8;  // light parents: one warp each
             const unsigned blocks = (unsigned)(pp.n_heavy + (pp.n_parents - pp.n_heavy + per_cta - 1) / per_cta);
-            skk_prior_link_kernel<<<blocks, pp.n_heavy > 0 ? 1024 : 256, 0, pl->side>>>(pp, pl->prior_grad, pl->link_val);
+            skk_prior_link_kernel<<<dim3(blocks, (unsigned)batch), pp.n_heavy > 0 ? 1024 : 256, 0, pl->side>>>(pp, pl->prior_grad, pl->link_val);
             ++launches;
         }
         CUDA_TRY(cudaEventRecord(pl->ev_join, pl->side));

@@ -120,7 +120,8 @@ skk_prior_kernel(const __grid_constant__ PriorParams pp, const T *__restrict__ t
         e_mu = pp.e_mu[j];
         e_sigma = pp.e_sigma[j];
     }
-    for (int b = 0; b < pp.batch; ++b) {
+    {
+        const int b = blockIdx.y;  // one chain per grid row
         const T *th = theta + (int64_t)b * pp.n_params;
         double lp = 0.0;
         if (valid) {
@@ -155,7 +156,6 @@ skk_prior_kernel(const __grid_constant__ PriorParams pp, const T *__restrict__ t
             for (int w = 0; w < kPriorThreads / 32; ++w) tot += part[w];
             prior_lp_part[(int64_t)b * gridDim.x + blockIdx.x] = tot;
         }
-        __syncthreads();
     }
 }
 
@@ -172,7 +172,8 @@ static __global__ void skk_prior_link_kernel(const __grid_constant__ PriorParams
     const int64_t first = heavy ? lo + threadIdx.x : lo + lane;
     const int64_t step = heavy ? blockDim.x : 32;
     const int32_t element = pp.parent[p];
-    for (int b = 0; b < pp.batch; ++b) {
+    {
+        const int b = blockIdx.y;  // one chain per grid row
         const double *val = link_val + (int64_t)b * pp.n_links;
         double acc = 0.0;
         int64_t e = first;
@@ -193,7 +194,6 @@ static __global__ void skk_prior_link_kernel(const __grid_constant__ PriorParams
                 for (int w = 0; w < warps; ++w) s += part[w];
                 prior_grad[(int64_t)b * pp.n_params + element] += s;
             }
-            __syncthreads();
         } else if (lane == 0) {
             prior_grad[(int64_t)b * pp.n_params + element] += acc;
         }
