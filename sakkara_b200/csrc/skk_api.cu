@@ -714,21 +714,27 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
 
     // K3: priors for the whole batch, next to the row kernel
     const bool priors = pl->include_priors && P > 0;
+    // (for large batches they are big enough to fill the GPU themselves: run them in line)
+    const bool fork = batch < kChainMinBatch;
+    cudaStream_t ps = fork ? pl->side : st;
     if (priors) {
-        CUDA_TRY(cudaEventRecord(pl->ev_fork, st));
-        CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
+        if (fork) {
+            CUDA_TRY(cudaEventRecord(pl->ev_fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
+        }
         PriorParams pp = pl->prior;
         pp.batch = batch;
-        skk_prior_kernel<T><<<dim3((unsigned)pl->prior_ctas, (unsigned)batch), kPriorThreads, 0, pl->side>>>(pp, th, pl->prior_grad, pl->prior_lp,
-                                                                                    pl->link_val);
+        skk_prior_kernel<T><<<dim3((unsigned)pl->prior_ctas, (unsigned)batch), kPriorThreads, 0, ps>>>(
+            pp, th, pl->prior_grad, pl->prior_lp, pl->link_val);
         ++launches;
         if (pp.n_parents > 0) {
             const int per_cta = pp.n_heavy > 0 ? 32 : 8;  // light parents: one warp each
             const unsigned blocks = (unsigned)(pp.n_heavy + (pp.n_parents - pp.n_heavy + per_cta - 1) / per_cta);
-            skk_prior_link_kernel<<<dim3(blocks, (unsigned)batch), pp.n_heavy > 0 ? 1024 : 256, 0, pl->side>>>(pp, pl->prior_grad, pl->link_val);
+            skk_prior_link_kernel<<<dim3(blocks, (unsigned)batch), pp.n_heavy > 0 ? 1024 : 256, 0, ps>>>(
+                pp, pl->prior_grad, pl->link_val);
             ++launches;
         }
-        CUDA_TRY(cudaEventRecord(pl->ev_join, pl->side));
+        if (fork) CUDA_TRY(cudaEventRecord(pl->ev_join, pl->side));
     }
 
     if (pl->chain_ready && batch >= kChainMinBatch && !sharded) {
@@ -777,7 +783,6 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         skk_chain_slot_kernel<<<dim3((unsigned)std::max<int64_t>(pl->ng + 1, std::min<int64_t>(std::max<int64_t>(1, pl->n_primary), 2048)), 2),
                                 threads, 0, st>>>(cr);
         ++launches;
-        if (priors) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
         skk_chain_final_kernel<T><<<(unsigned)std::min<size_t>(std::max<size_t>(1, P), 2048), threads, 0, st>>>(cr, th, out_logp, out_grad);
         ++launches;
         CUDA_TRY(cudaGetLastError());
@@ -827,7 +832,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         ++launches;
 
         // K4f: per theta element; single GPU: straight to the outputs (needs the priors)
-        if (!sharded && priors && !joined) {
+        if (!sharded && priors && fork && !joined) {
             CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
             joined = true;
         }
@@ -854,17 +859,17 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         if (pl->peer_ready) {
             skk_peer_push_kernel<<<1, 1024, 0, st>>>(pl->peer, pl->lik_vec, (int64_t)batch * (int64_t)(P + 2));
             ++launches;
-            if (priors) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+            if (priors && fork) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
             skk_final_kernel<T, true><<<grid, 256, 0, st>>>(fp, pl->peer, th, out_logp, out_grad);
         } else {
             NCCL_TRY(g_nccl.AllReduce(pl->lik_vec, pl->lik_vec, (size_t)batch * (P + 2), /*ncclDouble*/ 8,
                                       /*ncclSum*/ 0, pl->comm, st));
             ++launches;
-            if (priors) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+            if (priors && fork) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
             skk_final_kernel<T, false><<<grid, 256, 0, st>>>(fp, pl->peer, th, out_logp, out_grad);
         }
         ++launches;
-    } else if (priors && !joined) {
+    } else if (priors && fork && !joined) {
         CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
     }
     CUDA_TRY(cudaGetLastError());

@@ -237,8 +237,8 @@ struct ChainReduceParams {
 // blockIdx.y == 0: primary slots (thread = chain, blockIdx.x = slot); blockIdx.y == 1: global terms
 static __global__ void skk_chain_slot_kernel(const __grid_constant__ ChainReduceParams rp) {
     double *direct = rp.totals + (int64_t)(rp.ng + 1) * rp.bp;
-    for (int chain = threadIdx.x; chain < rp.batch; chain += blockDim.x) {
-        if (blockIdx.y == 0) {
+    if (blockIdx.y == 0) {
+        for (int chain = threadIdx.x; chain < rp.batch; chain += blockDim.x)
             for (int64_t slot = blockIdx.x; slot < rp.n_primary; slot += gridDim.x) {
                 const int4 d = rp.slot_desc[slot];
                 if (d.y < d.x) continue;
@@ -252,12 +252,18 @@ static __global__ void skk_chain_slot_kernel(const __grid_constant__ ChainReduce
                     direct[((int64_t)t * rp.n_primary + slot) * rp.bp + chain] = acc;
                 }
             }
-        } else {
-            for (int t = blockIdx.x; t <= rp.ng; t += gridDim.x) {
-                double acc = 0.0;
-                for (int c = 0; c < rp.ranges; ++c) acc += rp.glob[((int64_t)c * (rp.ng + 1) + t) * rp.bp + chain];
-                rp.totals[(int64_t)t * rp.bp + chain] = acc;
-            }
+    } else {
+        // global terms and the logp partial: block = (term, chunk of blockDim chains), ranges in order
+        const int chunks = (rp.batch + blockDim.x - 1) / blockDim.x;
+        for (int item = blockIdx.x; item < (rp.ng + 1) * chunks; item += gridDim.x) {
+            const int t = item % (rp.ng + 1), chain = (item / (rp.ng + 1)) * blockDim.x + threadIdx.x;
+            if (chain >= rp.batch) continue;
+            const double *src = rp.glob + (int64_t)t * rp.bp + chain;
+            const int64_t stride = (int64_t)(rp.ng + 1) * rp.bp;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < rp.ranges; ++c) acc += src[c * stride];
+            rp.totals[(int64_t)t * rp.bp + chain] = acc;
         }
     }
 }
