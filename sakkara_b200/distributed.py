@@ -45,6 +45,27 @@ def exchange_unique_id(skk_plan, group=None) -> bytes:
     return box[0]
 
 
+def _peer_access_everywhere(world: int, group=None) -> bool:
+    """True when every rank sees all GPUs of the box and can map every peer's memory (NVLink / P2P)."""
+    import torch
+    import torch.distributed as dist
+    ok = 1
+    try:
+        mine = torch.cuda.current_device()
+        if torch.cuda.device_count() < world:
+            ok = 0                              # ranks are isolated with CUDA_VISIBLE_DEVICES: cannot probe
+        else:
+            for other in range(world):
+                if other != mine and not torch.cuda.can_device_access_peer(mine, other):
+                    ok = 0
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32,
+                        device='cuda' if dist.get_backend(group) == 'nccl' else 'cpu')
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
 def connect(skk_plan, rank: int, world: int, collective: str = 'auto', group=None) -> str:
     """
     Enable the per-evaluation all-reduce on a plan.  ``'peer'``: one-shot exchange over NVLink peer
@@ -55,7 +76,7 @@ def connect(skk_plan, rank: int, world: int, collective: str = 'auto', group=Non
     if world == 1:
         return 'none'
     if collective == 'auto':
-        collective = 'peer' if world <= 8 else 'nccl'
+        collective = 'peer' if world <= 8 and _peer_access_everywhere(world, group) else 'nccl'
     if collective == 'peer':
         handles = [None] * world
         dist.all_gather_object(handles, skk_plan.peer_alloc(world), group=group)
