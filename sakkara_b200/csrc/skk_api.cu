@@ -149,12 +149,14 @@ struct skk_plan {
 
     void *x[kMaxXCols] = {nullptr};
     void *y = nullptr, *off = nullptr, *codes = nullptr;
-    int2 *tile_keys = nullptr;
+    int4 *tile_meta = nullptr;
     int64_t *seg_off = nullptr;
-    PrepParams prep{};
+    int n_terms = 0;
 
-    void *theta_dev = nullptr, *val_g = nullptr, *val_p = nullptr, *val_s = nullptr;
-    double *totals = nullptr, *direct_p = nullptr;  // direct_p = totals + (ng + 1) * bt (per launch)
+    void *theta_dev = nullptr;
+    double *totals = nullptr;
+    double *direct_p = nullptr, *direct_p1 = nullptr;  // per batch-tile width (4 / 1): the entries the row kernel
+                                                       // writes are fixed per width, the rest must stay zero
     double *tile_head = nullptr, *tile_tail = nullptr, *cta_glob = nullptr, *cta_sec = nullptr;
     double *lik_vec = nullptr, *prior_grad = nullptr, *prior_lp = nullptr, *link_val = nullptr;
     void *out_dev = nullptr;  // [B*P grad | B logp]
@@ -324,10 +326,6 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             keys[t] = make_int2(std::min<int>(kf, (int)d->n_primary - 1), std::min<int>(kl, (int)d->n_primary - 1));
         }
     }
-    {
-        int rc = dev_upload(pl, &pl->tile_keys, keys.data(), keys.size());
-        if (rc) return rc;
-    }
 
     // ---- terms: value-table layout and the reduce CSR ------------------------------------------------
     struct Entry {
@@ -337,8 +335,8 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     };
     std::vector<Entry> entries;
     int cnt[3] = {0, 0, 0};
-    pl->prep.n_terms = d->n_terms;
-    pl->prep.n_params = d->n_params;
+    pl->n_terms = d->n_terms;
+    const int32_t *host_ti_p[kMaxTermsPerLevel] = {nullptr, nullptr};
     for (int i = 0; i < d->n_terms; ++i) {
         const skk_term_desc &td = d->terms[i];
         const int t = cnt[td.level]++;
@@ -346,7 +344,8 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
         int rc = dev_upload(pl, &ti, td.theta_index, (size_t)td.n_slots);
         if (rc) return rc;
         const int64_t slots = td.level == SKK_LEVEL_GLOBAL ? 1 : td.level == SKK_LEVEL_PRIMARY ? d->n_primary : d->n_secondary;
-        pl->prep.term[i] = PrepTerm{ti, td.n_slots, (int64_t)t * slots, td.level};
+        (void)slots;
+        if (td.level == SKK_LEVEL_PRIMARY) host_ti_p[t] = td.theta_index;
         pl->theta_index_dev[i] = ti;
         pl->term_level[i] = td.level;
         pl->term_slot_in_level[i] = t;
@@ -357,6 +356,15 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             entries.push_back(Entry{td.theta_index[s], (int8_t)td.level, (int8_t)t, (int32_t)s});
         }
     }
+    // tile meta: first / last primary slot and the theta elements of the primary terms at the first slot
+    {
+        std::vector<int4> meta(keys.size());
+        for (size_t t = 0; t < keys.size(); ++t)
+            meta[t] = make_int4(keys[t].x, keys[t].y, host_ti_p[0] ? host_ti_p[0][keys[t].x] : 0,
+                                host_ti_p[1] ? host_ti_p[1][keys[t].x] : 0);
+        if (int rc = dev_upload(pl, &pl->tile_meta, meta.data(), meta.size())) return rc;
+    }
+
     // theta element -> units of the `totals` buffer ([NG+1 global | NP*GP primary | NS*GS secondary])
     std::stable_sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) { return a.theta < b.theta; });
     auto unit_of = [&](const Entry &e) -> int64_t {
@@ -528,14 +536,10 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     T *tmp = nullptr;
     if (int rc = dev_alloc(pl, &tmp, B * P)) return rc;
     pl->theta_dev = tmp;
-    if (int rc = dev_alloc(pl, &tmp, (size_t)kMaxTermsPerLevel * bt, true)) return rc;
-    pl->val_g = tmp;
-    if (int rc = dev_alloc(pl, &tmp, std::max<size_t>(1, pl->np) * std::max<int64_t>(1, d->n_primary) * bt, true)) return rc;
-    pl->val_p = tmp;
-    if (int rc = dev_alloc(pl, &tmp, std::max<size_t>(1, pl->ns) * std::max<int64_t>(1, d->n_secondary) * bt, true)) return rc;
-    pl->val_s = tmp;
     const size_t units = (size_t)(pl->ng + 1) + (size_t)pl->np * d->n_primary + (size_t)pl->ns * d->n_secondary;
     if (int rc = dev_alloc(pl, &pl->totals, units * bt, true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->direct_p, std::max<size_t>(1, pl->np) * std::max<int64_t>(1, d->n_primary) * bt, true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->direct_p1, std::max<size_t>(1, pl->np) * std::max<int64_t>(1, d->n_primary), true)) return rc;
     if (int rc = dev_alloc(pl, &pl->tile_head, (size_t)pl->n_tiles * std::max(1, pl->np) * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->tile_tail, (size_t)pl->n_tiles * std::max(1, pl->np) * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->cta_glob, (size_t)grid_max * (pl->ng + 1) * bt, true)) return rc;
@@ -557,6 +561,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     rp.cta_glob = pl->cta_glob;
     rp.cta_sec = pl->cta_sec;
     rp.totals = pl->totals;
+    rp.direct_p = pl->direct_p;
     rp.single_unit = single_dev;
     rp.multi_elem = multi_elem_dev;
     rp.multi_ptr = multi_ptr_dev;
@@ -666,7 +671,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
 // evaluation
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, int bt) {
+static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *th, int b_valid, int bt) {
     RowParams<T> rp{};
     for (int c = 0; c < pl->n_x; ++c) rp.x[c] = static_cast<const T *>(pl->x[c]);
     rp.y = pl->y_u8 ? nullptr : static_cast<const T *>(pl->y);
@@ -678,7 +683,7 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, int bt) {
     rp.n_rows = pl->n_rows;
     rp.n_tiles = pl->n_tiles;
     rp.stages = pl->stages;
-    rp.tile_keys = pl->tile_keys;
+    rp.tile_meta = pl->tile_meta;
     rp.seg_offsets = pl->seg_off;
     rp.n_primary = (int32_t)pl->n_primary;
     rp.n_secondary = (int32_t)pl->n_secondary;
@@ -687,10 +692,15 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, int bt) {
         rp.xcol_p[t] = pl->xcol_p[t];
         rp.xcol_s[t] = pl->xcol_s[t];
     }
-    rp.val_g = static_cast<const T *>(pl->val_g);
-    rp.val_p = static_cast<const T *>(pl->val_p);
-    rp.val_s = static_cast<const T *>(pl->val_s);
-    rp.direct_p = pl->totals + (size_t)(pl->ng + 1) * bt;
+    rp.theta = th;
+    rp.n_params = pl->n_params;
+    rp.b_valid = b_valid;
+    for (int i = 0; i < pl->n_terms; ++i) {
+        const int t = pl->term_slot_in_level[i];
+        (pl->term_level[i] == SKK_LEVEL_GLOBAL ? rp.ti_g : pl->term_level[i] == SKK_LEVEL_PRIMARY ? rp.ti_p : rp.ti_s)[t] =
+            pl->theta_index_dev[i];
+    }
+    rp.direct_p = bt == 4 ? pl->direct_p : pl->direct_p1;
     rp.tile_head = pl->tile_head;
     rp.tile_tail = pl->tile_tail;
     rp.cta_glob = pl->cta_glob;
@@ -750,7 +760,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         cp.range_keys = pl->chain_keys;
         cp.seg_offsets = pl->seg_off;
         cp.n_primary = (int32_t)pl->n_primary;
-        for (int i = 0; i < pl->prep.n_terms; ++i) {
+        for (int i = 0; i < pl->n_terms; ++i) {
             const int t = pl->term_slot_in_level[i];
             if (pl->term_level[i] == SKK_LEVEL_GLOBAL) {
                 cp.xcol_g[t] = pl->xcol_g[t];
@@ -797,29 +807,15 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         const int bt = wide ? 4 : 1;
         const int b_valid = std::min(bt, remaining);
         const LaunchCfg &cfg = wide ? pl->cfg4 : pl->cfg1;
-        double *direct_p = pl->totals + (size_t)(pl->ng + 1) * bt;
-
-        // K0: value tables in slot order (+ clears the primary accumulators)
-        if (pl->prep.n_terms > 0) {
-            PrepParams pp = pl->prep;
-            pp.bt = bt;
-            pp.b_valid = b_valid;
-            int64_t most = 1;
-            for (int i = 0; i < pp.n_terms; ++i) most = std::max(most, pp.term[i].n_slots);
-            dim3 grid((unsigned)std::min<int64_t>((most + 255) / 256, 1024), (unsigned)pp.n_terms);
-            skk_prepare_kernel<T><<<grid, 256, 0, st>>>(pp, th + (size_t)b0 * P, static_cast<T *>(pl->val_g),
-                                                        static_cast<T *>(pl->val_p), static_cast<T *>(pl->val_s), direct_p);
-            ++launches;
-        }
-
         // K1: the rows
-        if (int rc = launch_rows<T>(pl, cfg, timed, bt)) return rc;
+        if (int rc = launch_rows<T>(pl, cfg, timed, th + (size_t)b0 * P, b_valid, bt)) return rc;
         ++launches;
         pl->stats.row_kernel_launches++;
 
         // K4a: totals per slot
         ReduceParams rp = pl->reduce;
         rp.bt = bt;
+        rp.direct_p = bt == 4 ? pl->direct_p : pl->direct_p1;
         rp.b0 = b0;
         rp.b_valid = b_valid;
         rp.grid = cfg.grid;

@@ -2,8 +2,6 @@
 // internally and add in a fixed order (serial per thread, or lane-strided + fixed shuffle tree), so
 // the whole evaluation is bit-reproducible.  Every kernel is latency-bound (a few dependent loads
 // per thread), so the data they walk is flattened at plan time to at most two dependent levels.
-//   K0  prepare      : gather theta into the value tables the row kernel reads (slot order); clears
-//                      the per-slot accumulators of the primary level
 //   K3a prior terms  : per theta element, its own prior logp term and gradient, and what it
 //                      contributes to the gradient of its prior's mu / sigma hyper-parameters
 //   K3b prior links  : per hyper-parameter element, the sum over its children (contiguous)
@@ -47,38 +45,7 @@ __device__ __forceinline__ void warp_cooperative_lists(bool heavy, int64_t first
     }
 }
 
-// ---- K0 -------------------------------------------------------------------------------------
-struct PrepTerm {
-    const int32_t *theta_index;  // [n_slots]
-    int64_t n_slots;
-    int64_t out_offset;          // element offset (in units of BT values) into the level's table
-    int32_t level;
-};
 constexpr int kMaxTerms = 3 * kMaxTermsPerLevel;
-struct PrepParams {
-    PrepTerm term[kMaxTerms];
-    int32_t n_terms;
-    int32_t bt;          // chains in this batch tile
-    int32_t b_valid;     // chains of the tile that exist (others read chain 0 and are discarded)
-    int64_t n_params;
-};
-
-template <typename T>
-__global__ void skk_prepare_kernel(const __grid_constant__ PrepParams pp, const T *__restrict__ theta,
-                                   T *__restrict__ val_g, T *__restrict__ val_p, T *__restrict__ val_s,
-                                   double *__restrict__ direct_p) {
-    const PrepTerm &tm = pp.term[blockIdx.y];
-    T *out = tm.level == SKK_LEVEL_GLOBAL ? val_g : tm.level == SKK_LEVEL_PRIMARY ? val_p : val_s;
-    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < tm.n_slots;
-         s += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = tm.theta_index[s];
-        for (int b = 0; b < pp.bt; ++b) {
-            const int bs = b < pp.b_valid ? b : 0;
-            out[(tm.out_offset + s) * pp.bt + b] = theta[(int64_t)bs * pp.n_params + j];
-            if (tm.level == SKK_LEVEL_PRIMARY) direct_p[(tm.out_offset + s) * pp.bt + b] = 0.0;
-        }
-    }
-}
 
 // ---- K3 -------------------------------------------------------------------------------------
 // Priors, flattened per theta element (structure of arrays) so that a thread needs one level of
@@ -201,8 +168,8 @@ static __global__ void skk_prior_link_kernel(const __grid_constant__ PriorParams
 }
 
 // ---- K4 -------------------------------------------------------------------------------------
-// `totals` is one buffer of BT-wide units: [NG+1 global terms + logp | NP*GP primary slots
-// (= direct_p, written by the row kernel) | NS*GS secondary slots].
+// `totals` is one buffer of BT-wide units: [NG+1 global terms + logp | NP*GP primary slots |
+// NS*GS secondary slots], written by the slot-total kernel.
 struct ReduceParams {
     // primary slots: tile range and which partial of the first / last tile belongs to the slot
     const int4 *slot_desc;      // [GP] {t_lo, t_hi (t_hi < t_lo: empty), kind of first, kind of last}; kind 0 none, 1 head, 2 tail
@@ -210,6 +177,7 @@ struct ReduceParams {
     const double *tile_tail;
     const double *cta_glob;     // [grid][NG+1][BT]
     const double *cta_sec;      // [grid][NS][GS][BT]
+    const double *direct_p;     // [NP][GP][BT] written by the row kernel (groups inside one tile), else zero
     double *totals;
     // theta elements
     const int32_t *single_unit; // [P] unit of `totals` for elements fed by exactly one slot, -1: none, -2: several
@@ -242,8 +210,9 @@ struct ReduceParams {
 template <int BT>
 __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_constant__ ReduceParams rp) {
     const int lane = threadIdx.x & 31;
-    double *direct_p = rp.totals + (int64_t)(rp.ng + 1) * BT;
-    double *sec_tot = direct_p + (int64_t)rp.np * rp.n_primary * BT;
+    const double *direct_p = rp.direct_p;
+    double *prim_tot = rp.totals + (int64_t)(rp.ng + 1) * BT;
+    double *sec_tot = prim_tot + (int64_t)rp.np * rp.n_primary * BT;
     if ((int)blockIdx.x < rp.blocks_p) {
         const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
         const bool valid = slot < rp.n_primary;
@@ -259,6 +228,9 @@ __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_consta
             return src ? src[(tile * rp.np + t) * BT + b] : 0.0;
         };
         for (int t = 0; t < rp.np; ++t) {
+            if (valid && !heavy && t_hi < t_lo)  // empty group
+#pragma unroll
+                for (int b = 0; b < BT; ++b) prim_tot[((int64_t)t * rp.n_primary + slot) * BT + b] = 0.0;
             if (valid && !heavy && t_hi >= t_lo) {
                 double acc[BT];
 #pragma unroll
@@ -273,12 +245,15 @@ __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_consta
 #pragma unroll
                     for (int b = 0; b < BT; ++b) acc[b] += addend(d, t_hi, t, b);
 #pragma unroll
-                for (int b = 0; b < BT; ++b) direct_p[((int64_t)t * rp.n_primary + slot) * BT + b] = acc[b];
+                for (int b = 0; b < BT; ++b) prim_tot[((int64_t)t * rp.n_primary + slot) * BT + b] = acc[b];
             }
             warp_cooperative_lists<BT>(
                 heavy, t_lo, t_hi + 1, slot,
                 [&](int64_t s, int64_t tile, int b) { return addend(rp.slot_desc[s], tile, t, b); },
-                [&](int64_t s, int b, double sum) { direct_p[((int64_t)t * rp.n_primary + s) * BT + b] += sum; });
+                [&](int64_t s, int b, double sum) {
+                    const int64_t at = ((int64_t)t * rp.n_primary + s) * BT + b;
+                    prim_tot[at] = direct_p[at] + sum;
+                });
         }
     } else if ((int)blockIdx.x < rp.blocks_p + rp.blocks_s) {
         // 32 consecutive slots (coalesced) x 8 sub-ranges of CTAs, combined in fixed order

@@ -33,19 +33,23 @@ struct RowParams {
     int32_t n_tiles;
     int32_t stages;          // smem ring depth per warp
     // structure
-    const int2 *tile_keys;   // {first, last} primary slot of every tile
+    const int4 *tile_meta;   // per tile {first, last primary slot, theta element of primary term 0 / 1 at the first slot}
     const int64_t *seg_offsets;  // [n_primary + 1]
     int32_t n_primary;
     int32_t n_secondary;
     int32_t xcol_g[kMaxTermsPerLevel];
     int32_t xcol_p[kMaxTermsPerLevel];
     int32_t xcol_s[kMaxTermsPerLevel];
-    // per-evaluation values written by the prepare kernel (K0); b = chain within the batch tile
-    const T *val_g;          // [NG][BT]
-    const T *val_p;          // [NP][n_primary][BT]
-    const T *val_s;          // [NS][n_secondary][BT]
+    // parameter values are read straight from theta through the slot -> theta tables of the terms
+    const T *theta;          // [b_valid][n_params], first chain of this batch tile
+    int64_t n_params;
+    int32_t b_valid;         // chains of the batch tile that exist (the others repeat chain 0)
+    const int32_t *ti_g[kMaxTermsPerLevel];  // [1]
+    const int32_t *ti_p[kMaxTermsPerLevel];  // [n_primary]
+    const int32_t *ti_s[kMaxTermsPerLevel];  // [n_secondary]
     // outputs, all fp64
-    double *direct_p;        // [NP][n_primary][BT]   groups that lie inside one tile (zeroed per eval)
+    double *direct_p;        // [NP][n_primary][BT]   groups that lie inside one tile; the set of groups written
+                             //                       here is fixed by the tiling, all others stay zero
     double *tile_head;       // [n_tiles][NP][BT]     partial of the tile's first group
     double *tile_tail;       // [n_tiles][NP][BT]     partial of the tile's last group (if != first)
     double *cta_glob;        // [grid][NG + 1][BT]    global-term partials, last entry = logp partial

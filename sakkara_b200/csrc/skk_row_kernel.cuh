@@ -139,6 +139,11 @@ struct RowKernel {
         int kf, kl;
     };
 
+    // theta[chain b of the batch tile][element]; chains beyond b_valid repeat chain 0 (results discarded)
+    static __device__ __forceinline__ T theta_at(const RowParams<T> &p, int b, int element) {
+        return p.theta[(int64_t)(b < p.b_valid ? b : 0) * p.n_params + element];
+    }
+
     // -----------------------------------------------------------------------------------------
     template <bool FASTP, bool FULL>
     static __device__ __forceinline__ void process(const RowParams<T> &p, const Tile &tl, const T (&vp_first)[NPa][BT],
@@ -213,8 +218,7 @@ struct RowKernel {
             for (int t = 0; t < NP; ++t)
 #pragma unroll
                 for (int b = 0; b < BT; ++b)
-                    vp[t][b] = staged ? s_val[((k - tl.kf) * NP + t) * BT + b]
-                                      : p.val_p[((int64_t)t * p.n_primary + k) * BT + b];
+                    vp[t][b] = staged ? s_val[((k - tl.kf) * NP + t) * BT + b] : theta_at(p, b, p.ti_p[t][k]);
         };
         if constexpr (NP > 0 && !FASTP) {
             if (staged) {
@@ -224,11 +228,20 @@ struct RowKernel {
                     for (int t = 0; t < NP; ++t)
 #pragma unroll
                         for (int b = 0; b < BT; ++b) {
-                            s_val[(lane * NP + t) * BT + b] = p.val_p[((int64_t)t * p.n_primary + tl.kf + lane) * BT + b];
+                            s_val[(lane * NP + t) * BT + b] = theta_at(p, b, p.ti_p[t][tl.kf + lane]);
                             s_acc[(lane * NP + t) * BT + b] = 0.0;
                         }
                     s_touch[lane] = 0;
                 }
+                __syncwarp();
+            } else {
+                // more groups than the scratch holds: partial sums are accumulated in direct_p itself,
+                // so the tile's inner groups are cleared first (nothing else ever writes them)
+                for (int k = tl.kf + 1 + lane; k < tl.kl; k += 32)
+#pragma unroll
+                    for (int t = 0; t < NP; ++t)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) p.direct_p[((int64_t)t * p.n_primary + k) * BT + b] = 0.0;
                 __syncwarp();
             }
             if (nvalid > 0) {
@@ -411,6 +424,8 @@ struct RowKernel {
                 double *head = p.tile_head + (int64_t)tl.tile * NP * BT;
                 double *tail = p.tile_tail + (int64_t)tl.tile * NP * BT;
                 if (!staged) {
+                    // more groups than the scratch holds: accumulate in global memory; the groups of the
+                    // tile that no single lane stored are cleared first (this set never changes)
                     if (lane < NP * BT) {
                         head[lane] = 0.0;
                         tail[lane] = 0.0;
@@ -541,12 +556,12 @@ struct RowKernel {
                         WT * (uint32_t)p.sec_code_bytes, bar);
     }
 
-    static __device__ __forceinline__ void load_vp(const RowParams<T> &p, int key, T (&vp)[NPa][BT]) {
+    // values of the primary terms at a tile's first slot (their theta elements ride in the tile meta)
+    static __device__ __forceinline__ void load_vp(const RowParams<T> &p, const int4 &meta, T (&vp)[NPa][BT]) {
 #pragma unroll
         for (int t = 0; t < NPa; ++t)
 #pragma unroll
-            for (int b = 0; b < BT; ++b)
-                vp[t][b] = (NP > 0) ? p.val_p[((int64_t)t * p.n_primary + key) * BT + b] : T(0);
+            for (int b = 0; b < BT; ++b) vp[t][b] = (NP > 0) ? theta_at(p, b, t == 0 ? meta.z : meta.w) : T(0);
     }
 
     // -----------------------------------------------------------------------------------------
@@ -587,7 +602,10 @@ struct RowKernel {
 
         if constexpr (NS > 0) {
             const int n = NS * p.n_secondary * BT;
-            for (int k = threadIdx.x; k < n; k += blockDim.x) valS[k] = p.val_s[k];
+            for (int k = threadIdx.x; k < n; k += blockDim.x) {
+                const int b = k % BT, slot = (k / BT) % p.n_secondary, t = k / (BT * p.n_secondary);
+                valS[k] = theta_at(p, b, p.ti_s[t][slot]);
+            }
             for (int k = threadIdx.x; k < n * warps; k += blockDim.x) gradS_all[k] = T(0);
             __syncthreads();
         }
@@ -596,7 +614,7 @@ struct RowKernel {
 #pragma unroll
         for (int t = 0; t < NGa; ++t)
 #pragma unroll
-            for (int b = 0; b < BT; ++b) vg[t][b] = (NG > 0) ? p.val_g[t * BT + b] : T(0);
+            for (int b = 0; b < BT; ++b) vg[t][b] = (NG > 0) ? theta_at(p, b, p.ti_g[t][0]) : T(0);
 
         double accG64[NG + 1][BT];
 #pragma unroll
@@ -606,23 +624,23 @@ struct RowKernel {
 
         // software prefetch of the tile keys (two tiles ahead) and primary values (one ahead)
         int tile = tile_begin + warp;
-        int2 k0 = make_int2(0, 0), k1 = make_int2(0, 0);
+        int4 k0 = make_int4(0, 0, 0, 0), k1 = make_int4(0, 0, 0, 0);
         T vp0[NPa][BT];
         if constexpr (NP > 0) {
-            if (tile < tile_end) k0 = p.tile_keys[tile];
-            if (tile + warps < tile_end) k1 = p.tile_keys[tile + warps];
+            if (tile < tile_end) k0 = p.tile_meta[tile];
+            if (tile + warps < tile_end) k1 = p.tile_meta[tile + warps];
         }
-        load_vp(p, k0.x, vp0);
+        load_vp(p, k0, vp0);
 
         for (int it = 0; tile < tile_end; tile += warps, ++it) {
             const int s = it % stages;
             const uint32_t parity = (uint32_t)(it / stages) & 1u;
-            int2 k2 = make_int2(0, 0);
+            int4 k2 = make_int4(0, 0, 0, 0);
             T vp1[NPa][BT];
             if constexpr (NP > 0) {
-                if (tile + 2 * warps < tile_end) k2 = p.tile_keys[tile + 2 * warps];
+                if (tile + 2 * warps < tile_end) k2 = p.tile_meta[tile + 2 * warps];
             }
-            load_vp(p, k1.x, vp1);
+            load_vp(p, k1, vp1);
 
             mbar_wait(bars + s, parity);
 
