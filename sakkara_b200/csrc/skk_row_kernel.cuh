@@ -602,9 +602,19 @@ struct RowKernel {
 
         if constexpr (NS > 0) {
             const int n = NS * p.n_secondary * BT;
-            for (int k = threadIdx.x; k < n; k += blockDim.x) {
-                const int b = k % BT, slot = (k / BT) % p.n_secondary, t = k / (BT * p.n_secondary);
-                valS[k] = theta_at(p, b, p.ti_s[t][slot]);
+            // theta[ti_s[slot]]: issue the index loads of four entries, then the four value loads
+            for (int k0 = threadIdx.x; k0 < n; k0 += 4 * blockDim.x) {
+                int element[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u * blockDim.x;
+                    element[u] = k < n ? p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u * blockDim.x;
+                    if (element[u] >= 0) valS[k] = theta_at(p, k % BT, element[u]);
+                }
             }
             for (int k = threadIdx.x; k < n * warps; k += blockDim.x) gradS_all[k] = T(0);
             __syncthreads();
