@@ -147,6 +147,7 @@ struct RowKernel {
     // -----------------------------------------------------------------------------------------
     template <bool FASTP, bool FULL>
     static __device__ __forceinline__ void process(const RowParams<T> &p, const Tile &tl, const T (&vp_first)[NPa][BT],
+                                                   const int (&staged_element)[NPa],
                                                    const T (&vg)[NGa][BT], double (&accG64)[NG + 1][BT],
                                                    const T *__restrict__ valS, T *__restrict__ gradS,
                                                    unsigned char *scratch, int lane) {
@@ -228,7 +229,7 @@ struct RowKernel {
                     for (int t = 0; t < NP; ++t)
 #pragma unroll
                         for (int b = 0; b < BT; ++b) {
-                            s_val[(lane * NP + t) * BT + b] = theta_at(p, b, p.ti_p[t][tl.kf + lane]);
+                            s_val[(lane * NP + t) * BT + b] = theta_at(p, b, staged_element[t]);
                             s_acc[(lane * NP + t) * BT + b] = 0.0;
                         }
                     s_touch[lane] = 0;
@@ -641,6 +642,15 @@ struct RowKernel {
             if (tile + warps < tile_end) k1 = p.tile_meta[tile + warps];
         }
         load_vp(p, k0, vp0);
+        // lane j of a straddling tile stages group kf + j: its theta elements are fetched one tile ahead
+        auto staged_elements = [&](const int4 &meta, int (&out)[NPa]) {
+#pragma unroll
+            for (int t = 0; t < NPa; ++t)
+                out[t] = (NP > 0 && meta.x != meta.y && lane <= meta.y - meta.x && meta.y - meta.x < kStagedGroups)
+                             ? p.ti_p[t][meta.x + lane] : 0;
+        };
+        int se0[NPa], se1[NPa];
+        staged_elements(k0, se0);
 
         for (int it = 0; tile < tile_end; tile += warps, ++it) {
             const int s = it % stages;
@@ -651,6 +661,7 @@ struct RowKernel {
                 if (tile + 2 * warps < tile_end) k2 = p.tile_meta[tile + 2 * warps];
             }
             load_vp(p, k1, vp1);
+            staged_elements(k1, se1);
 
             mbar_wait(bars + s, parity);
 
@@ -658,11 +669,11 @@ struct RowKernel {
             const bool full = (int64_t)(tile + 1) * WT <= p.n_rows;
             if (NP == 0 || k0.x == k0.y) {
                 if (full)
-                    process<true, true>(p, tl, vp0, vg, accG64, valS, gradS, scratch, lane);
+                    process<true, true>(p, tl, vp0, se0, vg, accG64, valS, gradS, scratch, lane);
                 else
-                    process<true, false>(p, tl, vp0, vg, accG64, valS, gradS, scratch, lane);
+                    process<true, false>(p, tl, vp0, se0, vg, accG64, valS, gradS, scratch, lane);
             } else {
-                process<false, false>(p, tl, vp0, vg, accG64, valS, gradS, scratch, lane);
+                process<false, false>(p, tl, vp0, se0, vg, accG64, valS, gradS, scratch, lane);
             }
 
             __syncwarp();
@@ -673,6 +684,8 @@ struct RowKernel {
             }
             k0 = k1;
             k1 = k2;
+#pragma unroll
+            for (int t = 0; t < NPa; ++t) se0[t] = se1[t];
 #pragma unroll
             for (int t = 0; t < NPa; ++t)
 #pragma unroll
