@@ -2,6 +2,7 @@
 // internally and add in a fixed order (serial per thread, or lane-strided + fixed shuffle tree), so
 // the whole evaluation is bit-reproducible.  Every kernel is latency-bound (a few dependent loads
 // per thread), so the data they walk is flattened at plan time to at most two dependent levels.
+//   (the row kernel reads theta itself through the terms' slot -> theta tables; there is no prepare kernel)
 //   K3a prior terms  : per theta element, its own prior logp term and gradient, and what it
 //                      contributes to the gradient of its prior's mu / sigma hyper-parameters
 //   K3b prior links  : per hyper-parameter element, the sum over its children (contiguous)
@@ -443,7 +444,7 @@ __device__ __forceinline__ unsigned long long peer_wait(const PeerParams &pp) {
         volatile unsigned long long *flag = pp.peer_flag[pp.rank] + threadIdx.x;
         const long long t0 = clock64();
         while (*flag < seq) {
-            if (clock64() - t0 > (1ll << 32)) {  // ~2 s: report and go on
+            if (clock64() - t0 > (1ll << 36)) {  // ~35 s: report and go on
                 *pp.status = 1;
                 break;
             }
