@@ -328,16 +328,15 @@ def main():
         return [s.elapsed_time(e) for s, e in zip(starts, ends)] if timed else None
 
     # ---- device-resident timing: W warm-up steps, then exactly K timed steps -------------------------
+    sampler = ClockSampler(local)       # samples every 100 ms from the warm-up to the end of all timed loops
+    sampler.start()
     device_steps(args.warmup, False)
-    sampler = ClockSampler(local)
     launches0 = skk.stats()['launches']
     barrier()
-    sampler.start()
     wall0 = time.perf_counter()
     step_ms = device_steps(args.steps, True)
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
     launches = skk.stats()['launches'] - launches0
     ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -388,6 +387,7 @@ def main():
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()
     e2e_value = work * args.steps / float(t_e2e.item())
     e2e = {'value': e2e_value, 'unit': 'row-evals/s', 'h2d_bytes_per_step': batch * P * esize,
            'd2h_bytes_per_step': batch * (P + 1) * esize, 'ms_per_step': 1e3 * float(t_e2e.item()) / args.steps}
