@@ -72,9 +72,12 @@ def connect(skk_plan, rank: int, world: int, collective: str = 'auto', group=Non
     memory written by our own kernels (ranks of one box, <= 8); ``'nccl'``: ncclAllReduce;
     ``'auto'``: peer when possible.  Returns the collective in use.
     """
-    import torch.distributed as dist
     if world == 1:
+        if os.environ.get('SKK_FORCE_PEER'):       # measure the sharded pipeline on one GPU (self exchange)
+            skk_plan.peer_init([skk_plan.peer_alloc(1)], 0, 1)
+            return 'peer (self)'
         return 'none'
+    import torch.distributed as dist
     if collective == 'auto':
         collective = 'peer' if world <= 8 and _peer_access_everywhere(world, group) else 'nccl'
     if collective == 'peer':
