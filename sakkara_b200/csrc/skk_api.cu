@@ -832,17 +832,16 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
             joined = true;
         }
-        if (sharded) {
-            if (bt == 4)
-                skk_theta_kernel<T, 4, false><<<theta_blocks, 256, 0, st>>>(rp, th, out_logp, out_grad);
-            else
-                skk_theta_kernel<T, 1, false><<<theta_blocks, 256, 0, st>>>(rp, th, out_logp, out_grad);
+        rp.batch_total = batch;
+        const int mode = !sharded ? 0 : (pl->peer_ready ? 2 : 1);
+#define SKK_THETA(BTV, MODEV) \
+    skk_theta_kernel<T, BTV, MODEV><<<theta_blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad)
+        if (bt == 4) {
+            if (mode == 0) SKK_THETA(4, 0); else if (mode == 1) SKK_THETA(4, 1); else SKK_THETA(4, 2);
         } else {
-            if (bt == 4)
-                skk_theta_kernel<T, 4, true><<<theta_blocks, 256, 0, st>>>(rp, th, out_logp, out_grad);
-            else
-                skk_theta_kernel<T, 1, true><<<theta_blocks, 256, 0, st>>>(rp, th, out_logp, out_grad);
+            if (mode == 0) SKK_THETA(1, 0); else if (mode == 1) SKK_THETA(1, 1); else SKK_THETA(1, 2);
         }
+#undef SKK_THETA
         ++launches;
         b0 += b_valid;
     }
@@ -853,8 +852,6 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
                        pl->sigma_idx, pl->sigma_const, pl->family, pl->include_priors};
         dim3 grid((unsigned)std::max<size_t>(1, (P + 255) / 256), (unsigned)batch);
         if (pl->peer_ready) {
-            skk_peer_push_kernel<<<1, 1024, 0, st>>>(pl->peer, pl->lik_vec, (int64_t)batch * (int64_t)(P + 2));
-            ++launches;
             if (priors && fork) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
             skk_final_kernel<T, true><<<grid, 256, 0, st>>>(fp, pl->peer, th, out_logp, out_grad);
         } else {
@@ -1199,7 +1196,7 @@ int skk_peer_init(skk_plan *pl, const void *handles, int32_t rank, int32_t nrank
         pp.peer_flag[r] = reinterpret_cast<unsigned long long *>(static_cast<double *>(base) + (size_t)2 * nranks * stride);
     }
     unsigned long long *words = nullptr;
-    if (int rc = dev_alloc(pl, &words, 2, true)) return rc;
+    if (int rc = dev_alloc(pl, &words, 2, true)) return rc;  // seq | done[0], done[1]
     pp.seq = words;
     pp.done = reinterpret_cast<unsigned int *>(words + 1);
     CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&pl->peer_status), sizeof(int), cudaHostAllocMapped));

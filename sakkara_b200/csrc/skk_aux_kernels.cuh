@@ -192,6 +192,7 @@ struct ReduceParams {
     int64_t n_primary, n_secondary;
     int32_t ng, np, ns;
     int32_t bt, b0, b_valid;
+    int32_t batch_total;        // chains of the whole evaluation (the last batch tile publishes)
     int32_t grid;               // CTAs of the row kernel
     int32_t blocks_p, blocks_s; // CTAs of the slot-total kernel working on the primary / secondary level
     double logp_const;
@@ -294,17 +295,63 @@ __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_consta
     }
 }
 
+// ---- one-shot all-reduce over NVLink peer memory ----------------------------------------------
+// Every rank owns a buffer of 2 (parity) x R slots of `stride` doubles plus R flags, mapped into
+// all peers with CUDA IPC.  Evaluation number seq (1, 2, ...):
+//   push : the theta kernel stores the rank's vector straight into slot [seq & 1][rank] of EVERY
+//          peer (plain stores over NVLink); its last CTA fences and stores flag[rank] = seq on every peer;
+//   final: every rank waits until all R flags of its own buffer reach seq and adds the R slots in
+//          rank order -- the same order everywhere, so all ranks obtain bit-identical results.
+// A rank can be at most one evaluation ahead of a peer (it needs that peer's flag to finish), hence
+// two parities suffice.  Spins are bounded: on timeout a status word in mapped host memory is set
+// and the kernel carries on, so a lost peer can never hang the GPU.
+constexpr int kMaxPeers = 8;
+struct PeerParams {
+    double *peer_buf[kMaxPeers];              // peer_buf[r]: rank r's buffer as seen from this rank
+    unsigned long long *peer_flag[kMaxPeers]; // rank r's flags
+    unsigned long long *seq;                  // this rank's evaluation counter (device)
+    unsigned int *done;                       // [0] CTAs of the final kernel that have read their slots,
+                                              // [1] CTAs of the theta kernel that have stored theirs
+    int *status;                              // mapped host word, != 0 after a timeout
+    int64_t stride;                           // doubles per slot
+    int32_t rank, nranks;
+};
+
+// waits until every peer's vector of this evaluation has arrived (called by all threads of a CTA)
+__device__ __forceinline__ unsigned long long peer_wait(const PeerParams &pp) {
+    const unsigned long long seq = *pp.seq + 1;
+    if (threadIdx.x < pp.nranks) {
+        volatile unsigned long long *flag = pp.peer_flag[pp.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        while (*flag < seq) {
+            if (clock64() - t0 > (1ll << 36)) {  // ~35 s: report and go on
+                *pp.status = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    return seq;
+}
+
 // What the last step does with the likelihood gradient of one theta element.
-template <typename T, int BT, bool FUSED>
-__device__ __forceinline__ void finish_element(const ReduceParams &rp, const T *__restrict__ theta,
+// MODE 0: single GPU, the final combination; 1: hand lik_vec to ncclAllReduce; 2: store the value
+// into this rank's slot of every peer (one-shot all-reduce, see above)
+template <typename T, int BT, int MODE>
+__device__ __forceinline__ void finish_element(const ReduceParams &rp, const PeerParams &pp, const T *__restrict__ theta,
                                                T *__restrict__ out_grad, int64_t j, const double (&lik)[BT]) {
     const int64_t P = rp.n_params;
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
         if (b >= rp.b_valid) continue;
         const int64_t row = rp.b0 + b;
-        if constexpr (!FUSED) {
+        if constexpr (MODE == 1) {
             rp.lik_vec[row * (P + 2) + j] = lik[b];
+        } else if constexpr (MODE == 2) {
+            const unsigned long long seq = *pp.seq + 1;
+            const int64_t at = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride + row * (P + 2) + j;
+            for (int r = 0; r < pp.nranks; ++r) pp.peer_buf[r][at] = lik[b];
         } else {
             double g = lik[b];
             if (rp.family == SKK_LIK_NORMAL) {
@@ -323,11 +370,12 @@ __device__ __forceinline__ void finish_element(const ReduceParams &rp, const T *
 
 // K4f: CTAs [0, theta_blocks): one thread per theta element (elements fed by at most one slot);
 // the following CTAs: one warp per element fed by several slots (lane-strided, fixed tree).
-// CTA 0 also produces logp.  FUSED: write the final outputs; else: write lik_vec for the all-reduce.
-template <typename T, int BT, bool FUSED>
+// CTA 0 also produces logp (MODE 0) or the two scalar entries of the exchanged vector.  In MODE 2
+// the last CTA to finish raises this rank's flag on every peer.
+template <typename T, int BT, int MODE>
 __global__ void __launch_bounds__(256)
-skk_theta_kernel(const __grid_constant__ ReduceParams rp, const T *__restrict__ theta, T *__restrict__ out_logp,
-                 T *__restrict__ out_grad) {
+skk_theta_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp,
+                 const T *__restrict__ theta, T *__restrict__ out_logp, T *__restrict__ out_grad) {
     const int lane = threadIdx.x & 31;
     const int64_t P = rp.n_params;
     if ((int)blockIdx.x < rp.theta_blocks) {
@@ -338,11 +386,11 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const T *__restrict__ 
                 double lik[BT];
 #pragma unroll
                 for (int b = 0; b < BT; ++b) lik[b] = unit >= 0 ? rp.totals[(int64_t)unit * BT + b] : 0.0;
-                finish_element<T, BT, FUSED>(rp, theta, out_grad, j, lik);
+                finish_element<T, BT, MODE>(rp, pp, theta, out_grad, j, lik);
             }
         }
         if (blockIdx.x == 0) {
-            if constexpr (FUSED) {
+            if constexpr (MODE == 0) {
                 // logp: CTA partials of the prior kernel in fixed order (strided per thread, fixed tree)
                 __shared__ double part[8];
                 for (int b = 0; b < rp.b_valid; ++b) {
@@ -371,16 +419,26 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const T *__restrict__ 
                 }
             } else if (threadIdx.x == 0) {
                 for (int b = 0; b < rp.b_valid; ++b) {
-                    double *row = rp.lik_vec + (int64_t)(rp.b0 + b) * (P + 2);
-                    row[P] = rp.totals[rp.ng * BT + b];  // likelihood logp partial
-                    row[P + 1] = rp.logp_const;
+                    const int64_t row = rp.b0 + b;
+                    const double L = rp.totals[rp.ng * BT + b];  // likelihood logp partial
+                    if constexpr (MODE == 1) {
+                        rp.lik_vec[row * (P + 2) + P] = L;
+                        rp.lik_vec[row * (P + 2) + P + 1] = rp.logp_const;
+                    } else {
+                        const unsigned long long seq = *pp.seq + 1;
+                        const int64_t at = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride + row * (P + 2);
+                        for (int r = 0; r < pp.nranks; ++r) {
+                            pp.peer_buf[r][at + P] = L;
+                            pp.peer_buf[r][at + P + 1] = rp.logp_const;
+                        }
+                    }
                 }
             }
         }
     } else {
         const int64_t m = ((int64_t)blockIdx.x - rp.theta_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        if (m >= rp.n_multi) return;
-        const int64_t lo = rp.multi_ptr[m], hi = rp.multi_ptr[m + 1];
+        const bool have = m < rp.n_multi;
+        const int64_t lo = have ? rp.multi_ptr[m] : 0, hi = have ? rp.multi_ptr[m + 1] : 0;
         double acc[BT];
 #pragma unroll
         for (int b = 0; b < BT; ++b) acc[b] = 0.0;
@@ -392,67 +450,25 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const T *__restrict__ 
         double lik[BT];
 #pragma unroll
         for (int b = 0; b < BT; ++b) lik[b] = __shfl_sync(kFull, warp_sum(acc[b]), 0);
-        if (lane == 0) finish_element<T, BT, FUSED>(rp, theta, out_grad, rp.multi_elem[m], lik);
+        if (lane == 0 && have) finish_element<T, BT, MODE>(rp, pp, theta, out_grad, rp.multi_elem[m], lik);
     }
-}
-
-// ---- one-shot all-reduce over NVLink peer memory ----------------------------------------------
-// Every rank owns a buffer of 2 (parity) x R slots of `stride` doubles plus R flags, mapped into
-// all peers with CUDA IPC.  Evaluation number seq (1, 2, ...):
-//   push : the rank stores its vector into slot [seq & 1][rank] of EVERY peer (plain stores over
-//          NVLink), fences, then stores flag[rank] = seq on every peer;
-//   final: every rank waits until all R flags of its own buffer reach seq and adds the R slots in
-//          rank order -- the same order everywhere, so all ranks obtain bit-identical results.
-// A rank can be at most one evaluation ahead of a peer (it needs that peer's flag to finish), hence
-// two parities suffice.  Spins are bounded: on timeout a status word in mapped host memory is set
-// and the kernel carries on, so a lost peer can never hang the GPU.
-constexpr int kMaxPeers = 8;
-struct PeerParams {
-    double *peer_buf[kMaxPeers];              // peer_buf[r]: rank r's buffer as seen from this rank
-    unsigned long long *peer_flag[kMaxPeers]; // rank r's flags
-    unsigned long long *seq;                  // this rank's evaluation counter (device)
-    unsigned int *done;                       // CTAs of the final kernel that have read their slots
-    int *status;                              // mapped host word, != 0 after a timeout
-    int64_t stride;                           // doubles per slot
-    int32_t rank, nranks;
-};
-
-static __global__ void __launch_bounds__(1024) skk_peer_push_kernel(const __grid_constant__ PeerParams pp,
-                                                             const double *__restrict__ vec, int64_t n) {
-    const unsigned long long seq = *pp.seq + 1;
-    const int64_t slot = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride;
-    const int64_t n2 = n >> 1;
-    const double2 *src2 = reinterpret_cast<const double2 *>(vec);
-    for (int r = 0; r < pp.nranks; ++r) {
-        double *dst = pp.peer_buf[r] + slot;
-        double2 *dst2 = reinterpret_cast<double2 *>(dst);
-        for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) dst2[i] = src2[i];
-        if ((n & 1) && threadIdx.x == 0) dst[n - 1] = vec[n - 1];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < pp.nranks) {
-        volatile unsigned long long *flag = pp.peer_flag[threadIdx.x] + pp.rank;
-        *flag = seq;
-    }
-}
-
-// waits until every peer's vector of this evaluation has arrived (called by all threads of a CTA)
-__device__ __forceinline__ unsigned long long peer_wait(const PeerParams &pp) {
-    const unsigned long long seq = *pp.seq + 1;
-    if (threadIdx.x < pp.nranks) {
-        volatile unsigned long long *flag = pp.peer_flag[pp.rank] + threadIdx.x;
-        const long long t0 = clock64();
-        while (*flag < seq) {
-            if (clock64() - t0 > (1ll << 36)) {  // ~35 s: report and go on
-                *pp.status = 1;
-                break;
+    if constexpr (MODE == 2) {
+        // every store of this CTA is visible system-wide before the CTA counts itself done; the last
+        // CTA of the last batch tile then publishes the vector by raising the flags
+        __threadfence_system();
+        __syncthreads();
+        __shared__ bool last;
+        if (threadIdx.x == 0) last = atomicAdd(pp.done + 1, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (last) {
+            if (threadIdx.x == 0) pp.done[1] = 0;
+            if (rp.b0 + rp.b_valid >= rp.batch_total && threadIdx.x < pp.nranks) {
+                __threadfence_system();
+                volatile unsigned long long *flag = pp.peer_flag[threadIdx.x] + pp.rank;
+                *flag = *pp.seq + 1;
             }
         }
     }
-    __syncthreads();
-    __threadfence_system();
-    return seq;
 }
 
 // ---- K4b (sharded runs: after the all-reduce) ------------------------------------------------
