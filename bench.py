@@ -99,7 +99,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.device}', f'--query-gpu={self.QUERY}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -328,7 +328,7 @@ def main():
         return [s.elapsed_time(e) for s, e in zip(starts, ends)] if timed else None
 
     # ---- device-resident timing: W warm-up steps, then exactly K timed steps -------------------------
-    sampler = ClockSampler(local)       # samples every 100 ms from the warm-up to the end of all timed loops
+    sampler = ClockSampler(local)       # samples every 20 ms from the warm-up to the end of all timed loops
     sampler.start()
     device_steps(args.warmup, False)
     launches0 = skk.stats()['launches']
