@@ -37,8 +37,7 @@ extern "C" {
 #define SKK_ERR_INVALID (-1)     /* malformed descriptor / argument */
 #define SKK_ERR_UNSUPPORTED (-2) /* model shape outside what the kernels cover */
 #define SKK_ERR_CUDA (-3)        /* CUDA runtime failure, including "no device" */
-#define SKK_ERR_NCCL (-4)        /* NCCL failure or libnccl not loadable */
-#define SKK_ERR_NOMEM (-5)
+#define SKK_ERR_NCCL (-4)        /* collective failure: NCCL error, libnccl not loadable, peer time-out */
 
 /* floating type of data, theta and results (pytensor.config.floatX on the reference side) */
 #define SKK_F32 0

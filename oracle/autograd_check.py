@@ -8,7 +8,6 @@ with autograd.  It shares no code with the plan lowering nor with the closed-for
 the NumPy oracle, so agreement between the two pins the lowering (theta layout, gather
 composition, linearisation) and the hand-derived derivatives of SURVEY.md §A at once.
 """
-import math
 
 import numpy as np
 import torch

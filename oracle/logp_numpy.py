@@ -24,7 +24,7 @@ PyMC call sites in the reference that this restates: ``sakkara/model/utils.py:31
 ``sakkara/model/fixed/data.py:41`` (``pm.ConstantData``), ``sakkara/relation/representation.py:253``
 (advanced indexing), ``README.md:34`` (``pm.sample`` -> ``logp_dlogp_function`` per leapfrog step).
 """
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 from scipy.special import gammaln

@@ -9,7 +9,6 @@
 
 namespace skk {
 
-constexpr int kWarp = 32;
 constexpr int kMaxXCols = 6;      // float data columns a plan may stage (besides y / offset)
 constexpr int kMaxTermsPerLevel = 2;
 constexpr unsigned kFull = 0xffffffffu;
@@ -111,10 +110,6 @@ __device__ __forceinline__ void fence_proxy_async() {
 // ---------------------------------------------------------------------------------------------
 // warp primitives (all reductions use a fixed tree => bit-reproducible)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double shfl_down_f64(double v, int delta) {
-    return __shfl_down_sync(kFull, v, delta);
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(kFull, v, d);
@@ -152,8 +147,8 @@ __device__ __forceinline__ bool warp_match_sum(bool has, int key, double (&v)[NV
 
 // Same contract for keys that are non-decreasing along the participating lanes (equal keys occupy
 // consecutive lanes): a fixed five-step shuffle tree, no loops and no divergence.
-template <int NV>
-__device__ __forceinline__ bool warp_sorted_run_sum(bool has, int key, double (&v)[NV]) {
+template <typename V, int NV>
+__device__ __forceinline__ bool warp_sorted_run_sum(bool has, int key, V (&v)[NV]) {
     const int lane = threadIdx.x & 31;
     const int k = has ? key : -1 - lane;  // lanes without a value never merge with a neighbour
 #pragma unroll
@@ -162,7 +157,7 @@ __device__ __forceinline__ bool warp_sorted_run_sum(bool has, int key, double (&
         const bool take = (lane + d < 32) && (other == k);
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
-            const double w = __shfl_down_sync(kFull, v[q], d);
+            const V w = __shfl_down_sync(kFull, v[q], d);
             if (take) v[q] += w;
         }
     }

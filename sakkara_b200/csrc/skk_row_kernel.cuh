@@ -453,7 +453,7 @@ struct RowKernel {
                     }
                     // first-run keys ascend with the lane and equal keys sit in consecutive lanes; a last
                     // run that began inside its lane is the only pending piece of its group in this round
-                    const bool leader = round == 0 ? warp_sorted_run_sum<NPa * BT>(has, key, v) : has;
+                    const bool leader = round == 0 ? warp_sorted_run_sum<double, NPa * BT>(has, key, v) : has;
                     if (leader) {
                         if (staged) {
 #pragma unroll
@@ -497,14 +497,16 @@ struct RowKernel {
         if constexpr (NS > 0) {
             double v[NSa * BT];
             if constexpr (FASTP) {
-                // codes ascend with the lane: one sorted-run sum, the first lane of each run updates the table
+                // codes ascend with the lane: one sorted-run sum (in the table's own type), the first
+                // lane of each run updates the table
                 __syncwarp();
+                T w[NSa * BT];
 #pragma unroll
-                for (int k = 0; k < NS * BT; ++k) v[k] = (double)accS[k / BT][k % BT];
-                if (warp_sorted_run_sum<NSa * BT>(nvalid > 0, scur, v)) {
+                for (int k = 0; k < NS * BT; ++k) w[k] = accS[k / BT][k % BT];
+                if (warp_sorted_run_sum<T, NSa * BT>(nvalid > 0, scur, w)) {
 #pragma unroll
                     for (int k = 0; k < NS * BT; ++k)
-                        gradS[((int64_t)(k / BT) * p.n_secondary + scur) * BT + (k % BT)] += (T)v[k];
+                        gradS[((int64_t)(k / BT) * p.n_secondary + scur) * BT + (k % BT)] += w[k];
                 }
                 __syncwarp();
             } else {
@@ -539,22 +541,21 @@ struct RowKernel {
     static __device__ __forceinline__ void issue_tile(const RowParams<T> &p, int tile, unsigned char *stage,
                                                       const StageLayout &sl, uint64_t *bar) {
         const int64_t row = (int64_t)tile * WT;
-        const uint32_t ybytes = p.y8 ? WT : WT * (uint32_t)sizeof(T);
-        uint32_t total = (uint32_t)p.n_x * WT * (uint32_t)sizeof(T) + ybytes;
-        if (p.eta_offset) total += WT * (uint32_t)sizeof(T);
-        if (NS > 0) total += WT * (uint32_t)p.sec_code_bytes;
-        mbar_arrive_expect_tx(bar, total);
-        for (int c = 0; c < p.n_x; ++c)
-            tma_load_1d(stage + c * sl.x_stride, p.x[c] + row, WT * (uint32_t)sizeof(T), bar);
-        if (p.y8)
+        const bool y_u8 = Spec::y_u8(p), has_off = Spec::has_off(p);
+        const uint32_t xbytes = WT * (uint32_t)sizeof(T);
+        const uint32_t ybytes = y_u8 ? WT : xbytes;
+        const uint32_t cbytes = NS > 0 ? WT * (Spec::code16(p) ? 2u : 4u) : 0u;
+        mbar_arrive_expect_tx(bar, (uint32_t)p.n_x * xbytes + ybytes + (has_off ? xbytes : 0u) + cbytes);
+        for (int c = 0; c < p.n_x; ++c) tma_load_1d(stage + c * sl.x_stride, p.x[c] + row, xbytes, bar);
+        if (y_u8)
             tma_load_1d(stage + sl.y_off, p.y8 + row, ybytes, bar);
         else
             tma_load_1d(stage + sl.y_off, p.y + row, ybytes, bar);
-        if (p.eta_offset) tma_load_1d(stage + sl.off_off, p.eta_offset + row, WT * (uint32_t)sizeof(T), bar);
+        if (has_off) tma_load_1d(stage + sl.off_off, p.eta_offset + row, xbytes, bar);
         if (NS > 0)
             tma_load_1d(stage + sl.code_off,
-                        reinterpret_cast<const unsigned char *>(p.sec_codes) + row * p.sec_code_bytes,
-                        WT * (uint32_t)p.sec_code_bytes, bar);
+                        reinterpret_cast<const unsigned char *>(p.sec_codes) + row * (Spec::code16(p) ? 2 : 4), cbytes,
+                        bar);
     }
 
     // values of the primary terms at a tile's first slot (their theta elements ride in the tile meta)

@@ -11,7 +11,6 @@ reference relies on, so it is kept.  What differs is what a built ``variable`` i
 small symbolic graph that the plan lowering consumes, not a PyTensor variable.
 """
 import operator
-import warnings
 from itertools import chain
 from typing import Any, Callable, Dict, Optional, Set, Tuple, Union
 

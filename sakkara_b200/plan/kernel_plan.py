@@ -22,7 +22,7 @@ Decisions taken here:
   uint8; identical data columns are stored once.
 """
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import pandas as pd

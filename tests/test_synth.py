@@ -1,5 +1,4 @@
 """The direct plan builders of sakkara_b200.synth produce what build() lowers from the DSL models."""
-import numpy as np
 import pandas as pd
 
 from golden.plan_io import assert_same, plan_to_arrays
@@ -12,11 +11,6 @@ def _dsl(df, make):
     return plan_to_arrays(build_model((df, make)).plan)
 
 
-def _drop_names(arrays):
-    """direct plans carry the same structure; only variable names of the zoo models may differ"""
-    return arrays
-
-
 def test_linreg_plan_equals_dsl():
     cols, _ = synth.linreg_columns(500, 13, seed=7)
     df = pd.DataFrame(cols)
@@ -24,9 +18,6 @@ def test_linreg_plan_equals_dsl():
 
 
 def test_logistic_plan_equals_dsl():
-    import sakkara_b200.model as api
-    from sakkara_b200.model import dist as pm
-
     cols, _ = synth.logistic_columns(800, 5, 4, seed=7)
     df = pd.DataFrame(cols)
 
