@@ -518,12 +518,12 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             return fail(SKK_ERR_UNSUPPORTED, "secondary level with %lld members does not fit in shared memory",
                         (long long)pl->n_secondary);
     }
-    // two resident CTAs per SM hide more latency than a third pipeline stage
+    // resident CTAs per SM hide more latency than a third pipeline stage: prefer the depth that fits more CTAs
     if (!getenv("SKK_STAGES") && pl->stages > 2) {
         const int per_sm = (int)prop.sharedMemPerMultiprocessor;
-        if (2 * (cta_smem<T>(pl, pl->warps, pl->stages, 1) + 1024) > per_sm &&
-            2 * (cta_smem<T>(pl, pl->warps, 2, 1) + 1024) <= per_sm)
-            pl->stages = 2;
+        // (the kernels are compiled for two CTAs per SM: 128 registers x 256 threads)
+        auto fit = [&](int stages) { return std::min(2, per_sm / (cta_smem<T>(pl, pl->warps, stages, 1) + 1024)); };
+        if (fit(2) > fit(pl->stages)) pl->stages = 2;
     }
     if (int rc = configure_launch<T>(pl, 1, &pl->cfg1)) return rc;
     if (bt_max == 4)

@@ -8,6 +8,8 @@
 namespace skk {
 
 constexpr int kRowsPerLane = 17;  // R: odd => conflict-free lane-strided shared-memory reads
+                                  // (R = 9 with three resident CTAs per SM measured slower on the crossed model:
+                                  //  the per-tile work does not shrink with the tile, profiles/README.md)
 
 // spec bits (see RowSpec): x columns of global / primary / secondary terms, y as uint8, 16-bit codes
 constexpr int kSpecXG0 = 1, kSpecXP0 = 4, kSpecY8 = 64, kSpecCode16 = 256;
