@@ -102,6 +102,19 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
         : "memory");
 }
 
+// One lane of a converged warp, chosen by the hardware (SASS ELECT): unlike `lane == 0` the
+// predicate is warp-uniform for the compiler, so the address arithmetic of the TMA issue that
+// follows stays in the uniform datapath.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // order generic-proxy accesses to shared memory before later async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

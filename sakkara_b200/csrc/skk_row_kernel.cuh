@@ -595,7 +595,7 @@ struct RowKernel {
         }
         __syncwarp();
         // start the pipeline before touching anything else
-        if (lane == 0) {
+        if (elect_one()) {
             for (int s = 0; s < stages; ++s) {
                 const int t = tile_begin + warp + s * warps;
                 if (t < tile_end) issue_tile(p, t, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
@@ -679,9 +679,11 @@ struct RowKernel {
 
             __syncwarp();
             const int next = tile + stages * warps;
-            if (lane == 0 && next < tile_end) {
-                fence_proxy_async();
-                issue_tile(p, next, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
+            if (next < tile_end) {
+                if (elect_one()) {
+                    fence_proxy_async();
+                    issue_tile(p, next, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
+                }
             }
             k0 = k1;
             k1 = k2;
