@@ -139,6 +139,14 @@ struct RowKernel {
         int kf, kl;
     };
 
+    // position of (term t, code, chain b) in the shared-memory tables of the secondary level
+    static __device__ __forceinline__ int s_at(const RowParams<T> &p, int t, int code, int b) {
+        if constexpr (NS <= 1)
+            return code * BT + b;  // one term: no multiplication by the table length
+        else
+            return (t * p.n_secondary + code) * BT + b;
+    }
+
     // theta[chain b of the batch tile][element]; chains beyond b_valid repeat chain 0 (results discarded)
     static __device__ __forceinline__ T theta_at(const RowParams<T> &p, int b, int element) {
         return p.theta[(int64_t)(b < p.b_valid ? b : 0) * p.n_params + element];
@@ -323,7 +331,7 @@ struct RowKernel {
                     for (int t = 0; t < NS; ++t)
 #pragma unroll
                         for (int b = 0; b < BT; ++b) {
-                            T *slot = gradS + ((int64_t)t * p.n_secondary + scur) * BT + b;
+                            T *slot = gradS + s_at(p, t, scur, b);
                             const T updated = *slot + accS[t][b];
                             if (change) *slot = updated;
                         }
@@ -341,7 +349,7 @@ struct RowKernel {
                         for (int t = 0; t < NS; ++t)
 #pragma unroll
                             for (int b = 0; b < BT; ++b)
-                                gradS[((int64_t)t * p.n_secondary + scur) * BT + b] += (T)v[t * BT + b];
+                                gradS[s_at(p, t, scur, b)] += (T)v[t * BT + b];
                     }
                     __syncwarp();
                     if (change && !s_changed) {
@@ -364,7 +372,7 @@ struct RowKernel {
 #pragma unroll
                 for (int t = 0; t < NS; ++t)
 #pragma unroll
-                    for (int b = 0; b < BT; ++b) vs[t][b] = valS[((int64_t)t * p.n_secondary + c) * BT + b];
+                    for (int b = 0; b < BT; ++b) vs[t][b] = valS[s_at(p, t, c, b)];
             }
 
             // data of the row
