@@ -157,7 +157,7 @@ struct RowKernel {
     static __device__ __forceinline__ void process(const RowParams<T> &p, const Tile &tl, const T (&vp_first)[NPa][BT],
                                                    const int (&staged_element)[NPa],
                                                    const T (&vg)[NGa][BT], double (&accG64)[NG + 1][BT],
-                                                   const T *__restrict__ valS, T *__restrict__ gradS,
+                                                   const T *__restrict__ valS, T *__restrict__ gradS, uint32_t gradS_addr,
                                                    unsigned char *scratch, int lane) {
         const int li = lane * R;
         const int64_t row0 = (int64_t)tl.tile * WT + li;
@@ -331,9 +331,9 @@ struct RowKernel {
                     for (int t = 0; t < NS; ++t)
 #pragma unroll
                         for (int b = 0; b < BT; ++b) {
-                            T *slot = gradS + s_at(p, t, scur, b);
-                            const T updated = *slot + accS[t][b];
-                            if (change) *slot = updated;
+                            const uint32_t slot = gradS_addr + (uint32_t)s_at(p, t, scur, b) * (uint32_t)sizeof(T);
+                            const T updated = lds(slot, T(0)) + accS[t][b];
+                            if (change) sts(slot, updated);
                         }
                 } else {
                     // the tile straddles primary segments: a code may occur in several runs of the
@@ -578,7 +578,9 @@ struct RowKernel {
     static __device__ void run(const RowParams<T> &p) {
         extern __shared__ __align__(128) unsigned char smem[];
         const int warps = blockDim.x >> 5;
-        const int warp = threadIdx.x >> 5;
+        // broadcast from lane 0: provably warp-uniform, so everything derived from it (the warp's
+        // barriers, staging ring, scratch and accumulator table) can live in uniform registers
+        const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
         const int lane = threadIdx.x & 31;
         const int stages = p.stages;
 
@@ -589,6 +591,10 @@ struct RowKernel {
         T *valS = reinterpret_cast<T *>(smem + cl.vals_off);
         T *gradS_all = reinterpret_cast<T *>(smem + cl.grads_off);
         T *gradS = gradS_all + (int64_t)warp * NS * p.n_secondary * BT;
+        // the table base as a 32-bit shared address pinned in a register: without the opaque move the
+        // compiler re-derives warp * n_secondary in every row of the unrolled loop
+        uint32_t gradS_addr = smem_addr(gradS);
+        asm volatile("mov.u32 %0, %0;" : "+r"(gradS_addr));
         unsigned char *stage0 = smem + cl.stage_off + (int64_t)warp * stages * sl.bytes;
         unsigned char *scratch = smem + cl.scratch_off + warp * cl.scratch_bytes;
 
@@ -678,11 +684,11 @@ struct RowKernel {
             const bool full = (int64_t)(tile + 1) * WT <= p.n_rows;
             if (NP == 0 || k0.x == k0.y) {
                 if (full)
-                    process<true, true>(p, tl, vp0, se0, vg, accG64, valS, gradS, scratch, lane);
+                    process<true, true>(p, tl, vp0, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
                 else
-                    process<true, false>(p, tl, vp0, se0, vg, accG64, valS, gradS, scratch, lane);
+                    process<true, false>(p, tl, vp0, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
             } else {
-                process<false, false>(p, tl, vp0, se0, vg, accG64, valS, gradS, scratch, lane);
+                process<false, false>(p, tl, vp0, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
             }
 
             __syncwarp();
