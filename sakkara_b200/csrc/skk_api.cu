@@ -149,6 +149,7 @@ struct skk_plan {
     void *x[kMaxXCols] = {nullptr};
     void *y = nullptr, *off = nullptr, *codes = nullptr;
     int4 *tile_meta = nullptr;
+    int32_t *tile_split = nullptr;
     int64_t *seg_off = nullptr;
     int n_terms = 0;
 
@@ -362,6 +363,12 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             meta[t] = make_int4(keys[t].x, keys[t].y, host_ti_p[0] ? host_ti_p[0][keys[t].x] : 0,
                                 host_ti_p[1] ? host_ti_p[1][keys[t].x] : 0);
         if (int rc = dev_upload(pl, &pl->tile_meta, meta.data(), meta.size())) return rc;
+        // tiles that hold exactly two groups: where the second one starts (row inside the tile)
+        std::vector<int32_t> split(keys.size(), -1);
+        if (d->n_primary > 0)
+            for (int t = 0; t < pl->n_tiles; ++t)
+                if (keys[t].y == keys[t].x + 1) split[t] = (int32_t)(seg[keys[t].y] - (int64_t)t * WT);
+        if (int rc = dev_upload(pl, &pl->tile_split, split.data(), split.size())) return rc;
     }
 
     // theta element -> units of the `totals` buffer ([NG+1 global | NP*GP primary | NS*GS secondary])
@@ -683,6 +690,7 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
     rp.n_tiles = pl->n_tiles;
     rp.stages = pl->stages;
     rp.tile_meta = pl->tile_meta;
+    rp.tile_split = pl->tile_split;
     rp.seg_offsets = pl->seg_off;
     rp.n_primary = (int32_t)pl->n_primary;
     rp.n_secondary = (int32_t)pl->n_secondary;

@@ -33,6 +33,8 @@ struct RowParams {
     int32_t stages;          // smem ring depth per warp
     // structure
     const int4 *tile_meta;   // per tile {first, last primary slot, theta element of primary term 0 / 1 at the first slot}
+    const int32_t *tile_split;  // per tile: row (inside the tile) where its second group starts when the tile
+                                // holds exactly two groups, else -1
     const int64_t *seg_offsets;  // [n_primary + 1]
     int32_t n_primary;
     int32_t n_secondary;

@@ -153,8 +153,11 @@ struct RowKernel {
     }
 
     // -----------------------------------------------------------------------------------------
-    template <bool FASTP, bool FULL>
+    // FASTP: no per-row segment bookkeeping (the tile lies in one segment, or -- MID -- in exactly two:
+    // rows from `split` on belong to the second group, whose values are vp_second)
+    template <bool FASTP, bool FULL, bool MID = false>
     static __device__ __forceinline__ void process(const RowParams<T> &p, const Tile &tl, const T (&vp_first)[NPa][BT],
+                                                   const T (&vp_second)[NPa][BT], int split,
                                                    const int (&staged_element)[NPa],
                                                    const T (&vg)[NGa][BT], double (&accG64)[NG + 1][BT],
                                                    const T *__restrict__ valS, T *__restrict__ gradS, uint32_t gradS_addr,
@@ -188,7 +191,11 @@ struct RowKernel {
         const bool code16 = Spec::code16(p);
 
         // per-span accumulators in T; folded into fp64 at run / span boundaries
-        T accL[BT], accG[NGa][BT], accP[NPa][BT], accS[NSa][BT];
+        T accL[BT], accG[NGa][BT], accP[NPa][BT], accS[NSa][BT], accP2[NPa][BT];
+#pragma unroll
+        for (int t = 0; t < NPa; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) accP2[t][b] = T(0);
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
             accL[b] = T(0);
@@ -392,7 +399,7 @@ struct RowKernel {
 #pragma unroll
                 for (int t = 0; t < NG; ++t) eta += vg[t][b] * xg[t];
 #pragma unroll
-                for (int t = 0; t < NP; ++t) eta += vp[t][b] * xp[t];
+                for (int t = 0; t < NP; ++t) eta += (MID && li + i >= split ? vp_second[t][b] : vp[t][b]) * xp[t];
 #pragma unroll
                 for (int t = 0; t < NS; ++t) eta += vs[t][b] * xs[t];
                 T lp, d;
@@ -405,7 +412,15 @@ struct RowKernel {
 #pragma unroll
                 for (int t = 0; t < NG; ++t) accG[t][b] += d * xg[t];
 #pragma unroll
-                for (int t = 0; t < NP; ++t) accP[t][b] += d * xp[t];
+                for (int t = 0; t < NP; ++t) {
+                    if constexpr (MID) {
+                        const bool second = li + i >= split;
+                        accP[t][b] += second ? T(0) : d * xp[t];
+                        accP2[t][b] += second ? d * xp[t] : T(0);
+                    } else {
+                        accP[t][b] += d * xp[t];
+                    }
+                }
 #pragma unroll
                 for (int t = 0; t < NS; ++t) accS[t][b] += d * xs[t];
             }
@@ -428,6 +443,10 @@ struct RowKernel {
                     for (int b = 0; b < BT; ++b) {
                         const double s = warp_sum((double)accP[t][b]);
                         if (lane == 0) p.tile_head[((int64_t)tl.tile * NP + t) * BT + b] = s;
+                        if constexpr (MID) {
+                            const double s2 = warp_sum((double)accP2[t][b]);
+                            if (lane == 0) p.tile_tail[((int64_t)tl.tile * NP + t) * BT + b] = s2;
+                        }
                     }
             } else {
                 double *head = p.tile_head + (int64_t)tl.tile * NP * BT;
@@ -666,6 +685,24 @@ struct RowKernel {
         };
         int se0[NPa], se1[NPa];
         staged_elements(k0, se0);
+        // tiles with exactly two groups (and no secondary level) take the two-group path: the split row
+        // and the second group's values are fetched ahead like the first group's
+        int sp0 = -1, sp1 = -1;
+        T vq0[NPa][BT], vq1[NPa][BT];
+        auto load_second = [&](const int4 &meta, const int (&se)[NPa], T (&vq)[NPa][BT]) {
+#pragma unroll
+            for (int t = 0; t < NPa; ++t) {
+                const int element = __shfl_sync(kFull, se[t], 1);  // lane 1 holds the element of group kf + 1
+#pragma unroll
+                for (int b = 0; b < BT; ++b)
+                    vq[t][b] = (NP > 0 && NS == 0 && meta.y == meta.x + 1) ? theta_at(p, b, element) : T(0);
+            }
+        };
+        if constexpr (NP > 0 && NS == 0) {
+            if (tile < tile_end) sp0 = p.tile_split[tile];
+            if (tile + warps < tile_end) sp1 = p.tile_split[tile + warps];
+        }
+        load_second(k0, se0, vq0);
 
         for (int it = 0; tile < tile_end; tile += warps, ++it) {
             const int s = it % stages;
@@ -677,6 +714,11 @@ struct RowKernel {
             }
             load_vp(p, k1, vp1);
             staged_elements(k1, se1);
+            load_second(k1, se1, vq1);
+            int sp2 = -1;
+            if constexpr (NP > 0 && NS == 0) {
+                if (tile + 2 * warps < tile_end) sp2 = p.tile_split[tile + 2 * warps];
+            }
 
             mbar_wait(bars + s, parity);
 
@@ -684,11 +726,13 @@ struct RowKernel {
             const bool full = (int64_t)(tile + 1) * WT <= p.n_rows;
             if (NP == 0 || k0.x == k0.y) {
                 if (full)
-                    process<true, true>(p, tl, vp0, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
+                    process<true, true>(p, tl, vp0, vq0, -1, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
                 else
-                    process<true, false>(p, tl, vp0, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
+                    process<true, false>(p, tl, vp0, vq0, -1, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
+            } else if (NS == 0 && full && sp0 >= 0) {
+                process<true, true, true>(p, tl, vp0, vq0, sp0, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
             } else {
-                process<false, false>(p, tl, vp0, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
+                process<false, false>(p, tl, vp0, vq0, -1, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
             }
 
             __syncwarp();
@@ -701,8 +745,14 @@ struct RowKernel {
             }
             k0 = k1;
             k1 = k2;
+            sp0 = sp1;
+            sp1 = sp2;
 #pragma unroll
-            for (int t = 0; t < NPa; ++t) se0[t] = se1[t];
+            for (int t = 0; t < NPa; ++t) {
+                se0[t] = se1[t];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) vq0[t][b] = vq1[t][b];
+            }
 #pragma unroll
             for (int t = 0; t < NPa; ++t)
 #pragma unroll
