@@ -164,6 +164,7 @@ struct skk_plan {
     PriorParams prior{};
     ReduceParams reduce{};
     int prior_ctas = 0;
+    bool fused_ok = false;  // single-GPU evaluation = row kernel (with priors) + finish kernel
 
     void *h_in = nullptr, *h_out = nullptr;  // pinned staging
 
@@ -395,6 +396,10 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
         }
         k = e;
     }
+    std::vector<int32_t> multi_of(d->n_params, -1);
+    for (size_t m = 0; m < multi_elem.size(); ++m) multi_of[multi_elem[m]] = (int32_t)m;
+    int32_t *multi_of_dev = nullptr;
+    if (int rc = dev_upload(pl, &multi_of_dev, multi_of.data(), multi_of.size())) return rc;
     int32_t *single_dev = nullptr, *multi_elem_dev = nullptr, *multi_unit_dev = nullptr;
     int64_t *multi_ptr_dev = nullptr;
     if (int rc = dev_upload(pl, &single_dev, single_unit.data(), single_unit.size())) return rc;
@@ -509,6 +514,23 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
                             parent_dev, link_ptr_dev, (int32_t)parents.size(), n_heavy, d->n_params,
                             (int64_t)links.size(), 0};
     pl->prior_ctas = (int)((Pn + kPriorThreads - 1) / kPriorThreads);
+    // Single GPU, batches below the chain kernel's: the row kernel evaluates the prior terms in its
+    // prologue and one finish kernel does the rest.  That kernel finishes a hyper-parameter where it
+    // sums over its children, so no term may feed one (otherwise the separate kernels run).
+    std::vector<int32_t> none_elem;
+    {
+        std::vector<char> is_parent(Pn, 0);
+        pl->fused_ok = true;
+        for (const Parent &q : parents) {
+            is_parent[q.element] = 1;
+            if (single_unit[q.element] != -1 || (d->family == SKK_LIK_NORMAL && q.element == d->sigma_theta_index))
+                pl->fused_ok = false;
+        }
+        for (size_t j = 0; j < Pn; ++j)
+            if (single_unit[j] == -1 && !is_parent[j]) none_elem.push_back((int32_t)j);
+    }
+    int32_t *none_dev = nullptr;
+    if (int rc = dev_upload(pl, &none_dev, none_elem.data(), none_elem.size())) return rc;
 
     // ---- launch geometry -------------------------------------------------------------------------------------
     cudaDeviceProp prop;
@@ -552,7 +574,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     if (int rc = dev_alloc(pl, &pl->cta_sec, (size_t)grid_max * std::max(1, pl->ns) * std::max<int64_t>(1, d->n_secondary) * bt, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->lik_vec, B * (P + 2), true)) return rc;
     if (int rc = dev_alloc(pl, &pl->prior_grad, B * P, true)) return rc;
-    if (int rc = dev_alloc(pl, &pl->prior_lp, B * (size_t)(pl->prior_ctas + 1), true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->prior_lp, B * std::max<size_t>(pl->prior_ctas + 1, (size_t)grid_max * 8), true)) return rc;
     if (int rc = dev_alloc(pl, &pl->link_val, B * std::max<size_t>(1, links.size()), true)) return rc;
     if (int rc = dev_alloc(pl, &tmp, B * P + B, true)) return rc;
     pl->out_dev = tmp;
@@ -573,6 +595,27 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     rp.multi_ptr = multi_ptr_dev;
     rp.multi_unit = multi_unit_dev;
     rp.n_multi = (int32_t)multi_elem.size();
+    rp.none_elem = none_dev;
+    rp.n_none = (int32_t)none_elem.size();
+    rp.none_blocks = (int32_t)((none_elem.size() + 255) / 256);
+    {
+        unsigned int *ticket = nullptr;
+        if (int rc = dev_alloc(pl, &ticket, multi_elem.size() + 1, true)) return rc;
+        rp.ticket = ticket;
+        rp.multi_of = multi_of_dev;
+        rp.parent = pl->prior.parent;
+        rp.link_ptr = pl->prior.link_ptr;
+        rp.link_val = pl->link_val;
+        rp.n_links = pl->prior.n_links;
+        rp.n_parents = pl->prior.n_parents;
+        rp.n_heavy = pl->prior.n_heavy;
+        rp.parent_blocks = rp.n_heavy + (rp.n_parents - rp.n_heavy + 7) / 8;
+    }
+    for (int i = 0; i < d->n_terms; ++i) {
+        const int t = pl->term_slot_in_level[i];
+        (pl->term_level[i] == SKK_LEVEL_GLOBAL ? rp.ti_g : pl->term_level[i] == SKK_LEVEL_PRIMARY ? rp.ti_p : rp.ti_s)[t] =
+            pl->theta_index_dev[i];
+    }
     rp.theta_blocks = (int32_t)std::max<size_t>(1, (P + 255) / 256);
     rp.lik_vec = pl->lik_vec;
     rp.n_params = d->n_params;
@@ -628,13 +671,9 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             auto kind = [&](int c) { return rk[c].x == sl ? 1 : (rk[c].y == sl ? 2 : 0); };
             cdesc[sl] = make_int4(c_lo, c_hi, kind(c_lo), kind(c_hi));
         }
-        std::vector<int32_t> multi_of(P, -1);
-        for (size_t m = 0; m < multi_elem.size(); ++m) multi_of[multi_elem[m]] = (int32_t)m;
         int4 *cdesc_dev = nullptr;
-        int32_t *multi_of_dev = nullptr;
         if (int rc = dev_upload(pl, &pl->chain_keys, rk.data(), rk.size())) return rc;
         if (int rc = dev_upload(pl, &cdesc_dev, cdesc.data(), cdesc.size())) return rc;
-        if (int rc = dev_upload(pl, &multi_of_dev, multi_of.data(), multi_of.size())) return rc;
         const size_t bp = (size_t)pl->chain_bp;
         const size_t cunits = (size_t)(pl->ng + 1) + (size_t)pl->np * d->n_primary;
         if (int rc = dev_alloc(pl, &pl->chain_totals, cunits * bp, true)) return rc;
@@ -677,7 +716,8 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
 // evaluation
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *th, int b_valid, int bt) {
+static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *th, int b_valid, int bt, int b0,
+                       bool with_priors) {
     RowParams<T> rp{};
     for (int c = 0; c < pl->n_x; ++c) rp.x[c] = static_cast<const T *>(pl->x[c]);
     rp.y = pl->y_u8 ? nullptr : static_cast<const T *>(pl->y);
@@ -712,6 +752,20 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
     rp.tile_tail = pl->tile_tail;
     rp.cta_glob = pl->cta_glob;
     rp.cta_sec = pl->cta_sec;
+    if (with_priors) {
+        const PriorParams &pp = pl->prior;
+        rp.prior_family = pp.family;
+        rp.prior_a_src = pp.a_src;
+        rp.prior_b_src = pp.b_src;
+        rp.prior_e_mu = pp.e_mu;
+        rp.prior_e_sigma = pp.e_sigma;
+        rp.prior_a_const = pp.a_const;
+        rp.prior_b_const = pp.b_const;
+        rp.n_links = pp.n_links;
+        rp.prior_grad = pl->prior_grad + (size_t)b0 * pl->n_params;
+        rp.link_val = pl->link_val + (size_t)b0 * pp.n_links;
+        rp.prior_lp_part = pl->prior_lp + (size_t)b0 * cfg.grid * pl->warps;
+    }
     void *args[] = {&rp};
     if (timed) CUDA_TRY(cudaEventRecord(pl->evk0, pl->stream));
     CUDA_TRY(cudaLaunchKernel(cfg.fn, dim3(cfg.grid), dim3(pl->warps * 32), args, cfg.smem, pl->stream));
@@ -731,10 +785,13 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
 
     // K3: priors for the whole batch, next to the row kernel
     const bool priors = pl->include_priors && P > 0;
+    const bool chain = pl->chain_ready && batch >= kChainMinBatch && !sharded;
+    // single GPU, row kernel: the priors ride in the row kernel's prologue and one finish kernel follows
+    const bool fused = !sharded && !chain && pl->fused_ok && env_int("SKK_NO_FUSED_FINISH", 0) == 0;
     // (for large batches they are big enough to fill the GPU themselves: run them in line)
     const bool fork = batch < kChainMinBatch;
     cudaStream_t ps = fork ? pl->side : st;
-    if (priors) {
+    if (priors && !fused) {
         if (fork) {
             CUDA_TRY(cudaEventRecord(pl->ev_fork, st));
             CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
@@ -754,7 +811,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         if (fork) CUDA_TRY(cudaEventRecord(pl->ev_join, pl->side));
     }
 
-    if (pl->chain_ready && batch >= kChainMinBatch && !sharded) {
+    if (chain) {
         // K2: lane = chain; one pass over the rows for the whole batch
         ChainParams<T> cp{};
         for (int c = 0; c < pl->n_x; ++c) cp.x[c] = static_cast<const T *>(pl->x[c]);
@@ -815,18 +872,30 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         const int b_valid = std::min(bt, remaining);
         const LaunchCfg &cfg = wide ? pl->cfg4 : pl->cfg1;
         // K1: the rows
-        if (int rc = launch_rows<T>(pl, cfg, timed, th + (size_t)b0 * P, b_valid, bt)) return rc;
+        if (int rc = launch_rows<T>(pl, cfg, timed, th + (size_t)b0 * P, b_valid, bt, b0, fused && priors)) return rc;
         ++launches;
         pl->stats.row_kernel_launches++;
 
-        // K4a: totals per slot
+        // K4: totals per slot, then per theta element
         ReduceParams rp = pl->reduce;
         rp.bt = bt;
         rp.direct_p = bt == 4 ? pl->direct_p : pl->direct_p1;
         rp.b0 = b0;
         rp.b_valid = b_valid;
         rp.grid = cfg.grid;
+        rp.batch_total = batch;
         const unsigned slot_blocks = (unsigned)(rp.blocks_p + rp.blocks_s + 1);
+        if (fused) {
+            if (priors) rp.prior_ctas = cfg.grid * pl->warps;  // one logp partial per warp of the row kernel
+            const unsigned blocks = slot_blocks + (unsigned)(rp.parent_blocks + rp.none_blocks);
+            if (bt == 4)
+                skk_finish_kernel<T, 4><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
+            else
+                skk_finish_kernel<T, 1><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
+            ++launches;
+            b0 += b_valid;
+            continue;
+        }
         const unsigned theta_blocks = (unsigned)(rp.theta_blocks + (rp.n_multi + 7) / 8);
         if (bt == 4)
             skk_slot_total_kernel<4><<<slot_blocks, 256, 0, st>>>(rp);
@@ -839,7 +908,6 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
             joined = true;
         }
-        rp.batch_total = batch;
         const int mode = !sharded ? 0 : (pl->peer_ready ? 2 : 1);
 #define SKK_THETA(BTV, MODEV) \
     skk_theta_kernel<T, BTV, MODEV><<<theta_blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad)
@@ -869,7 +937,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             skk_final_kernel<T, false><<<grid, 256, 0, st>>>(fp, pl->peer, th, out_logp, out_grad);
         }
         ++launches;
-    } else if (priors && fork && !joined) {
+    } else if (priors && !fused && fork && !joined) {
         CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
     }
     CUDA_TRY(cudaGetLastError());

@@ -16,8 +16,6 @@
 
 namespace skk {
 
-constexpr double kLogSqrt2Pi = 0.91893853320467274178032973640562;
-constexpr double kLogSqrt2OverPi = -0.22579135264472743236309761494744;
 constexpr int kSerialLimit = 48;  // longer partial lists are summed by a whole warp
 
 // All 32 lanes cooperate on the long lists of the warp's lanes, one list at a time: lane-strided
@@ -94,24 +92,12 @@ skk_prior_kernel(const __grid_constant__ PriorParams pp, const T *__restrict__ t
         double lp = 0.0;
         if (valid) {
             const double v = (double)th[j];
-            double grad;
-            if (fam == SKK_PRIOR_NORMAL) {
-                const double mu = a_src >= 0 ? (double)th[a_src] : a_c;
-                const double sd = b_src >= 0 ? exp((double)th[b_src]) : b_c;
-                const double z = (v - mu) / sd;
-                lp = -0.5 * z * z - kLogSqrt2Pi - log(sd);
-                grad = -z / sd;
-                if (e_mu >= 0) link_val[(int64_t)b * pp.n_links + e_mu] = z / sd;           // d/d mu
-                if (e_sigma >= 0) link_val[(int64_t)b * pp.n_links + e_sigma] = z * z - 1.0;  // d/d log(sigma)
-            } else if (fam == SKK_PRIOR_HALFNORMAL) {
-                const double q = exp(v) / a_c;
-                lp = -0.5 * q * q + kLogSqrt2OverPi - log(a_c) + v;
-                grad = -q * q + 1.0;
-            } else {  // SKK_PRIOR_EXPONENTIAL
-                const double sv = exp(v);
-                lp = log(a_c) - a_c * sv + v;
-                grad = -a_c * sv + 1.0;
-            }
+            double grad, d_mu, d_log_sd;
+            const double a = a_src >= 0 ? (double)th[a_src] : a_c;
+            const double sd = b_src >= 0 ? exp((double)th[b_src]) : b_c;
+            lp = prior_term(fam, v, a, sd, grad, d_mu, d_log_sd);
+            if (e_mu >= 0) link_val[(int64_t)b * pp.n_links + e_mu] = d_mu;
+            if (e_sigma >= 0) link_val[(int64_t)b * pp.n_links + e_sigma] = d_log_sd;
             prior_grad[(int64_t)b * pp.n_params + j] = grad;
         }
         // logp of the priors: fixed tree per CTA; the CTA partials are added in order by the final kernel
@@ -205,6 +191,20 @@ struct ReduceParams {
     int64_t sigma_theta_index;  // -1: constant sigma
     double sigma_const;
     int32_t family;
+    // single-GPU fused finish (skk_finish_kernel)
+    const int32_t *ti_g[kMaxTermsPerLevel];  // slot -> theta element of every term
+    const int32_t *ti_p[kMaxTermsPerLevel];
+    const int32_t *ti_s[kMaxTermsPerLevel];
+    const int32_t *none_elem;   // theta elements that no term feeds and that have no children
+    int32_t n_none, none_blocks;
+    // hyper-parameters (elements with children in the priors; no term feeds them on this path)
+    const int32_t *parent;      // [n_parents] those with many children first (a CTA each, then a warp each)
+    const int64_t *link_ptr;    // [n_parents + 1] ranges of link_val
+    const double *link_val;     // [B][n_links] written by the row kernel's prior prologue
+    int64_t n_links;
+    int32_t n_parents, n_heavy, parent_blocks;
+    const int32_t *multi_of;    // [P] position in the multi list, -1
+    unsigned int *ticket;       // [n_multi] slots of a shared element that have stored their total
 };
 
 // blockIdx.x in [0, blocks_p): primary slots, one per thread;  [blocks_p, blocks_p + blocks_s):
@@ -340,7 +340,8 @@ __device__ __forceinline__ unsigned long long peer_wait(const PeerParams &pp) {
 // into this rank's slot of every peer (one-shot all-reduce, see above)
 template <typename T, int BT, int MODE>
 __device__ __forceinline__ void finish_element(const ReduceParams &rp, const PeerParams &pp, const T *__restrict__ theta,
-                                               T *__restrict__ out_grad, int64_t j, const double (&lik)[BT]) {
+                                               T *__restrict__ out_grad, int64_t j, const double (&lik)[BT],
+                                               const double *prior_extra = nullptr) {
     const int64_t P = rp.n_params;
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
@@ -362,7 +363,7 @@ __device__ __forceinline__ void finish_element(const ReduceParams &rp, const Pee
                 if (j == rp.sigma_theta_index)
                     g += rp.totals[rp.ng * BT + b] * scale - (double)rp.n_rows_total;  // sum(r^2 - 1)
             }
-            if (rp.include_priors) g += rp.prior_grad[row * P + j];
+            if (rp.include_priors) g += rp.prior_grad[row * P + j] + (prior_extra ? prior_extra[b] : 0.0);
             out_grad[row * P + j] = (T)g;
         }
     }
@@ -466,6 +467,242 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant_
                 __threadfence_system();
                 volatile unsigned long long *flag = pp.peer_flag[threadIdx.x] + pp.rank;
                 *flag = *pp.seq + 1;
+            }
+        }
+    }
+}
+
+// ---- K4 fused (single GPU): slot totals -> theta elements -> outputs in one launch ------------------
+// CTA classes by blockIdx.x: [0, blocks_p) primary slots (one per thread); then blocks_s CTAs of
+// secondary slots (32 per CTA x 8 ranges of row-kernel CTAs); one CTA for the global terms, logp and
+// the likelihood's sigma; parent_blocks CTAs for the hyper-parameters (sum over their children's
+// contributions, a CTA or a warp per element); none_blocks CTAs for the remaining elements.  A thread that
+// completes the total of a slot finishes the theta element fed by that slot alone.  An element fed by
+// several slots (a term on a parent of the sorted level) is finished by the thread that stores the
+// last of its slot totals (one ticket counter per element); it adds them in the fixed order of the
+// element's slot list, so the result does not depend on which thread that was.
+template <typename T, int BT>
+__global__ void __launch_bounds__(256)
+skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp,
+                  const T *__restrict__ theta, T *__restrict__ out_logp, T *__restrict__ out_grad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t P = rp.n_params;
+    double *prim_tot = rp.totals + (int64_t)(rp.ng + 1) * BT;
+    double *sec_tot = prim_tot + (int64_t)rp.np * rp.n_primary * BT;
+    // called by the thread that has just stored totals[unit] (= lik), the total of a slot of element j
+    auto finish_if_single = [&](int64_t j, int64_t unit, const double (&lik)[BT]) {
+        // (the likelihood's sigma needs the global sum of squares: finished by the global CTA)
+        if (rp.family == SKK_LIK_NORMAL && j == rp.sigma_theta_index) return;
+        const int32_t su = rp.single_unit[j];
+        if (su == (int32_t)unit) {
+            finish_element<T, BT, 0>(rp, pp, theta, out_grad, j, lik);
+        } else if (su == -2) {
+            const int32_t m = rp.multi_of[j];
+            const int64_t e0 = rp.multi_ptr[m], e1 = rp.multi_ptr[m + 1];
+            __threadfence();
+            if (atomicAdd(rp.ticket + m, 1u) != (unsigned)(e1 - e0 - 1)) return;
+            rp.ticket[m] = 0;
+            __threadfence();
+            double acc[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+#pragma unroll 4
+            for (int64_t e = e0; e < e1; ++e) {
+                const int64_t u = rp.multi_unit[e];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] += __ldcg(rp.totals + u * BT + b);
+            }
+            finish_element<T, BT, 0>(rp, pp, theta, out_grad, j, acc);
+        }
+    };
+    const int b_glob = rp.blocks_p + rp.blocks_s;
+    if ((int)blockIdx.x < rp.blocks_p) {
+        const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        const bool valid = slot < rp.n_primary;
+        int4 d = make_int4(0, -1, 0, 0);
+        if (valid) d = rp.slot_desc[slot];
+        const int64_t t_lo = d.x, t_hi = d.y;
+        const bool heavy = valid && (t_hi - t_lo + 1 > kSerialLimit);
+        auto addend = [&](int4 dd, int64_t tile, int t, int b) -> double {
+            const int kind = tile == dd.x ? dd.z : (tile == dd.y ? dd.w : 1);
+            const double *src = kind == 1 ? rp.tile_head : (kind == 2 ? rp.tile_tail : nullptr);
+            return src ? src[(tile * rp.np + t) * BT + b] : 0.0;
+        };
+        for (int t = 0; t < rp.np; ++t) {
+            const int64_t unit = (rp.ng + 1) + (int64_t)t * rp.n_primary + slot;
+            if (valid && !heavy) {
+                double acc[BT];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+                if (t_hi >= t_lo) {
+#pragma unroll
+                    for (int b = 0; b < BT; ++b)
+                        acc[b] = rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b] + addend(d, t_lo, t, b);
+#pragma unroll 4
+                    for (int64_t tile = t_lo + 1; tile < t_hi; ++tile)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) acc[b] += rp.tile_head[(tile * rp.np + t) * BT + b];
+                    if (t_hi > t_lo)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) acc[b] += addend(d, t_hi, t, b);
+                }
+#pragma unroll
+                for (int b = 0; b < BT; ++b) prim_tot[((int64_t)t * rp.n_primary + slot) * BT + b] = acc[b];
+                finish_if_single(rp.ti_p[t][slot], unit, acc);
+            }
+            // groups that span many tiles: the whole warp sums one list at a time, then lane 0 finishes
+            unsigned todo = __ballot_sync(kFull, heavy);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t s2 = __shfl_sync(kFull, slot, src);
+                const int4 dd = rp.slot_desc[s2];
+                double acc[BT];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+                for (int64_t tile = dd.x + lane; tile <= dd.y; tile += 32)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) acc[b] += addend(dd, tile, t, b);
+#pragma unroll
+                for (int b = 0; b < BT; ++b)
+                    acc[b] = warp_sum(acc[b]) + rp.direct_p[((int64_t)t * rp.n_primary + s2) * BT + b];
+                if (lane == 0) {
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) prim_tot[((int64_t)t * rp.n_primary + s2) * BT + b] = acc[b];
+                    finish_if_single(rp.ti_p[t][s2], (rp.ng + 1) + (int64_t)t * rp.n_primary + s2, acc);
+                }
+            }
+        }
+    } else if ((int)blockIdx.x < b_glob) {
+        __shared__ double part[8][32];
+        const int sub = threadIdx.x >> 5;
+        const int64_t slot = ((int64_t)blockIdx.x - rp.blocks_p) * 32 + lane;
+        const int per = (rp.grid + 7) / 8;
+        const int c0 = sub * per, c1 = min(rp.grid, c0 + per);
+        for (int t = 0; t < rp.ns; ++t) {
+            double lik[BT];
+            for (int b = 0; b < BT; ++b) {
+                double acc = 0.0;
+                if (slot < rp.n_secondary) {
+                    const double *src = rp.cta_sec + ((int64_t)t * rp.n_secondary + slot) * BT + b;
+                    const int64_t stride = (int64_t)rp.ns * rp.n_secondary * BT;
+#pragma unroll 4
+                    for (int c = c0; c < c1; ++c) acc += src[c * stride];
+                }
+                part[sub][lane] = acc;
+                __syncthreads();
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s += part[k][lane];
+                lik[b] = s;
+                __syncthreads();
+            }
+            if (sub == 0 && slot < rp.n_secondary) {
+#pragma unroll
+                for (int b = 0; b < BT; ++b) sec_tot[((int64_t)t * rp.n_secondary + slot) * BT + b] = lik[b];
+                finish_if_single(rp.ti_s[t][slot], (rp.ng + 1) + (int64_t)rp.np * rp.n_primary + (int64_t)t * rp.n_secondary + slot,
+                                 lik);
+            }
+        }
+    } else if ((int)blockIdx.x == b_glob) {
+        // global terms and the logp partial: one warp per (term, chain), CTAs of the row kernel in order
+        const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+        for (int item = warp; item < (rp.ng + 1) * BT; item += warps) {
+            double acc = 0.0;
+            for (int c = lane; c < rp.grid; c += 32) acc += rp.cta_glob[(int64_t)c * (rp.ng + 1) * BT + item];
+            acc = warp_sum(acc);
+            if (lane == 0) rp.totals[item] = acc;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < rp.ng) {
+            double lik[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) lik[b] = rp.totals[threadIdx.x * BT + b];
+            finish_if_single(rp.ti_g[threadIdx.x][0], threadIdx.x, lik);
+        }
+        if (threadIdx.x == 32 && rp.family == SKK_LIK_NORMAL && rp.sigma_theta_index >= 0) {
+            double lik[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) lik[b] = 0.0;
+            finish_element<T, BT, 0>(rp, pp, theta, out_grad, rp.sigma_theta_index, lik);
+        }
+        // logp: CTA partials of the prior kernel in fixed order (strided per thread, fixed tree)
+        __shared__ double lp_part[8];
+        for (int b = 0; b < rp.b_valid; ++b) {
+            const int64_t row = rp.b0 + b;
+            double s = 0.0;
+            if (rp.include_priors)
+                for (int k = threadIdx.x; k < rp.prior_ctas; k += blockDim.x) s += rp.prior_lp_part[row * rp.prior_ctas + k];
+            s = warp_sum(s);
+            if (lane == 0) lp_part[threadIdx.x >> 5] = s;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += lp_part[w];
+                const double L = rp.totals[rp.ng * BT + b];
+                double ll = L;
+                if (rp.family == SKK_LIK_NORMAL) {
+                    const double sigma = rp.sigma_theta_index >= 0 ? exp((double)theta[row * P + rp.sigma_theta_index])
+                                                                   : rp.sigma_const;
+                    ll = -0.5 * L / (sigma * sigma) - (double)rp.n_rows_total * (kLogSqrt2Pi + log(sigma));
+                }
+                out_logp[row] = (T)(tot + ll + rp.logp_const);
+            }
+            __syncthreads();
+        }
+    } else if ((int)blockIdx.x <= b_glob + rp.parent_blocks) {
+        // hyper-parameters: own prior term + the sum over the children, which are contiguous in link_val
+        __shared__ double hp_part[8];
+        const int warp = threadIdx.x >> 5;
+        const int pb = (int)blockIdx.x - b_glob - 1;
+        const bool heavy = pb < rp.n_heavy;
+        const int64_t q = heavy ? pb : rp.n_heavy + ((int64_t)pb - rp.n_heavy) * 8 + warp;
+        if (!heavy && q >= rp.n_parents) return;
+        const int64_t lo = rp.link_ptr[q], hi = rp.link_ptr[q + 1];
+        const int64_t first = lo + (heavy ? threadIdx.x : lane), step = heavy ? blockDim.x : 32;
+        double sum[BT];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            sum[b] = 0.0;
+            if (b >= rp.b_valid) continue;  // uniform
+            const double *val = rp.link_val + (rp.b0 + b) * rp.n_links;
+            double acc = 0.0;
+            int64_t e = first;
+            for (; e + 7 * step < hi; e += 8 * step) {  // eight independent loads in flight
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = val[e + u * step];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += v[u];
+            }
+            for (; e < hi; e += step) acc += val[e];
+            acc = warp_sum(acc);
+            if (heavy) {
+                if (lane == 0) hp_part[warp] = acc;
+                __syncthreads();
+                acc = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) acc += hp_part[w];
+                __syncthreads();
+            }
+            sum[b] = acc;
+        }
+        if (heavy ? threadIdx.x == 0 : lane == 0) {
+            double lik[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) lik[b] = 0.0;
+            finish_element<T, BT, 0>(rp, pp, theta, out_grad, rp.parent[q], lik, sum);
+        }
+    } else {
+        // elements that no term feeds and that have no children: own prior term only
+        const int64_t k = ((int64_t)blockIdx.x - b_glob - 1 - rp.parent_blocks) * blockDim.x + threadIdx.x;
+        if (k < rp.n_none) {
+            const int64_t j = rp.none_elem[k];
+            if (!(rp.family == SKK_LIK_NORMAL && j == rp.sigma_theta_index)) {
+                double lik[BT];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) lik[b] = 0.0;
+                finish_element<T, BT, 0>(rp, pp, theta, out_grad, j, lik);
             }
         }
     }

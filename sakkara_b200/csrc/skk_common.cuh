@@ -55,6 +55,15 @@ struct RowParams {
     double *tile_tail;       // [n_tiles][NP][BT]     partial of the tile's last group (if != first)
     double *cta_glob;        // [grid][NG + 1][BT]    global-term partials, last entry = logp partial
     double *cta_sec;         // [grid][NS][n_secondary][BT]
+    // prior terms, evaluated by the row kernel while its first tiles are in flight (single-GPU path;
+    // prior_family == nullptr: the prior kernels run instead).  Flat per theta element, see PriorParams.
+    const int8_t *prior_family;
+    const int32_t *prior_a_src, *prior_b_src, *prior_e_mu, *prior_e_sigma;
+    const double *prior_a_const, *prior_b_const;
+    double *prior_grad;      // [b_valid][n_params]      d prior / d element (own term only)
+    double *link_val;        // [b_valid][n_links]       what an element adds to the gradient of its prior's parameters
+    double *prior_lp_part;   // [b_valid][grid * warps]  prior logp, one partial per warp
+    int64_t n_links;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -209,6 +218,33 @@ template <typename T>
 struct Math;
 // float: hardware approximations (MUFU.EX2 / LG2 / RCP, ~2^-21 relative error) -- three orders of
 // magnitude inside the 1e-4 tolerance stated for fp32; double: the accurate library functions.
+constexpr double kLogSqrt2Pi = 0.91893853320467274178032973640562;
+constexpr double kLogSqrt2OverPi = -0.22579135264472743236309761494744;
+
+// One prior term in fp64.  v: the (transformed) element; a, b: mu and sd (Normal) or the rate /
+// scale in a (Exponential, HalfNormal; sampled as log, the log-Jacobian v is included).
+// Returns logp; grad = d/dv; for the Normal also d/d mu and d/d log(sd).
+__device__ __forceinline__ double prior_term(int family, double v, double a, double b, double &grad, double &d_mu,
+                                             double &d_log_sd) {
+    d_mu = 0.0;
+    d_log_sd = 0.0;
+    if (family == SKK_PRIOR_NORMAL) {
+        const double z = (v - a) / b;
+        grad = -z / b;
+        d_mu = z / b;
+        d_log_sd = z * z - 1.0;
+        return -0.5 * z * z - kLogSqrt2Pi - log(b);
+    }
+    if (family == SKK_PRIOR_HALFNORMAL) {
+        const double q = exp(v) / a;
+        grad = -q * q + 1.0;
+        return -0.5 * q * q + kLogSqrt2OverPi - log(a) + v;
+    }
+    const double sv = exp(v);  // SKK_PRIOR_EXPONENTIAL
+    grad = -a * sv + 1.0;
+    return log(a) - a * sv + v;
+}
+
 template <>
 struct Math<float> {
     static __device__ __forceinline__ float ex2(float x) {

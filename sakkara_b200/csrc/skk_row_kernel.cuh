@@ -594,6 +594,42 @@ struct RowKernel {
     }
 
     // -----------------------------------------------------------------------------------------
+    // Prior terms of a slice of theta (element = thread, grid-strided), hidden behind the latency of
+    // the first tiles.  Own gradient term -> prior_grad, contribution to the gradient of the prior's
+    // parameters -> link_val (summed per hyper-parameter by the finish kernel), logp -> one partial
+    // per warp.  Same arithmetic as skk_prior_kernel.
+    static __device__ __forceinline__ void priors(const RowParams<T> &p) {
+        double lp[BT];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) lp[b] = 0.0;
+        for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.n_params;
+             j += (int64_t)gridDim.x * blockDim.x) {
+            const int family = p.prior_family[j];
+            const int a_src = p.prior_a_src[j], b_src = p.prior_b_src[j];
+            const int e_mu = p.prior_e_mu[j], e_sigma = p.prior_e_sigma[j];
+            const double a_c = p.prior_a_const[j], b_c = p.prior_b_const[j];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                if (b >= p.b_valid) continue;
+                const T *th = p.theta + (int64_t)b * p.n_params;
+                const double a = a_src >= 0 ? (double)th[a_src] : a_c;
+                const double sd = b_src >= 0 ? exp((double)th[b_src]) : b_c;
+                double grad, d_mu, d_log_sd;
+                lp[b] += prior_term(family, (double)th[j], a, sd, grad, d_mu, d_log_sd);
+                p.prior_grad[(int64_t)b * p.n_params + j] = grad;
+                if (e_mu >= 0) p.link_val[(int64_t)b * p.n_links + e_mu] = d_mu;
+                if (e_sigma >= 0) p.link_val[(int64_t)b * p.n_links + e_sigma] = d_log_sd;
+            }
+        }
+        const int64_t parts = (int64_t)gridDim.x * (blockDim.x >> 5);
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            const double s = warp_sum(lp[b]);
+            if ((threadIdx.x & 31) == 0 && b < p.b_valid)
+                p.prior_lp_part[b * parts + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = s;
+        }
+    }
+
     static __device__ void run(const RowParams<T> &p) {
         extern __shared__ __align__(128) unsigned char smem[];
         const int warps = blockDim.x >> 5;
@@ -634,6 +670,8 @@ struct RowKernel {
                 if (t < tile_end) issue_tile(p, t, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
             }
         }
+
+        if (p.prior_family != nullptr) priors(p);
 
         if constexpr (NS > 0) {
             const int n = NS * p.n_secondary * BT;
