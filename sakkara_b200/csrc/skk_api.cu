@@ -159,6 +159,11 @@ struct skk_plan {
                                                        // writes are fixed per width, the rest must stay zero
     double *tile_head = nullptr, *tile_tail = nullptr, *cta_glob = nullptr, *cta_sec = nullptr;
     double *lik_vec = nullptr, *prior_grad = nullptr, *prior_lp = nullptr, *link_val = nullptr;
+    // links in chunk order (fused single-GPU path)
+    int32_t *lk_child = nullptr, *lk_a_src = nullptr, *lk_b_src = nullptr;
+    int8_t *lk_kind = nullptr;
+    double *lk_a_const = nullptr, *lk_b_const = nullptr, *link_part = nullptr;
+    int64_t n_chunks = 0;
     void *out_dev = nullptr;  // [B*P grad | B logp]
 
     PriorParams prior{};
@@ -258,6 +263,8 @@ static int configure_launch(skk_plan *pl, int bt, LaunchCfg *cfg) {
     if (pl->y_u8) spec |= 64;
     if (pl->has_off) spec |= 128;
     if (pl->ns > 0 && pl->sec_code_bytes == 2) spec |= 256;
+    // the fixed kernels count the staged x columns from the spec: one column per term that has one
+    if (__builtin_popcount(spec & 63) != pl->n_x) spec = -2;
     if (env_int("SKK_GENERIC", 0)) spec = -2;  // force the run-time kernels (testing)
     cfg->fn = lookup_kernel(pl->dtype, pl->family, bt, pl->ng, pl->np, pl->ns, spec);
     if (!cfg->fn)
@@ -520,7 +527,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     std::vector<int32_t> none_elem;
     {
         std::vector<char> is_parent(Pn, 0);
-        pl->fused_ok = true;
+        pl->fused_ok = multi_elem.empty();  // an element fed by several slots needs the slot totals first
         for (const Parent &q : parents) {
             is_parent[q.element] = 1;
             if (single_unit[q.element] != -1 || (d->family == SKK_LIK_NORMAL && q.element == d->sigma_theta_index))
@@ -531,6 +538,43 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     }
     int32_t *none_dev = nullptr;
     if (int rc = dev_upload(pl, &none_dev, none_elem.data(), none_elem.size())) return rc;
+    // The same links once more in link order, every hyper-parameter's range padded to whole chunks of 32
+    // and each link carrying its child's prior parameters: the row kernel's prologue reduces a chunk per
+    // warp, the finish kernel adds the chunk partials of a hyper-parameter.
+    std::vector<int32_t> lk_child, lk_a_src, lk_b_src;
+    std::vector<int8_t> lk_kind;
+    std::vector<double> lk_a_const, lk_b_const;
+    std::vector<int64_t> chunk_ptr(parents.size() + 1, 0);
+    for (size_t q = 0; q < parents.size(); ++q) {
+        chunk_ptr[q] = (int64_t)(lk_child.size() / 32);
+        for (int64_t e = parents[q].lo; e < parents[q].hi; ++e) {
+            const int32_t j = links[e].child;
+            lk_child.push_back(j);
+            lk_kind.push_back(links[e].kind);
+            lk_a_src.push_back(a_src[j]);
+            lk_b_src.push_back(b_src[j]);
+            lk_a_const.push_back(a_const[j]);
+            lk_b_const.push_back(b_const[j]);
+        }
+        while (lk_child.size() % 32) {
+            lk_child.push_back(-1);
+            lk_kind.push_back(0);
+            lk_a_src.push_back(-1);
+            lk_b_src.push_back(-1);
+            lk_a_const.push_back(0.0);
+            lk_b_const.push_back(1.0);
+        }
+    }
+    chunk_ptr[parents.size()] = (int64_t)(lk_child.size() / 32);
+    pl->n_chunks = (int64_t)(lk_child.size() / 32);
+    int64_t *chunk_ptr_dev = nullptr;
+    if (int rc = dev_upload(pl, &pl->lk_child, lk_child.data(), lk_child.size())) return rc;
+    if (int rc = dev_upload(pl, &pl->lk_kind, lk_kind.data(), lk_kind.size())) return rc;
+    if (int rc = dev_upload(pl, &pl->lk_a_src, lk_a_src.data(), lk_a_src.size())) return rc;
+    if (int rc = dev_upload(pl, &pl->lk_b_src, lk_b_src.data(), lk_b_src.size())) return rc;
+    if (int rc = dev_upload(pl, &pl->lk_a_const, lk_a_const.data(), lk_a_const.size())) return rc;
+    if (int rc = dev_upload(pl, &pl->lk_b_const, lk_b_const.data(), lk_b_const.size())) return rc;
+    if (int rc = dev_upload(pl, &chunk_ptr_dev, chunk_ptr.data(), chunk_ptr.size())) return rc;
 
     // ---- launch geometry -------------------------------------------------------------------------------------
     cudaDeviceProp prop;
@@ -576,6 +620,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     if (int rc = dev_alloc(pl, &pl->prior_grad, B * P, true)) return rc;
     if (int rc = dev_alloc(pl, &pl->prior_lp, B * std::max<size_t>(pl->prior_ctas + 1, (size_t)grid_max * 8), true)) return rc;
     if (int rc = dev_alloc(pl, &pl->link_val, B * std::max<size_t>(1, links.size()), true)) return rc;
+    if (int rc = dev_alloc(pl, &pl->link_part, B * std::max<size_t>(1, (size_t)pl->n_chunks), true)) return rc;
     if (int rc = dev_alloc(pl, &tmp, B * P + B, true)) return rc;
     pl->out_dev = tmp;
     CUDA_TRY(cudaMallocHost(&pl->h_in, std::max<size_t>(16, B * P * sizeof(T))));
@@ -599,14 +644,10 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     rp.n_none = (int32_t)none_elem.size();
     rp.none_blocks = (int32_t)((none_elem.size() + 255) / 256);
     {
-        unsigned int *ticket = nullptr;
-        if (int rc = dev_alloc(pl, &ticket, multi_elem.size() + 1, true)) return rc;
-        rp.ticket = ticket;
-        rp.multi_of = multi_of_dev;
         rp.parent = pl->prior.parent;
-        rp.link_ptr = pl->prior.link_ptr;
-        rp.link_val = pl->link_val;
-        rp.n_links = pl->prior.n_links;
+        rp.chunk_ptr = chunk_ptr_dev;
+        rp.link_part = pl->link_part;
+        rp.n_chunks = pl->n_chunks;
         rp.n_parents = pl->prior.n_parents;
         rp.n_heavy = pl->prior.n_heavy;
         rp.parent_blocks = rp.n_heavy + (rp.n_parents - rp.n_heavy + 7) / 8;
@@ -757,14 +798,18 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
         rp.prior_family = pp.family;
         rp.prior_a_src = pp.a_src;
         rp.prior_b_src = pp.b_src;
-        rp.prior_e_mu = pp.e_mu;
-        rp.prior_e_sigma = pp.e_sigma;
         rp.prior_a_const = pp.a_const;
         rp.prior_b_const = pp.b_const;
-        rp.n_links = pp.n_links;
         rp.prior_grad = pl->prior_grad + (size_t)b0 * pl->n_params;
-        rp.link_val = pl->link_val + (size_t)b0 * pp.n_links;
         rp.prior_lp_part = pl->prior_lp + (size_t)b0 * cfg.grid * pl->warps;
+        rp.link_child = pl->lk_child;
+        rp.link_kind = pl->lk_kind;
+        rp.link_a_src = pl->lk_a_src;
+        rp.link_b_src = pl->lk_b_src;
+        rp.link_a_const = pl->lk_a_const;
+        rp.link_b_const = pl->lk_b_const;
+        rp.link_part = pl->link_part + (size_t)b0 * pl->n_chunks;
+        rp.n_chunks = pl->n_chunks;
     }
     void *args[] = {&rp};
     if (timed) CUDA_TRY(cudaEventRecord(pl->evk0, pl->stream));
@@ -886,7 +931,10 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         rp.batch_total = batch;
         const unsigned slot_blocks = (unsigned)(rp.blocks_p + rp.blocks_s + 1);
         if (fused) {
-            if (priors) rp.prior_ctas = cfg.grid * pl->warps;  // one logp partial per warp of the row kernel
+            if (priors) {
+                rp.prior_ctas = cfg.grid * pl->warps;  // one logp partial per warp of the row kernel, of which
+                rp.n_lp_parts = (int32_t)std::min<int64_t>(rp.prior_ctas, (pl->n_params + 31) / 32);  // these hold elements
+            }
             const unsigned blocks = slot_blocks + (unsigned)(rp.parent_blocks + rp.none_blocks);
             if (bt == 4)
                 skk_finish_kernel<T, 4><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);

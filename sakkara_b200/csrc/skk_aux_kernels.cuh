@@ -199,12 +199,11 @@ struct ReduceParams {
     int32_t n_none, none_blocks;
     // hyper-parameters (elements with children in the priors; no term feeds them on this path)
     const int32_t *parent;      // [n_parents] those with many children first (a CTA each, then a warp each)
-    const int64_t *link_ptr;    // [n_parents + 1] ranges of link_val
-    const double *link_val;     // [B][n_links] written by the row kernel's prior prologue
-    int64_t n_links;
+    const int64_t *chunk_ptr;   // [n_parents + 1] ranges of link_part (chunks of 32 children)
+    const double *link_part;    // [B][n_chunks] written by the row kernel's prior prologue
+    int64_t n_chunks;
     int32_t n_parents, n_heavy, parent_blocks;
-    const int32_t *multi_of;    // [P] position in the multi list, -1
-    unsigned int *ticket;       // [n_multi] slots of a shared element that have stored their total
+    int32_t n_lp_parts;         // warp partials of the prior logp that the row kernel's prologue writes per chain
 };
 
 // blockIdx.x in [0, blocks_p): primary slots, one per thread;  [blocks_p, blocks_p + blocks_s):
@@ -473,54 +472,57 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant_
 }
 
 // ---- K4 fused (single GPU): slot totals -> theta elements -> outputs in one launch ------------------
+// Used when every theta element is fed by at most one slot (no term sits on a parent of a grouping
+// level) and no term feeds a hyper-parameter; other models run the separate kernels above.
 // CTA classes by blockIdx.x: [0, blocks_p) primary slots (one per thread); then blocks_s CTAs of
 // secondary slots (32 per CTA x 8 ranges of row-kernel CTAs); one CTA for the global terms, logp and
 // the likelihood's sigma; parent_blocks CTAs for the hyper-parameters (sum over their children's
-// contributions, a CTA or a warp per element); none_blocks CTAs for the remaining elements.  A thread that
-// completes the total of a slot finishes the theta element fed by that slot alone.  An element fed by
-// several slots (a term on a parent of the sorted level) is finished by the thread that stores the
-// last of its slot totals (one ticket counter per element); it adds them in the fixed order of the
-// element's slot list, so the result does not depend on which thread that was.
+// chunk partials, a CTA or a warp per element); none_blocks CTAs for the remaining elements.  The
+// thread that completes the total of a slot finishes the slot's theta element on the spot.  Every
+// thread is latency-bound, so whatever it will need (descriptor, element, the element's own prior
+// gradient) is loaded up front and the chain of dependent loads is two deep.
 template <typename T, int BT>
 __global__ void __launch_bounds__(256)
 skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp,
                   const T *__restrict__ theta, T *__restrict__ out_logp, T *__restrict__ out_grad) {
     const int lane = threadIdx.x & 31;
     const int64_t P = rp.n_params;
-    double *prim_tot = rp.totals + (int64_t)(rp.ng + 1) * BT;
-    double *sec_tot = prim_tot + (int64_t)rp.np * rp.n_primary * BT;
-    // called by the thread that has just stored totals[unit] (= lik), the total of a slot of element j
-    auto finish_if_single = [&](int64_t j, int64_t unit, const double (&lik)[BT]) {
-        // (the likelihood's sigma needs the global sum of squares: finished by the global CTA)
-        if (rp.family == SKK_LIK_NORMAL && j == rp.sigma_theta_index) return;
-        const int32_t su = rp.single_unit[j];
-        if (su == (int32_t)unit) {
-            finish_element<T, BT, 0>(rp, pp, theta, out_grad, j, lik);
-        } else if (su == -2) {
-            const int32_t m = rp.multi_of[j];
-            const int64_t e0 = rp.multi_ptr[m], e1 = rp.multi_ptr[m + 1];
-            __threadfence();
-            if (atomicAdd(rp.ticket + m, 1u) != (unsigned)(e1 - e0 - 1)) return;
-            rp.ticket[m] = 0;
-            __threadfence();
-            double acc[BT];
+    // 1 / sigma^2 of the Normal likelihood per chain (1 for the other families)
+    double scale[BT];
 #pragma unroll
-            for (int b = 0; b < BT; ++b) acc[b] = 0.0;
-#pragma unroll 4
-            for (int64_t e = e0; e < e1; ++e) {
-                const int64_t u = rp.multi_unit[e];
-#pragma unroll
-                for (int b = 0; b < BT; ++b) acc[b] += __ldcg(rp.totals + u * BT + b);
-            }
-            finish_element<T, BT, 0>(rp, pp, theta, out_grad, j, acc);
+    for (int b = 0; b < BT; ++b) {
+        scale[b] = 1.0;
+        if (rp.family == SKK_LIK_NORMAL && b < rp.b_valid) {
+            const double sigma = rp.sigma_theta_index >= 0
+                                     ? exp((double)theta[(int64_t)(rp.b0 + b) * P + rp.sigma_theta_index])
+                                     : rp.sigma_const;
+            scale[b] = 1.0 / (sigma * sigma);
         }
+    }
+    // gradient of element j = likelihood part (scaled) + own prior term (+ children, hyper-parameters)
+    auto prior_of = [&](int64_t j, double (&pg)[BT]) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+            pg[b] = (rp.include_priors && j >= 0 && b < rp.b_valid) ? rp.prior_grad[(int64_t)(rp.b0 + b) * P + j] : 0.0;
     };
+    auto store = [&](int64_t j, const double (&lik)[BT], const double (&pg)[BT]) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+            if (b < rp.b_valid) out_grad[(int64_t)(rp.b0 + b) * P + j] = (T)(lik[b] * scale[b] + pg[b]);
+    };
+    const bool sigma_is_param = rp.family == SKK_LIK_NORMAL && rp.sigma_theta_index >= 0;
     const int b_glob = rp.blocks_p + rp.blocks_s;
     if ((int)blockIdx.x < rp.blocks_p) {
         const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
         const bool valid = slot < rp.n_primary;
         int4 d = make_int4(0, -1, 0, 0);
         if (valid) d = rp.slot_desc[slot];
+        int32_t elem[kMaxTermsPerLevel];
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) elem[t] = (valid && t < rp.np) ? rp.ti_p[t][slot] : -1;
+        double pg[kMaxTermsPerLevel][BT];
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) prior_of(elem[t], pg[t]);
         const int64_t t_lo = d.x, t_hi = d.y;
         const bool heavy = valid && (t_hi - t_lo + 1 > kSerialLimit);
         auto addend = [&](int4 dd, int64_t tile, int t, int b) -> double {
@@ -528,8 +530,9 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
             const double *src = kind == 1 ? rp.tile_head : (kind == 2 ? rp.tile_tail : nullptr);
             return src ? src[(tile * rp.np + t) * BT + b] : 0.0;
         };
-        for (int t = 0; t < rp.np; ++t) {
-            const int64_t unit = (rp.ng + 1) + (int64_t)t * rp.n_primary + slot;
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) {
+            if (t >= rp.np) break;
             if (valid && !heavy) {
                 double acc[BT];
 #pragma unroll
@@ -546,11 +549,9 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
 #pragma unroll
                         for (int b = 0; b < BT; ++b) acc[b] += addend(d, t_hi, t, b);
                 }
-#pragma unroll
-                for (int b = 0; b < BT; ++b) prim_tot[((int64_t)t * rp.n_primary + slot) * BT + b] = acc[b];
-                finish_if_single(rp.ti_p[t][slot], unit, acc);
+                store(elem[t], acc, pg[t]);
             }
-            // groups that span many tiles: the whole warp sums one list at a time, then lane 0 finishes
+            // groups that span many tiles: the whole warp sums one list at a time, then its owner finishes
             unsigned todo = __ballot_sync(kFull, heavy);
             while (todo) {
                 const int src = __ffs(todo) - 1;
@@ -565,28 +566,34 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
                     for (int b = 0; b < BT; ++b) acc[b] += addend(dd, tile, t, b);
 #pragma unroll
                 for (int b = 0; b < BT; ++b)
-                    acc[b] = warp_sum(acc[b]) + rp.direct_p[((int64_t)t * rp.n_primary + s2) * BT + b];
-                if (lane == 0) {
-#pragma unroll
-                    for (int b = 0; b < BT; ++b) prim_tot[((int64_t)t * rp.n_primary + s2) * BT + b] = acc[b];
-                    finish_if_single(rp.ti_p[t][s2], (rp.ng + 1) + (int64_t)t * rp.n_primary + s2, acc);
-                }
+                    acc[b] = __shfl_sync(kFull, warp_sum(acc[b]), 0) +
+                             rp.direct_p[((int64_t)t * rp.n_primary + s2) * BT + b];
+                if (lane == src) store(elem[t], acc, pg[t]);
             }
         }
     } else if ((int)blockIdx.x < b_glob) {
         __shared__ double part[8][32];
         const int sub = threadIdx.x >> 5;
         const int64_t slot = ((int64_t)blockIdx.x - rp.blocks_p) * 32 + lane;
+        const bool valid = slot < rp.n_secondary;
         const int per = (rp.grid + 7) / 8;
         const int c0 = sub * per, c1 = min(rp.grid, c0 + per);
-        for (int t = 0; t < rp.ns; ++t) {
+        int32_t elem[kMaxTermsPerLevel];
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) elem[t] = (sub == 0 && valid && t < rp.ns) ? rp.ti_s[t][slot] : -1;
+        double pg[kMaxTermsPerLevel][BT];
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) prior_of(elem[t], pg[t]);
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) {
+            if (t >= rp.ns) break;
             double lik[BT];
             for (int b = 0; b < BT; ++b) {
                 double acc = 0.0;
-                if (slot < rp.n_secondary) {
+                if (valid) {
                     const double *src = rp.cta_sec + ((int64_t)t * rp.n_secondary + slot) * BT + b;
                     const int64_t stride = (int64_t)rp.ns * rp.n_secondary * BT;
-#pragma unroll 4
+#pragma unroll 8
                     for (int c = c0; c < c1; ++c) acc += src[c * stride];
                 }
                 part[sub][lane] = acc;
@@ -597,112 +604,121 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
                 lik[b] = s;
                 __syncthreads();
             }
-            if (sub == 0 && slot < rp.n_secondary) {
-#pragma unroll
-                for (int b = 0; b < BT; ++b) sec_tot[((int64_t)t * rp.n_secondary + slot) * BT + b] = lik[b];
-                finish_if_single(rp.ti_s[t][slot], (rp.ng + 1) + (int64_t)rp.np * rp.n_primary + (int64_t)t * rp.n_secondary + slot,
-                                 lik);
-            }
+            if (sub == 0 && valid) store(elem[t], lik, pg[t]);
         }
     } else if ((int)blockIdx.x == b_glob) {
-        // global terms and the logp partial: one warp per (term, chain), CTAs of the row kernel in order
+        // global terms and the likelihood's logp partial: one warp per (term, chain), CTAs of the row kernel in order
+        __shared__ double glob[(kMaxTermsPerLevel + 1) * BT];
+        __shared__ double lp_part[8];
         const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
         for (int item = warp; item < (rp.ng + 1) * BT; item += warps) {
             double acc = 0.0;
             for (int c = lane; c < rp.grid; c += 32) acc += rp.cta_glob[(int64_t)c * (rp.ng + 1) * BT + item];
             acc = warp_sum(acc);
-            if (lane == 0) rp.totals[item] = acc;
+            if (lane == 0) glob[item] = acc;
         }
+        // prior logp: the warp partials of the row kernel's prologue, 8 / BT warps per chain
+        constexpr int WPC = 8 / BT;  // BT is 1 or 4
+        const int chain = warp / WPC, sub = warp % WPC;
+        double s = 0.0;
+        if (rp.include_priors && chain < rp.b_valid)
+            for (int k = sub * 32 + lane; k < rp.n_lp_parts; k += WPC * 32)
+                s += rp.prior_lp_part[(int64_t)(rp.b0 + chain) * rp.prior_ctas + k];
+        s = warp_sum(s);
+        if (lane == 0) lp_part[warp] = s;
         __syncthreads();
         if ((int)threadIdx.x < rp.ng) {
-            double lik[BT];
+            double lik[BT], pg[BT];
+            const int32_t j = rp.ti_g[threadIdx.x][0];
 #pragma unroll
-            for (int b = 0; b < BT; ++b) lik[b] = rp.totals[threadIdx.x * BT + b];
-            finish_if_single(rp.ti_g[threadIdx.x][0], threadIdx.x, lik);
+            for (int b = 0; b < BT; ++b) lik[b] = glob[threadIdx.x * BT + b];
+            prior_of(j, pg);
+            if (!(sigma_is_param && j == rp.sigma_theta_index)) store(j, lik, pg);
         }
-        if (threadIdx.x == 32 && rp.family == SKK_LIK_NORMAL && rp.sigma_theta_index >= 0) {
-            double lik[BT];
+        if (threadIdx.x == 32 && sigma_is_param) {
+            // d/d log(sigma) = sum(r^2) / sigma^2 - N (+ its own prior term; sigma has no children on this path)
+            double lik[BT], pg[BT];
+            prior_of(rp.sigma_theta_index, pg);
 #pragma unroll
-            for (int b = 0; b < BT; ++b) lik[b] = 0.0;
-            finish_element<T, BT, 0>(rp, pp, theta, out_grad, rp.sigma_theta_index, lik);
-        }
-        // logp: CTA partials of the prior kernel in fixed order (strided per thread, fixed tree)
-        __shared__ double lp_part[8];
-        for (int b = 0; b < rp.b_valid; ++b) {
-            const int64_t row = rp.b0 + b;
-            double s = 0.0;
-            if (rp.include_priors)
-                for (int k = threadIdx.x; k < rp.prior_ctas; k += blockDim.x) s += rp.prior_lp_part[row * rp.prior_ctas + k];
-            s = warp_sum(s);
-            if (lane == 0) lp_part[threadIdx.x >> 5] = s;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double tot = 0.0;
-                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += lp_part[w];
-                const double L = rp.totals[rp.ng * BT + b];
-                double ll = L;
-                if (rp.family == SKK_LIK_NORMAL) {
-                    const double sigma = rp.sigma_theta_index >= 0 ? exp((double)theta[row * P + rp.sigma_theta_index])
-                                                                   : rp.sigma_const;
-                    ll = -0.5 * L / (sigma * sigma) - (double)rp.n_rows_total * (kLogSqrt2Pi + log(sigma));
-                }
-                out_logp[row] = (T)(tot + ll + rp.logp_const);
+            for (int b = 0; b < BT; ++b) {
+                lik[b] = glob[rp.ng * BT + b];
+                pg[b] -= (double)rp.n_rows_total;
             }
-            __syncthreads();
+            store(rp.sigma_theta_index, lik, pg);
+        }
+        if ((int)threadIdx.x >= 64 && (int)threadIdx.x < 64 + BT && (int)threadIdx.x - 64 < rp.b_valid) {
+            const int b = threadIdx.x - 64;
+            const int64_t row = rp.b0 + b;
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < WPC; ++w) tot += lp_part[b * WPC + w];
+            const double L = glob[rp.ng * BT + b];
+            double ll = L;
+            if (rp.family == SKK_LIK_NORMAL) {
+                const double log_sigma =
+                    sigma_is_param ? (double)theta[row * P + rp.sigma_theta_index] : log(rp.sigma_const);
+                double sc = 1.0;
+#pragma unroll
+                for (int k = 0; k < BT; ++k) sc = k == b ? scale[k] : sc;  // (no dynamically indexed register array)
+                ll = -0.5 * L * sc - (double)rp.n_rows_total * (kLogSqrt2Pi + log_sigma);
+            }
+            out_logp[row] = (T)(tot + ll + rp.logp_const);
         }
     } else if ((int)blockIdx.x <= b_glob + rp.parent_blocks) {
-        // hyper-parameters: own prior term + the sum over the children, which are contiguous in link_val
-        __shared__ double hp_part[8];
+        // hyper-parameters: own prior term + the sum over the children's chunk partials (contiguous)
+        __shared__ double hp_part[8][BT];
         const int warp = threadIdx.x >> 5;
         const int pb = (int)blockIdx.x - b_glob - 1;
         const bool heavy = pb < rp.n_heavy;
         const int64_t q = heavy ? pb : rp.n_heavy + ((int64_t)pb - rp.n_heavy) * 8 + warp;
         if (!heavy && q >= rp.n_parents) return;
-        const int64_t lo = rp.link_ptr[q], hi = rp.link_ptr[q + 1];
+        const int64_t lo = rp.chunk_ptr[q], hi = rp.chunk_ptr[q + 1];
+        const int32_t j = rp.parent[q];
+        double pg[BT];
+        prior_of(j, pg);
         const int64_t first = lo + (heavy ? threadIdx.x : lane), step = heavy ? blockDim.x : 32;
+        const double *part = rp.link_part + (int64_t)rp.b0 * rp.n_chunks;
         double sum[BT];
 #pragma unroll
-        for (int b = 0; b < BT; ++b) {
-            sum[b] = 0.0;
-            if (b >= rp.b_valid) continue;  // uniform
-            const double *val = rp.link_val + (rp.b0 + b) * rp.n_links;
-            double acc = 0.0;
-            int64_t e = first;
-            for (; e + 7 * step < hi; e += 8 * step) {  // eight independent loads in flight
-                double v[8];
+        for (int b = 0; b < BT; ++b) sum[b] = 0.0;
+        for (int64_t e = first; e < hi; e += step)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = val[e + u * step];
+            for (int b = 0; b < BT; ++b)
+                if (b < rp.b_valid) sum[b] += part[(int64_t)b * rp.n_chunks + e];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc += v[u];
+        for (int b = 0; b < BT; ++b) sum[b] = warp_sum(sum[b]);
+        if (heavy) {
+            if (lane == 0)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) hp_part[warp][b] = sum[b];
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                sum[b] = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sum[b] += hp_part[w][b];
             }
-            for (; e < hi; e += step) acc += val[e];
-            acc = warp_sum(acc);
-            if (heavy) {
-                if (lane == 0) hp_part[warp] = acc;
-                __syncthreads();
-                acc = 0.0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) acc += hp_part[w];
-                __syncthreads();
-            }
-            sum[b] = acc;
         }
         if (heavy ? threadIdx.x == 0 : lane == 0) {
             double lik[BT];
 #pragma unroll
-            for (int b = 0; b < BT; ++b) lik[b] = 0.0;
-            finish_element<T, BT, 0>(rp, pp, theta, out_grad, rp.parent[q], lik, sum);
+            for (int b = 0; b < BT; ++b) {
+                lik[b] = 0.0;
+                pg[b] += rp.include_priors ? sum[b] : 0.0;
+            }
+            store(j, lik, pg);
         }
     } else {
         // elements that no term feeds and that have no children: own prior term only
         const int64_t k = ((int64_t)blockIdx.x - b_glob - 1 - rp.parent_blocks) * blockDim.x + threadIdx.x;
         if (k < rp.n_none) {
             const int64_t j = rp.none_elem[k];
-            if (!(rp.family == SKK_LIK_NORMAL && j == rp.sigma_theta_index)) {
-                double lik[BT];
+            if (!(sigma_is_param && j == rp.sigma_theta_index)) {
+                double lik[BT], pg[BT];
+                prior_of(j, pg);
 #pragma unroll
                 for (int b = 0; b < BT; ++b) lik[b] = 0.0;
-                finish_element<T, BT, 0>(rp, pp, theta, out_grad, j, lik);
+                store(j, lik, pg);
             }
         }
     }

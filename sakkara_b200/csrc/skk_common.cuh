@@ -58,12 +58,19 @@ struct RowParams {
     // prior terms, evaluated by the row kernel while its first tiles are in flight (single-GPU path;
     // prior_family == nullptr: the prior kernels run instead).  Flat per theta element, see PriorParams.
     const int8_t *prior_family;
-    const int32_t *prior_a_src, *prior_b_src, *prior_e_mu, *prior_e_sigma;
+    const int32_t *prior_a_src, *prior_b_src;
     const double *prior_a_const, *prior_b_const;
     double *prior_grad;      // [b_valid][n_params]      d prior / d element (own term only)
-    double *link_val;        // [b_valid][n_links]       what an element adds to the gradient of its prior's parameters
     double *prior_lp_part;   // [b_valid][grid * warps]  prior logp, one partial per warp
-    int64_t n_links;
+    // What the children add to the gradient of their priors' parameters, in link order: the links of
+    // a hyper-parameter are contiguous and padded to whole chunks of 32 (child -1), so a warp sums one
+    // chunk and the finish kernel adds 32 times fewer values per hyper-parameter.
+    const int32_t *link_child;   // [n_chunks * 32] theta element of the child (Normal prior), -1: padding
+    const int8_t *link_kind;     //                 0: link to the prior's mu, 1: to its sigma
+    const int32_t *link_a_src, *link_b_src;   //    the child's prior parameters, as in PriorParams
+    const double *link_a_const, *link_b_const;
+    double *link_part;       // [b_valid][n_chunks]
+    int64_t n_chunks;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -142,6 +149,44 @@ __device__ __forceinline__ void sts(uint32_t a, float v) {
 }
 __device__ __forceinline__ void sts(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// The same accesses as pure operations for the compiler, for the read-modify-write of the secondary
+// accumulator table inside the row loop.  There every table entry is touched by one
+// read-modify-write per tile (codes ascend inside a primary segment, so a lane never returns to an
+// entry it has stored), the table aliases none of the plain loads of the loop (staging ring, value
+// table), and an entry's address depends on data loaded after the tile's mbarrier wait.  So the load
+// may be scheduled freely inside the tile (`lds_free`), and the predicated store (`sts_free_if`) is
+// tied only to its operands and to a token that `table_stores_done` consumes before the __syncwarp
+// that precedes the plain accesses to the table after the loop.  The loads of the following rows
+// can then overtake a row's store instead of waiting for its load -> add -> store chain.
+// (The predicate is applied inside the asm: a pure asm under an `if` could be if-converted.)
+__device__ __forceinline__ float lds_free(uint32_t a, float) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_free(uint32_t a, double) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_free_if(bool pred, uint32_t a, float v, uint32_t &token) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %3, 0;\n\t"
+        "@p st.shared.f32 [%1], %2;\n\t}"
+        : "+r"(token)
+        : "r"(a), "f"(v), "r"((uint32_t)pred));
+}
+__device__ __forceinline__ void sts_free_if(bool pred, uint32_t a, double v, uint32_t &token) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %3, 0;\n\t"
+        "@p st.shared.f64 [%1], %2;\n\t}"
+        : "+r"(token)
+        : "r"(a), "d"(v), "r"((uint32_t)pred));
+}
+__device__ __forceinline__ void table_stores_done(uint32_t token) {
+    asm volatile("" ::"r"(token) : "memory");
 }
 
 // order generic-proxy accesses to shared memory before later async-proxy (TMA) writes

@@ -61,6 +61,18 @@ struct CtaLayout {
     int total;
 };
 
+#ifndef SKK_PIPE_ROWS
+#define SKK_PIPE_ROWS 4
+#endif
+// rows per step of the hand-pipelined common path (0: plain loop); fewer where a row holds more
+// registers (fp64, batch tile of 4) so that the step's loads stay in registers
+constexpr int kPipeRows = SKK_PIPE_ROWS;
+template <typename T, int BT>
+struct PipeRows {
+    static constexpr int value =
+        kPipeRows == 0 ? 0 : ((int)sizeof(T) * BT <= 4 ? kPipeRows : ((int)sizeof(T) * BT <= 8 ? 2 : 1));
+};
+
 constexpr int kStagedGroups = 32;  // straddling tiles with up to this many segments are handled on chip
 
 // scratch of one warp: segment offsets [33] | values [32][NP][BT] T | accumulators [32][NP][BT] f64 | touched [32]
@@ -109,12 +121,18 @@ struct AtLeast1 {
 template <int SPEC>
 struct RowSpec {
     static constexpr bool fixed = SPEC >= 0;
+    static constexpr int x_bits = (SPEC & 1) + ((SPEC >> 1) & 1) + ((SPEC >> 2) & 1) + ((SPEC >> 3) & 1) +
+                                  ((SPEC >> 4) & 1) + ((SPEC >> 5) & 1);
     template <typename P>
     static __device__ __forceinline__ bool xg(const P &p, int t) { return fixed ? ((SPEC >> t) & 1) : p.xcol_g[t] >= 0; }
     template <typename P>
     static __device__ __forceinline__ bool xp(const P &p, int t) { return fixed ? ((SPEC >> (2 + t)) & 1) : p.xcol_p[t] >= 0; }
     template <typename P>
     static __device__ __forceinline__ bool xs(const P &p, int t) { return fixed ? ((SPEC >> (4 + t)) & 1) : p.xcol_s[t] >= 0; }
+    // number of staged x columns: with a fixed SPEC every term that has a column has its own (the host
+    // falls back to the generic kernel otherwise)
+    template <typename P>
+    static __device__ __forceinline__ int n_x(const P &p) { return fixed ? x_bits : p.n_x; }
     template <typename P>
     static __device__ __forceinline__ bool y_u8(const P &p) { return fixed ? ((SPEC >> 6) & 1) : p.y8 != nullptr; }
     template <typename P>
@@ -288,7 +306,95 @@ struct RowKernel {
             if (nvalid > 0) scur = code16 ? (int)sc16[0] : sc32[0];
         }
 
+        uint32_t table_token = 0;  // ties the in-loop stores to the accumulator table to the fence after the loop
         // ---- the rows ---------------------------------------------------------------------------
+        if constexpr (NS > 0 && FASTP && FULL && !MID && PipeRows<T, BT>::value > 0) {
+            // The common tile of a model with a secondary level (whole tile inside one primary segment,
+            // all rows valid), software-pipelined by hand.  The hardware keeps shared-memory accesses in
+            // program order and the assembler cannot prove that the accumulator table aliases nothing
+            // else, so in the plain loop below every row's loads wait behind the previous row's
+            // load -> add -> store of its table entry.  Here the rows go in steps of kPipeRows: the
+            // loads of the next step (data, gathered values, table entries) are issued before the
+            // stores of the current one, and within a step nothing is stored before everything is loaded.
+            // A row's table entry belongs to the run that ends in front of it, i.e. to the previous row's
+            // code; it is only stored when the code changes (same arithmetic and order as the loop below).
+            constexpr int K = PipeRows<T, BT>::value;
+            int code[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) code[i] = code16 ? (int)sc16[i] : sc32[i];
+            struct Raw {
+                T y, off, xg[NGa], xp[NPa], xs[NSa], vs[NSa][BT], tab[NSa][BT];
+            };
+            auto load_raw = [&](int i, Raw &r) {
+                r.y = y_u8 ? (T)sy8[i] : sy[i];
+                r.off = has_off ? soff[i] : T(0);
+#pragma unroll
+                for (int t = 0; t < NG; ++t) r.xg[t] = Spec::xg(p, t) ? pxg[t][i] : T(1);
+#pragma unroll
+                for (int t = 0; t < NP; ++t) r.xp[t] = Spec::xp(p, t) ? pxp[t][i] : T(1);
+#pragma unroll
+                for (int t = 0; t < NS; ++t) r.xs[t] = Spec::xs(p, t) ? pxs[t][i] : T(1);
+#pragma unroll
+                for (int t = 0; t < NS; ++t)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) {
+                        r.vs[t][b] = valS[s_at(p, t, code[i], b)];
+                        r.tab[t][b] = i > 0 ? lds_free(gradS_addr + (uint32_t)s_at(p, t, code[i - 1], b) * (uint32_t)sizeof(T), T(0))
+                                            : T(0);
+                    }
+            };
+            Raw cur[K], nxt[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (k < R) load_raw(k, cur[k]);
+#pragma unroll
+            for (int i0 = 0; i0 < R; i0 += K) {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (i0 + K + k < R) load_raw(i0 + K + k, nxt[k]);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int i = i0 + k;
+                    if (i < R) {
+                        const Raw &r = cur[k];
+                        if (i > 0) {
+                            const bool change = code[i] != code[i - 1];
+#pragma unroll
+                            for (int t = 0; t < NS; ++t)
+#pragma unroll
+                                for (int b = 0; b < BT; ++b) {
+                                    const uint32_t slot =
+                                        gradS_addr + (uint32_t)s_at(p, t, code[i - 1], b) * (uint32_t)sizeof(T);
+                                    sts_free_if(change, slot, r.tab[t][b] + accS[t][b], table_token);
+                                    if (change) accS[t][b] = T(0);
+                                }
+                        }
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) {
+                            T eta = r.off;
+#pragma unroll
+                            for (int t = 0; t < NG; ++t) eta += vg[t][b] * r.xg[t];
+#pragma unroll
+                            for (int t = 0; t < NP; ++t) eta += vp[t][b] * r.xp[t];
+#pragma unroll
+                            for (int t = 0; t < NS; ++t) eta += r.vs[t][b] * r.xs[t];
+                            T lp, d;
+                            family_row<T, FAM>(r.y, eta, lp, d);
+                            accL[b] += lp;
+#pragma unroll
+                            for (int t = 0; t < NG; ++t) accG[t][b] += d * r.xg[t];
+#pragma unroll
+                            for (int t = 0; t < NP; ++t) accP[t][b] += d * r.xp[t];
+#pragma unroll
+                            for (int t = 0; t < NS; ++t) accS[t][b] += d * r.xs[t];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) cur[k] = nxt[k];
+            }
+            scur = code[R - 1];
+        } else
         // Only the common path (tile inside one segment, all rows valid) is unrolled; the other
         // variants stay rolled to keep the kernel inside the instruction cache.
 #pragma unroll(FASTP && FULL ? R : 1)
@@ -339,8 +445,8 @@ struct RowKernel {
 #pragma unroll
                         for (int b = 0; b < BT; ++b) {
                             const uint32_t slot = gradS_addr + (uint32_t)s_at(p, t, scur, b) * (uint32_t)sizeof(T);
-                            const T updated = lds(slot, T(0)) + accS[t][b];
-                            if (change) sts(slot, updated);
+                            const T updated = lds_free(slot, T(0)) + accS[t][b];
+                            sts_free_if(change, slot, updated, table_token);
                         }
                 } else {
                     // the tile straddles primary segments: a code may occur in several runs of the
@@ -425,6 +531,8 @@ struct RowKernel {
                 for (int t = 0; t < NS; ++t) accS[t][b] += d * xs[t];
             }
         }
+
+        if constexpr (NS > 0 && FASTP) table_stores_done(table_token);
 
         // ---- global terms and logp: lane-private fp64 accumulators over the CTA's whole range ------
 #pragma unroll
@@ -572,8 +680,11 @@ struct RowKernel {
         const uint32_t xbytes = WT * (uint32_t)sizeof(T);
         const uint32_t ybytes = y_u8 ? WT : xbytes;
         const uint32_t cbytes = NS > 0 ? WT * (Spec::code16(p) ? 2u : 4u) : 0u;
-        mbar_arrive_expect_tx(bar, (uint32_t)p.n_x * xbytes + ybytes + (has_off ? xbytes : 0u) + cbytes);
-        for (int c = 0; c < p.n_x; ++c) tma_load_1d(stage + c * sl.x_stride, p.x[c] + row, xbytes, bar);
+        const int n_x = Spec::n_x(p);
+        mbar_arrive_expect_tx(bar, (uint32_t)n_x * xbytes + ybytes + (has_off ? xbytes : 0u) + cbytes);
+#pragma unroll
+        for (int c = 0; c < kMaxXCols; ++c)
+            if (c < n_x) tma_load_1d(stage + c * sl.x_stride, p.x[c] + row, xbytes, bar);
         if (y_u8)
             tma_load_1d(stage + sl.y_off, p.y8 + row, ybytes, bar);
         else
@@ -595,18 +706,19 @@ struct RowKernel {
 
     // -----------------------------------------------------------------------------------------
     // Prior terms of a slice of theta (element = thread, grid-strided), hidden behind the latency of
-    // the first tiles.  Own gradient term -> prior_grad, contribution to the gradient of the prior's
-    // parameters -> link_val (summed per hyper-parameter by the finish kernel), logp -> one partial
-    // per warp.  Same arithmetic as skk_prior_kernel.
+    // the first tiles.  Own gradient term -> prior_grad, logp -> one partial per warp; then, in link
+    // order, what the children contribute to the gradient of their priors' parameters -> one partial
+    // per chunk of 32 links (summed per hyper-parameter by the finish kernel).  Same arithmetic as
+    // skk_prior_kernel.
     static __device__ __forceinline__ void priors(const RowParams<T> &p) {
         double lp[BT];
 #pragma unroll
         for (int b = 0; b < BT; ++b) lp[b] = 0.0;
-        for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.n_params;
-             j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t j = first; j < p.n_params; j += stride) {
             const int family = p.prior_family[j];
             const int a_src = p.prior_a_src[j], b_src = p.prior_b_src[j];
-            const int e_mu = p.prior_e_mu[j], e_sigma = p.prior_e_sigma[j];
             const double a_c = p.prior_a_const[j], b_c = p.prior_b_const[j];
 #pragma unroll
             for (int b = 0; b < BT; ++b) {
@@ -617,8 +729,6 @@ struct RowKernel {
                 double grad, d_mu, d_log_sd;
                 lp[b] += prior_term(family, (double)th[j], a, sd, grad, d_mu, d_log_sd);
                 p.prior_grad[(int64_t)b * p.n_params + j] = grad;
-                if (e_mu >= 0) p.link_val[(int64_t)b * p.n_links + e_mu] = d_mu;
-                if (e_sigma >= 0) p.link_val[(int64_t)b * p.n_links + e_sigma] = d_log_sd;
             }
         }
         const int64_t parts = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -627,6 +737,27 @@ struct RowKernel {
             const double s = warp_sum(lp[b]);
             if ((threadIdx.x & 31) == 0 && b < p.b_valid)
                 p.prior_lp_part[b * parts + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = s;
+        }
+        // links: a warp holds one whole chunk (the loop bound is a multiple of 32, so it is warp-uniform)
+        for (int64_t w = first; w < p.n_chunks * 32; w += stride) {
+            const int j = p.link_child[w];
+            const int kind = p.link_kind[w];
+            const int a_src = p.link_a_src[w], b_src = p.link_b_src[w];
+            const double a_c = p.link_a_const[w], b_c = p.link_b_const[w];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                double v = 0.0;
+                if (j >= 0 && b < p.b_valid) {
+                    const T *th = p.theta + (int64_t)b * p.n_params;
+                    const double a = a_src >= 0 ? (double)th[a_src] : a_c;
+                    const double sd = b_src >= 0 ? exp((double)th[b_src]) : b_c;
+                    double grad, d_mu, d_log_sd;
+                    prior_term(SKK_PRIOR_NORMAL, (double)th[j], a, sd, grad, d_mu, d_log_sd);
+                    v = kind == 0 ? d_mu : d_log_sd;
+                }
+                v = warp_sum(v);
+                if ((threadIdx.x & 31) == 0 && b < p.b_valid) p.link_part[(int64_t)b * p.n_chunks + (w >> 5)] = v;
+            }
         }
     }
 
@@ -742,9 +873,9 @@ struct RowKernel {
         }
         load_second(k0, se0, vq0);
 
-        for (int it = 0; tile < tile_end; tile += warps, ++it) {
-            const int s = it % stages;
-            const uint32_t parity = (uint32_t)(it / stages) & 1u;
+        int s = 0;             // stage of the ring that holds the current tile, and the parity of its barrier
+        uint32_t parity = 0;   // (counted, not derived from the iteration number: no integer division per tile)
+        for (; tile < tile_end; tile += warps) {
             int4 k2 = make_int4(0, 0, 0, 0);
             T vp1[NPa][BT];
             if constexpr (NP > 0) {
@@ -780,6 +911,10 @@ struct RowKernel {
                     fence_proxy_async();
                     issue_tile(p, next, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
                 }
+            }
+            if (++s == stages) {
+                s = 0;
+                parity ^= 1u;
             }
             k0 = k1;
             k1 = k2;
