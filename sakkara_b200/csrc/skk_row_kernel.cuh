@@ -170,6 +170,54 @@ struct RowKernel {
         return p.theta[(int64_t)(b < p.b_valid ? b : 0) * p.n_params + element];
     }
 
+    // eta = offset + sum of the terms.  With a fixed SPEC the terms without a data column are added
+    // first and those with one are fused on top (eta = fma(value, x, eta)), and nothing is added to a
+    // literal zero: one instruction per row less than the generic order below.
+    static __device__ __forceinline__ T eta_of(const RowParams<T> &p, T off, const T (&vgb)[NGa], const T (&xg)[NGa],
+                                               const T (&vpb)[NPa], const T (&xp)[NPa], const T (&vsb)[NSa],
+                                               const T (&xs)[NSa]) {
+        if constexpr (Spec::fixed) {
+            T eta = off;
+            bool have = Spec::has_off(p);
+            auto add = [&](T v) {
+                eta = have ? eta + v : v;
+                have = true;
+            };
+            auto fuse = [&](T v, T x) {
+                eta = have ? v * x + eta : v * x;
+                have = true;
+            };
+#pragma unroll
+            for (int t = 0; t < NG; ++t)
+                if (!Spec::xg(p, t)) add(vgb[t]);
+#pragma unroll
+            for (int t = 0; t < NP; ++t)
+                if (!Spec::xp(p, t)) add(vpb[t]);
+#pragma unroll
+            for (int t = 0; t < NS; ++t)
+                if (!Spec::xs(p, t)) add(vsb[t]);
+#pragma unroll
+            for (int t = 0; t < NG; ++t)
+                if (Spec::xg(p, t)) fuse(vgb[t], xg[t]);
+#pragma unroll
+            for (int t = 0; t < NP; ++t)
+                if (Spec::xp(p, t)) fuse(vpb[t], xp[t]);
+#pragma unroll
+            for (int t = 0; t < NS; ++t)
+                if (Spec::xs(p, t)) fuse(vsb[t], xs[t]);
+            return have ? eta : T(0);
+        } else {
+            T eta = off;
+#pragma unroll
+            for (int t = 0; t < NG; ++t) eta += vgb[t] * xg[t];
+#pragma unroll
+            for (int t = 0; t < NP; ++t) eta += vpb[t] * xp[t];
+#pragma unroll
+            for (int t = 0; t < NS; ++t) eta += vsb[t] * xs[t];
+            return eta;
+        }
+    }
+
     // -----------------------------------------------------------------------------------------
     // FASTP: no per-row segment bookkeeping (the tile lies in one segment, or -- MID -- in exactly two:
     // rows from `split` on belong to the second group, whose values are vp_second)
@@ -371,13 +419,14 @@ struct RowKernel {
                         }
 #pragma unroll
                         for (int b = 0; b < BT; ++b) {
-                            T eta = r.off;
+                            T vgb[NGa], vpb[NPa], vsb[NSa];
 #pragma unroll
-                            for (int t = 0; t < NG; ++t) eta += vg[t][b] * r.xg[t];
+                            for (int t = 0; t < NGa; ++t) vgb[t] = vg[t][b];
 #pragma unroll
-                            for (int t = 0; t < NP; ++t) eta += vp[t][b] * r.xp[t];
+                            for (int t = 0; t < NPa; ++t) vpb[t] = vp[t][b];
 #pragma unroll
-                            for (int t = 0; t < NS; ++t) eta += r.vs[t][b] * r.xs[t];
+                            for (int t = 0; t < NSa; ++t) vsb[t] = r.vs[t][b];
+                            const T eta = eta_of(p, r.off, vgb, r.xg, vpb, r.xp, vsb, r.xs);
                             T lp, d;
                             family_row<T, FAM>(r.y, eta, lp, d);
                             accL[b] += lp;
@@ -397,7 +446,7 @@ struct RowKernel {
         } else
         // Only the common path (tile inside one segment, all rows valid) is unrolled; the other
         // variants stay rolled to keep the kernel inside the instruction cache.
-#pragma unroll(FASTP && FULL ? R : 1)
+#pragma unroll(FASTP && FULL && !(MID && NS > 0) ? R : 1)
         for (int i = 0; i < R; ++i) {
             const bool valid = FULL || i < nvalid;
 
@@ -435,7 +484,27 @@ struct RowKernel {
             if constexpr (NS > 0) {
                 const int c = code16 ? (int)sc16[i] : sc32[i];
                 const bool change = valid && (c != scur);
-                if constexpr (FASTP) {
+                if constexpr (FASTP && MID) {
+                    // Two groups in the tile: inside either one the codes ascend, so among the runs that
+                    // end in the first group (or at the split) no two lanes hold the same code, and
+                    // likewise in the second group -- but a code may end a run on both sides in the same
+                    // step, and a lane that holds the split may meet a code twice.  Hence two ordered
+                    // read-modify-writes per row, one per side (the run that ends here lies where the
+                    // previous row lies).
+                    const bool in_second = li + i > split;
+#pragma unroll
+                    for (int side = 0; side < 2; ++side) {
+#pragma unroll
+                        for (int t = 0; t < NS; ++t)
+#pragma unroll
+                            for (int b = 0; b < BT; ++b) {
+                                const uint32_t slot = gradS_addr + (uint32_t)s_at(p, t, scur, b) * (uint32_t)sizeof(T);
+                                const T updated = lds(slot, T(0)) + accS[t][b];
+                                if (change && in_second == (side == 1)) sts(slot, updated);
+                            }
+                        __syncwarp();
+                    }
+                } else if constexpr (FASTP) {
                     // Inside one segment equal codes are contiguous, so the run that ends here ends in
                     // this lane only: its sum goes to the table with a plain read-modify-write (lanes
                     // that hold the same code in their *last* run add theirs after the loop).  Written
@@ -501,13 +570,14 @@ struct RowKernel {
 
 #pragma unroll
             for (int b = 0; b < BT; ++b) {
-                T eta = off;
+                T vgb[NGa], vpb[NPa], vsb[NSa];
 #pragma unroll
-                for (int t = 0; t < NG; ++t) eta += vg[t][b] * xg[t];
+                for (int t = 0; t < NGa; ++t) vgb[t] = vg[t][b];
 #pragma unroll
-                for (int t = 0; t < NP; ++t) eta += (MID && li + i >= split ? vp_second[t][b] : vp[t][b]) * xp[t];
+                for (int t = 0; t < NPa; ++t) vpb[t] = (MID && li + i >= split) ? vp_second[t][b] : vp[t][b];
 #pragma unroll
-                for (int t = 0; t < NS; ++t) eta += vs[t][b] * xs[t];
+                for (int t = 0; t < NSa; ++t) vsb[t] = vs[t][b];
+                const T eta = eta_of(p, off, vgb, xg, vpb, xp, vsb, xs);
                 T lp, d;
                 family_row<T, FAM>(yv, eta, lp, d);
                 if (!valid) {
@@ -633,17 +703,22 @@ struct RowKernel {
             double v[NSa * BT];
             if constexpr (FASTP) {
                 // codes ascend with the lane: one sorted-run sum (in the table's own type), the first
-                // lane of each run updates the table
+                // lane of each run updates the table.  (Two groups in the tile: the lanes that end in the
+                // first group, then those that end in the second -- the codes ascend within either set.)
                 __syncwarp();
-                T w[NSa * BT];
 #pragma unroll
-                for (int k = 0; k < NS * BT; ++k) w[k] = accS[k / BT][k % BT];
-                if (warp_sorted_run_sum<T, NSa * BT>(nvalid > 0, scur, w)) {
+                for (int side = 0; side < (MID ? 2 : 1); ++side) {
+                    const bool mine = !MID || ((li + R - 1 >= split) == (side == 1));
+                    T w[NSa * BT];
 #pragma unroll
-                    for (int k = 0; k < NS * BT; ++k)
-                        gradS[((int64_t)(k / BT) * p.n_secondary + scur) * BT + (k % BT)] += w[k];
+                    for (int k = 0; k < NS * BT; ++k) w[k] = accS[k / BT][k % BT];
+                    if (warp_sorted_run_sum<T, NSa * BT>(nvalid > 0 && mine, scur, w)) {
+#pragma unroll
+                        for (int k = 0; k < NS * BT; ++k)
+                            gradS[((int64_t)(k / BT) * p.n_secondary + scur) * BT + (k % BT)] += w[k];
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             } else {
                 // a tile that straddles segments may repeat a code anywhere: general grouping, first
                 // runs (or only runs) in round A, last runs in round B
@@ -900,6 +975,19 @@ struct RowKernel {
                     process<true, false>(p, tl, vp0, vq0, -1, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
             } else if (NS == 0 && full && sp0 >= 0) {
                 process<true, true, true>(p, tl, vp0, vq0, sp0, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
+            } else if (NS > 0 && full && k0.y == k0.x + 1) {
+                // two groups and a secondary level: the split row and the second group's values are
+                // fetched here (two dependent loads, a few times per warp) rather than carried through
+                // the loop next to the common path, which runs at the register limit
+                const int split = p.tile_split[tile];
+                T vsecond[NPa][BT];
+#pragma unroll
+                for (int t = 0; t < NPa; ++t)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b)
+                        vsecond[t][b] = (NP > 0 && t < NP) ? theta_at(p, b, p.ti_p[t][k0.y]) : T(0);
+                process<true, true, true>(p, tl, vp0, vsecond, split, se0, vg, accG64, valS, gradS, gradS_addr, scratch,
+                                          lane);
             } else {
                 process<false, false>(p, tl, vp0, vq0, -1, se0, vg, accG64, valS, gradS, gradS_addr, scratch, lane);
             }

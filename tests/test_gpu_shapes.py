@@ -69,6 +69,18 @@ def test_crossed_poisson(n, a, b, dtype):
 
 
 @pytest.mark.parametrize('dtype', ['float64', 'float32'])
+@pytest.mark.parametrize('batch', [1, 3])
+@pytest.mark.parametrize('n,a,b', [(120_000, 60, 7), (90_000, 100, 2), (64_000, 40, 300)])
+def test_crossed_poisson_two_group_tiles(n, a, b, batch, dtype):
+    """
+    primary groups of a few tiles: most straddling tiles hold exactly two groups and take the two-pass
+    path; with few secondary codes the same code sits on both sides of the split (and in one lane)
+    """
+    cols, _ = synth.poisson_columns(n, a, b, seed=n % 97)
+    check(synth.poisson_plan(cols), dtype, batch=batch)
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
 def test_batch_of_chains(dtype):
     cols, _ = synth.linreg_columns(300_000, 1000, seed=3)
     check(synth.linreg_plan(cols), dtype, batch=9)

@@ -1,6 +1,5 @@
 #!/bin/bash
-# A/B session on the GPU box: tests, fused vs separate finish kernels, shard-size sweep, launch lists.
-# Results -> gpurun_out/
+# A/B session on the GPU box.  Results -> gpurun_out/
 mkdir -p gpurun_out
 timeout 500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 B="--steps 100 --warmup 10 --no-cpu-baseline"
@@ -13,20 +12,9 @@ except Exception as e:
     print(sys.argv[1], 'FAILED', e)
 PY
 }
-for c in c4 c3 c2; do
-  timeout 200 python bench.py --config $c $B > gpurun_out/ab_${c}_fused.json 2>gpurun_out/ab_${c}_fused.err; summ ${c}_fused gpurun_out/ab_${c}_fused.json
-  SKK_NO_FUSED_FINISH=1 timeout 200 python bench.py --config $c $B > gpurun_out/ab_${c}_sep.json 2>gpurun_out/ab_${c}_sep.err; summ ${c}_separate gpurun_out/ab_${c}_sep.json
+timeout 300 python bench.py --config c4 --rows 20000000 --check --steps 5 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "check"
+for r in 100000000 12500000; do
+  timeout 200 python bench.py --config c4 --rows $r $B > gpurun_out/ab_c4_new_$r.json 2>gpurun_out/ab_c4_new_$r.err; summ c4_new_$r gpurun_out/ab_c4_new_$r.json
+  SKK_B200_LIB=$PWD/sakkara_b200/lib/variants/libskk_b200_head.so timeout 200 python bench.py --config c4 --rows $r $B > gpurun_out/ab_c4_head_$r.json 2>gpurun_out/ab_c4_head_$r.err; summ c4_head_$r gpurun_out/ab_c4_head_$r.json
 done
-for r in 12500000 25000000 50000000; do
-  timeout 200 python bench.py --config c4 --rows $r $B > gpurun_out/ab_c4_rows$r.json 2>gpurun_out/ab_c4_rows$r.err; summ c4_rows$r gpurun_out/ab_c4_rows$r.json
-done
-for c in c3 c4 c2; do
-  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/ab_launches_$c.csv python bench.py --config $c --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_ncu_$c.log 2>&1
-  python - gpurun_out/ab_launches_$c.csv <<'PY'
-import csv,sys
-rows=[r for r in csv.reader(open(sys.argv[1])) if len(r)>5]
-hdr=rows[0]; ik=hdr.index('Kernel Name'); iv=hdr.index('Metric Value'); iu=hdr.index('Metric Unit')
-for r in rows[1:][-6:]:
-    print('  ', r[ik][:70], r[iv], r[iu])
-PY
-done
+timeout 200 python bench.py --config c4 $B > gpurun_out/ab_c4_new2.json 2>/dev/null; summ c4_new_again gpurun_out/ab_c4_new2.json
