@@ -171,6 +171,28 @@ __device__ __forceinline__ double lds_free(uint32_t a, double) {
     asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
     return v;
 }
+// load under a predicate (the value is unspecified where the predicate is false): lanes that will not
+// store their entry do not take part in the gather, which removes most of its bank conflicts
+__device__ __forceinline__ float lds_free_if(bool pred, uint32_t a, float) {
+    float v;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\t"
+        "@p ld.shared.f32 %0, [%1];\n\t}"
+        : "=f"(v)
+        : "r"(a), "r"((uint32_t)pred));
+    return v;
+}
+__device__ __forceinline__ double lds_free_if(bool pred, uint32_t a, double) {
+    double v;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "mov.f64 %0, 0d0000000000000000;\n\t"
+        "@p ld.shared.f64 %0, [%1];\n\t}"
+        : "=d"(v)
+        : "r"(a), "r"((uint32_t)pred));
+    return v;
+}
 __device__ __forceinline__ void sts_free_if(bool pred, uint32_t a, float v, uint32_t &token) {
     asm("{\n\t.reg .pred p;\n\t"
         "setp.ne.u32 p, %3, 0;\n\t"

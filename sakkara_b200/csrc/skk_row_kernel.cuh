@@ -387,7 +387,9 @@ struct RowKernel {
 #pragma unroll
                     for (int b = 0; b < BT; ++b) {
                         r.vs[t][b] = valS[s_at(p, t, code[i], b)];
-                        r.tab[t][b] = i > 0 ? lds_free(gradS_addr + (uint32_t)s_at(p, t, code[i - 1], b) * (uint32_t)sizeof(T), T(0))
+                        // (only the lanes whose run ends here take part in the gather: fewer bank conflicts)
+                        r.tab[t][b] = i > 0 ? lds_free_if(code[i] != code[i - 1],
+                                                          gradS_addr + (uint32_t)s_at(p, t, code[i - 1], b) * (uint32_t)sizeof(T), T(0))
                                             : T(0);
                     }
             };
@@ -514,7 +516,7 @@ struct RowKernel {
 #pragma unroll
                         for (int b = 0; b < BT; ++b) {
                             const uint32_t slot = gradS_addr + (uint32_t)s_at(p, t, scur, b) * (uint32_t)sizeof(T);
-                            const T updated = lds_free(slot, T(0)) + accS[t][b];
+                            const T updated = lds_free_if(change, slot, T(0)) + accS[t][b];
                             sts_free_if(change, slot, updated, table_token);
                         }
                 } else {
