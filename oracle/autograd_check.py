@@ -25,6 +25,10 @@ def _evaluate(node, env):
     if isinstance(node, sym.Gather):
         base = _evaluate(node.base, env)
         return base[tuple(torch.as_tensor(np.ascontiguousarray(i), dtype=torch.long) for i in node.indices)]
+    if isinstance(node, sym.Masked):
+        value = _evaluate(node.value, env)
+        fill = _evaluate(node.fill, env)
+        return torch.where(torch.as_tensor(node.mask), fill, value)
     if isinstance(node, sym.BinOp):
         left, right = _evaluate(node.left, env), _evaluate(node.right, env)
         return sym.BinOp.OPS[node.op](left, right)

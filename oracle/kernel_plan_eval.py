@@ -40,8 +40,9 @@ def likelihood_from_kernel_plan(kp, theta):
         d = y - sigmoid(eta)
     else:
         mu = np.exp(eta)
-        logp = np.sum(y * eta - mu) + kp.logp_const
+        logp = np.sum(y * eta - mu)
         d = y - mu
+    logp += kp.logp_const    # -sum(lgamma(y + 1)) of a Poisson model; rows masked out for NaN observations
     for t, slot in zip(kp.terms, slot_rows):
         x = 1.0 if t.xcol < 0 else kp.xcols[t.xcol].astype(np.float64)
         np.add.at(grad, t.theta_index.astype(np.int64)[slot], d * x)

@@ -43,7 +43,7 @@ def priors_only(plan):
     lik = dataclasses.replace(plan.likelihood, y=plan.likelihood.y[:0],
                               offset=None if plan.likelihood.offset is None else plan.likelihood.offset[:0])
     terms = [Term(t.block, t.index[:0], None if t.x is None else t.x[:0]) for t in plan.terms]
-    return dataclasses.replace(plan, terms=terms, likelihood=lik, n_rows=0)
+    return dataclasses.replace(plan, terms=terms, likelihood=lik, n_rows=0, logp_const=0.0, n_masked_rows=0)
 
 
 class COracle:
@@ -83,6 +83,7 @@ class COracle:
             d.sigma_theta_index = plan.blocks[lik.sigma_block].offset + lik.sigma_index
         self.desc = d
         self.const = -float(np.sum(gammaln(lik.y + 1.0))) if lik.family == 'Poisson' else 0.0
+        self.const += float(getattr(plan, 'logp_const', 0.0))   # rows masked out for NaN observations
         self.fn = self.lib.skk_oracle_likelihood_f64 if self.dtype == np.float64 else self.lib.skk_oracle_likelihood_f32
 
     def __call__(self, theta):

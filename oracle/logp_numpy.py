@@ -164,6 +164,8 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
             raise NotImplementedError('positive blocks in the linear predictor')
         acc(t.block, t.index, d_eta if x is None else d_eta * x)
 
+    logp += np.float64(getattr(plan, 'logp_const', 0.0))      # rows masked out for NaN observations
+    logp_mass += abs(np.float64(getattr(plan, 'logp_const', 0.0)))
     logp_out = np.dtype(dtype).type(logp)
     if return_mass:
         return logp_out, grad, logp_mass, mass

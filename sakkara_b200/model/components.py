@@ -11,6 +11,7 @@ reference relies on, so it is kept.  What differs is what a built ``variable`` i
 small symbolic graph that the plan lowering consumes, not a PyTensor variable.
 """
 import operator
+import warnings
 from itertools import chain
 from typing import Any, Callable, Dict, Optional, Set, Tuple, Union
 
@@ -394,22 +395,53 @@ class DistributionComponent(HierarchicalComponent):
 class Likelihood(DistributionComponent):
     """
     Observed distribution (reference ``composable/hierarchical/likelihood.py:12-62``).
-    Rows with NaN observations (the reference's per-row ``GroupComponent`` masking) are not part
-    of the fused-kernel path.
+
+    Rows whose observation is NaN are masked like in the reference: their distribution parameters
+    are replaced by the constants of ``nan_param_mask`` and their observation by ``nan_data_mask``,
+    so they add a constant to logp and nothing to the gradient.  The reference composes this with a
+    per-row ``GroupComponent`` (one Python object per row); here the parameters are wrapped in
+    :class:`sakkara_b200.model.sym.Masked` nodes and the lowering drops the rows from the kernel plan
+    and keeps their constant.
     """
 
     def __init__(self, generator: Callable, observed: DataComponent, name: str = 'likelihood',
                  group: Union[str, Tuple[str, ...]] = 'obs', nan_param_mask: Dict[str, Any] = None,
                  nan_data_mask: Any = None, **kwargs: Any):
         values = np.asarray(observed.values)
+        self.nan_rows: Optional[np.ndarray] = None
+        self.nan_param_mask: Optional[Dict[str, Any]] = None
+        params = dict(kwargs)
         if values.dtype.kind == 'f' and np.isnan(values).any():
+            # (same condition as the reference, likelihood.py:33: a mask for the parameters is required
+            #  and the data mask has to be falsy -- in practice 0)
             if nan_param_mask is None or nan_data_mask:
                 raise ValueError('Both nan_param_mask and nan_data_mask must be defined when there is '
                                  'Nan in the observed data.')
-            raise NotImplementedError('NaN-masked likelihoods are outside the B200 hot path (SURVEY.md §2 row 8)')
-        params = dict(kwargs)
-        params['observed'] = observed
+            warnings.warn('Observables contains NaN values, these will be ignored in likelihood computation.',
+                          UserWarning)
+            for k in kwargs:
+                if k not in nan_param_mask:
+                    raise ValueError('Mask values for all parameters must be defined in nan_param_mask')
+            self.nan_rows = np.isnan(values)
+            self.nan_param_mask = {k: nan_param_mask[k] for k in kwargs}
+            fill = 0.0 if nan_data_mask is None else nan_data_mask
+            params['observed'] = DataComponent(np.where(self.nan_rows, fill, values), group,
+                                               name='masked_' + str(observed.name))
+        else:
+            params['observed'] = observed
         super().__init__(generator, name, group, **params)
+
+    def build_variable(self) -> None:
+        if self.nan_rows is None:
+            return super().build_variable()
+        family = _dist.resolve_generator(self.generator)
+        built = self.get_built_components()
+        shape = self.representation.get_shape()
+        if tuple(shape) != self.nan_rows.shape:
+            raise ValueError(f'NaN mask of shape {self.nan_rows.shape} for a likelihood of shape {tuple(shape)}')
+        for key, fill in self.nan_param_mask.items():
+            built[key] = sym.Masked(built[key], self.nan_rows, fill)
+        self.variable = family(self.name, **built, shape=shape, dims=self.dims())
 
 
 class MinibatchLikelihood(Likelihood):

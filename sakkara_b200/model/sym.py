@@ -85,6 +85,21 @@ class UnaryOp(Var):
         self.shape = shape_of(arg)
 
 
+class Masked(Var):
+    """
+    ``fill`` in the cells where ``mask`` is true, ``value`` elsewhere: what the reference's
+    per-row ``GroupComponent`` composes for the parameters of a likelihood whose observations
+    contain NaN (``composable/hierarchical/likelihood.py:41-53``: the rows with NaN get the
+    constant ``nan_param_mask[param]``, all other rows the parameter's own component).
+    """
+
+    def __init__(self, value: Any, mask: np.ndarray, fill: Any):
+        self.value = value
+        self.mask = np.asarray(mask, dtype=bool)
+        self.fill = fill
+        self.shape = np.broadcast_shapes(shape_of(value), self.mask.shape)
+
+
 class DataVar(Var):
     """Constant data registered in the model (reference: ``pm.ConstantData``, ``fixed/data.py:41``)."""
 

@@ -361,6 +361,10 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     logp_const = 0.0
     if lik.family == 'Poisson':
         logp_const = -float(np.sum(gammaln(y_rows + 1.0), dtype=np.float64))
+    if plan.logp_const:
+        # rows masked out for NaN observations (ModelPlan.logp_const): every rank adds its share, so that
+        # the all-reduced constant of a sharded run is the whole
+        logp_const += float(plan.logp_const) * (n / total if total else 1.0)
 
     sigma_const, sigma_theta_index = 1.0, -1
     if lik.family == 'Normal':

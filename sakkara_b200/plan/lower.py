@@ -149,6 +149,50 @@ def _prior_param(value: Any, block_of, size: int, what: str) -> PriorParam:
     return PriorParam(block=block_of[id(m.var)], index=index)
 
 
+def _masked_likelihood(obs: sym.RandomVar, y: np.ndarray):
+    """
+    NaN-masked likelihood (reference ``hierarchical/likelihood.py:32-57``): every parameter of the
+    observed variable is a ``sym.Masked`` node over the same rows.  Returns the parameters without
+    the wrappers, the row mask and the constant the masked rows add to logp (their parameters and
+    their observation are constants), or ``(params, None, 0.0)`` for an ordinary likelihood.
+    """
+    wrapped = {k: v for k, v in obs.params.items() if isinstance(v, sym.Masked)}
+    if not wrapped:
+        return dict(obs.params), None, 0.0
+    if len(wrapped) != len(obs.params):
+        raise UnsupportedModelError('Either all or none of the likelihood parameters carry a NaN mask')
+    mask = None
+    for node in wrapped.values():
+        rows = np.broadcast_to(node.mask, obs.shape).reshape(-1)
+        if mask is not None and not np.array_equal(mask, rows):
+            raise UnsupportedModelError('Likelihood parameters are masked on different rows')
+        mask = rows
+    fill = {}
+    for key, node in wrapped.items():
+        form = _lower(node.fill)
+        if not form.is_const:
+            raise UnsupportedModelError(f'nan_param_mask[{key}] must be a constant')
+        fill[key] = np.broadcast_to(np.asarray(form.const_value(), dtype=np.float64), obs.shape).reshape(-1)[mask]
+    y0 = y[mask]
+    if obs.family == 'Normal':
+        z = (y0 - fill['mu']) / fill['sigma']
+        terms = -0.5 * z * z - np.log(fill['sigma']) - 0.91893853320467274178032973640562
+    elif obs.family == 'Bernoulli':
+        if 'logit_p' in fill:
+            terms = y0 * fill['logit_p'] - np.logaddexp(0.0, fill['logit_p'])
+        else:
+            with np.errstate(divide='ignore', invalid='ignore'):   # 0 * log(0) counts as 0
+                terms = np.where(y0 > 0, y0 * np.log(fill['p']), 0.0) + \
+                    np.where(y0 < 1, (1.0 - y0) * np.log1p(-fill['p']), 0.0)
+    elif obs.family == 'Poisson':
+        from scipy.special import gammaln
+        with np.errstate(divide='ignore', invalid='ignore'):
+            terms = np.where(y0 > 0, y0 * np.log(fill['mu']), 0.0) - fill['mu'] - gammaln(y0 + 1.0)
+    else:
+        raise UnsupportedModelError(f'Likelihood family {obs.family} is not supported')
+    return {k: v.value for k, v in wrapped.items()}, mask, float(np.sum(terms, dtype=np.float64))
+
+
 def lower_model(model: sym.Model) -> ModelPlan:
     """
     Turn a recorded model into the flat plan.  theta is the concatenation of the free variables in
@@ -187,13 +231,19 @@ def lower_model(model: sym.Model) -> ModelPlan:
         raise UnsupportedModelError('Observed data must be constant')
     y = np.ascontiguousarray(np.broadcast_to(y_form.const_value(), obs.shape), dtype=np.float64).reshape(-1)
     n_rows = y.size
+    # rows masked for NaN observations: lowered like all others (so that the indices stay the reference's),
+    # then dropped from the plan; what they add to logp does not depend on theta
+    obs_params, masked, masked_logp = _masked_likelihood(obs, y)
 
     spec = LikelihoodSpec(family=obs.family, name=obs.name, y=y)
     if obs.family == 'Normal':
-        eta_node = obs.params['mu']
-        sigma = _lower(obs.params['sigma'])
+        eta_node = obs_params['mu']
+        sigma = _lower(obs_params['sigma'])
         if sigma.is_const:
-            value = np.unique(np.asarray(sigma.const_value(), dtype=np.float64))
+            value = np.asarray(sigma.const_value(), dtype=np.float64)
+            if masked is not None and value.size == n_rows:
+                value = value.reshape(-1)[~masked]
+            value = np.unique(value)
             if value.size != 1:
                 raise UnsupportedModelError('Row-dependent constant sigma is not supported')
             spec.sigma_const = float(value[0])
@@ -201,7 +251,8 @@ def lower_model(model: sym.Model) -> ModelPlan:
             m = sigma.monomials
             if len(m) != 1 or not np.all(np.asarray(m[0].coef) == 1.0):
                 raise UnsupportedModelError('Likelihood sigma must be a constant or a single positive variable')
-            element = np.unique(m[0].index)
+            element = np.unique(np.broadcast_to(m[0].index, sigma.shape).reshape(-1)[~masked]
+                                if masked is not None and np.size(m[0].index) == n_rows else m[0].index)
             source = block_of[id(m[0].var)]
             if element.size != 1:
                 raise UnsupportedModelError('Group-dependent likelihood sigma is not supported yet (SURVEY.md §8f.3)')
@@ -209,14 +260,14 @@ def lower_model(model: sym.Model) -> ModelPlan:
                 raise UnsupportedModelError('Likelihood sigma must be a positive (HalfNormal/Exponential) variable')
             spec.sigma_block, spec.sigma_index = source, int(element[0])
     elif obs.family == 'Bernoulli':
-        if 'logit_p' in obs.params:
-            eta_node = obs.params['logit_p']
+        if 'logit_p' in obs_params:
+            eta_node = obs_params['logit_p']
         else:
-            eta_node = _unwrap_link(obs.params['p'], 'sigmoid', 'Bernoulli p')
+            eta_node = _unwrap_link(obs_params['p'], 'sigmoid', 'Bernoulli p')
         if not np.isin(y, (0.0, 1.0)).all():
             raise ValueError('Bernoulli observations must be 0 or 1')
     elif obs.family == 'Poisson':
-        eta_node = _unwrap_link(obs.params['mu'], 'exp', 'Poisson mu')
+        eta_node = _unwrap_link(obs_params['mu'], 'exp', 'Poisson mu')
         if (y < 0).any() or (y != np.floor(y)).any():
             raise ValueError('Poisson observations must be non-negative integers')
     else:
@@ -244,8 +295,21 @@ def lower_model(model: sym.Model) -> ModelPlan:
     if const is not None and np.any(np.asarray(const) != 0.0):
         spec.offset = np.ascontiguousarray(np.broadcast_to(const, (n_rows,)), dtype=np.float64)
 
-    return ModelPlan(blocks=blocks, terms=terms, likelihood=spec, n_rows=n_rows,
+    plan = ModelPlan(blocks=blocks, terms=terms, likelihood=spec, n_rows=n_rows,
                      coords={k: np.asarray(v) for k, v in model.coords.items()})
+    if masked is not None:
+        keep = ~masked
+        spec.y = np.ascontiguousarray(spec.y[keep])
+        if spec.offset is not None:
+            spec.offset = np.ascontiguousarray(spec.offset[keep])
+        for t in terms:
+            t.index = np.ascontiguousarray(t.index[keep])
+            if t.x is not None:
+                t.x = np.ascontiguousarray(t.x[keep])
+        plan.n_rows = int(keep.sum())
+        plan.logp_const = masked_logp
+        plan.n_masked_rows = int(masked.sum())
+    return plan
 
 
 def _unwrap_link(node: Any, link: str, what: str):

@@ -75,6 +75,8 @@ class ModelPlan:
     likelihood: LikelihoodSpec
     n_rows: int
     coords: Dict[str, np.ndarray] = field(default_factory=dict)
+    logp_const: float = 0.0                    # constant added to logp: the rows masked out for NaN observations
+    n_masked_rows: int = 0                     # how many rows those were (they are not in n_rows / the arrays)
 
     @property
     def n_params(self) -> int:
