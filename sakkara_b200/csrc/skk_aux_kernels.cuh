@@ -339,8 +339,7 @@ __device__ __forceinline__ unsigned long long peer_wait(const PeerParams &pp) {
 // into this rank's slot of every peer (one-shot all-reduce, see above)
 template <typename T, int BT, int MODE>
 __device__ __forceinline__ void finish_element(const ReduceParams &rp, const PeerParams &pp, const T *__restrict__ theta,
-                                               T *__restrict__ out_grad, int64_t j, const double (&lik)[BT],
-                                               const double *prior_extra = nullptr) {
+                                               T *__restrict__ out_grad, int64_t j, const double (&lik)[BT]) {
     const int64_t P = rp.n_params;
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
@@ -362,7 +361,7 @@ __device__ __forceinline__ void finish_element(const ReduceParams &rp, const Pee
                 if (j == rp.sigma_theta_index)
                     g += rp.totals[rp.ng * BT + b] * scale - (double)rp.n_rows_total;  // sum(r^2 - 1)
             }
-            if (rp.include_priors) g += rp.prior_grad[row * P + j] + (prior_extra ? prior_extra[b] : 0.0);
+            if (rp.include_priors) g += rp.prior_grad[row * P + j];
             out_grad[row * P + j] = (T)g;
         }
     }

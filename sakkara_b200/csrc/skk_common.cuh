@@ -156,23 +156,13 @@ __device__ __forceinline__ void sts(uint32_t a, double v) {
 // read-modify-write per tile (codes ascend inside a primary segment, so a lane never returns to an
 // entry it has stored), the table aliases none of the plain loads of the loop (staging ring, value
 // table), and an entry's address depends on data loaded after the tile's mbarrier wait.  So the load
-// may be scheduled freely inside the tile (`lds_free`), and the predicated store (`sts_free_if`) is
+// may be scheduled freely inside the tile (`lds_free_if`), and the predicated store (`sts_free_if`) is
 // tied only to its operands and to a token that `table_stores_done` consumes before the __syncwarp
 // that precedes the plain accesses to the table after the loop.  The loads of the following rows
 // can then overtake a row's store instead of waiting for its load -> add -> store chain.
-// (The predicate is applied inside the asm: a pure asm under an `if` could be if-converted.)
-__device__ __forceinline__ float lds_free(uint32_t a, float) {
-    float v;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ double lds_free(uint32_t a, double) {
-    double v;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
-// load under a predicate (the value is unspecified where the predicate is false): lanes that will not
-// store their entry do not take part in the gather, which removes most of its bank conflicts
+// (The predicates are applied inside the asm: a pure asm under an `if` could be if-converted.)
+// The load is predicated too (the value is zero where the predicate is false): lanes that will not
+// store their entry do not take part in the gather, which removes most of its bank conflicts.
 __device__ __forceinline__ float lds_free_if(bool pred, uint32_t a, float) {
     float v;
     asm("{\n\t.reg .pred p;\n\t"
