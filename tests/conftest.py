@@ -28,3 +28,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_report_header(config):
+    """Which oracle pins the floating-point half."""
+    try:
+        from oracle import pymc_oracle
+        return 'oracle: ' + pymc_oracle.describe()
+    except Exception as exc:  # pragma: no cover
+        return f'oracle: unknown ({exc})'
+
