@@ -135,7 +135,9 @@ typedef struct {
     double sigma_const;         /* Normal likelihood: fixed sigma ...            */
     int64_t sigma_theta_index;  /* ... or index of log(sigma) in theta; -1: const */
     double logp_const;          /* theta-independent part of logp of this shard
-                                   (Poisson: -sum lgamma(y+1))                   */
+                                   (Poisson: -sum lgamma(y+1); the rows masked for NaN
+                                   observations, likelihood.py:32-57, which the plan
+                                   does not contain)                             */
     int64_t n_rows_total;       /* rows over all ranks (= n_rows on one GPU)     */
     int32_t include_priors;     /* 1: this rank adds the prior terms (after the all-reduce) */
     int32_t reserved;
