@@ -386,7 +386,15 @@ struct RowKernel {
                 for (int t = 0; t < NS; ++t)
 #pragma unroll
                     for (int b = 0; b < BT; ++b) {
+#ifdef SKK_PRED_VALUE_LOAD
+                        // experiment (off by default, not yet timed): gather the value once per run -- only
+                        // the lanes whose code changes at this row take part, the others keep their value
+                        r.vs[t][b] = i > 0 ? lds_free_if(code[i] != code[i - 1],
+                                                         smem_addr(valS) + (uint32_t)s_at(p, t, code[i], b) * (uint32_t)sizeof(T), T(0))
+                                           : valS[s_at(p, t, code[i], b)];
+#else
                         r.vs[t][b] = valS[s_at(p, t, code[i], b)];
+#endif
                         // (only the lanes whose run ends here take part in the gather: fewer bank conflicts)
                         r.tab[t][b] = i > 0 ? lds_free_if(code[i] != code[i - 1],
                                                           gradS_addr + (uint32_t)s_at(p, t, code[i - 1], b) * (uint32_t)sizeof(T), T(0))
@@ -426,8 +434,16 @@ struct RowKernel {
                             for (int t = 0; t < NGa; ++t) vgb[t] = vg[t][b];
 #pragma unroll
                             for (int t = 0; t < NPa; ++t) vpb[t] = vp[t][b];
+#ifdef SKK_PRED_VALUE_LOAD
+#pragma unroll
+                            for (int t = 0; t < NSa; ++t) {
+                                if (t < NS && (i == 0 || code[i] != code[i - 1])) vs[t][b] = r.vs[t][b];
+                                vsb[t] = vs[t][b];
+                            }
+#else
 #pragma unroll
                             for (int t = 0; t < NSa; ++t) vsb[t] = r.vs[t][b];
+#endif
                             const T eta = eta_of(p, r.off, vgb, r.xg, vpb, r.xp, vsb, r.xs);
                             T lp, d;
                             family_row<T, FAM>(r.y, eta, lp, d);
