@@ -7,7 +7,10 @@
 
 namespace skk {
 
-constexpr int kRowsPerLane = 17;  // R: odd => conflict-free lane-strided shared-memory reads
+#ifndef SKK_ROWS_PER_LANE
+#define SKK_ROWS_PER_LANE 17
+#endif
+constexpr int kRowsPerLane = SKK_ROWS_PER_LANE;  // R: odd => conflict-free lane-strided shared-memory reads
                                   // (R = 9 with three resident CTAs per SM measured slower on the crossed model:
                                   //  the per-tile work does not shrink with the tile, profiles/README.md)
 
