@@ -27,14 +27,14 @@ def main():
     os.makedirs(lib_dir, exist_ok=True)
     only = os.environ.get('SKK_VARIANT_ONLY')   # e.g. "poisson_bt1": other objects are taken from the main build
 
-    # With SKK_VARIANT_ONLY=<type>_<family> (e.g. f32_poisson) the library holds the row kernels of that
-    # family only (lookups of the others return null: plans of other families fail at creation), which
+    # With SKK_VARIANT_ONLY=<pattern>[,<pattern>...] (e.g. f32_poisson, or chain_f64,f64_normal) the library
+    # holds the kernels of the matching sources only (lookups of the others return null: plans of other families fail at creation), which
     # keeps a variant at ~15 MB instead of ~85 MB.
     stub_names = []
 
     def compile_one(src):
         base = os.path.basename(src)[:-3]
-        if only and base != 'skk_api' and only not in base:
+        if only and base != 'skk_api' and not any(pat in base for pat in only.split(',')):
             if base.startswith('skk_row_'):
                 stub_names.append(('row', base[len('skk_row_'):]))
             else:
