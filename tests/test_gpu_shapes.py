@@ -157,3 +157,24 @@ def test_chain_per_lane_nested_logistic(dtype):
     for b in (0, 31, 32, 63):
         assert_parity(logp[b], grad[b], plan, theta[b], dtype)
     f.close()
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+@pytest.mark.parametrize('shape', ['crossed_long_segments', 'crossed_two_group_tiles', 'nested', 'linreg'])
+def test_generic_kernels_on_tiled_shapes(shape, dtype, monkeypatch):
+    """
+    The run-time (non-specialised) row kernels on shapes with whole tiles inside one segment and with
+    two-group tiles: the same paths as the specialised kernels of the BASELINE shapes (hand-pipelined
+    common path, one-pass two-group path), which the small models of the test zoo never reach.
+    """
+    monkeypatch.setenv('SKK_GENERIC', '1')
+    if shape == 'crossed_long_segments':
+        plan = synth.poisson_plan(synth.poisson_columns(200_000, 20, 1000, seed=20)[0])
+    elif shape == 'crossed_two_group_tiles':
+        plan = synth.poisson_plan(synth.poisson_columns(120_000, 60, 7, seed=23)[0])
+    elif shape == 'nested':
+        plan = synth.logistic_plan(synth.logistic_columns(150_000, 50, 2, seed=9)[0])
+    else:
+        plan = synth.linreg_plan(synth.linreg_columns(100_000, 40, seed=3)[0])
+    check(plan, dtype)
+    check(plan, dtype, batch=3)
