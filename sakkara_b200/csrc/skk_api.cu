@@ -833,10 +833,14 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
     const bool chain = pl->chain_ready && batch >= kChainMinBatch && !sharded;
     // single GPU, row kernel: the priors ride in the row kernel's prologue and one finish kernel follows
     const bool fused = !sharded && !chain && pl->fused_ok && env_int("SKK_NO_FUSED_FINISH", 0) == 0;
+    // EXPERIMENT (off by default, not yet run on a GPU): the same for a row-sharded run -- priors in the row
+    // kernel's prologue, one kernel that hands the likelihood parts to the exchange (skk_finish_push_kernel)
+    const bool fused_sharded = sharded && !chain && pl->fused_ok && batch <= 4 && env_int("SKK_SHARDED_FINISH", 0) == 1;
+    const bool in_row = fused || fused_sharded;  // the prior terms ride in the row kernel
     // (for large batches they are big enough to fill the GPU themselves: run them in line)
     const bool fork = batch < kChainMinBatch;
     cudaStream_t ps = fork ? pl->side : st;
-    if (priors && !fused) {
+    if (priors && !in_row) {
         if (fork) {
             CUDA_TRY(cudaEventRecord(pl->ev_fork, st));
             CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
@@ -910,6 +914,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
     }
 
     bool joined = false;
+    int sharded_lp_stride = 0;
     for (int b0 = 0; b0 < batch;) {
         const int remaining = batch - b0;
         const bool wide = remaining >= 2 && pl->cfg4.fn != nullptr;
@@ -917,7 +922,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         const int b_valid = std::min(bt, remaining);
         const LaunchCfg &cfg = wide ? pl->cfg4 : pl->cfg1;
         // K1: the rows
-        if (int rc = launch_rows<T>(pl, cfg, timed, th + (size_t)b0 * P, b_valid, bt, b0, fused && priors)) return rc;
+        if (int rc = launch_rows<T>(pl, cfg, timed, th + (size_t)b0 * P, b_valid, bt, b0, in_row && priors)) return rc;
         ++launches;
         pl->stats.row_kernel_launches++;
 
@@ -940,6 +945,20 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
                 skk_finish_kernel<T, 4><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
             else
                 skk_finish_kernel<T, 1><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
+            ++launches;
+            b0 += b_valid;
+            continue;
+        }
+        if (fused_sharded) {
+            const unsigned blocks = slot_blocks + (unsigned)(rp.parent_blocks + rp.none_blocks);
+            sharded_lp_stride = cfg.grid * pl->warps;  // the final kernel reads the prologue's warp partials
+#define SKK_PUSH(BTV, MODEV) skk_finish_push_kernel<T, BTV, MODEV><<<blocks, 256, 0, st>>>(rp, pl->peer)
+            if (bt == 4) {
+                if (pl->peer_ready) SKK_PUSH(4, 2); else SKK_PUSH(4, 1);
+            } else {
+                if (pl->peer_ready) SKK_PUSH(1, 2); else SKK_PUSH(1, 1);
+            }
+#undef SKK_PUSH
             ++launches;
             b0 += b_valid;
             continue;
@@ -971,17 +990,17 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
 
     if (sharded) {
         // one all-reduce of [dlogp, logp partial, constant] per evaluation, then the final combination
-        FinalParams fp{pl->lik_vec, pl->prior_grad, pl->prior_lp, pl->prior_ctas, pl->n_params, pl->n_rows_total,
-                       pl->sigma_idx, pl->sigma_const, pl->family, pl->include_priors};
+        FinalParams fp{pl->lik_vec, pl->prior_grad, pl->prior_lp, fused_sharded ? sharded_lp_stride : pl->prior_ctas,
+                       pl->n_params, pl->n_rows_total, pl->sigma_idx, pl->sigma_const, pl->family, pl->include_priors};
         dim3 grid((unsigned)std::max<size_t>(1, (P + 255) / 256), (unsigned)batch);
         if (pl->peer_ready) {
-            if (priors && fork) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+            if (priors && fork && !in_row) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
             skk_final_kernel<T, true><<<grid, 256, 0, st>>>(fp, pl->peer, th, out_logp, out_grad);
         } else {
             NCCL_TRY(g_nccl.AllReduce(pl->lik_vec, pl->lik_vec, (size_t)batch * (P + 2), /*ncclDouble*/ 8,
                                       /*ncclSum*/ 0, pl->comm, st));
             ++launches;
-            if (priors && fork) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+            if (priors && fork && !in_row) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
             skk_final_kernel<T, false><<<grid, 256, 0, st>>>(fp, pl->peer, th, out_logp, out_grad);
         }
         ++launches;

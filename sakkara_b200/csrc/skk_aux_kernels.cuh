@@ -723,6 +723,222 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
     }
 }
 
+// ---- K4 fused, sharded (EXPERIMENT, off by default: SKK_SHARDED_FINISH=1; not yet run on a GPU) --------
+// The finish kernel's work split for a row-sharded run: instead of finishing a theta element, the thread
+// that completes a slot total hands the element's likelihood part to the exchange (MODE 1: lik_vec for
+// ncclAllReduce, MODE 2: this rank's slot in every peer, see the one-shot all-reduce above); elements
+// that nothing feeds on this rank are sent as zeros; the hyper-parameter CTAs add their children's
+// chunk partials to prior_grad (read by the final kernel after the exchange).  Replaces K3a, K3b, K4a
+// and K4f of a sharded evaluation (the prior terms ride in the row kernel's prologue): row kernel ->
+// this kernel -> [ncclAllReduce] -> K4b.
+template <typename T, int BT, int MODE>
+__global__ void __launch_bounds__(256)
+skk_finish_push_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp) {
+    static_assert(MODE == 1 || MODE == 2, "MODE 0 is skk_finish_kernel");
+    const int lane = threadIdx.x & 31;
+    const int64_t P = rp.n_params;
+    auto push_at = [&](int64_t k, const double (&v)[BT]) {   // k: element, or P (logp partial), P + 1 (constant)
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            if (b >= rp.b_valid) continue;
+            const int64_t row = rp.b0 + b;
+            if constexpr (MODE == 1) {
+                rp.lik_vec[row * (P + 2) + k] = v[b];
+            } else {
+                const unsigned long long seq = *pp.seq + 1;
+                const int64_t at = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride + row * (P + 2) + k;
+                for (int r = 0; r < pp.nranks; ++r) pp.peer_buf[r][at] = v[b];
+            }
+        }
+    };
+    double zeros[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) zeros[b] = 0.0;
+    const bool sigma_is_param = rp.family == SKK_LIK_NORMAL && rp.sigma_theta_index >= 0;
+    const int b_glob = rp.blocks_p + rp.blocks_s;
+    if ((int)blockIdx.x < rp.blocks_p) {
+        const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        const bool valid = slot < rp.n_primary;
+        int4 d = make_int4(0, -1, 0, 0);
+        if (valid) d = rp.slot_desc[slot];
+        int32_t elem[kMaxTermsPerLevel];
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) elem[t] = (valid && t < rp.np) ? rp.ti_p[t][slot] : -1;
+        const int64_t t_lo = d.x, t_hi = d.y;
+        const bool heavy = valid && (t_hi - t_lo + 1 > kSerialLimit);
+        auto addend = [&](int4 dd, int64_t tile, int t, int b) -> double {
+            const int kind = tile == dd.x ? dd.z : (tile == dd.y ? dd.w : 1);
+            const double *src = kind == 1 ? rp.tile_head : (kind == 2 ? rp.tile_tail : nullptr);
+            return src ? src[(tile * rp.np + t) * BT + b] : 0.0;
+        };
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) {
+            if (t >= rp.np) break;
+            if (valid && !heavy) {
+                double acc[BT];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+                if (t_hi >= t_lo) {
+#pragma unroll
+                    for (int b = 0; b < BT; ++b)
+                        acc[b] = rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b] + addend(d, t_lo, t, b);
+#pragma unroll 4
+                    for (int64_t tile = t_lo + 1; tile < t_hi; ++tile)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) acc[b] += rp.tile_head[(tile * rp.np + t) * BT + b];
+                    if (t_hi > t_lo)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) acc[b] += addend(d, t_hi, t, b);
+                }
+                push_at(elem[t], acc);
+            }
+            unsigned todo = __ballot_sync(kFull, heavy);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t s2 = __shfl_sync(kFull, slot, src);
+                const int4 dd = rp.slot_desc[s2];
+                double acc[BT];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+                for (int64_t tile = dd.x + lane; tile <= dd.y; tile += 32)
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) acc[b] += addend(dd, tile, t, b);
+#pragma unroll
+                for (int b = 0; b < BT; ++b)
+                    acc[b] = __shfl_sync(kFull, warp_sum(acc[b]), 0) +
+                             rp.direct_p[((int64_t)t * rp.n_primary + s2) * BT + b];
+                if (lane == src) push_at(elem[t], acc);
+            }
+        }
+    } else if ((int)blockIdx.x < b_glob) {
+        __shared__ double part[8][32];
+        const int sub = threadIdx.x >> 5;
+        const int64_t slot = ((int64_t)blockIdx.x - rp.blocks_p) * 32 + lane;
+        const bool valid = slot < rp.n_secondary;
+        const int per = (rp.grid + 7) / 8;
+        const int c0 = sub * per, c1 = min(rp.grid, c0 + per);
+        int32_t elem[kMaxTermsPerLevel];
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) elem[t] = (sub == 0 && valid && t < rp.ns) ? rp.ti_s[t][slot] : -1;
+#pragma unroll
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) {
+            if (t >= rp.ns) break;
+            double lik[BT];
+            for (int b = 0; b < BT; ++b) {
+                double acc = 0.0;
+                if (valid) {
+                    const double *src = rp.cta_sec + ((int64_t)t * rp.n_secondary + slot) * BT + b;
+                    const int64_t stride = (int64_t)rp.ns * rp.n_secondary * BT;
+#pragma unroll 8
+                    for (int c = c0; c < c1; ++c) acc += src[c * stride];
+                }
+                part[sub][lane] = acc;
+                __syncthreads();
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s += part[k][lane];
+                lik[b] = s;
+                __syncthreads();
+            }
+            if (sub == 0 && valid) push_at(elem[t], lik);
+        }
+    } else if ((int)blockIdx.x == b_glob) {
+        __shared__ double glob[(kMaxTermsPerLevel + 1) * BT];
+        const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+        for (int item = warp; item < (rp.ng + 1) * BT; item += warps) {
+            double acc = 0.0;
+            for (int c = lane; c < rp.grid; c += 32) acc += rp.cta_glob[(int64_t)c * (rp.ng + 1) * BT + item];
+            acc = warp_sum(acc);
+            if (lane == 0) glob[item] = acc;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < rp.ng) {
+            double lik[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) lik[b] = glob[threadIdx.x * BT + b];
+            push_at(rp.ti_g[threadIdx.x][0], lik);
+        }
+        if (threadIdx.x == 32 && sigma_is_param) push_at(rp.sigma_theta_index, zeros);  // its part travels as L
+        if (threadIdx.x == 64) {
+            double L[BT], c[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                L[b] = glob[rp.ng * BT + b];
+                c[b] = rp.logp_const;
+            }
+            push_at(P, L);
+            push_at(P + 1, c);
+        }
+    } else if ((int)blockIdx.x <= b_glob + rp.parent_blocks) {
+        // hyper-parameters: children's chunk partials -> prior_grad (own term written by the row kernel's
+        // prologue; this thread is the element's only other writer), likelihood part zero
+        __shared__ double hp_part[8][BT];
+        const int warp = threadIdx.x >> 5;
+        const int pb = (int)blockIdx.x - b_glob - 1;
+        const bool heavy = pb < rp.n_heavy;
+        const int64_t q = heavy ? pb : rp.n_heavy + ((int64_t)pb - rp.n_heavy) * 8 + warp;
+        const bool active = heavy || q < rp.n_parents;   // (no early return: every thread reaches the tail below)
+        double sum[BT];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) sum[b] = 0.0;
+        if (active) {
+            const int64_t lo = rp.chunk_ptr[q], hi = rp.chunk_ptr[q + 1];
+            const int64_t first = lo + (heavy ? threadIdx.x : lane), step = heavy ? blockDim.x : 32;
+            const double *part = rp.link_part + (int64_t)rp.b0 * rp.n_chunks;
+            for (int64_t e = first; e < hi; e += step)
+#pragma unroll
+                for (int b = 0; b < BT; ++b)
+                    if (b < rp.b_valid) sum[b] += part[(int64_t)b * rp.n_chunks + e];
+        }
+#pragma unroll
+        for (int b = 0; b < BT; ++b) sum[b] = warp_sum(sum[b]);
+        if (heavy) {
+            if (lane == 0)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) hp_part[warp][b] = sum[b];
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                sum[b] = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sum[b] += hp_part[w][b];
+            }
+        }
+        if (active && (heavy ? threadIdx.x == 0 : lane == 0)) {
+            const int64_t j = rp.parent[q];
+            double *prior_grad = const_cast<double *>(rp.prior_grad);
+#pragma unroll
+            for (int b = 0; b < BT; ++b)
+                if (b < rp.b_valid && rp.include_priors) prior_grad[(int64_t)(rp.b0 + b) * P + j] += sum[b];
+            push_at(j, zeros);
+        }
+    } else {
+        const int64_t k = ((int64_t)blockIdx.x - b_glob - 1 - rp.parent_blocks) * blockDim.x + threadIdx.x;
+        if (k < rp.n_none) {
+            const int64_t j = rp.none_elem[k];
+            if (!(sigma_is_param && j == rp.sigma_theta_index)) push_at(j, zeros);
+        }
+    }
+    if constexpr (MODE == 2) {
+        // as in skk_theta_kernel: every store of this CTA is visible system-wide before the CTA counts
+        // itself done; the last CTA of the last batch tile publishes the vector by raising the flags
+        __threadfence_system();
+        __syncthreads();
+        __shared__ bool last;
+        if (threadIdx.x == 0) last = atomicAdd(pp.done + 1, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (last) {
+            if (threadIdx.x == 0) pp.done[1] = 0;
+            if (rp.b0 + rp.b_valid >= rp.batch_total && threadIdx.x < pp.nranks) {
+                __threadfence_system();
+                volatile unsigned long long *flag = pp.peer_flag[threadIdx.x] + pp.rank;
+                *flag = *pp.seq + 1;
+            }
+        }
+    }
+}
+
 // ---- K4b (sharded runs: after the all-reduce) ------------------------------------------------
 struct FinalParams {
     const double *lik_vec;      // [B][P+2], all-reduced over ranks
