@@ -2,9 +2,13 @@
 //   plan creation : validate the descriptor, upload the row columns (padded to whole tiles), derive
 //                   the tile keys, the reduce CSR and the prior link CSR, pick the kernel
 //                   specialisation and its launch geometry, allocate every work buffer once.
-//   evaluation    : H2D theta -> K3 priors -> per batch tile {K0 prepare, K1 rows, K4a reduce}
-//                   -> [NCCL all-reduce when row-sharded] -> K4b final -> D2H.  One stream, no
-//                   allocation, no host synchronisation before the final copy.
+//   evaluation    : single GPU, every theta element fed by at most one slot:
+//                     H2D theta -> per batch tile {K1 rows (priors in its prologue), finish} -> D2H;
+//                   otherwise: H2D theta -> {K3a, K3b priors on a parallel branch} || per batch tile
+//                     {K1 rows, K4a slot totals, K4f theta} -> [peer exchange | NCCL all-reduce -> K4b final
+//                     when row-sharded] -> D2H;  batches >= 32 without a secondary level: K2 chain kernels.
+//                   No allocation, no host synchronisation before the final copy; the sequence is
+//                   captured once per (batch, buffers) and replayed as a CUDA graph.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 

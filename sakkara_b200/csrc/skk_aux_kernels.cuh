@@ -10,6 +10,8 @@
 //   K4f theta/final  : per theta element: sum of its slots' totals; then either the final
 //                      combination (single GPU) or the vector handed to the all-reduce
 //   K4b final        : (sharded runs) Normal scale, + priors, + constants -> logp[B], dlogp[B, P]
+//   finish           : (single GPU, no element fed by several slots) K4a + K4f + the hyper-parameter sums
+//                      in one launch; the prior terms then come from the row kernel's prologue
 #pragma once
 
 #include "skk_common.cuh"
