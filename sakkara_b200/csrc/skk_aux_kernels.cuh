@@ -472,7 +472,7 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant_
     }
 }
 
-// ---- K4 fused (single GPU): slot totals -> theta elements -> outputs in one launch ------------------
+// ---- K4 fused: slot totals -> theta elements -> outputs (or the exchange) in one launch ---------------
 // Used when every theta element is fed by at most one slot (no term sits on a parent of a grouping
 // level) and no term feeds a hyper-parameter; other models run the separate kernels above.
 // CTA classes by blockIdx.x: [0, blocks_p) primary slots (one per thread); then blocks_s CTAs of
@@ -482,10 +482,16 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant_
 // thread that completes the total of a slot finishes the slot's theta element on the spot.  Every
 // thread is latency-bound, so whatever it will need (descriptor, element, the element's own prior
 // gradient) is loaded up front and the chain of dependent loads is two deep.
-template <typename T, int BT>
-__global__ void __launch_bounds__(256)
-skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp,
-                  const T *__restrict__ theta, T *__restrict__ out_logp, T *__restrict__ out_grad) {
+//   MODE 0 (skk_finish_kernel, single GPU): the element's gradient and logp go to the outputs.
+//   MODE 1 / 2 (skk_finish_push_kernel; EXPERIMENT, off by default: SKK_SHARDED_FINISH=1, not yet run on a
+//   GPU): a row-sharded run -- the element's likelihood part is handed to the exchange instead (1: lik_vec
+//   for ncclAllReduce, 2: this rank's slot in every peer, see the one-shot all-reduce above), elements
+//   that nothing feeds on this rank are sent as zeros, the hyper-parameter CTAs add their children's
+//   chunk partials to prior_grad (read by K4b after the exchange).  Replaces K3a, K3b, K4a and K4f of a
+//   sharded evaluation: row kernel (priors in its prologue) -> this kernel -> [ncclAllReduce] -> K4b.
+template <typename T, int BT, int MODE>
+__device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerParams &pp, const T *__restrict__ theta,
+                                            T *__restrict__ out_logp, T *__restrict__ out_grad) {
     const int lane = threadIdx.x & 31;
     const int64_t P = rp.n_params;
     // 1 / sigma^2 of the Normal likelihood per chain (1 for the other families)
@@ -493,7 +499,7 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
         scale[b] = 1.0;
-        if (rp.family == SKK_LIK_NORMAL && b < rp.b_valid) {
+        if (MODE == 0 && rp.family == SKK_LIK_NORMAL && b < rp.b_valid) {
             const double sigma = rp.sigma_theta_index >= 0
                                      ? exp((double)theta[(int64_t)(rp.b0 + b) * P + rp.sigma_theta_index])
                                      : rp.sigma_const;
@@ -504,12 +510,25 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
     auto prior_of = [&](int64_t j, double (&pg)[BT]) {
 #pragma unroll
         for (int b = 0; b < BT; ++b)
-            pg[b] = (rp.include_priors && j >= 0 && b < rp.b_valid) ? rp.prior_grad[(int64_t)(rp.b0 + b) * P + j] : 0.0;
+            pg[b] = (MODE == 0 && rp.include_priors && j >= 0 && b < rp.b_valid)
+                        ? rp.prior_grad[(int64_t)(rp.b0 + b) * P + j] : 0.0;
     };
-    auto store = [&](int64_t j, const double (&lik)[BT], const double (&pg)[BT]) {
+    // k: a theta element, or (MODE 1 / 2) P for the logp partial and P + 1 for the constant
+    auto store = [&](int64_t k, const double (&lik)[BT], const double (&pg)[BT]) {
 #pragma unroll
-        for (int b = 0; b < BT; ++b)
-            if (b < rp.b_valid) out_grad[(int64_t)(rp.b0 + b) * P + j] = (T)(lik[b] * scale[b] + pg[b]);
+        for (int b = 0; b < BT; ++b) {
+            if (b >= rp.b_valid) continue;
+            const int64_t row = rp.b0 + b;
+            if constexpr (MODE == 0) {
+                out_grad[row * P + k] = (T)(lik[b] * scale[b] + pg[b]);
+            } else if constexpr (MODE == 1) {
+                rp.lik_vec[row * (P + 2) + k] = lik[b];
+            } else {
+                const unsigned long long seq = *pp.seq + 1;
+                const int64_t at = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride + row * (P + 2) + k;
+                for (int r = 0; r < pp.nranks; ++r) pp.peer_buf[r][at] = lik[b];
+            }
+        }
     };
     const bool sigma_is_param = rp.family == SKK_LIK_NORMAL && rp.sigma_theta_index >= 0;
     const int b_glob = rp.blocks_p + rp.blocks_s;
@@ -619,14 +638,17 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
             if (lane == 0) glob[item] = acc;
         }
         // prior logp: the warp partials of the row kernel's prologue, 8 / BT warps per chain
+        // (sharded runs: K4b adds them after the exchange)
         constexpr int WPC = 8 / BT;  // BT is 1 or 4
-        const int chain = warp / WPC, sub = warp % WPC;
-        double s = 0.0;
-        if (rp.include_priors && chain < rp.b_valid)
-            for (int k = sub * 32 + lane; k < rp.n_lp_parts; k += WPC * 32)
-                s += rp.prior_lp_part[(int64_t)(rp.b0 + chain) * rp.prior_ctas + k];
-        s = warp_sum(s);
-        if (lane == 0) lp_part[warp] = s;
+        if constexpr (MODE == 0) {
+            const int chain = warp / WPC, sub = warp % WPC;
+            double s = 0.0;
+            if (rp.include_priors && chain < rp.b_valid)
+                for (int k = sub * 32 + lane; k < rp.n_lp_parts; k += WPC * 32)
+                    s += rp.prior_lp_part[(int64_t)(rp.b0 + chain) * rp.prior_ctas + k];
+            s = warp_sum(s);
+            if (lane == 0) lp_part[warp] = s;
+        }
         __syncthreads();
         if ((int)threadIdx.x < rp.ng) {
             double lik[BT], pg[BT];
@@ -638,32 +660,45 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
         }
         if (threadIdx.x == 32 && sigma_is_param) {
             // d/d log(sigma) = sum(r^2) / sigma^2 - N (+ its own prior term; sigma has no children on this path)
+            // (sharded runs: zero here, its part travels as the logp partial)
             double lik[BT], pg[BT];
             prior_of(rp.sigma_theta_index, pg);
 #pragma unroll
             for (int b = 0; b < BT; ++b) {
-                lik[b] = glob[rp.ng * BT + b];
+                lik[b] = MODE == 0 ? glob[rp.ng * BT + b] : 0.0;
                 pg[b] -= (double)rp.n_rows_total;
             }
             store(rp.sigma_theta_index, lik, pg);
         }
-        if ((int)threadIdx.x >= 64 && (int)threadIdx.x < 64 + BT && (int)threadIdx.x - 64 < rp.b_valid) {
-            const int b = threadIdx.x - 64;
-            const int64_t row = rp.b0 + b;
-            double tot = 0.0;
+        if constexpr (MODE == 0) {
+            if ((int)threadIdx.x >= 64 && (int)threadIdx.x < 64 + BT && (int)threadIdx.x - 64 < rp.b_valid) {
+                const int b = threadIdx.x - 64;
+                const int64_t row = rp.b0 + b;
+                double tot = 0.0;
 #pragma unroll
-            for (int w = 0; w < WPC; ++w) tot += lp_part[b * WPC + w];
-            const double L = glob[rp.ng * BT + b];
-            double ll = L;
-            if (rp.family == SKK_LIK_NORMAL) {
-                const double log_sigma =
-                    sigma_is_param ? (double)theta[row * P + rp.sigma_theta_index] : log(rp.sigma_const);
-                double sc = 1.0;
+                for (int w = 0; w < WPC; ++w) tot += lp_part[b * WPC + w];
+                const double L = glob[rp.ng * BT + b];
+                double ll = L;
+                if (rp.family == SKK_LIK_NORMAL) {
+                    const double log_sigma =
+                        sigma_is_param ? (double)theta[row * P + rp.sigma_theta_index] : log(rp.sigma_const);
+                    double sc = 1.0;
 #pragma unroll
-                for (int k = 0; k < BT; ++k) sc = k == b ? scale[k] : sc;  // (no dynamically indexed register array)
-                ll = -0.5 * L * sc - (double)rp.n_rows_total * (kLogSqrt2Pi + log_sigma);
+                    for (int k = 0; k < BT; ++k) sc = k == b ? scale[k] : sc;  // (no dynamically indexed register array)
+                    ll = -0.5 * L * sc - (double)rp.n_rows_total * (kLogSqrt2Pi + log_sigma);
+                }
+                out_logp[row] = (T)(tot + ll + rp.logp_const);
             }
-            out_logp[row] = (T)(tot + ll + rp.logp_const);
+        } else if (threadIdx.x == 64) {
+            double L[BT], c[BT], none[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                L[b] = glob[rp.ng * BT + b];
+                c[b] = rp.logp_const;
+                none[b] = 0.0;
+            }
+            store(P, L, none);
+            store(P + 1, c, none);
         }
     } else if ((int)blockIdx.x <= b_glob + rp.parent_blocks) {
         // hyper-parameters: own prior term + the sum over the children's chunk partials (contiguous)
@@ -672,220 +707,18 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
         const int pb = (int)blockIdx.x - b_glob - 1;
         const bool heavy = pb < rp.n_heavy;
         const int64_t q = heavy ? pb : rp.n_heavy + ((int64_t)pb - rp.n_heavy) * 8 + warp;
-        if (!heavy && q >= rp.n_parents) return;
-        const int64_t lo = rp.chunk_ptr[q], hi = rp.chunk_ptr[q + 1];
-        const int32_t j = rp.parent[q];
-        double pg[BT];
-        prior_of(j, pg);
-        const int64_t first = lo + (heavy ? threadIdx.x : lane), step = heavy ? blockDim.x : 32;
-        const double *part = rp.link_part + (int64_t)rp.b0 * rp.n_chunks;
-        double sum[BT];
+        const bool active = heavy || q < rp.n_parents;
+        if constexpr (MODE == 0) {
+            if (!active) return;
+        }  // (MODE 2: every thread has to reach the tail of the kernel)
+        int32_t j = 0;
+        double pg[BT], sum[BT];
 #pragma unroll
-        for (int b = 0; b < BT; ++b) sum[b] = 0.0;
-        for (int64_t e = first; e < hi; e += step)
-#pragma unroll
-            for (int b = 0; b < BT; ++b)
-                if (b < rp.b_valid) sum[b] += part[(int64_t)b * rp.n_chunks + e];
-#pragma unroll
-        for (int b = 0; b < BT; ++b) sum[b] = warp_sum(sum[b]);
-        if (heavy) {
-            if (lane == 0)
-#pragma unroll
-                for (int b = 0; b < BT; ++b) hp_part[warp][b] = sum[b];
-            __syncthreads();
-#pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                sum[b] = 0.0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) sum[b] += hp_part[w][b];
-            }
-        }
-        if (heavy ? threadIdx.x == 0 : lane == 0) {
-            double lik[BT];
-#pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                lik[b] = 0.0;
-                pg[b] += rp.include_priors ? sum[b] : 0.0;
-            }
-            store(j, lik, pg);
-        }
-    } else {
-        // elements that no term feeds and that have no children: own prior term only
-        const int64_t k = ((int64_t)blockIdx.x - b_glob - 1 - rp.parent_blocks) * blockDim.x + threadIdx.x;
-        if (k < rp.n_none) {
-            const int64_t j = rp.none_elem[k];
-            if (!(sigma_is_param && j == rp.sigma_theta_index)) {
-                double lik[BT], pg[BT];
-                prior_of(j, pg);
-#pragma unroll
-                for (int b = 0; b < BT; ++b) lik[b] = 0.0;
-                store(j, lik, pg);
-            }
-        }
-    }
-}
-
-// ---- K4 fused, sharded (EXPERIMENT, off by default: SKK_SHARDED_FINISH=1; not yet run on a GPU) --------
-// The finish kernel's work split for a row-sharded run: instead of finishing a theta element, the thread
-// that completes a slot total hands the element's likelihood part to the exchange (MODE 1: lik_vec for
-// ncclAllReduce, MODE 2: this rank's slot in every peer, see the one-shot all-reduce above); elements
-// that nothing feeds on this rank are sent as zeros; the hyper-parameter CTAs add their children's
-// chunk partials to prior_grad (read by the final kernel after the exchange).  Replaces K3a, K3b, K4a
-// and K4f of a sharded evaluation (the prior terms ride in the row kernel's prologue): row kernel ->
-// this kernel -> [ncclAllReduce] -> K4b.
-template <typename T, int BT, int MODE>
-__global__ void __launch_bounds__(256)
-skk_finish_push_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp) {
-    static_assert(MODE == 1 || MODE == 2, "MODE 0 is skk_finish_kernel");
-    const int lane = threadIdx.x & 31;
-    const int64_t P = rp.n_params;
-    auto push_at = [&](int64_t k, const double (&v)[BT]) {   // k: element, or P (logp partial), P + 1 (constant)
-#pragma unroll
-        for (int b = 0; b < BT; ++b) {
-            if (b >= rp.b_valid) continue;
-            const int64_t row = rp.b0 + b;
-            if constexpr (MODE == 1) {
-                rp.lik_vec[row * (P + 2) + k] = v[b];
-            } else {
-                const unsigned long long seq = *pp.seq + 1;
-                const int64_t at = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride + row * (P + 2) + k;
-                for (int r = 0; r < pp.nranks; ++r) pp.peer_buf[r][at] = v[b];
-            }
-        }
-    };
-    double zeros[BT];
-#pragma unroll
-    for (int b = 0; b < BT; ++b) zeros[b] = 0.0;
-    const bool sigma_is_param = rp.family == SKK_LIK_NORMAL && rp.sigma_theta_index >= 0;
-    const int b_glob = rp.blocks_p + rp.blocks_s;
-    if ((int)blockIdx.x < rp.blocks_p) {
-        const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        const bool valid = slot < rp.n_primary;
-        int4 d = make_int4(0, -1, 0, 0);
-        if (valid) d = rp.slot_desc[slot];
-        int32_t elem[kMaxTermsPerLevel];
-#pragma unroll
-        for (int t = 0; t < kMaxTermsPerLevel; ++t) elem[t] = (valid && t < rp.np) ? rp.ti_p[t][slot] : -1;
-        const int64_t t_lo = d.x, t_hi = d.y;
-        const bool heavy = valid && (t_hi - t_lo + 1 > kSerialLimit);
-        auto addend = [&](int4 dd, int64_t tile, int t, int b) -> double {
-            const int kind = tile == dd.x ? dd.z : (tile == dd.y ? dd.w : 1);
-            const double *src = kind == 1 ? rp.tile_head : (kind == 2 ? rp.tile_tail : nullptr);
-            return src ? src[(tile * rp.np + t) * BT + b] : 0.0;
-        };
-#pragma unroll
-        for (int t = 0; t < kMaxTermsPerLevel; ++t) {
-            if (t >= rp.np) break;
-            if (valid && !heavy) {
-                double acc[BT];
-#pragma unroll
-                for (int b = 0; b < BT; ++b) acc[b] = 0.0;
-                if (t_hi >= t_lo) {
-#pragma unroll
-                    for (int b = 0; b < BT; ++b)
-                        acc[b] = rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b] + addend(d, t_lo, t, b);
-#pragma unroll 4
-                    for (int64_t tile = t_lo + 1; tile < t_hi; ++tile)
-#pragma unroll
-                        for (int b = 0; b < BT; ++b) acc[b] += rp.tile_head[(tile * rp.np + t) * BT + b];
-                    if (t_hi > t_lo)
-#pragma unroll
-                        for (int b = 0; b < BT; ++b) acc[b] += addend(d, t_hi, t, b);
-                }
-                push_at(elem[t], acc);
-            }
-            unsigned todo = __ballot_sync(kFull, heavy);
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int64_t s2 = __shfl_sync(kFull, slot, src);
-                const int4 dd = rp.slot_desc[s2];
-                double acc[BT];
-#pragma unroll
-                for (int b = 0; b < BT; ++b) acc[b] = 0.0;
-                for (int64_t tile = dd.x + lane; tile <= dd.y; tile += 32)
-#pragma unroll
-                    for (int b = 0; b < BT; ++b) acc[b] += addend(dd, tile, t, b);
-#pragma unroll
-                for (int b = 0; b < BT; ++b)
-                    acc[b] = __shfl_sync(kFull, warp_sum(acc[b]), 0) +
-                             rp.direct_p[((int64_t)t * rp.n_primary + s2) * BT + b];
-                if (lane == src) push_at(elem[t], acc);
-            }
-        }
-    } else if ((int)blockIdx.x < b_glob) {
-        __shared__ double part[8][32];
-        const int sub = threadIdx.x >> 5;
-        const int64_t slot = ((int64_t)blockIdx.x - rp.blocks_p) * 32 + lane;
-        const bool valid = slot < rp.n_secondary;
-        const int per = (rp.grid + 7) / 8;
-        const int c0 = sub * per, c1 = min(rp.grid, c0 + per);
-        int32_t elem[kMaxTermsPerLevel];
-#pragma unroll
-        for (int t = 0; t < kMaxTermsPerLevel; ++t) elem[t] = (sub == 0 && valid && t < rp.ns) ? rp.ti_s[t][slot] : -1;
-#pragma unroll
-        for (int t = 0; t < kMaxTermsPerLevel; ++t) {
-            if (t >= rp.ns) break;
-            double lik[BT];
-            for (int b = 0; b < BT; ++b) {
-                double acc = 0.0;
-                if (valid) {
-                    const double *src = rp.cta_sec + ((int64_t)t * rp.n_secondary + slot) * BT + b;
-                    const int64_t stride = (int64_t)rp.ns * rp.n_secondary * BT;
-#pragma unroll 8
-                    for (int c = c0; c < c1; ++c) acc += src[c * stride];
-                }
-                part[sub][lane] = acc;
-                __syncthreads();
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) s += part[k][lane];
-                lik[b] = s;
-                __syncthreads();
-            }
-            if (sub == 0 && valid) push_at(elem[t], lik);
-        }
-    } else if ((int)blockIdx.x == b_glob) {
-        __shared__ double glob[(kMaxTermsPerLevel + 1) * BT];
-        const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-        for (int item = warp; item < (rp.ng + 1) * BT; item += warps) {
-            double acc = 0.0;
-            for (int c = lane; c < rp.grid; c += 32) acc += rp.cta_glob[(int64_t)c * (rp.ng + 1) * BT + item];
-            acc = warp_sum(acc);
-            if (lane == 0) glob[item] = acc;
-        }
-        __syncthreads();
-        if ((int)threadIdx.x < rp.ng) {
-            double lik[BT];
-#pragma unroll
-            for (int b = 0; b < BT; ++b) lik[b] = glob[threadIdx.x * BT + b];
-            push_at(rp.ti_g[threadIdx.x][0], lik);
-        }
-        if (threadIdx.x == 32 && sigma_is_param) push_at(rp.sigma_theta_index, zeros);  // its part travels as L
-        if (threadIdx.x == 64) {
-            double L[BT], c[BT];
-#pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                L[b] = glob[rp.ng * BT + b];
-                c[b] = rp.logp_const;
-            }
-            push_at(P, L);
-            push_at(P + 1, c);
-        }
-    } else if ((int)blockIdx.x <= b_glob + rp.parent_blocks) {
-        // hyper-parameters: children's chunk partials -> prior_grad (own term written by the row kernel's
-        // prologue; this thread is the element's only other writer), likelihood part zero
-        __shared__ double hp_part[8][BT];
-        const int warp = threadIdx.x >> 5;
-        const int pb = (int)blockIdx.x - b_glob - 1;
-        const bool heavy = pb < rp.n_heavy;
-        const int64_t q = heavy ? pb : rp.n_heavy + ((int64_t)pb - rp.n_heavy) * 8 + warp;
-        const bool active = heavy || q < rp.n_parents;   // (no early return: every thread reaches the tail below)
-        double sum[BT];
-#pragma unroll
-        for (int b = 0; b < BT; ++b) sum[b] = 0.0;
+        for (int b = 0; b < BT; ++b) sum[b] = pg[b] = 0.0;
         if (active) {
             const int64_t lo = rp.chunk_ptr[q], hi = rp.chunk_ptr[q + 1];
+            j = rp.parent[q];
+            prior_of(j, pg);
             const int64_t first = lo + (heavy ? threadIdx.x : lane), step = heavy ? blockDim.x : 32;
             const double *part = rp.link_part + (int64_t)rp.b0 * rp.n_chunks;
             for (int64_t e = first; e < hi; e += step)
@@ -908,18 +741,32 @@ skk_finish_push_kernel(const __grid_constant__ ReduceParams rp, const __grid_con
             }
         }
         if (active && (heavy ? threadIdx.x == 0 : lane == 0)) {
-            const int64_t j = rp.parent[q];
-            double *prior_grad = const_cast<double *>(rp.prior_grad);
+            double lik[BT];
 #pragma unroll
-            for (int b = 0; b < BT; ++b)
-                if (b < rp.b_valid && rp.include_priors) prior_grad[(int64_t)(rp.b0 + b) * P + j] += sum[b];
-            push_at(j, zeros);
+            for (int b = 0; b < BT; ++b) {
+                lik[b] = 0.0;
+                if constexpr (MODE == 0) {
+                    pg[b] += rp.include_priors ? sum[b] : 0.0;
+                } else {
+                    // own term written by the row kernel's prologue; this thread is the element's only other writer
+                    if (b < rp.b_valid && rp.include_priors)
+                        const_cast<double *>(rp.prior_grad)[(int64_t)(rp.b0 + b) * P + j] += sum[b];
+                }
+            }
+            store(j, lik, pg);
         }
     } else {
+        // elements that no term feeds and that have no children: own prior term only
         const int64_t k = ((int64_t)blockIdx.x - b_glob - 1 - rp.parent_blocks) * blockDim.x + threadIdx.x;
         if (k < rp.n_none) {
             const int64_t j = rp.none_elem[k];
-            if (!(sigma_is_param && j == rp.sigma_theta_index)) push_at(j, zeros);
+            if (!(sigma_is_param && j == rp.sigma_theta_index)) {
+                double lik[BT], pg[BT];
+                prior_of(j, pg);
+#pragma unroll
+                for (int b = 0; b < BT; ++b) lik[b] = 0.0;
+                store(j, lik, pg);
+            }
         }
     }
     if constexpr (MODE == 2) {
@@ -939,6 +786,20 @@ skk_finish_push_kernel(const __grid_constant__ ReduceParams rp, const __grid_con
             }
         }
     }
+}
+
+template <typename T, int BT>
+__global__ void __launch_bounds__(256)
+skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp,
+                  const T *__restrict__ theta, T *__restrict__ out_logp, T *__restrict__ out_grad) {
+    finish_body<T, BT, 0>(rp, pp, theta, out_logp, out_grad);
+}
+
+template <typename T, int BT, int MODE>
+__global__ void __launch_bounds__(256)
+skk_finish_push_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp) {
+    static_assert(MODE == 1 || MODE == 2, "MODE 0 is skk_finish_kernel");
+    finish_body<T, BT, MODE>(rp, pp, static_cast<const T *>(nullptr), static_cast<T *>(nullptr), static_cast<T *>(nullptr));
 }
 
 // ---- K4b (sharded runs: after the all-reduce) ------------------------------------------------
