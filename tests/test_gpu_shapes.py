@@ -169,7 +169,7 @@ def test_generic_kernels_on_tiled_shapes(shape, dtype, monkeypatch):
     """
     monkeypatch.setenv('SKK_GENERIC', '1')
     if shape == 'crossed_long_segments':
-        plan = synth.poisson_plan(synth.poisson_columns(200_000, 20, 1000, seed=20)[0])
+        plan = synth.poisson_plan(synth.poisson_columns(200_000, 20, 300, seed=20)[0])
     elif shape == 'crossed_two_group_tiles':
         plan = synth.poisson_plan(synth.poisson_columns(120_000, 60, 7, seed=23)[0])
     elif shape == 'nested':
