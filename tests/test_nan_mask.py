@@ -166,3 +166,27 @@ def test_gpu_parity_with_masked_rows(family, dtype):
         logp, grad = f(theta)
         assert_parity(logp, grad, model.plan, theta, dtype)
     f.close()
+
+
+def test_random_masks_agree_with_the_recorded_graph():
+    """random NaN positions (including none and whole groups), all three families"""
+    rng = np.random.default_rng(99)
+    for trial in range(6):
+        n = int(rng.integers(20, 120))
+        groups = int(rng.integers(2, 6))      # (a one-member group is a twin of 'global', as in the reference)
+        k = int(rng.integers(0, n // 2))
+        nan_rows = tuple(sorted(rng.choice(np.arange(groups, n), size=min(k, n - groups), replace=False).tolist()))
+        df, _ = frame(n=n, groups=groups, seed=100 + trial, nan_rows=nan_rows if nan_rows else (groups,))
+        family = ['normal', 'bernoulli', 'poisson'][trial % 3]
+        model = build(df, family)
+        assert model.plan.n_rows + model.plan.n_masked_rows == n
+        theta = rng.normal(0.0, 0.4, model.plan.n_params)
+        logp, grad = logp_dlogp(model.plan, theta)
+        ref_logp, ref_grad = logp_dlogp_autograd(model.recorded, theta)
+        assert logp == pytest.approx(ref_logp, rel=1e-11)
+        np.testing.assert_allclose(grad, ref_grad, rtol=1e-9, atol=1e-11)
+        kp = make_kernel_plan(model.plan, dtype='float64')
+        lik_l, lik_g = likelihood_from_kernel_plan(kp, theta)
+        pr_l, pr_g = logp_dlogp(priors_only(model.plan), theta)
+        assert lik_l + pr_l == pytest.approx(logp, rel=1e-11)
+        np.testing.assert_allclose(lik_g + pr_g, grad, rtol=1e-9, atol=1e-11)
