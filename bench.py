@@ -222,6 +222,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--collective', default='auto', choices=['auto', 'peer', 'nccl'])
     ap.add_argument('--check', action='store_true', help='verify one evaluation against the oracle (small --rows)')
+    ap.add_argument('--emulate-world', type=int, default=1,
+                    help='one GPU runs the shard of rank 0 of W ranks through the sharded pipeline (self exchange)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -249,7 +251,13 @@ def main():
     if chains_sharded:
         batch = batch_total // world + (1 if rank < batch_total % world else 0)
     t0 = time.time()
-    plan = make_plan(args.config, rows_total, rank, world)
+    if args.emulate_world > 1:
+        if world != 1:
+            raise SystemExit('--emulate-world runs on one GPU')
+        os.environ['SKK_FORCE_PEER'] = '1'
+        plan = make_plan(args.config, rows_total, 0, args.emulate_world)
+    else:
+        plan = make_plan(args.config, rows_total, rank, world)
     t_gen = time.time() - t0
     f = ValueGradFunction(plan, dtype=dtype, max_batch=batch, device=local,
                           n_rows_total=plan.n_rows if chains_sharded else rows_total)

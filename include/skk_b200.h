@@ -204,6 +204,15 @@ int skk_stats(skk_plan *plan, skk_stats_t *out);
 /* cudaStream_t the plan launches on (so that callers can record their own events on it). */
 void *skk_stream(skk_plan *plan);
 
+/*
+ * Diagnostics: per-warp timeline of the row kernel (%globaltimer at entry, end of the prologue, arrival of
+ * the first tile, end of the tile loop, exit).  skk_trace_read copies [grid * warps][8] words of the last
+ * evaluation (at most `capacity` words) and returns the number of words, or a negative SKK_ERR_* code.
+ * No counterpart in the reference; used by tools/trace_rows.py to attribute the per-launch cost.
+ */
+int skk_trace_enable(skk_plan *plan, int32_t on);
+int64_t skk_trace_read(skk_plan *plan, uint64_t *out, int64_t capacity);
+
 int skk_abi_version(void);
 
 #ifdef __cplusplus

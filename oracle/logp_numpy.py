@@ -101,7 +101,9 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
             logp_mass += np.sum(np.abs(terms), dtype=np.float64)
             acc(number, None, -z / sd)
             if not mu_p.is_const:
-                acc(mu_p.block, mu_p.index, z / sd)
+                # a mu that is a positive variable is sampled as u = log(mu): chain rule d mu / d u = mu
+                d_mu = z / sd
+                acc(mu_p.block, mu_p.index, d_mu * mu if plan.blocks[mu_p.block].transform == 'log' else d_mu)
             if not sd_p.is_const:
                 # d/d sigma = (z^2 - 1)/sigma, times d sigma / d u = sigma
                 acc(sd_p.block, sd_p.index, z * z - T(1))

@@ -195,6 +195,11 @@ struct skk_plan {
     void *peer_opened[kMaxPeers] = {nullptr};
     int *peer_status = nullptr;            // mapped host memory
     int peer_nranks = 0;
+    bool peer_failed = false;              // an exchange timed out: the ranks' counters may disagree from then on
+    int exchange_ctas_max = 0;             // CTAs of skk_finish_exchange_kernel that are resident at once
+
+    unsigned long long *trace = nullptr;   // per-warp timeline of the row kernel (skk_trace_enable)
+    size_t trace_words = 0;
 
     skk_stats_t stats{};
 };
@@ -441,12 +446,22 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
         int8_t kind;
     };
     std::vector<Link> links;
+    // family of the block every theta element belongs to (a linked parameter may refer to any other block)
+    std::vector<int8_t> elem_family(Pn, -1);
     for (int k = 0; k < d->n_blocks; ++k) {
         const skk_block_desc &bd = d->blocks[k];
         if (bd.offset < 0 || bd.size < 0 || bd.offset + bd.size > d->n_params)
             return fail(SKK_ERR_INVALID, "block %d outside theta", k);
         if (bd.family != SKK_PRIOR_NORMAL && bd.family != SKK_PRIOR_HALFNORMAL && bd.family != SKK_PRIOR_EXPONENTIAL)
             return fail(SKK_ERR_UNSUPPORTED, "block %d: unknown prior family %d", k, bd.family);
+        for (int64_t g = 0; g < bd.size; ++g) {
+            if (elem_family[bd.offset + g] != -1)
+                return fail(SKK_ERR_INVALID, "blocks overlap at theta[%lld]", (long long)(bd.offset + g));
+            elem_family[bd.offset + g] = (int8_t)bd.family;
+        }
+    }
+    for (int k = 0; k < d->n_blocks; ++k) {
+        const skk_block_desc &bd = d->blocks[k];
         const bool normal = bd.family == SKK_PRIOR_NORMAL;
         if (!normal && (bd.a_index || bd.b_index))
             return fail(SKK_ERR_UNSUPPORTED, "block %d: only Normal priors take random parameters", k);
@@ -456,18 +471,26 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             return fail(SKK_ERR_INVALID, "block %d: bad b_const_len", k);
         for (int64_t g = 0; g < bd.size; ++g) {
             const int64_t j = bd.offset + g;
-            if (fam[j] != -1) return fail(SKK_ERR_INVALID, "blocks overlap at theta[%lld]", (long long)j);
             fam[j] = (int8_t)bd.family;
             if (bd.a_index) {
-                a_src[j] = bd.a_index[g];
-                links.push_back(Link{bd.a_index[g], (int32_t)j, 0});
+                const int64_t src = bd.a_index[g];
+                if (src < 0 || src >= d->n_params) return fail(SKK_ERR_INVALID, "prior link outside theta");
+                // a mu that is a positive variable is sampled as its log: mu = exp(theta[src])
+                const bool mu_is_log = elem_family[src] != SKK_PRIOR_NORMAL;
+                if (mu_is_log) fam[j] = (int8_t)(fam[j] | kPriorMuIsLog);
+                a_src[j] = (int32_t)src;
+                links.push_back(Link{src, (int32_t)j, 0});
             } else {
                 a_const[j] = bd.a_const[bd.a_const_len == 1 ? 0 : g];
             }
             if (normal) {
                 if (bd.b_index) {
-                    b_src[j] = bd.b_index[g];
-                    links.push_back(Link{bd.b_index[g], (int32_t)j, 1});
+                    const int64_t src = bd.b_index[g];
+                    if (src < 0 || src >= d->n_params) return fail(SKK_ERR_INVALID, "prior link outside theta");
+                    if (elem_family[src] == SKK_PRIOR_NORMAL)
+                        return fail(SKK_ERR_INVALID, "block %d: a linked sigma must be a positive (log-transformed) variable", k);
+                    b_src[j] = (int32_t)src;
+                    links.push_back(Link{src, (int32_t)j, 1});
                 } else {
                     b_const[j] = bd.b_const[bd.b_const_len == 1 ? 0 : g];
                 }
@@ -531,7 +554,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     std::vector<int32_t> none_elem;
     {
         std::vector<char> is_parent(Pn, 0);
-        pl->fused_ok = multi_elem.empty();  // an element fed by several slots needs the slot totals first
+        pl->fused_ok = true;
         for (const Parent &q : parents) {
             is_parent[q.element] = 1;
             if (single_unit[q.element] != -1 || (d->family == SKK_LIK_NORMAL && q.element == d->sigma_theta_index))
@@ -554,7 +577,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
         for (int64_t e = parents[q].lo; e < parents[q].hi; ++e) {
             const int32_t j = links[e].child;
             lk_child.push_back(j);
-            lk_kind.push_back(links[e].kind);
+            lk_kind.push_back((int8_t)(links[e].kind | ((fam[j] & kPriorMuIsLog) ? 4 : 0)));  // bit 2: the child's mu is exp(u)
             lk_a_src.push_back(a_src[j]);
             lk_b_src.push_back(b_src[j]);
             lk_a_const.push_back(a_const[j]);
@@ -647,6 +670,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     rp.none_elem = none_dev;
     rp.n_none = (int32_t)none_elem.size();
     rp.none_blocks = (int32_t)((none_elem.size() + 255) / 256);
+    rp.multi_blocks = (int32_t)((multi_elem.size() + 7) / 8);
     {
         rp.parent = pl->prior.parent;
         rp.chunk_ptr = chunk_ptr_dev;
@@ -815,6 +839,7 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
         rp.link_part = pl->link_part + (size_t)b0 * pl->n_chunks;
         rp.n_chunks = pl->n_chunks;
     }
+    rp.trace = pl->trace;
     void *args[] = {&rp};
     if (timed) CUDA_TRY(cudaEventRecord(pl->evk0, pl->stream));
     CUDA_TRY(cudaLaunchKernel(cfg.fn, dim3(cfg.grid), dim3(pl->warps * 32), args, cfg.smem, pl->stream));
@@ -837,9 +862,11 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
     const bool chain = pl->chain_ready && batch >= kChainMinBatch && !sharded;
     // single GPU, row kernel: the priors ride in the row kernel's prologue and one finish kernel follows
     const bool fused = !sharded && !chain && pl->fused_ok && env_int("SKK_NO_FUSED_FINISH", 0) == 0;
-    // EXPERIMENT (off by default, not yet run on a GPU): the same for a row-sharded run -- priors in the row
-    // kernel's prologue, one kernel that hands the likelihood parts to the exchange (skk_finish_push_kernel)
-    const bool fused_sharded = sharded && !chain && pl->fused_ok && batch <= 4 && env_int("SKK_SHARDED_FINISH", 0) == 1;
+    // a row-sharded run likewise: priors in the row kernel's prologue, then one kernel that hands the likelihood
+    // parts to the exchange -- over peer memory that kernel also waits for the other ranks and writes the
+    // outputs (skk_finish_exchange_kernel: two launches per evaluation); SKK_SHARDED_FINISH=0 forces the
+    // separate kernels
+    const bool fused_sharded = sharded && !chain && pl->fused_ok && batch <= 4 && env_int("SKK_SHARDED_FINISH", 1) == 1;
     const bool in_row = fused || fused_sharded;  // the prior terms ride in the row kernel
     // (for large batches they are big enough to fill the GPU themselves: run them in line)
     const bool fork = batch < kChainMinBatch;
@@ -917,7 +944,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         return SKK_OK;
     }
 
-    bool joined = false;
+    bool joined = false, one_launch = false;
     int sharded_lp_stride = 0;
     for (int b0 = 0; b0 < batch;) {
         const int remaining = batch - b0;
@@ -941,10 +968,10 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         const unsigned slot_blocks = (unsigned)(rp.blocks_p + rp.blocks_s + 1);
         if (fused) {
             if (priors) {
-                rp.prior_ctas = cfg.grid * pl->warps;  // one logp partial per warp of the row kernel, of which
-                rp.n_lp_parts = (int32_t)std::min<int64_t>(rp.prior_ctas, (pl->n_params + 31) / 32);  // these hold elements
+                rp.prior_ctas = cfg.grid * pl->warps;  // one logp partial per warp of the row kernel
+                rp.n_lp_parts = rp.prior_ctas;
             }
-            const unsigned blocks = slot_blocks + (unsigned)(rp.parent_blocks + rp.none_blocks);
+            const unsigned blocks = slot_blocks + (unsigned)(rp.parent_blocks + rp.none_blocks + rp.multi_blocks);
             if (bt == 4)
                 skk_finish_kernel<T, 4><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
             else
@@ -954,15 +981,26 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             continue;
         }
         if (fused_sharded) {
-            const unsigned blocks = slot_blocks + (unsigned)(rp.parent_blocks + rp.none_blocks);
-            sharded_lp_stride = cfg.grid * pl->warps;  // the final kernel reads the prologue's warp partials
-#define SKK_PUSH(BTV, MODEV) skk_finish_push_kernel<T, BTV, MODEV><<<blocks, 256, 0, st>>>(rp, pl->peer)
-            if (bt == 4) {
-                if (pl->peer_ready) SKK_PUSH(4, 2); else SKK_PUSH(4, 1);
+            const unsigned blocks = slot_blocks + (unsigned)(rp.parent_blocks + rp.none_blocks + rp.multi_blocks);
+            rp.prior_ctas = cfg.grid * pl->warps;  // the prologue's warp partials of the prior logp
+            rp.n_lp_parts = rp.prior_ctas;
+            sharded_lp_stride = rp.prior_ctas;
+            // every CTA of the one-launch exchange waits inside the kernel: all of them must be resident
+            one_launch = pl->peer_ready && (int)blocks <= pl->exchange_ctas_max && env_int("SKK_SHARDED_FINISH_SPLIT", 0) == 0;
+            if (one_launch) {
+                if (bt == 4)
+                    skk_finish_exchange_kernel<T, 4><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
+                else
+                    skk_finish_exchange_kernel<T, 1><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
             } else {
-                if (pl->peer_ready) SKK_PUSH(1, 2); else SKK_PUSH(1, 1);
-            }
+#define SKK_PUSH(BTV, MODEV) skk_finish_push_kernel<T, BTV, MODEV><<<blocks, 256, 0, st>>>(rp, pl->peer)
+                if (bt == 4) {
+                    if (pl->peer_ready) SKK_PUSH(4, 2); else SKK_PUSH(4, 1);
+                } else {
+                    if (pl->peer_ready) SKK_PUSH(1, 2); else SKK_PUSH(1, 1);
+                }
 #undef SKK_PUSH
+            }
             ++launches;
             b0 += b_valid;
             continue;
@@ -992,7 +1030,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         b0 += b_valid;
     }
 
-    if (sharded) {
+    if (sharded && !one_launch) {
         // one all-reduce of [dlogp, logp partial, constant] per evaluation, then the final combination
         FinalParams fp{pl->lik_vec, pl->prior_grad, pl->prior_lp, fused_sharded ? sharded_lp_stride : pl->prior_ctas,
                        pl->n_params, pl->n_rows_total, pl->sigma_idx, pl->sigma_const, pl->family, pl->include_priors};
@@ -1008,7 +1046,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             skk_final_kernel<T, false><<<grid, 256, 0, st>>>(fp, pl->peer, th, out_logp, out_grad);
         }
         ++launches;
-    } else if (priors && !fused && fork && !joined) {
+    } else if (priors && !in_row && fork && !joined) {
         CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
     }
     CUDA_TRY(cudaGetLastError());
@@ -1023,6 +1061,12 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
     const bool timed = flags & SKK_EVAL_TIME_KERNELS;
     cudaStream_t st = pl->stream;
     CUDA_TRY(cudaSetDevice(pl->device));
+    // a timed-out exchange leaves the ranks' sequence counters out of step: the plan refuses further work
+    // (the status word is host-mapped, so enqueue-only evaluations notice it at the next call)
+    if (pl->peer_status && *pl->peer_status) pl->peer_failed = true;
+    if (pl->peer_failed)
+        return fail(SKK_ERR_NCCL, "peer all-reduce timed out waiting for another rank; destroy the plans of all ranks "
+                                  "and connect again");
 
     const T *th = dev_io ? static_cast<const T *>(theta) : static_cast<const T *>(pl->theta_dev);
     T *out_grad = dev_io ? static_cast<T *>(grad_out) : static_cast<T *>(pl->out_dev);
@@ -1093,7 +1137,7 @@ enqueued:
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     if (pl->peer_status && *pl->peer_status) {
-        *pl->peer_status = 0;
+        pl->peer_failed = true;
         return fail(SKK_ERR_NCCL, "peer all-reduce timed out waiting for another rank");
     }
     if (!dev_io) {
@@ -1349,6 +1393,18 @@ int skk_peer_init(skk_plan *pl, const void *handles, int32_t rank, int32_t nrank
     *pl->peer_status = 0;
     CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&pp.status), pl->peer_status, 0));
     pl->peer = pp;
+    {
+        // CTAs of the one-launch exchange kernel that fit on the device at once (they wait for each other)
+        int per_sm1 = 0, per_sm4 = 0;
+        if (pl->dtype == SKK_F64) {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, skk_finish_exchange_kernel<double, 1>, 256, 0));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, skk_finish_exchange_kernel<double, 4>, 256, 0));
+        } else {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, skk_finish_exchange_kernel<float, 1>, 256, 0));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, skk_finish_exchange_kernel<float, 4>, 256, 0));
+        }
+        pl->exchange_ctas_max = pl->n_sms * std::min(per_sm1, per_sm4);
+    }
     for (GraphEntry &g : pl->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     pl->graphs.clear();
@@ -1365,5 +1421,30 @@ int skk_stats(skk_plan *pl, skk_stats_t *out) {
 }
 
 void *skk_stream(skk_plan *pl) { return pl ? pl->stream : nullptr; }
+
+int skk_trace_enable(skk_plan *pl, int32_t on) {
+    if (!pl) return fail(SKK_ERR_INVALID, "null plan");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    for (GraphEntry &g : pl->graphs)   // the pointer is a kernel argument: recorded graphs are stale
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    pl->graphs.clear();
+    if (on && !pl->trace) {
+        pl->trace_words = (size_t)std::max(pl->cfg1.grid, pl->cfg4.grid) * pl->warps * kTraceWords;
+        if (int rc = dev_alloc(pl, &pl->trace, pl->trace_words, true)) return rc;
+    }
+    if (!on) pl->trace = nullptr;  // (the buffer stays with the plan's allocations)
+    return SKK_OK;
+}
+
+int64_t skk_trace_read(skk_plan *pl, uint64_t *out, int64_t capacity) {
+    if (!pl || !out) return fail(SKK_ERR_INVALID, "null argument");
+    if (!pl->trace) return fail(SKK_ERR_INVALID, "tracing is not enabled");
+    CUDA_TRY(cudaSetDevice(pl->device));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    const int64_t n = std::min<int64_t>(capacity, (int64_t)pl->trace_words);
+    CUDA_TRY(cudaMemcpy(out, pl->trace, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return n;
+}
 
 }  // extern "C"

@@ -52,7 +52,7 @@ constexpr int kMaxTerms = 3 * kMaxTermsPerLevel;
 // Priors, flattened per theta element (structure of arrays) so that a thread needs one level of
 // descriptor loads and one level of theta loads.
 struct PriorParams {
-    const int8_t *family;     // [P] SKK_PRIOR_*
+    const int8_t *family;     // [P] SKK_PRIOR_* (| kPriorMuIsLog)
     const int32_t *a_src;     // [P] theta element holding parameter a (mu), -1: constant
     const int32_t *b_src;     // [P] theta element holding log(parameter b) (sigma), -1: constant
     const double *a_const;    // [P]
@@ -95,10 +95,11 @@ skk_prior_kernel(const __grid_constant__ PriorParams pp, const T *__restrict__ t
         if (valid) {
             const double v = (double)th[j];
             double grad, d_mu, d_log_sd;
-            const double a = a_src >= 0 ? (double)th[a_src] : a_c;
+            const double a = a_src >= 0 ? prior_mu_of(fam, (double)th[a_src]) : a_c;
             const double sd = b_src >= 0 ? exp((double)th[b_src]) : b_c;
-            lp = prior_term(fam, v, a, sd, grad, d_mu, d_log_sd);
-            if (e_mu >= 0) link_val[(int64_t)b * pp.n_links + e_mu] = d_mu;
+            lp = prior_term(fam & kPriorFamilyMask, v, a, sd, grad, d_mu, d_log_sd);
+            // (mu = exp(u) of a positive variable: d/du = d/dmu * mu)
+            if (e_mu >= 0) link_val[(int64_t)b * pp.n_links + e_mu] = (fam & kPriorMuIsLog) ? d_mu * a : d_mu;
             if (e_sigma >= 0) link_val[(int64_t)b * pp.n_links + e_sigma] = d_log_sd;
             prior_grad[(int64_t)b * pp.n_params + j] = grad;
         }
@@ -206,6 +207,7 @@ struct ReduceParams {
     int64_t n_chunks;
     int32_t n_parents, n_heavy, parent_blocks;
     int32_t n_lp_parts;         // warp partials of the prior logp that the row kernel's prologue writes per chain
+    int32_t multi_blocks;       // CTAs of the finish kernel for the elements fed by several slots (8 each)
 };
 
 // blockIdx.x in [0, blocks_p): primary slots, one per thread;  [blocks_p, blocks_p + blocks_s):
@@ -473,22 +475,30 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant_
 }
 
 // ---- K4 fused: slot totals -> theta elements -> outputs (or the exchange) in one launch ---------------
-// Used when every theta element is fed by at most one slot (no term sits on a parent of a grouping
-// level) and no term feeds a hyper-parameter; other models run the separate kernels above.
+// Used unless a term feeds a hyper-parameter (those models run the separate kernels above).
 // CTA classes by blockIdx.x: [0, blocks_p) primary slots (one per thread); then blocks_s CTAs of
 // secondary slots (32 per CTA x 8 ranges of row-kernel CTAs); one CTA for the global terms, logp and
 // the likelihood's sigma; parent_blocks CTAs for the hyper-parameters (sum over their children's
-// chunk partials, a CTA or a warp per element); none_blocks CTAs for the remaining elements.  The
-// thread that completes the total of a slot finishes the slot's theta element on the spot.  Every
-// thread is latency-bound, so whatever it will need (descriptor, element, the element's own prior
-// gradient) is loaded up front and the chain of dependent loads is two deep.
+// chunk partials, a CTA or a warp per element); none_blocks CTAs for the elements nothing feeds;
+// multi_blocks CTAs for the elements fed by several slots (a term on a parent of a grouping level: a
+// warp per element re-adds the raw partials of its slots, lane-strided, fixed tree).  The thread that
+// completes the total of a slot finishes the slot's theta element on the spot.  Every thread is
+// latency-bound, so whatever it will need (descriptor, element, the element's own prior gradient) is
+// loaded up front and the chain of dependent loads stays short.
 //   MODE 0 (skk_finish_kernel, single GPU): the element's gradient and logp go to the outputs.
-//   MODE 1 / 2 (skk_finish_push_kernel; EXPERIMENT, off by default: SKK_SHARDED_FINISH=1, not yet run on a
-//   GPU): a row-sharded run -- the element's likelihood part is handed to the exchange instead (1: lik_vec
-//   for ncclAllReduce, 2: this rank's slot in every peer, see the one-shot all-reduce above), elements
-//   that nothing feeds on this rank are sent as zeros, the hyper-parameter CTAs add their children's
-//   chunk partials to prior_grad (read by K4b after the exchange).  Replaces K3a, K3b, K4a and K4f of a
-//   sharded evaluation: row kernel (priors in its prologue) -> this kernel -> [ncclAllReduce] -> K4b.
+//   MODE 1 / 2 (skk_finish_push_kernel): a row-sharded run -- the element's likelihood part is handed to
+//   the exchange instead (1: lik_vec for ncclAllReduce, 2: this rank's slot in every peer, see the
+//   one-shot all-reduce above), the hyper-parameter CTAs add their children's chunk partials to
+//   prior_grad (read by K4b after the exchange).  Elements that nothing feeds on this rank are sent as
+//   zeros in MODE 1 and not at all over peer memory (their entries of the slot are zero since the
+//   allocation and are never written).
+//   MODE 3 (skk_finish_exchange_kernel): MODE 2 and K4b in one launch -- after the push every CTA waits
+//   for the flags of all ranks and then combines a grid-strided slice of theta from the R slots of its
+//   own buffer (rank order), adds the priors and writes the outputs.  All CTAs must be co-resident
+//   (the host checks the occupancy and falls back to MODE 2 + K4b otherwise).  A sharded evaluation is
+//   then two launches: the row kernel (priors in its prologue) and this one.
+__device__ __forceinline__ double load_volatile(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
+
 template <typename T, int BT, int MODE>
 __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerParams &pp, const T *__restrict__ theta,
                                             T *__restrict__ out_logp, T *__restrict__ out_grad) {
@@ -513,7 +523,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             pg[b] = (MODE == 0 && rp.include_priors && j >= 0 && b < rp.b_valid)
                         ? rp.prior_grad[(int64_t)(rp.b0 + b) * P + j] : 0.0;
     };
-    // k: a theta element, or (MODE 1 / 2) P for the logp partial and P + 1 for the constant
+    // k: a theta element, or (MODE >= 1) P for the logp partial and P + 1 for the constant
     auto store = [&](int64_t k, const double (&lik)[BT], const double (&pg)[BT]) {
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
@@ -530,30 +540,48 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             }
         }
     };
+    // an element this rank's rows do not feed: its own prior term (MODE 0), a zero for ncclAllReduce, nothing
+    // over peer memory
+    auto store_unfed = [&](int64_t k, const double (&pg)[BT]) {
+        if constexpr (MODE <= 1) {
+            double zero[BT];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) zero[b] = 0.0;
+            store(k, zero, pg);
+        }
+    };
     const bool sigma_is_param = rp.family == SKK_LIK_NORMAL && rp.sigma_theta_index >= 0;
     const int b_glob = rp.blocks_p + rp.blocks_s;
+    const int b_none = b_glob + 1 + rp.parent_blocks;
+    const int b_multi = b_none + rp.none_blocks;
+    auto addend = [&](int4 dd, int64_t tile, int t, int b) -> double {
+        const int kind = tile == dd.x ? dd.z : (tile == dd.y ? dd.w : 1);
+        const double *src = kind == 1 ? rp.tile_head : (kind == 2 ? rp.tile_tail : nullptr);
+        return src ? src[(tile * rp.np + t) * BT + b] : 0.0;
+    };
     if ((int)blockIdx.x < rp.blocks_p) {
         const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
         const bool valid = slot < rp.n_primary;
         int4 d = make_int4(0, -1, 0, 0);
         if (valid) d = rp.slot_desc[slot];
         int32_t elem[kMaxTermsPerLevel];
+        bool single[kMaxTermsPerLevel];
 #pragma unroll
-        for (int t = 0; t < kMaxTermsPerLevel; ++t) elem[t] = (valid && t < rp.np) ? rp.ti_p[t][slot] : -1;
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) {
+            elem[t] = (valid && t < rp.np) ? rp.ti_p[t][slot] : -1;
+            // (an element fed by several slots is finished by its own warp below)
+            single[t] = elem[t] >= 0 && (rp.n_multi == 0 || rp.single_unit[elem[t]] != -2);
+            if (!single[t]) elem[t] = -1;
+        }
         double pg[kMaxTermsPerLevel][BT];
 #pragma unroll
         for (int t = 0; t < kMaxTermsPerLevel; ++t) prior_of(elem[t], pg[t]);
         const int64_t t_lo = d.x, t_hi = d.y;
         const bool heavy = valid && (t_hi - t_lo + 1 > kSerialLimit);
-        auto addend = [&](int4 dd, int64_t tile, int t, int b) -> double {
-            const int kind = tile == dd.x ? dd.z : (tile == dd.y ? dd.w : 1);
-            const double *src = kind == 1 ? rp.tile_head : (kind == 2 ? rp.tile_tail : nullptr);
-            return src ? src[(tile * rp.np + t) * BT + b] : 0.0;
-        };
 #pragma unroll
         for (int t = 0; t < kMaxTermsPerLevel; ++t) {
             if (t >= rp.np) break;
-            if (valid && !heavy) {
+            if (valid && !heavy && single[t]) {
                 double acc[BT];
 #pragma unroll
                 for (int b = 0; b < BT; ++b) acc[b] = 0.0;
@@ -572,7 +600,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 store(elem[t], acc, pg[t]);
             }
             // groups that span many tiles: the whole warp sums one list at a time, then its owner finishes
-            unsigned todo = __ballot_sync(kFull, heavy);
+            unsigned todo = __ballot_sync(kFull, heavy && single[t]);
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
@@ -600,7 +628,10 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         const int c0 = sub * per, c1 = min(rp.grid, c0 + per);
         int32_t elem[kMaxTermsPerLevel];
 #pragma unroll
-        for (int t = 0; t < kMaxTermsPerLevel; ++t) elem[t] = (sub == 0 && valid && t < rp.ns) ? rp.ti_s[t][slot] : -1;
+        for (int t = 0; t < kMaxTermsPerLevel; ++t) {
+            elem[t] = (sub == 0 && valid && t < rp.ns) ? rp.ti_s[t][slot] : -1;
+            if (elem[t] >= 0 && rp.n_multi != 0 && rp.single_unit[elem[t]] == -2) elem[t] = -1;
+        }
         double pg[kMaxTermsPerLevel][BT];
 #pragma unroll
         for (int t = 0; t < kMaxTermsPerLevel; ++t) prior_of(elem[t], pg[t]);
@@ -624,7 +655,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 lik[b] = s;
                 __syncthreads();
             }
-            if (sub == 0 && valid) store(elem[t], lik, pg[t]);
+            if (elem[t] >= 0) store(elem[t], lik, pg[t]);
         }
     } else if ((int)blockIdx.x == b_glob) {
         // global terms and the likelihood's logp partial: one warp per (term, chain), CTAs of the row kernel in order
@@ -638,7 +669,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             if (lane == 0) glob[item] = acc;
         }
         // prior logp: the warp partials of the row kernel's prologue, 8 / BT warps per chain
-        // (sharded runs: K4b adds them after the exchange)
+        // (sharded runs: added after the exchange)
         constexpr int WPC = 8 / BT;  // BT is 1 or 4
         if constexpr (MODE == 0) {
             const int chain = warp / WPC, sub = warp % WPC;
@@ -652,15 +683,16 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         __syncthreads();
         if ((int)threadIdx.x < rp.ng) {
             double lik[BT], pg[BT];
-            const int32_t j = rp.ti_g[threadIdx.x][0];
+            int32_t j = rp.ti_g[threadIdx.x][0];
+            if (rp.n_multi != 0 && rp.single_unit[j] == -2) j = -1;
 #pragma unroll
             for (int b = 0; b < BT; ++b) lik[b] = glob[threadIdx.x * BT + b];
             prior_of(j, pg);
-            if (!(sigma_is_param && j == rp.sigma_theta_index)) store(j, lik, pg);
+            if (j >= 0 && !(sigma_is_param && j == rp.sigma_theta_index)) store(j, lik, pg);
         }
         if (threadIdx.x == 32 && sigma_is_param) {
             // d/d log(sigma) = sum(r^2) / sigma^2 - N (+ its own prior term; sigma has no children on this path)
-            // (sharded runs: zero here, its part travels as the logp partial)
+            // (sharded runs: nothing here, its part travels as the logp partial)
             double lik[BT], pg[BT];
             prior_of(rp.sigma_theta_index, pg);
 #pragma unroll
@@ -668,7 +700,8 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 lik[b] = MODE == 0 ? glob[rp.ng * BT + b] : 0.0;
                 pg[b] -= (double)rp.n_rows_total;
             }
-            store(rp.sigma_theta_index, lik, pg);
+            if constexpr (MODE == 0) store(rp.sigma_theta_index, lik, pg);
+            else store_unfed(rp.sigma_theta_index, pg);
         }
         if constexpr (MODE == 0) {
             if ((int)threadIdx.x >= 64 && (int)threadIdx.x < 64 + BT && (int)threadIdx.x - 64 < rp.b_valid) {
@@ -700,7 +733,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             store(P, L, none);
             store(P + 1, c, none);
         }
-    } else if ((int)blockIdx.x <= b_glob + rp.parent_blocks) {
+    } else if ((int)blockIdx.x < b_none) {
         // hyper-parameters: own prior term + the sum over the children's chunk partials (contiguous)
         __shared__ double hp_part[8][BT];
         const int warp = threadIdx.x >> 5;
@@ -708,9 +741,6 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         const bool heavy = pb < rp.n_heavy;
         const int64_t q = heavy ? pb : rp.n_heavy + ((int64_t)pb - rp.n_heavy) * 8 + warp;
         const bool active = heavy || q < rp.n_parents;
-        if constexpr (MODE == 0) {
-            if (!active) return;
-        }  // (MODE 2: every thread has to reach the tail of the kernel)
         int32_t j = 0;
         double pg[BT], sum[BT];
 #pragma unroll
@@ -741,10 +771,8 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             }
         }
         if (active && (heavy ? threadIdx.x == 0 : lane == 0)) {
-            double lik[BT];
 #pragma unroll
             for (int b = 0; b < BT; ++b) {
-                lik[b] = 0.0;
                 if constexpr (MODE == 0) {
                     pg[b] += rp.include_priors ? sum[b] : 0.0;
                 } else {
@@ -753,25 +781,75 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                         const_cast<double *>(rp.prior_grad)[(int64_t)(rp.b0 + b) * P + j] += sum[b];
                 }
             }
-            store(j, lik, pg);
+            store_unfed(j, pg);
         }
-    } else {
+    } else if ((int)blockIdx.x < b_multi) {
         // elements that no term feeds and that have no children: own prior term only
-        const int64_t k = ((int64_t)blockIdx.x - b_glob - 1 - rp.parent_blocks) * blockDim.x + threadIdx.x;
+        const int64_t k = ((int64_t)blockIdx.x - b_none) * blockDim.x + threadIdx.x;
         if (k < rp.n_none) {
             const int64_t j = rp.none_elem[k];
             if (!(sigma_is_param && j == rp.sigma_theta_index)) {
-                double lik[BT], pg[BT];
+                double pg[BT];
                 prior_of(j, pg);
-#pragma unroll
-                for (int b = 0; b < BT; ++b) lik[b] = 0.0;
-                store(j, lik, pg);
+                store_unfed(j, pg);
             }
         }
+    } else {
+        // elements fed by several slots: one warp each, its units lane-strided (four in flight per lane)
+        const int64_t m = ((int64_t)blockIdx.x - b_multi) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const bool have = m < rp.n_multi;
+        const int64_t lo = have ? rp.multi_ptr[m] : 0, hi = have ? rp.multi_ptr[m + 1] : 0;
+        const int32_t j = have ? rp.multi_elem[m] : -1;
+        double pg[BT], acc[BT];
+        prior_of(j, pg);
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+        const int64_t first_p = rp.ng + 1, first_s = first_p + (int64_t)rp.np * rp.n_primary;
+        for (int64_t e0 = lo + lane; e0 < hi; e0 += 4 * 32) {
+            int64_t unit[4];
+            int4 d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) unit[u] = e0 + 32 * u < hi ? rp.multi_unit[e0 + 32 * u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                d[u] = (unit[u] >= first_p && unit[u] < first_s) ? rp.slot_desc[(unit[u] - first_p) % rp.n_primary]
+                                                                 : make_int4(0, -1, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (unit[u] < 0) continue;
+                if (unit[u] < first_p) {
+                    // a global term: CTA partials of the row kernel in order
+                    for (int c = 0; c < rp.grid; ++c)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) acc[b] += rp.cta_glob[((int64_t)c * (rp.ng + 1) + unit[u]) * BT + b];
+                } else if (unit[u] < first_s) {
+                    const int t = (int)((unit[u] - first_p) / rp.n_primary);
+                    const int64_t slot = (unit[u] - first_p) % rp.n_primary;
+                    if (d[u].y >= d[u].x) {
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) acc[b] += rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b];
+#pragma unroll 4
+                        for (int64_t tile = d[u].x; tile <= d[u].y; ++tile)
+#pragma unroll
+                            for (int b = 0; b < BT; ++b) acc[b] += addend(d[u], tile, t, b);
+                    }
+                } else {
+                    const int64_t at = unit[u] - first_s;  // t * n_secondary + slot
+                    const int64_t stride = (int64_t)rp.ns * rp.n_secondary * BT;
+                    for (int c = 0; c < rp.grid; ++c)
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) acc[b] += rp.cta_sec[c * stride + at * BT + b];
+                }
+            }
+        }
+        double lik[BT];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) lik[b] = warp_sum(acc[b]);
+        if (lane == 0 && have) store(j, lik, pg);
     }
-    if constexpr (MODE == 2) {
+    if constexpr (MODE >= 2) {
         // as in skk_theta_kernel: every store of this CTA is visible system-wide before the CTA counts
-        // itself done; the last CTA of the last batch tile publishes the vector by raising the flags
+        // itself done; the last CTA publishes the vector by raising the flags
         __threadfence_system();
         __syncthreads();
         __shared__ bool last;
@@ -783,6 +861,59 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 __threadfence_system();
                 volatile unsigned long long *flag = pp.peer_flag[threadIdx.x] + pp.rank;
                 *flag = *pp.seq + 1;
+            }
+        }
+    }
+    if constexpr (MODE == 3) {
+        // ---- wait for every rank's vector, then combine a slice of theta from the R slots (rank order) ----
+        const unsigned long long seq = peer_wait(pp);
+        const bool normal = rp.family == SKK_LIK_NORMAL;
+        for (int b = 0; b < rp.b_valid; ++b) {
+            const int64_t row = rp.b0 + b;
+            const double *mine = pp.peer_buf[pp.rank] + (int64_t)(seq & 1) * pp.nranks * pp.stride + row * (P + 2);
+            auto lik_at = [&](int64_t k) -> double {
+                double s = 0.0;
+                for (int r = 0; r < pp.nranks; ++r) s += load_volatile(mine + (int64_t)r * pp.stride + k);
+                return s;
+            };
+            double sc = 1.0, sigma = 1.0;
+            if (normal) {
+                sigma = rp.sigma_theta_index >= 0 ? exp((double)theta[row * P + rp.sigma_theta_index]) : rp.sigma_const;
+                sc = 1.0 / (sigma * sigma);
+            }
+            for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < P; j += (int64_t)gridDim.x * blockDim.x) {
+                double g = lik_at(j) * sc;
+                if (normal && j == rp.sigma_theta_index) g += lik_at(P) * sc - (double)rp.n_rows_total;
+                if (rp.include_priors) g += load_volatile(rp.prior_grad + row * P + j);
+                out_grad[row * P + j] = (T)g;
+            }
+            if (blockIdx.x == gridDim.x - 1) {
+                __shared__ double lp_tail[8];
+                double s = 0.0;
+                if (rp.include_priors)
+                    for (int k = threadIdx.x; k < rp.prior_ctas; k += blockDim.x)
+                        s += rp.prior_lp_part[row * rp.prior_ctas + k];
+                s = warp_sum(s);
+                if (lane == 0) lp_tail[threadIdx.x >> 5] = s;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double tot = 0.0;
+                    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += lp_tail[w];
+                    const double L = lik_at(P);
+                    const double ll = normal ? -0.5 * L * sc - (double)rp.n_rows_total * (kLogSqrt2Pi + log(sigma)) : L;
+                    out_logp[row] = (T)(tot + ll + lik_at(P + 1));
+                }
+                __syncthreads();
+            }
+        }
+        // the last CTA to finish closes the evaluation (the slots of this parity may be reused two
+        // evaluations later, the flags only grow)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(pp.done, 1u) == gridDim.x - 1) {
+                *pp.done = 0;
+                *pp.seq = seq;
             }
         }
     }
@@ -798,8 +929,15 @@ skk_finish_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant
 template <typename T, int BT, int MODE>
 __global__ void __launch_bounds__(256)
 skk_finish_push_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp) {
-    static_assert(MODE == 1 || MODE == 2, "MODE 0 is skk_finish_kernel");
+    static_assert(MODE == 1 || MODE == 2, "MODE 0 is skk_finish_kernel, MODE 3 skk_finish_exchange_kernel");
     finish_body<T, BT, MODE>(rp, pp, static_cast<const T *>(nullptr), static_cast<T *>(nullptr), static_cast<T *>(nullptr));
+}
+
+template <typename T, int BT>
+__global__ void __launch_bounds__(256)
+skk_finish_exchange_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant__ PeerParams pp,
+                           const T *theta, T *out_logp, T *out_grad) {
+    finish_body<T, BT, 3>(rp, pp, theta, out_logp, out_grad);
 }
 
 // ---- K4b (sharded runs: after the all-reduce) ------------------------------------------------

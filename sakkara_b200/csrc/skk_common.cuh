@@ -66,12 +66,25 @@ struct RowParams {
     // a hyper-parameter are contiguous and padded to whole chunks of 32 (child -1), so a warp sums one
     // chunk and the finish kernel adds 32 times fewer values per hyper-parameter.
     const int32_t *link_child;   // [n_chunks * 32] theta element of the child (Normal prior), -1: padding
-    const int8_t *link_kind;     //                 0: link to the prior's mu, 1: to its sigma
+    const int8_t *link_kind;     //                 0: link to the prior's mu, 1: to its sigma (+4: the child's mu is exp(u))
     const int32_t *link_a_src, *link_b_src;   //    the child's prior parameters, as in PriorParams
     const double *link_a_const, *link_b_const;
     double *link_part;       // [b_valid][n_chunks]
     int64_t n_chunks;
+    // optional per-warp timeline (skk_trace_enable): [grid * warps][kTraceWords], null in normal operation
+    unsigned long long *trace;
 };
+
+// words of one warp's trace record
+//   0 %globaltimer at kernel entry     1 ... when the prologue is done (before the first tile wait)
+//   2 ... when the first tile has arrived   3 ... at the end of the tile loop   4 ... at kernel exit
+constexpr int kTraceWords = 8;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -277,6 +290,14 @@ struct Math;
 // magnitude inside the 1e-4 tolerance stated for fp32; double: the accurate library functions.
 constexpr double kLogSqrt2Pi = 0.91893853320467274178032973640562;
 constexpr double kLogSqrt2OverPi = -0.22579135264472743236309761494744;
+
+// The per-element family byte of the flattened priors: SKK_PRIOR_* in the low bits, plus a flag when the
+// Normal prior's mu is a positive (log-transformed) variable u, i.e. mu = exp(u).
+constexpr int kPriorFamilyMask = 15;
+constexpr int kPriorMuIsLog = 16;
+__device__ __forceinline__ double prior_mu_of(int family_byte, double raw) {
+    return (family_byte & kPriorMuIsLog) ? exp(raw) : raw;
+}
 
 // One prior term in fp64.  v: the (transformed) element; a, b: mu and sd (Normal) or the rate /
 // scale in a (Exponential, HalfNormal; sampled as log, the log-Jacobian v is included).

@@ -798,18 +798,22 @@ struct RowKernel {
     }
 
     // -----------------------------------------------------------------------------------------
-    // Prior terms of a slice of theta (element = thread, grid-strided), hidden behind the latency of
-    // the first tiles.  Own gradient term -> prior_grad, logp -> one partial per warp; then, in link
-    // order, what the children contribute to the gradient of their priors' parameters -> one partial
-    // per chunk of 32 links (summed per hyper-parameter by the finish kernel).  Same arithmetic as
-    // skk_prior_kernel.
-    static __device__ __forceinline__ void priors(const RowParams<T> &p) {
+    // Prior terms, evaluated next to the first tiles.  theta is cut into groups of 32 elements and the
+    // links into their chunks of 32; group / chunk q belongs to CTA q % grid and there to the warps
+    // from the top (warp W-1 first): the last warps of a CTA are the ones that hold one tile less when
+    // the tiles do not divide evenly, and no warp of the grid gets more than ceil(groups / grid) of them.
+    // Own gradient term -> prior_grad, logp -> one partial per warp; then, in link order, what the
+    // children contribute to the gradient of their priors' parameters -> one partial per chunk of 32
+    // links (summed per hyper-parameter by the finish kernel).  Same arithmetic as skk_prior_kernel.
+    static __device__ __forceinline__ void priors(const RowParams<T> &p, int warp, int lane) {
+        const int warps = blockDim.x >> 5;
         double lp[BT];
 #pragma unroll
         for (int b = 0; b < BT; ++b) lp[b] = 0.0;
-        const int64_t first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-        for (int64_t j = first; j < p.n_params; j += stride) {
+        for (int64_t q = (int64_t)(warps - 1 - warp) * gridDim.x + blockIdx.x; q * 32 < p.n_params;
+             q += (int64_t)warps * gridDim.x) {
+            const int64_t j = q * 32 + lane;
+            if (j >= p.n_params) continue;
             const int family = p.prior_family[j];
             const int a_src = p.prior_a_src[j], b_src = p.prior_b_src[j];
             const double a_c = p.prior_a_const[j], b_c = p.prior_b_const[j];
@@ -817,22 +821,23 @@ struct RowKernel {
             for (int b = 0; b < BT; ++b) {
                 if (b >= p.b_valid) continue;
                 const T *th = p.theta + (int64_t)b * p.n_params;
-                const double a = a_src >= 0 ? (double)th[a_src] : a_c;
+                const double a = a_src >= 0 ? prior_mu_of(family, (double)th[a_src]) : a_c;
                 const double sd = b_src >= 0 ? exp((double)th[b_src]) : b_c;
                 double grad, d_mu, d_log_sd;
-                lp[b] += prior_term(family, (double)th[j], a, sd, grad, d_mu, d_log_sd);
+                lp[b] += prior_term(family & kPriorFamilyMask, (double)th[j], a, sd, grad, d_mu, d_log_sd);
                 p.prior_grad[(int64_t)b * p.n_params + j] = grad;
             }
         }
-        const int64_t parts = (int64_t)gridDim.x * (blockDim.x >> 5);
+        const int64_t parts = (int64_t)gridDim.x * warps;
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
             const double s = warp_sum(lp[b]);
-            if ((threadIdx.x & 31) == 0 && b < p.b_valid)
-                p.prior_lp_part[b * parts + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = s;
+            if (lane == 0 && b < p.b_valid) p.prior_lp_part[b * parts + blockIdx.x * warps + warp] = s;
         }
-        // links: a warp holds one whole chunk (the loop bound is a multiple of 32, so it is warp-uniform)
-        for (int64_t w = first; w < p.n_chunks * 32; w += stride) {
+        // links: a warp holds one whole chunk
+        for (int64_t c = (int64_t)(warps - 1 - warp) * gridDim.x + blockIdx.x; c < p.n_chunks;
+             c += (int64_t)warps * gridDim.x) {
+            const int64_t w = c * 32 + lane;
             const int j = p.link_child[w];
             const int kind = p.link_kind[w];
             const int a_src = p.link_a_src[w], b_src = p.link_b_src[w];
@@ -842,14 +847,17 @@ struct RowKernel {
                 double v = 0.0;
                 if (j >= 0 && b < p.b_valid) {
                     const T *th = p.theta + (int64_t)b * p.n_params;
-                    const double a = a_src >= 0 ? (double)th[a_src] : a_c;
+                    // kind bits 0-1: 0 link to the prior's mu, 1 to its sigma; bit 2: the child's mu is a
+                    // positive (log-transformed) variable, mu = exp(u), d/du = d/dmu * mu
+                    const bool mu_is_log = (kind & 4) != 0;
+                    const double a = a_src >= 0 ? (mu_is_log ? exp((double)th[a_src]) : (double)th[a_src]) : a_c;
                     const double sd = b_src >= 0 ? exp((double)th[b_src]) : b_c;
                     double grad, d_mu, d_log_sd;
                     prior_term(SKK_PRIOR_NORMAL, (double)th[j], a, sd, grad, d_mu, d_log_sd);
-                    v = kind == 0 ? d_mu : d_log_sd;
+                    v = (kind & 3) == 0 ? (mu_is_log ? d_mu * a : d_mu) : d_log_sd;
                 }
                 v = warp_sum(v);
-                if ((threadIdx.x & 31) == 0 && b < p.b_valid) p.link_part[(int64_t)b * p.n_chunks + (w >> 5)] = v;
+                if (lane == 0 && b < p.b_valid) p.link_part[(int64_t)b * p.n_chunks + c] = v;
             }
         }
     }
@@ -895,7 +903,12 @@ struct RowKernel {
             }
         }
 
-        if (p.prior_family != nullptr) priors(p);
+        // optional timeline of the warp (skk_trace_enable); nothing of it is carried through the tile loop
+        auto stamp = [&](int word) {
+            if (p.trace != nullptr && lane == 0)
+                p.trace[((int64_t)blockIdx.x * warps + warp) * kTraceWords + word] = global_timer_ns();
+        };
+        stamp(0);
 
         if constexpr (NS > 0) {
             const int n = NS * p.n_secondary * BT;
@@ -916,6 +929,9 @@ struct RowKernel {
             for (int k = threadIdx.x; k < n * warps; k += blockDim.x) gradS_all[k] = T(0);
             __syncthreads();
         }
+
+        // (after the barrier: the warps without prior work start on their tiles at once)
+        if (p.prior_family != nullptr) priors(p, warp, lane);
 
         T vg[NGa][BT];
 #pragma unroll
@@ -966,6 +982,11 @@ struct RowKernel {
         }
         load_second(k0, se0, vq0);
 
+        stamp(1);
+        if (p.trace != nullptr && tile < tile_end) {
+            mbar_wait(bars, 0);  // (the loop's own wait on this phase then returns at once)
+            stamp(2);
+        }
         int s = 0;             // stage of the ring that holds the current tile, and the parity of its barrier
         uint32_t parity = 0;   // (counted, not derived from the iteration number: no integer division per tile)
         for (; tile < tile_end; tile += warps) {
@@ -1038,6 +1059,7 @@ struct RowKernel {
                 for (int b = 0; b < BT; ++b) vp0[t][b] = vp1[t][b];
         }
 
+        stamp(3);
         // ---- CTA epilogue: fixed-order reductions over lanes, then warps ---------------------------
         __syncthreads();  // all warps are done with their staging buffers; reuse the first one
         double *red = reinterpret_cast<double *>(smem + cl.stage_off);  // [warps][(NG+1)*BT]
@@ -1063,6 +1085,7 @@ struct RowKernel {
                 p.cta_sec[(int64_t)blockIdx.x * n + k] = s;
             }
         }
+        stamp(4);
     }
 };
 

@@ -81,6 +81,13 @@ def connect(skk_plan, rank: int, world: int, collective: str = 'auto', group=Non
     if collective == 'auto':
         collective = 'peer' if world <= 8 and _peer_access_everywhere(world, group) else 'nccl'
     if collective == 'peer':
+        # the slots of the exchange are laid out from (n_params, max_batch): every rank must agree, or a
+        # rank would write into the wrong place of its peers' buffers
+        shapes = [None] * world
+        dist.all_gather_object(shapes, (int(skk_plan.n_params), int(skk_plan.max_batch), str(skk_plan.dtype)), group=group)
+        if len(set(shapes)) != 1:
+            raise ValueError(f'ranks disagree on (n_params, max_batch, dtype): {shapes}; every rank must build its '
+                             f'plan from the same model (same theta layout) and the same max_batch')
         handles = [None] * world
         dist.all_gather_object(handles, skk_plan.peer_alloc(world), group=group)
         skk_plan.peer_init(handles, rank, world)

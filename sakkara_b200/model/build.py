@@ -78,14 +78,26 @@ class B200Model:
         return to_pymc_model(self, dtype=dtype, device=device)
 
 
-def build(df: pd.DataFrame, component: ModelComponent) -> B200Model:
+def build(df: pd.DataFrame, component: ModelComponent, backend: str = 'auto', dtype: str = 'float64',
+          device: Optional[int] = None):
     """
     Build a model from a single component (typically a ``Likelihood``); all underlying components
     and their groups are traced from it.
 
     :param df: frame holding the columns that define the groups used by the components.
     :param component: component of the lowest hierarchy level.
+    :param backend: ``'auto'`` (default) returns what the reference returns whenever that is possible: a
+        ``pm.Model`` -- here one whose joint logp is the fused-kernel Op -- so that
+        ``with build(df, likelihood): pm.sample()`` (reference ``README.md:33-34``) works unchanged; without an
+        importable PyMC it returns the :class:`B200Model` (same context-manager surface, samplers take
+        ``model.logp_dlogp_function()``).  ``'pymc'`` insists on the former, ``'b200'`` on the latter.
+        The ``pm.Model`` carries the :class:`B200Model` as ``model.b200``.
+    :param dtype: floating type of the evaluator behind the ``pm.Model`` (``pytensor.config.floatX`` on the
+        reference side).
+    :param device: CUDA device ordinal (default: ``LOCAL_RANK`` or 0).
     """
+    if backend not in ('auto', 'pymc', 'b200'):
+        raise ValueError("backend must be 'auto', 'pymc' or 'b200'")
     from sakkara_b200.plan.lower import lower_model    # late import: plan.lower needs model.sym
 
     frame = df.copy()
@@ -100,4 +112,10 @@ def build(df: pd.DataFrame, component: ModelComponent) -> B200Model:
 
     with sym.Model(coords=groupset.coords()) as recorded:
         component.build(groupset)
-    return B200Model(recorded, groupset, lower_model(recorded))
+    model = B200Model(recorded, groupset, lower_model(recorded))
+    if backend == 'b200':
+        return model
+    from sakkara_b200.pytensor_op import pymc_available, to_pymc_model
+    if backend == 'pymc' or pymc_available():
+        return to_pymc_model(model, dtype=dtype, device=device)
+    return model

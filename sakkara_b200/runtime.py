@@ -55,7 +55,7 @@ class Stats(C.Structure):
 
 EXPORTS = ('skk_plan_create', 'skk_eval', 'skk_plan_destroy', 'skk_last_error', 'skk_comm_unique_id',
            'skk_comm_init', 'skk_comm_destroy', 'skk_peer_alloc', 'skk_peer_init', 'skk_stats', 'skk_stream',
-           'skk_abi_version')
+           'skk_trace_enable', 'skk_trace_read', 'skk_abi_version')
 
 _lib = None
 
@@ -92,6 +92,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.skk_stats.restype = C.c_int
     lib.skk_stream.argtypes = [C.c_void_p]
     lib.skk_stream.restype = C.c_void_p
+    lib.skk_trace_enable.argtypes = [C.c_void_p, C.c_int32]
+    lib.skk_trace_enable.restype = C.c_int
+    lib.skk_trace_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.skk_trace_read.restype = C.c_int64
     lib.skk_abi_version.argtypes = []
     lib.skk_abi_version.restype = C.c_int
     if lib.skk_abi_version() != ABI_VERSION:
@@ -233,6 +237,21 @@ class SkkPlan:
     def stream(self) -> int:
         self._guard()
         return int(self.lib.skk_stream(self._handle) or 0)
+
+    def trace_enable(self, on: bool = True) -> None:
+        """Per-warp timeline of the row kernel (diagnostics; see ``skk_trace_enable`` in the header)."""
+        self._guard()
+        _check(self.lib, self.lib.skk_trace_enable(self._handle, 1 if on else 0))
+
+    def trace_read(self) -> np.ndarray:
+        """``[grid * warps, 8]`` uint64: globaltimer ns at entry / prologue done / first tile / loop end / exit."""
+        self._guard()
+        st = self.stats()
+        out = np.zeros((st['grid'] * (st['block'] // 32), 8), dtype=np.uint64)
+        n = self.lib.skk_trace_read(self._handle, out.ctypes.data, out.size)
+        if n < 0:
+            _check(self.lib, int(n))
+        return out
 
     def _guard(self) -> None:
         if not self._handle:

@@ -132,6 +132,19 @@ def tuple_group_likelihood(df):
     return make
 
 
+# ---------------------------------------------------------------------------------------------
+# a Normal prior whose mu is a positive variable (valid in the reference: any component may be a parameter)
+# ---------------------------------------------------------------------------------------------
+def positive_mu_likelihood(df):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        k = DC(pm.Normal, name='k', group='group', mu=DC(pm.HalfNormal, name='level', sigma=1.0),
+               sigma=DC(pm.Exponential, name='spread', lam=2.0))
+        return api.Likelihood(pm.Normal, mu=k * data['x'], sigma=0.5, observed=data['y'])
+    return make
+
+
 def zoo():
     out = {}
     df = readme_df()
@@ -146,4 +159,6 @@ def zoo():
     out['crossed_poisson_dense'] = (df, crossed_poisson_likelihood(df, False))
     df = tuple_group_df()
     out['tuple_group'] = (df, tuple_group_likelihood(df))
+    df = shuffled_linreg_df(seed=5)
+    out['positive_mu'] = (df, positive_mu_likelihood(df))
     return out

@@ -84,7 +84,7 @@ def test_halfnormal_bernoulli_poisson_against_scipy():
     assert abs(logp_dlogp(plan, theta)[0] - (logp_dlogp(priors_only(plan), theta)[0] + lik)) < 1e-10 * abs(lik)
 
 
-@pytest.mark.parametrize('name', ['readme', 'nested_logistic', 'crossed_poisson', 'tuple_group'])
+@pytest.mark.parametrize('name', sorted(ZOO))
 def test_gradient_against_finite_differences(name):
     plan = build_model(ZOO[name]).plan
     theta = theta_points(plan, 2, seed=4, scale=0.3)[1]

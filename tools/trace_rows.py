@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""
+Per-warp timeline of the row kernel (skk_trace_enable / skk_trace_read): where the time of a launch goes.
+
+    python tools/trace_rows.py --config c4 [--rows N] [--emulate-world W] [--evals 5]
+
+Prints, over all warps of the grid: kernel span, prologue (entry -> ready for the first tile), wait for the
+first tile, tile loop, epilogue; and the loop time of a warp against the tiles it processed, by tile class
+(1 group / 2 groups / more), derived on the host from the plan's segment offsets.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--config', default='c4')
+    ap.add_argument('--rows', type=int, default=0)
+    ap.add_argument('--emulate-world', type=int, default=1)
+    ap.add_argument('--evals', type=int, default=5)
+    ap.add_argument('--out', default='')
+    a = ap.parse_args()
+    import torch
+    import bench
+    from sakkara_b200 import synth
+    from sakkara_b200.valuegrad import ValueGradFunction
+    cfg = bench.CONFIGS[a.config]
+    rows_total = a.rows or cfg['rows']
+    plan = bench.make_plan(a.config, rows_total, 0, a.emulate_world)
+    batch = min(cfg['batch'], 4)
+    f = ValueGradFunction(plan, dtype=cfg['dtype'], max_batch=batch, device=0, n_rows_total=rows_total)
+    skk = f.skk
+    if a.emulate_world > 1:
+        os.environ['SKK_FORCE_PEER'] = '1'
+        from sakkara_b200.distributed import connect
+        connect(skk, 0, 1)
+    theta = synth.start_point(plan, batch, dtype=cfg['dtype'])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda:0')
+    skk.trace_enable(True)
+    st = skk.stats()
+    grid, warps, wt = st['grid'], st['block'] // 32, st['rows_per_tile']
+    kp = f.kernel_plan
+    n_tiles = st['n_tiles']
+    # tile classes from the segment offsets
+    seg = kp.seg_offsets
+    cls = np.zeros(n_tiles, dtype=np.int64)
+    if kp.n_primary:
+        r0 = np.arange(n_tiles, dtype=np.int64) * wt
+        r1 = np.minimum(kp.n_rows, r0 + wt) - 1
+        kf = np.searchsorted(seg, r0, side='right') - 1
+        kl = np.searchsorted(seg, np.maximum(r0, r1), side='right') - 1
+        cls = np.minimum(kl - kf, 2)
+    per_warp = np.zeros((grid * warps, 3), dtype=np.int64)
+    for c in range(grid):
+        tb, te = n_tiles * c // grid, n_tiles * (c + 1) // grid
+        for w in range(warps):
+            t = np.arange(tb + w, te, warps)
+            per_warp[c * warps + w] = np.bincount(cls[t], minlength=3) if len(t) else 0
+    runs = []
+    for _ in range(a.evals):
+        flush.zero_()
+        torch.cuda.synchronize()
+        f(theta)
+        runs.append(skk.trace_read().astype(np.int64))
+    tr = runs[-1]
+    act = per_warp.sum(1) > 0
+    t0, t1, t2, t3, t4 = (tr[:, k] for k in range(5))
+    base = t0.min()
+    span = t4.max() - base
+
+    def q(x):
+        x = x[act] if len(x) == len(act) else x
+        return 'min %.1f  p50 %.1f  p90 %.1f  max %.1f us' % tuple(1e-3 * np.percentile(x, [0, 50, 90, 100]))
+    print(f'{a.config} rows/gpu={kp.n_rows} grid={grid}x{warps} warps tiles={n_tiles} ({n_tiles / (grid * warps):.1f} per warp) '
+          f'classes 1/2/3+ groups: {np.bincount(cls, minlength=3).tolist()}')
+    print(f'kernel span (first entry -> last exit): {1e-3 * span:.1f} us; spans of {a.evals} runs: '
+          + ', '.join('%.1f' % (1e-3 * (r[:, 4].max() - r[:, 0].min())) for r in runs))
+    print('entry after first entry :', q(t0 - base))
+    print('prologue (entry->ready)  :', q(t1 - t0))
+    print('wait for the first tile  :', q(t2 - t1))
+    print('tile loop                :', q(t3 - t2))
+    print('epilogue (loop end->exit):', q(t4 - t3))
+    print('loop end after first entry:', q(t3 - base))
+    # least-squares cost per tile class
+    A = per_warp[act].astype(np.float64)
+    y = (t3 - t2)[act].astype(np.float64) * 1e-3
+    cols = [k for k in range(3) if A[:, k].any()]
+    coef, *_ = np.linalg.lstsq(np.c_[A[:, cols], np.ones(len(A))], y, rcond=None)
+    print('loop time ~ ' + ' + '.join(f'{c:.2f} us x tiles[{["1 group", "2 groups", "3+ groups"][k]}]' for k, c in zip(cols, coef))
+          + f' + {coef[-1]:.2f} us')
+    slow = np.argsort(-(t3 - base))[:5]
+    for i in slow:
+        print(f'  slowest warp cta {i // warps} warp {i % warps}: tiles {per_warp[i].tolist()} entry +{1e-3 * (t0[i] - base):.1f} '
+              f'prologue {1e-3 * (t1[i] - t0[i]):.1f} wait {1e-3 * (t2[i] - t1[i]):.1f} loop {1e-3 * (t3[i] - t2[i]):.1f} '
+              f'end +{1e-3 * (t3[i] - base):.1f} us')
+    if a.out:
+        json.dump({'config': a.config, 'rows': int(kp.n_rows), 'span_us': 1e-3 * float(span),
+                   'trace': tr[:, :5].tolist(), 'tiles': per_warp.tolist()}, open(a.out, 'w'))
+    f.close()
+
+
+if __name__ == '__main__':
+    main()
