@@ -213,6 +213,13 @@ void *skk_stream(skk_plan *plan);
 int skk_trace_enable(skk_plan *plan, int32_t on);
 int64_t skk_trace_read(skk_plan *plan, uint64_t *out, int64_t capacity);
 
+/*
+ * Measured ALU peak of the device, thread-instructions per second of a dependency-free loop: kind 0 = fp64 FMA,
+ * 1 = fp32 FMA, 2 = MUFU.EX2 (multiply FMA rates by 2 for flop/s).  The denominator bench.py reports the
+ * chain-per-lane kernel (configuration 5, fp64-ALU-bound) against; MEASURED_PEAKS.json has no such entry.
+ */
+int skk_alu_peak(int32_t device, int32_t kind, double *ops_per_second);
+
 int skk_abi_version(void);
 
 #ifdef __cplusplus

@@ -13,6 +13,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <queue>
+#include <utility>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -118,6 +120,8 @@ struct LaunchCfg {
     const void *fn = nullptr;
     int grid = 0;
     int smem = 0;
+    int32_t *sched = nullptr;  // static tile schedule of this grid (device): [grid * warps][sched_len + 4]
+    int sched_len = 0, sched_folds = 0;
 };
 
 struct GraphEntry {
@@ -146,6 +150,8 @@ struct skk_plan {
     cudaStream_t stream = nullptr, side = nullptr;  // side: the prior kernels run next to the row kernel
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::vector<void *> allocs;
+    unsigned char *arena = nullptr;   // current arena of the small allocations
+    size_t arena_used = 0;
     size_t device_bytes = 0;
     bool use_graphs = true;
     std::vector<GraphEntry> graphs;
@@ -195,6 +201,7 @@ struct skk_plan {
     void *peer_opened[kMaxPeers] = {nullptr};
     int *peer_status = nullptr;            // mapped host memory
     int peer_nranks = 0;
+    std::vector<uint8_t> fed;              // [P + 2] entries of the exchanged vector this rank feeds
     bool peer_failed = false;              // an exchange timed out: the ranks' counters may disagree from then on
     int exchange_ctas_max = 0;             // CTAs of skk_finish_exchange_kernel that are resident at once
 
@@ -209,13 +216,31 @@ static const int64_t kHeavyLinks = 512;  // hyper-parameters with more children 
 
 static size_t elt_size(int dtype) { return dtype == SKK_F64 ? 8 : 4; }
 
+// Device memory of a plan.  Row columns and other large buffers are allocations of their own; everything small
+// (descriptors, slot tables, partial sums, theta and the outputs) is carved out of shared 4 MiB arenas, so that
+// what an evaluation touches besides the rows lies in a handful of pages -- after the caches and TLBs have
+// been swept (the bench flushes L2 between steps) every separate allocation costs its own page walk.
+static const size_t kArenaBytes = 4u << 20, kArenaMaxItem = 1u << 20;
+
 template <typename U>
 static int dev_alloc(skk_plan *pl, U **out, size_t count, bool zero = false) {
     void *p = nullptr;
-    const size_t bytes = std::max<size_t>(count * sizeof(U), 16);
-    CUDA_TRY(cudaMalloc(&p, bytes));
-    pl->allocs.push_back(p);
-    pl->device_bytes += bytes;
+    const size_t bytes = (std::max<size_t>(count * sizeof(U), 16) + 255) & ~(size_t)255;
+    if (bytes <= kArenaMaxItem) {
+        if (!pl->arena || pl->arena_used + bytes > kArenaBytes) {
+            CUDA_TRY(cudaMalloc(&p, kArenaBytes));
+            pl->allocs.push_back(p);
+            pl->device_bytes += kArenaBytes;
+            pl->arena = static_cast<unsigned char *>(p);
+            pl->arena_used = 0;
+        }
+        p = pl->arena + pl->arena_used;
+        pl->arena_used += bytes;
+    } else {
+        CUDA_TRY(cudaMalloc(&p, bytes));
+        pl->allocs.push_back(p);
+        pl->device_bytes += bytes;
+    }
     if (zero) CUDA_TRY(cudaMemset(p, 0, bytes));
     *out = static_cast<U *>(p);
     return SKK_OK;
@@ -288,6 +313,47 @@ static int configure_launch(skk_plan *pl, int bt, LaunchCfg *cfg) {
     const int want = (pl->n_tiles + pl->warps - 1) / pl->warps;
     cfg->grid = std::max(1, std::min(pl->n_sms * per_sm, want));
     return SKK_OK;
+}
+
+// Static schedule of the row kernel: which tiles every warp of the grid processes, and in which order.  Tiles are
+// handed out in index order to the warp with the least work so far -- measured per tile class (tools/trace_rows.py:
+// a tile with two groups costs ~1.85x a common one on models with a secondary level, the rolled generic path
+// more), and the warps that carry prior work in the prologue start with that much on their account.  A fixed
+// list per warp keeps every sum of the evaluation in a fixed order; the balance removes the tail in which a few
+// warps with several expensive tiles kept their SMs busy while all others had finished.
+static int build_schedule(skk_plan *pl, const std::vector<int2> &keys, int64_t n_rows, int64_t n_prior_groups,
+                          int64_t n_chunks, LaunchCfg *cfg) {
+    const int W = pl->warps, grid = cfg->grid, n_warps = grid * W, WT = pl->rows_per_tile;
+    const double cost_two = pl->ns > 0 ? 1.85 : 1.1, cost_generic = pl->ns > 0 ? 4.0 : 3.0, cost_prior = 1.0;
+    std::vector<double> load(n_warps, 0.0);
+    if (pl->fused_ok && pl->include_priors) {
+        // (skk_row_kernel.cuh: priors(): group / chunk q -> CTA q % grid, warp W - 1 - (q / grid) % W)
+        for (int64_t q = 0; q < n_prior_groups; ++q) load[(q % grid) * W + (W - 1 - (q / grid) % W)] += cost_prior;
+        for (int64_t q = 0; q < n_chunks; ++q) load[(q % grid) * W + (W - 1 - (q / grid) % W)] += cost_prior;
+    }
+    typedef std::pair<double, int> Item;
+    std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+    for (int w = 0; w < n_warps; ++w) heap.push(Item(load[w], w));
+    std::vector<std::vector<int32_t>> lists(n_warps);
+    for (int t = 0; t < pl->n_tiles; ++t) {
+        const bool full = (int64_t)(t + 1) * WT <= n_rows;
+        const int groups = pl->np > 0 ? keys[t].y - keys[t].x + 1 : 1;
+        const double cost = groups <= 1 ? (full ? 1.0 : 1.5) : (groups == 2 && full ? cost_two : cost_generic);
+        Item it = heap.top();
+        heap.pop();
+        lists[it.second].push_back(t);
+        heap.push(Item(it.first + cost, it.second));
+    }
+    size_t longest = 0, shortest = SIZE_MAX;
+    for (const auto &l : lists) {
+        longest = std::max(longest, l.size());
+        shortest = std::min(shortest, l.size());
+    }
+    cfg->sched_len = (int)((longest + 3) & ~(size_t)3);
+    cfg->sched_folds = pl->ns > 0 ? (int)(shortest / kFoldTiles) : 0;
+    std::vector<int32_t> flat((size_t)n_warps * (cfg->sched_len + 4), -1);
+    for (int w = 0; w < n_warps; ++w) std::copy(lists[w].begin(), lists[w].end(), flat.begin() + (size_t)w * (cfg->sched_len + 4));
+    return dev_upload(pl, &cfg->sched, flat.data(), flat.size());
 }
 
 template <typename T>
@@ -435,6 +501,47 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     int4 *slot_desc_dev = nullptr;
     if (int rc = dev_upload(pl, &slot_desc_dev, slot_desc.data(), slot_desc.size())) return rc;
 
+    // elements fed by several slots: per term whether none / all / some of its elements are such, and the raw
+    // partials of their primary slots as one flat list per element (the finish kernel's warp adds them)
+    int8_t term_multi[3][kMaxTermsPerLevel] = {{0, 0}, {0, 0}, {0, 0}};
+    {
+        int64_t n_of[3][kMaxTermsPerLevel] = {{0, 0}, {0, 0}, {0, 0}}, multi_of_term[3][kMaxTermsPerLevel] = {{0, 0}, {0, 0}, {0, 0}};
+        for (const Entry &e : entries) {
+            ++n_of[e.level][e.t];
+            if (single_unit[e.theta] == -2) ++multi_of_term[e.level][e.t];
+        }
+        for (int lv = 0; lv < 3; ++lv)
+            for (int t = 0; t < kMaxTermsPerLevel; ++t)
+                term_multi[lv][t] = multi_of_term[lv][t] == 0 ? 0 : (multi_of_term[lv][t] == n_of[lv][t] ? 1 : 2);
+    }
+    std::vector<int64_t> msrc_ptr(1, 0);
+    std::vector<uint32_t> msrc;
+    {
+        const int64_t first_p = pl->ng + 1, first_s = first_p + (int64_t)pl->np * d->n_primary;
+        if ((int64_t)pl->n_tiles * std::max(1, pl->np) >= (1 << 30) || (int64_t)pl->np * d->n_primary >= (1 << 30))
+            return fail(SKK_ERR_UNSUPPORTED, "too many tiles for the flattened partial lists");
+        for (size_t m = 0; m < multi_elem.size(); ++m) {
+            for (int64_t q = multi_ptr[m]; q < multi_ptr[m + 1]; ++q) {
+                const int64_t unit = multi_unit[q];
+                if (unit < first_p || unit >= first_s) continue;
+                const int t = (int)((unit - first_p) / d->n_primary);
+                const int64_t sl = (unit - first_p) % d->n_primary;
+                const int4 sd = slot_desc[sl];
+                if (sd.y < sd.x) continue;  // empty group
+                msrc.push_back((uint32_t)(t * d->n_primary + sl));
+                for (int tile = sd.x; tile <= sd.y; ++tile) {
+                    const int kind = tile == sd.x ? sd.z : (tile == sd.y ? sd.w : 1);
+                    if (kind) msrc.push_back(((uint32_t)kind << 30) | (uint32_t)(tile * pl->np + t));
+                }
+            }
+            msrc_ptr.push_back((int64_t)msrc.size());
+        }
+    }
+    int64_t *msrc_ptr_dev = nullptr;
+    uint32_t *msrc_dev = nullptr;
+    if (int rc = dev_upload(pl, &msrc_ptr_dev, msrc_ptr.data(), msrc_ptr.size())) return rc;
+    if (int rc = dev_upload(pl, &msrc_dev, msrc.data(), msrc.size())) return rc;
+
     // ---- priors, flattened per theta element; hyper-parameter links as contiguous ranges -----------------
     const size_t Pn = (size_t)d->n_params;
     std::vector<int8_t> fam(Pn, -1);
@@ -565,6 +672,14 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     }
     int32_t *none_dev = nullptr;
     if (int rc = dev_upload(pl, &none_dev, none_elem.data(), none_elem.size())) return rc;
+    // which entries of the exchanged vector this rank's rows feed (the logp partial and the constant always)
+    pl->fed.assign(Pn + 2, 0);
+    for (size_t j = 0; j < Pn; ++j) pl->fed[j] = single_unit[j] != -1 ? 1 : 0;
+    pl->fed[Pn] = pl->fed[Pn + 1] = 1;
+    std::vector<uint8_t> is_parent_host(std::max<size_t>(1, Pn), 0);
+    for (const Parent &q : parents) is_parent_host[q.element] = 1;
+    uint8_t *is_parent_dev = nullptr;
+    if (int rc = dev_upload(pl, &is_parent_dev, is_parent_host.data(), is_parent_host.size())) return rc;
     // The same links once more in link order, every hyper-parameter's range padded to whole chunks of 32
     // and each link carrying its child's prior parameters: the row kernel's prologue reduces a chunk per
     // warp, the finish kernel adds the chunk partials of a hyper-parameter.
@@ -609,7 +724,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     pl->n_sms = prop.multiProcessorCount;
     const int smem_limit = (int)prop.sharedMemPerBlockOptin;
     pl->warps = std::max(1, std::min(8, env_int("SKK_WARPS", 8)));  // kernels are compiled for <= 256 threads
-    pl->stages = std::max(2, std::min(8, env_int("SKK_STAGES", 3)));
+    pl->stages = std::max(2, std::min(3, env_int("SKK_STAGES", 3)));   // (the kernel looks three tiles ahead in its schedule)
     const int bt_max = d->max_batch > 1 ? 4 : 1;
     while (cta_smem<T>(pl, pl->warps, pl->stages, bt_max) > smem_limit) {
         if (pl->stages > 2) --pl->stages;
@@ -629,6 +744,12 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     if (bt_max == 4)
         if (int rc = configure_launch<T>(pl, 4, &pl->cfg4)) return rc;
     const int grid_max = std::max(pl->cfg1.grid, pl->cfg4.grid);
+    {
+        const int64_t n_prior_groups = ((int64_t)d->n_params + 31) / 32;
+        if (int rc = build_schedule(pl, keys, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg1)) return rc;
+        if (bt_max == 4)
+            if (int rc = build_schedule(pl, keys, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg4)) return rc;
+    }
 
     // ---- work buffers --------------------------------------------------------------------------------------------
     const size_t B = (size_t)pl->max_batch, P = (size_t)d->n_params, bt = (size_t)bt_max;
@@ -671,6 +792,14 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     rp.n_none = (int32_t)none_elem.size();
     rp.none_blocks = (int32_t)((none_elem.size() + 255) / 256);
     rp.multi_blocks = (int32_t)((multi_elem.size() + 7) / 8);
+    for (int t = 0; t < kMaxTermsPerLevel; ++t) {
+        rp.multi_g[t] = term_multi[SKK_LEVEL_GLOBAL][t];
+        rp.multi_p[t] = term_multi[SKK_LEVEL_PRIMARY][t];
+        rp.multi_s[t] = term_multi[SKK_LEVEL_SECONDARY][t];
+    }
+    rp.multi_src_ptr = msrc_ptr_dev;
+    rp.multi_src = msrc_dev;
+    rp.is_parent = is_parent_dev;
     {
         rp.parent = pl->prior.parent;
         rp.chunk_ptr = chunk_ptr_dev;
@@ -798,6 +927,9 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
     rp.n_rows = pl->n_rows;
     rp.n_tiles = pl->n_tiles;
     rp.stages = pl->stages;
+    rp.sched = cfg.sched;
+    rp.sched_len = cfg.sched_len;
+    rp.sched_folds = cfg.sched_folds;
     rp.tile_meta = pl->tile_meta;
     rp.tile_split = pl->tile_split;
     rp.seg_offsets = pl->seg_off;
@@ -840,11 +972,31 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
         rp.n_chunks = pl->n_chunks;
     }
     rp.trace = pl->trace;
+    rp.pdl_trigger = env_int("SKK_NO_PDL", 0) ? 0 : env_int("SKK_PDL_TRIGGER", 2);
     void *args[] = {&rp};
     if (timed) CUDA_TRY(cudaEventRecord(pl->evk0, pl->stream));
     CUDA_TRY(cudaLaunchKernel(cfg.fn, dim3(cfg.grid), dim3(pl->warps * 32), args, cfg.smem, pl->stream));
     if (timed) CUDA_TRY(cudaEventRecord(pl->evk1, pl->stream));
     return SKK_OK;
+}
+
+// Launch of a kernel that follows the row kernel in the stream.  With `pdl` it may start while the row kernel's last
+// CTAs are still running (programmatic dependent launch): its CTAs load their descriptors and then wait for the
+// row kernel's completion inside the kernel (grid_dep_wait), which hides the launch gap and the first level of
+// dependent loads.  Captured into the evaluation's CUDA graph like any other launch.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_after_rows(void (*kernel)(KArgs...), unsigned blocks, cudaStream_t st, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // Enqueues one evaluation on pl->stream (+ the prior kernels on pl->side, forked and joined with
@@ -868,6 +1020,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
     // separate kernels
     const bool fused_sharded = sharded && !chain && pl->fused_ok && batch <= 4 && env_int("SKK_SHARDED_FINISH", 1) == 1;
     const bool in_row = fused || fused_sharded;  // the prior terms ride in the row kernel
+    const bool pdl = env_int("SKK_NO_PDL", 0) == 0;  // the finish kernel starts under the row kernel's tail
     // (for large batches they are big enough to fill the GPU themselves: run them in line)
     const bool fork = batch < kChainMinBatch;
     cudaStream_t ps = fork ? pl->side : st;
@@ -973,9 +1126,9 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             }
             const unsigned blocks = slot_blocks + (unsigned)(rp.parent_blocks + rp.none_blocks + rp.multi_blocks);
             if (bt == 4)
-                skk_finish_kernel<T, 4><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
+                CUDA_TRY(launch_after_rows(skk_finish_kernel<T, 4>, blocks, st, pdl, rp, pl->peer, th, out_logp, out_grad));
             else
-                skk_finish_kernel<T, 1><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
+                CUDA_TRY(launch_after_rows(skk_finish_kernel<T, 1>, blocks, st, pdl, rp, pl->peer, th, out_logp, out_grad));
             ++launches;
             b0 += b_valid;
             continue;
@@ -989,11 +1142,11 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             one_launch = pl->peer_ready && (int)blocks <= pl->exchange_ctas_max && env_int("SKK_SHARDED_FINISH_SPLIT", 0) == 0;
             if (one_launch) {
                 if (bt == 4)
-                    skk_finish_exchange_kernel<T, 4><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
+                    CUDA_TRY(launch_after_rows(skk_finish_exchange_kernel<T, 4>, blocks, st, pdl, rp, pl->peer, th, out_logp, out_grad));
                 else
-                    skk_finish_exchange_kernel<T, 1><<<blocks, 256, 0, st>>>(rp, pl->peer, th, out_logp, out_grad);
+                    CUDA_TRY(launch_after_rows(skk_finish_exchange_kernel<T, 1>, blocks, st, pdl, rp, pl->peer, th, out_logp, out_grad));
             } else {
-#define SKK_PUSH(BTV, MODEV) skk_finish_push_kernel<T, BTV, MODEV><<<blocks, 256, 0, st>>>(rp, pl->peer)
+#define SKK_PUSH(BTV, MODEV) CUDA_TRY(launch_after_rows(skk_finish_push_kernel<T, BTV, MODEV>, blocks, st, pdl, rp, pl->peer))
                 if (bt == 4) {
                     if (pl->peer_ready) SKK_PUSH(4, 2); else SKK_PUSH(4, 1);
                 } else {
@@ -1340,8 +1493,7 @@ int skk_comm_destroy(skk_plan *pl) {
 }
 
 static int64_t peer_stride(const skk_plan *pl) {
-    const int64_t n = (int64_t)pl->max_batch * (pl->n_params + 2);
-    return (n + 1) & ~(int64_t)1;  // even: slots stay 16-byte aligned
+    return (int64_t)pl->max_batch * (pl->n_params + 2);  // 16-byte lines per slot
 }
 
 int skk_peer_alloc(skk_plan *pl, int32_t nranks, void *handle_out64) {
@@ -1350,8 +1502,9 @@ int skk_peer_alloc(skk_plan *pl, int32_t nranks, void *handle_out64) {
     if (pl->peer_local) return fail(SKK_ERR_INVALID, "peer buffer already allocated");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     CUDA_TRY(cudaSetDevice(pl->device));
-    const size_t bytes = (size_t)2 * nranks * peer_stride(pl) * sizeof(double) + (size_t)nranks * sizeof(unsigned long long);
-    CUDA_TRY(cudaMalloc(&pl->peer_local, bytes));
+    // [2 parities][nranks][stride] lines of 16 bytes | fed8 [n_params + 2] words of 8 bytes
+    const size_t bytes = (size_t)2 * nranks * peer_stride(pl) * sizeof(uint4) + (size_t)(pl->n_params + 2) * 8;
+    CUDA_TRY(cudaMalloc(&pl->peer_local, bytes));   // (its own allocation: the IPC handle exports the whole allocation)
     pl->allocs.push_back(pl->peer_local);
     pl->device_bytes += bytes;
     CUDA_TRY(cudaMemset(pl->peer_local, 0, bytes));
@@ -1370,6 +1523,7 @@ int skk_peer_init(skk_plan *pl, const void *handles, int32_t rank, int32_t nrank
     if (pl->peer_ready) return fail(SKK_ERR_INVALID, "peer all-reduce already initialised");
     CUDA_TRY(cudaSetDevice(pl->device));
     const int64_t stride = peer_stride(pl);
+    const int64_t fed8_line_offset = (int64_t)2 * nranks * stride;
     PeerParams pp{};
     pp.stride = stride;
     pp.rank = rank;
@@ -1382,17 +1536,27 @@ int skk_peer_init(skk_plan *pl, const void *handles, int32_t rank, int32_t nrank
             CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
             pl->peer_opened[r] = base;
         }
-        pp.peer_buf[r] = static_cast<double *>(base);
-        pp.peer_flag[r] = reinterpret_cast<unsigned long long *>(static_cast<double *>(base) + (size_t)2 * nranks * stride);
+        pp.peer_lines[r] = static_cast<uint4 *>(base);
     }
+    pp.fed8 = reinterpret_cast<const unsigned long long *>(static_cast<uint4 *>(pl->peer_local) + fed8_line_offset);
     unsigned long long *words = nullptr;
-    if (int rc = dev_alloc(pl, &words, 2, true)) return rc;  // seq | done[0], done[1]
+    if (int rc = dev_alloc(pl, &words, 2, true)) return rc;  // seq | done
     pp.seq = words;
     pp.done = reinterpret_cast<unsigned int *>(words + 1);
     CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&pl->peer_status), sizeof(int), cudaHostAllocMapped));
     *pl->peer_status = 0;
     CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&pp.status), pl->peer_status, 0));
     pl->peer = pp;
+    {
+        // this rank's byte of fed8 on every peer.  The caller synchronises the ranks (a barrier) between
+        // skk_peer_init and the first evaluation, as sakkara_b200/distributed.py does.
+        uint8_t *fed_dev = nullptr;
+        if (int rc = dev_upload(pl, &fed_dev, pl->fed.data(), pl->fed.size())) return rc;
+        const int64_t n = (int64_t)pl->fed.size();
+        skk_peer_fed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pl->stream>>>(pp, fed_dev, n, fed8_line_offset);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    }
     {
         // CTAs of the one-launch exchange kernel that fit on the device at once (they wait for each other)
         int per_sm1 = 0, per_sm4 = 0;

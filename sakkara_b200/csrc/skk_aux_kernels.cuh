@@ -208,6 +208,13 @@ struct ReduceParams {
     int32_t n_parents, n_heavy, parent_blocks;
     int32_t n_lp_parts;         // warp partials of the prior logp that the row kernel's prologue writes per chain
     int32_t multi_blocks;       // CTAs of the finish kernel for the elements fed by several slots (8 each)
+    // per term: 0 none of its elements is fed by several slots, 1 all of them are, 2 some (look at single_unit)
+    int8_t multi_g[kMaxTermsPerLevel], multi_p[kMaxTermsPerLevel], multi_s[kMaxTermsPerLevel];
+    // elements fed by several slots: the raw partials of their primary slots, flattened at plan time --
+    // (kind << 30) | index with kind 0: direct_p[index], 1: tile_head[index], 2: tile_tail[index] (x BT + chain)
+    const int64_t *multi_src_ptr;  // [n_multi + 1]
+    const uint32_t *multi_src;
+    const uint8_t *is_parent;      // [P] 1: the element is a hyper-parameter (has children in the priors)
 };
 
 // blockIdx.x in [0, blocks_p): primary slots, one per thread;  [blocks_p, blocks_p + blocks_s):
@@ -299,43 +306,68 @@ __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_consta
 }
 
 // ---- one-shot all-reduce over NVLink peer memory ----------------------------------------------
-// Every rank owns a buffer of 2 (parity) x R slots of `stride` doubles plus R flags, mapped into
-// all peers with CUDA IPC.  Evaluation number seq (1, 2, ...):
-//   push : the theta kernel stores the rank's vector straight into slot [seq & 1][rank] of EVERY
-//          peer (plain stores over NVLink); its last CTA fences and stores flag[rank] = seq on every peer;
-//   final: every rank waits until all R flags of its own buffer reach seq and adds the R slots in
-//          rank order -- the same order everywhere, so all ranks obtain bit-identical results.
-// A rank can be at most one evaluation ahead of a peer (it needs that peer's flag to finish), hence
-// two parities suffice.  Spins are bounded: on timeout a status word in mapped host memory is set
+// Every rank owns a receive buffer of 2 (parity) x R slots of `stride` 16-byte lines, mapped into all
+// peers with CUDA IPC.  A value travels as one line {low word, flag, high word, flag} with
+// flag = evaluation number: a 16-byte store may be split into two 8-byte halves on its way, each
+// half carries its own flag, and 8-byte stores are atomic -- so the receiver needs no fence and no
+// separate "vector complete" flag; it polls the line until both flags show the current evaluation
+// (the LL protocol of NCCL, here written by the kernel that produces the values).
+//   push   : the thread that completes the likelihood part of a theta element stores the line into
+//            slot [seq & 1][rank] of EVERY peer, straight from its registers;
+//   combine: the thread that finishes element j polls the lines of the ranks that feed j and adds
+//            them in rank order -- the same order on every rank, so all ranks obtain bit-identical
+//            results.  Which ranks feed which element is static: every rank writes its own byte of
+//            fed8[j] into all peers when the exchange is set up (skk_peer_init).
+// A rank can be at most one evaluation ahead of a peer (it needs that peer's lines to finish), hence
+// two parities suffice.  Polls are bounded: on timeout a status word in mapped host memory is set
 // and the kernel carries on, so a lost peer can never hang the GPU.
 constexpr int kMaxPeers = 8;
 struct PeerParams {
-    double *peer_buf[kMaxPeers];              // peer_buf[r]: rank r's buffer as seen from this rank
-    unsigned long long *peer_flag[kMaxPeers]; // rank r's flags
+    uint4 *peer_lines[kMaxPeers];             // peer_lines[r]: rank r's receive buffer as seen from this rank
+    const unsigned long long *fed8;           // [P + 2] own buffer: byte r != 0 when rank r feeds the element
     unsigned long long *seq;                  // this rank's evaluation counter (device)
-    unsigned int *done;                       // [0] CTAs of the final kernel that have read their slots,
-                                              // [1] CTAs of the theta kernel that have stored theirs
+    unsigned int *done;                       // CTAs of the combining kernel that have finished
     int *status;                              // mapped host word, != 0 after a timeout
-    int64_t stride;                           // doubles per slot
+    int64_t stride;                           // lines per slot
     int32_t rank, nranks;
 };
 
-// waits until every peer's vector of this evaluation has arrived (called by all threads of a CTA)
-__device__ __forceinline__ unsigned long long peer_wait(const PeerParams &pp) {
-    const unsigned long long seq = *pp.seq + 1;
-    if (threadIdx.x < pp.nranks) {
-        volatile unsigned long long *flag = pp.peer_flag[pp.rank] + threadIdx.x;
+__device__ __forceinline__ unsigned long long peer_seq(const PeerParams &pp) {
+    return *reinterpret_cast<volatile unsigned long long *>(pp.seq) + 1;
+}
+
+// stores `value` of evaluation `seq` at line `at` of this rank's slot in every peer
+__device__ __forceinline__ void peer_push(const PeerParams &pp, unsigned long long seq, int64_t at, double value) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(value);
+    const uint32_t flag = (uint32_t)seq, lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
+    const int64_t line = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride + at;
+    for (int r = 0; r < pp.nranks; ++r)
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pp.peer_lines[r] + line), "r"(lo), "r"(flag),
+                     "r"(hi), "r"(flag)
+                     : "memory");
+}
+
+// sum over the ranks that feed line `at` (rank order), each polled until it shows evaluation `seq`
+__device__ __forceinline__ double peer_combine(const PeerParams &pp, unsigned long long seq, int64_t at, unsigned long long fed) {
+    const uint32_t flag = (uint32_t)seq;
+    const uint4 *mine = pp.peer_lines[pp.rank] + (int64_t)(seq & 1) * pp.nranks * pp.stride + at;
+    double s = 0.0;
+    for (int r = 0; r < pp.nranks; ++r) {
+        if (((fed >> (8 * r)) & 0xffull) == 0) continue;
+        const uint4 *src = mine + (int64_t)r * pp.stride;
+        uint32_t lo, f1, hi, f2;
         const long long t0 = clock64();
-        while (*flag < seq) {
+        for (;;) {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(src) : "memory");
+            if (f1 == flag && f2 == flag) break;
             if (clock64() - t0 > (1ll << 36)) {  // ~35 s: report and go on
                 *pp.status = 1;
                 break;
             }
         }
+        s += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
     }
-    __syncthreads();
-    __threadfence_system();
-    return seq;
+    return s;
 }
 
 // What the last step does with the likelihood gradient of one theta element.
@@ -352,9 +384,7 @@ __device__ __forceinline__ void finish_element(const ReduceParams &rp, const Pee
         if constexpr (MODE == 1) {
             rp.lik_vec[row * (P + 2) + j] = lik[b];
         } else if constexpr (MODE == 2) {
-            const unsigned long long seq = *pp.seq + 1;
-            const int64_t at = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride + row * (P + 2) + j;
-            for (int r = 0; r < pp.nranks; ++r) pp.peer_buf[r][at] = lik[b];
+            peer_push(pp, peer_seq(pp), row * (P + 2) + j, lik[b]);
         } else {
             double g = lik[b];
             if (rp.family == SKK_LIK_NORMAL) {
@@ -385,7 +415,7 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant_
         const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
         if (j < P) {
             const int unit = rp.single_unit[j];
-            if (unit != -2) {
+            if (unit != -2 && (MODE != 2 || unit >= 0)) {   // (over peer memory only the elements this rank feeds travel)
                 double lik[BT];
 #pragma unroll
                 for (int b = 0; b < BT; ++b) lik[b] = unit >= 0 ? rp.totals[(int64_t)unit * BT + b] : 0.0;
@@ -428,12 +458,8 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant_
                         rp.lik_vec[row * (P + 2) + P] = L;
                         rp.lik_vec[row * (P + 2) + P + 1] = rp.logp_const;
                     } else {
-                        const unsigned long long seq = *pp.seq + 1;
-                        const int64_t at = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride + row * (P + 2);
-                        for (int r = 0; r < pp.nranks; ++r) {
-                            pp.peer_buf[r][at + P] = L;
-                            pp.peer_buf[r][at + P + 1] = rp.logp_const;
-                        }
+                        peer_push(pp, peer_seq(pp), row * (P + 2) + P, L);
+                        peer_push(pp, peer_seq(pp), row * (P + 2) + P + 1, rp.logp_const);
                     }
                 }
             }
@@ -454,23 +480,6 @@ skk_theta_kernel(const __grid_constant__ ReduceParams rp, const __grid_constant_
 #pragma unroll
         for (int b = 0; b < BT; ++b) lik[b] = __shfl_sync(kFull, warp_sum(acc[b]), 0);
         if (lane == 0 && have) finish_element<T, BT, MODE>(rp, pp, theta, out_grad, rp.multi_elem[m], lik);
-    }
-    if constexpr (MODE == 2) {
-        // every store of this CTA is visible system-wide before the CTA counts itself done; the last
-        // CTA of the last batch tile then publishes the vector by raising the flags
-        __threadfence_system();
-        __syncthreads();
-        __shared__ bool last;
-        if (threadIdx.x == 0) last = atomicAdd(pp.done + 1, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (last) {
-            if (threadIdx.x == 0) pp.done[1] = 0;
-            if (rp.b0 + rp.b_valid >= rp.batch_total && threadIdx.x < pp.nranks) {
-                __threadfence_system();
-                volatile unsigned long long *flag = pp.peer_flag[threadIdx.x] + pp.rank;
-                *flag = *pp.seq + 1;
-            }
-        }
     }
 }
 
@@ -534,9 +543,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             } else if constexpr (MODE == 1) {
                 rp.lik_vec[row * (P + 2) + k] = lik[b];
             } else {
-                const unsigned long long seq = *pp.seq + 1;
-                const int64_t at = ((int64_t)(seq & 1) * pp.nranks + pp.rank) * pp.stride + row * (P + 2) + k;
-                for (int r = 0; r < pp.nranks; ++r) pp.peer_buf[r][at] = lik[b];
+                peer_push(pp, peer_seq(pp), row * (P + 2) + k, lik[b]);
             }
         }
     };
@@ -568,11 +575,12 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         bool single[kMaxTermsPerLevel];
 #pragma unroll
         for (int t = 0; t < kMaxTermsPerLevel; ++t) {
-            elem[t] = (valid && t < rp.np) ? rp.ti_p[t][slot] : -1;
+            elem[t] = (valid && t < rp.np && rp.multi_p[t] != 1) ? rp.ti_p[t][slot] : -1;
             // (an element fed by several slots is finished by its own warp below)
-            single[t] = elem[t] >= 0 && (rp.n_multi == 0 || rp.single_unit[elem[t]] != -2);
+            single[t] = elem[t] >= 0 && (rp.multi_p[t] == 0 || rp.single_unit[elem[t]] != -2);
             if (!single[t]) elem[t] = -1;
         }
+        grid_dep_wait();  // descriptors are in flight; everything below reads what the row kernel wrote
         double pg[kMaxTermsPerLevel][BT];
 #pragma unroll
         for (int t = 0; t < kMaxTermsPerLevel; ++t) prior_of(elem[t], pg[t]);
@@ -629,9 +637,10 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         int32_t elem[kMaxTermsPerLevel];
 #pragma unroll
         for (int t = 0; t < kMaxTermsPerLevel; ++t) {
-            elem[t] = (sub == 0 && valid && t < rp.ns) ? rp.ti_s[t][slot] : -1;
-            if (elem[t] >= 0 && rp.n_multi != 0 && rp.single_unit[elem[t]] == -2) elem[t] = -1;
+            elem[t] = (sub == 0 && valid && t < rp.ns && rp.multi_s[t] != 1) ? rp.ti_s[t][slot] : -1;
+            if (elem[t] >= 0 && rp.multi_s[t] == 2 && rp.single_unit[elem[t]] == -2) elem[t] = -1;
         }
+        grid_dep_wait();
         double pg[kMaxTermsPerLevel][BT];
 #pragma unroll
         for (int t = 0; t < kMaxTermsPerLevel; ++t) prior_of(elem[t], pg[t]);
@@ -662,6 +671,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         __shared__ double glob[(kMaxTermsPerLevel + 1) * BT];
         __shared__ double lp_part[8];
         const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+        grid_dep_wait();
         for (int item = warp; item < (rp.ng + 1) * BT; item += warps) {
             double acc = 0.0;
             for (int c = lane; c < rp.grid; c += 32) acc += rp.cta_glob[(int64_t)c * (rp.ng + 1) * BT + item];
@@ -684,7 +694,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         if ((int)threadIdx.x < rp.ng) {
             double lik[BT], pg[BT];
             int32_t j = rp.ti_g[threadIdx.x][0];
-            if (rp.n_multi != 0 && rp.single_unit[j] == -2) j = -1;
+            if (rp.multi_g[threadIdx.x] == 1 || (rp.multi_g[threadIdx.x] == 2 && rp.single_unit[j] == -2)) j = -1;
 #pragma unroll
             for (int b = 0; b < BT; ++b) lik[b] = glob[threadIdx.x * BT + b];
             prior_of(j, pg);
@@ -745,9 +755,14 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         double pg[BT], sum[BT];
 #pragma unroll
         for (int b = 0; b < BT; ++b) sum[b] = pg[b] = 0.0;
+        int64_t lo = 0, hi = 0;
         if (active) {
-            const int64_t lo = rp.chunk_ptr[q], hi = rp.chunk_ptr[q + 1];
+            lo = rp.chunk_ptr[q];
+            hi = rp.chunk_ptr[q + 1];
             j = rp.parent[q];
+        }
+        grid_dep_wait();
+        if (active) {
             prior_of(j, pg);
             const int64_t first = lo + (heavy ? threadIdx.x : lane), step = heavy ? blockDim.x : 32;
             const double *part = rp.link_part + (int64_t)rp.b0 * rp.n_chunks;
@@ -775,6 +790,11 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             for (int b = 0; b < BT; ++b) {
                 if constexpr (MODE == 0) {
                     pg[b] += rp.include_priors ? sum[b] : 0.0;
+                } else if constexpr (MODE == 3) {
+                    // nothing feeds a hyper-parameter on any rank: own prior term + the children, straight to the output
+                    if (b < rp.b_valid)
+                        out_grad[(int64_t)(rp.b0 + b) * P + j] =
+                            (T)(rp.include_priors ? rp.prior_grad[(int64_t)(rp.b0 + b) * P + j] + sum[b] : 0.0);
                 } else {
                     // own term written by the row kernel's prologue; this thread is the element's only other writer
                     if (b < rp.b_valid && rp.include_priors)
@@ -786,8 +806,9 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
     } else if ((int)blockIdx.x < b_multi) {
         // elements that no term feeds and that have no children: own prior term only
         const int64_t k = ((int64_t)blockIdx.x - b_none) * blockDim.x + threadIdx.x;
-        if (k < rp.n_none) {
-            const int64_t j = rp.none_elem[k];
+        const int64_t j = k < rp.n_none ? rp.none_elem[k] : -1;
+        grid_dep_wait();
+        if (j >= 0) {
             if (!(sigma_is_param && j == rp.sigma_theta_index)) {
                 double pg[BT];
                 prior_of(j, pg);
@@ -795,51 +816,54 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             }
         }
     } else {
-        // elements fed by several slots: one warp each, its units lane-strided (four in flight per lane)
+        // elements fed by several slots: one warp each.  The raw partials of the element's primary slots were
+        // flattened at plan time (one index load, one value load, lane-strided); global / secondary units --
+        // a block used by terms of different levels -- are walked the long way.
         const int64_t m = ((int64_t)blockIdx.x - b_multi) * (blockDim.x >> 5) + (threadIdx.x >> 5);
         const bool have = m < rp.n_multi;
         const int64_t lo = have ? rp.multi_ptr[m] : 0, hi = have ? rp.multi_ptr[m + 1] : 0;
+        const int64_t lo2 = have ? rp.multi_src_ptr[m] : 0, hi2 = have ? rp.multi_src_ptr[m + 1] : 0;
         const int32_t j = have ? rp.multi_elem[m] : -1;
+        constexpr uint32_t kNoSrc = 0xffffffffu;
+        uint32_t src0[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) src0[u] = lo2 + lane + 32 * u < hi2 ? rp.multi_src[lo2 + lane + 32 * u] : kNoSrc;
+        grid_dep_wait();
         double pg[BT], acc[BT];
         prior_of(j, pg);
 #pragma unroll
         for (int b = 0; b < BT; ++b) acc[b] = 0.0;
+        auto add_src = [&](uint32_t src) {
+            if (src == kNoSrc) return;
+            const int kind = (int)(src >> 30);
+            const int64_t at = (int64_t)(src & 0x3fffffffu) * BT;
+            const double *base = kind == 0 ? rp.direct_p : (kind == 1 ? rp.tile_head : rp.tile_tail);
+#pragma unroll
+            for (int b = 0; b < BT; ++b) acc[b] += base[at + b];
+        };
+#pragma unroll
+        for (int u = 0; u < 4; ++u) add_src(src0[u]);
+        for (int64_t e0 = lo2 + lane + 128; e0 < hi2; e0 += 128) {
+            uint32_t src[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) src[u] = e0 + 32 * u < hi2 ? rp.multi_src[e0 + 32 * u] : kNoSrc;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) add_src(src[u]);
+        }
         const int64_t first_p = rp.ng + 1, first_s = first_p + (int64_t)rp.np * rp.n_primary;
-        for (int64_t e0 = lo + lane; e0 < hi; e0 += 4 * 32) {
-            int64_t unit[4];
-            int4 d[4];
+        for (int64_t e = lo + lane; e < hi; e += 32) {
+            const int64_t unit = rp.multi_unit[e];
+            if (unit < first_p) {
+                // a global term: CTA partials of the row kernel in order
+                for (int c = 0; c < rp.grid; ++c)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) unit[u] = e0 + 32 * u < hi ? rp.multi_unit[e0 + 32 * u] : -1;
+                    for (int b = 0; b < BT; ++b) acc[b] += rp.cta_glob[((int64_t)c * (rp.ng + 1) + unit) * BT + b];
+            } else if (unit >= first_s) {
+                const int64_t at = unit - first_s;  // t * n_secondary + slot
+                const int64_t stride = (int64_t)rp.ns * rp.n_secondary * BT;
+                for (int c = 0; c < rp.grid; ++c)
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                d[u] = (unit[u] >= first_p && unit[u] < first_s) ? rp.slot_desc[(unit[u] - first_p) % rp.n_primary]
-                                                                 : make_int4(0, -1, 0, 0);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (unit[u] < 0) continue;
-                if (unit[u] < first_p) {
-                    // a global term: CTA partials of the row kernel in order
-                    for (int c = 0; c < rp.grid; ++c)
-#pragma unroll
-                        for (int b = 0; b < BT; ++b) acc[b] += rp.cta_glob[((int64_t)c * (rp.ng + 1) + unit[u]) * BT + b];
-                } else if (unit[u] < first_s) {
-                    const int t = (int)((unit[u] - first_p) / rp.n_primary);
-                    const int64_t slot = (unit[u] - first_p) % rp.n_primary;
-                    if (d[u].y >= d[u].x) {
-#pragma unroll
-                        for (int b = 0; b < BT; ++b) acc[b] += rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b];
-#pragma unroll 4
-                        for (int64_t tile = d[u].x; tile <= d[u].y; ++tile)
-#pragma unroll
-                            for (int b = 0; b < BT; ++b) acc[b] += addend(d[u], tile, t, b);
-                    }
-                } else {
-                    const int64_t at = unit[u] - first_s;  // t * n_secondary + slot
-                    const int64_t stride = (int64_t)rp.ns * rp.n_secondary * BT;
-                    for (int c = 0; c < rp.grid; ++c)
-#pragma unroll
-                        for (int b = 0; b < BT; ++b) acc[b] += rp.cta_sec[c * stride + at * BT + b];
-                }
+                    for (int b = 0; b < BT; ++b) acc[b] += rp.cta_sec[c * stride + at * BT + b];
             }
         }
         double lik[BT];
@@ -847,44 +871,25 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         for (int b = 0; b < BT; ++b) lik[b] = warp_sum(acc[b]);
         if (lane == 0 && have) store(j, lik, pg);
     }
-    if constexpr (MODE >= 2) {
-        // as in skk_theta_kernel: every store of this CTA is visible system-wide before the CTA counts
-        // itself done; the last CTA publishes the vector by raising the flags
-        __threadfence_system();
-        __syncthreads();
-        __shared__ bool last;
-        if (threadIdx.x == 0) last = atomicAdd(pp.done + 1, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (last) {
-            if (threadIdx.x == 0) pp.done[1] = 0;
-            if (rp.b0 + rp.b_valid >= rp.batch_total && threadIdx.x < pp.nranks) {
-                __threadfence_system();
-                volatile unsigned long long *flag = pp.peer_flag[threadIdx.x] + pp.rank;
-                *flag = *pp.seq + 1;
-            }
-        }
-    }
     if constexpr (MODE == 3) {
-        // ---- wait for every rank's vector, then combine a slice of theta from the R slots (rank order) ----
-        const unsigned long long seq = peer_wait(pp);
+        // ---- combine a slice of theta from the R slots of the own buffer (rank order), as the lines arrive ----
+        // (hyper-parameters were finished above: nothing feeds them on any rank)
+        const unsigned long long seq = peer_seq(pp);
         const bool normal = rp.family == SKK_LIK_NORMAL;
         for (int b = 0; b < rp.b_valid; ++b) {
             const int64_t row = rp.b0 + b;
-            const double *mine = pp.peer_buf[pp.rank] + (int64_t)(seq & 1) * pp.nranks * pp.stride + row * (P + 2);
-            auto lik_at = [&](int64_t k) -> double {
-                double s = 0.0;
-                for (int r = 0; r < pp.nranks; ++r) s += load_volatile(mine + (int64_t)r * pp.stride + k);
-                return s;
-            };
+            const int64_t base = row * (P + 2);
             double sc = 1.0, sigma = 1.0;
             if (normal) {
                 sigma = rp.sigma_theta_index >= 0 ? exp((double)theta[row * P + rp.sigma_theta_index]) : rp.sigma_const;
                 sc = 1.0 / (sigma * sigma);
             }
             for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < P; j += (int64_t)gridDim.x * blockDim.x) {
-                double g = lik_at(j) * sc;
-                if (normal && j == rp.sigma_theta_index) g += lik_at(P) * sc - (double)rp.n_rows_total;
-                if (rp.include_priors) g += load_volatile(rp.prior_grad + row * P + j);
+                if (rp.is_parent[j]) continue;
+                double g = peer_combine(pp, seq, base + j, pp.fed8[j]) * sc;
+                if (normal && j == rp.sigma_theta_index)
+                    g += peer_combine(pp, seq, base + P, pp.fed8[P]) * sc - (double)rp.n_rows_total;
+                if (rp.include_priors) g += rp.prior_grad[row * P + j];
                 out_grad[row * P + j] = (T)g;
             }
             if (blockIdx.x == gridDim.x - 1) {
@@ -899,15 +904,15 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 if (threadIdx.x == 0) {
                     double tot = 0.0;
                     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += lp_tail[w];
-                    const double L = lik_at(P);
+                    const double L = peer_combine(pp, seq, base + P, pp.fed8[P]);
                     const double ll = normal ? -0.5 * L * sc - (double)rp.n_rows_total * (kLogSqrt2Pi + log(sigma)) : L;
-                    out_logp[row] = (T)(tot + ll + lik_at(P + 1));
+                    out_logp[row] = (T)(tot + ll + peer_combine(pp, seq, base + P + 1, pp.fed8[P + 1]));
                 }
                 __syncthreads();
             }
         }
         // the last CTA to finish closes the evaluation (the slots of this parity may be reused two
-        // evaluations later, the flags only grow)
+        // evaluations later)
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -962,16 +967,11 @@ __global__ void skk_final_kernel(const __grid_constant__ FinalParams fp, const _
     const int b = blockIdx.y;
     const int64_t P = fp.n_params;
     const double *lik_in = fp.lik_vec + (int64_t)b * (P + 2);
-    const double *mine = nullptr;
-    if constexpr (PEER) {
-        const unsigned long long seq = peer_wait(pp);
-        mine = pp.peer_buf[pp.rank] + (int64_t)(seq & 1) * pp.nranks * pp.stride + (int64_t)b * (P + 2);
-    }
+    unsigned long long seq = 0;
+    if constexpr (PEER) seq = peer_seq(pp);
     auto lik_at = [&](int64_t k) -> double {
         if constexpr (PEER) {
-            double s = 0.0;
-            for (int r = 0; r < pp.nranks; ++r) s += mine[(int64_t)r * pp.stride + k];
-            return s;
+            return peer_combine(pp, seq, (int64_t)b * (P + 2) + k, pp.fed8[k]);
         } else {
             return lik_in[k];
         }
@@ -1011,18 +1011,28 @@ __global__ void skk_final_kernel(const __grid_constant__ FinalParams fp, const _
     }
     if constexpr (PEER) {
         // the last CTA to finish closes the evaluation (the slots of this parity may be reused two
-        // evaluations later, the flags only grow)
+        // evaluations later)
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
             const unsigned int total = gridDim.x * gridDim.y;
             if (atomicAdd(pp.done, 1u) == total - 1) {
                 *pp.done = 0;
-                *pp.seq = *pp.seq + 1;
+                *pp.seq = seq;
             }
         }
     }
 }
 
+// set-up of the exchange: this rank's byte of fed8[j] on every peer (1: the rank feeds element j)
+static __global__ void skk_peer_fed_kernel(const __grid_constant__ PeerParams pp, const uint8_t *__restrict__ fed, int64_t n,
+                                           int64_t fed8_line_offset) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int r = 0; r < pp.nranks; ++r) {
+        uint8_t *dst = reinterpret_cast<uint8_t *>(pp.peer_lines[r] + fed8_line_offset) + j * 8 + pp.rank;
+        *dst = fed[j];
+    }
+}
 
 }  // namespace skk

@@ -32,6 +32,9 @@ struct RowParams {
     int32_t n_tiles;
     int32_t stages;          // smem ring depth per warp
     // structure
+    const int32_t *sched;    // static schedule: [grid * warps][sched_len + 4] tiles of every warp in order, -1 padded
+    int32_t sched_len;       // multiple of 4
+    int32_t sched_folds;     // folds of the fp32 accumulator tables every kFoldTiles tiles (same for all warps)
     const int4 *tile_meta;   // per tile {first, last primary slot, theta element of primary term 0 / 1 at the first slot}
     const int32_t *tile_split;  // per tile: row (inside the tile) where its second group starts when the tile
                                 // holds exactly two groups, else -1
@@ -73,11 +76,15 @@ struct RowParams {
     int64_t n_chunks;
     // optional per-warp timeline (skk_trace_enable): [grid * warps][kTraceWords], null in normal operation
     unsigned long long *trace;
+    // when the kernel that follows in the stream (launched with the PDL attribute) may start: 0 at this
+    // kernel's end as usual, 1 as soon as this kernel runs, 2 when the tile loops are through
+    int32_t pdl_trigger;
 };
 
 // words of one warp's trace record
 //   0 %globaltimer at kernel entry     1 ... when the prologue is done (before the first tile wait)
 //   2 ... when the first tile has arrived   3 ... at the end of the tile loop   4 ... at kernel exit
+//   5, 6, 7 tiles of the warp with one group / two groups / more
 constexpr int kTraceWords = 8;
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -213,6 +220,14 @@ __device__ __forceinline__ void sts_free_if(bool pred, uint32_t a, double v, uin
 __device__ __forceinline__ void table_stores_done(uint32_t token) {
     asm volatile("" ::"r"(token) : "memory");
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may start while its predecessor in the stream is still running -- as soon as every CTA of the predecessor
+// has executed grid_dep_launch_dependents() (or exited) and SM resources are free -- and must call
+// grid_dep_wait() before it touches anything the predecessor writes; the wait returns when the predecessor
+// has completed and its memory is visible.  Both are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // order generic-proxy accesses to shared memory before later async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async() {

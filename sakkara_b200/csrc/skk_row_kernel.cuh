@@ -73,6 +73,7 @@ struct PipeRows {
         kPipeRows == 0 ? 0 : ((int)sizeof(T) * BT <= 4 ? kPipeRows : ((int)sizeof(T) * BT <= 8 ? 2 : 1));
 };
 
+constexpr int kFoldTiles = 128;    // (power of two) tiles of a warp between two folds of the fp32 accumulator tables into fp64
 constexpr int kStagedGroups = 32;  // straddling tiles with up to this many segments are handled on chip
 
 // scratch of one warp: segment offsets [33] | values [32][NP][BT] T | accumulators [32][NP][BT] f64 | touched [32]
@@ -862,6 +863,23 @@ struct RowKernel {
         }
     }
 
+    // CTA-wide: the warps' accumulator tables -> the CTA's fp64 partial, tables cleared (all warps call it at the
+    // same point of their tile lists)
+    static __device__ __forceinline__ void fold_tables(const RowParams<T> &p, T *gradS_all, int warps, bool first) {
+        const int n = NS * p.n_secondary * BT;
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            double s = 0.0;
+            for (int w = 0; w < warps; ++w) {
+                s += (double)gradS_all[(int64_t)w * n + k];
+                gradS_all[(int64_t)w * n + k] = T(0);
+            }
+            double *dst = p.cta_sec + (int64_t)blockIdx.x * n + k;
+            *dst = first ? s : *dst + s;
+        }
+        __syncthreads();
+    }
+
     static __device__ void run(const RowParams<T> &p) {
         extern __shared__ __align__(128) unsigned char smem[];
         const int warps = blockDim.x >> 5;
@@ -885,10 +903,13 @@ struct RowKernel {
         unsigned char *stage0 = smem + cl.stage_off + (int64_t)warp * stages * sl.bytes;
         unsigned char *scratch = smem + cl.scratch_off + warp * cl.scratch_bytes;
 
-        // contiguous, balanced range of tiles for this CTA; its warps interleave inside the range
-        const int64_t nt = p.n_tiles;
-        const int tile_begin = (int)((nt * blockIdx.x) / gridDim.x);
-        const int tile_end = (int)((nt * (blockIdx.x + 1)) / gridDim.x);
+        // The tiles of this warp, in order, from the plan's static schedule (cost-balanced over all warps of the
+        // grid at plan creation: tiles with two or more groups cost more than the common ones, and so does the
+        // prior work some warps carry).  A fixed list per warp keeps every sum in a fixed order.
+        // [sched_len + 4] entries per warp, -1 behind the last tile; sched_len is a multiple of 4.
+        const int32_t *my_tiles = p.sched + ((int64_t)blockIdx.x * warps + warp) * (p.sched_len + 4);
+        const int4 first4 = *reinterpret_cast<const int4 *>(my_tiles);
+        int t0 = first4.x, t1 = first4.y, t2 = first4.z, t3 = first4.w;
 
         if (lane == 0) {
             for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
@@ -897,9 +918,9 @@ struct RowKernel {
         __syncwarp();
         // start the pipeline before touching anything else
         if (elect_one()) {
-            for (int s = 0; s < stages; ++s) {
-                const int t = tile_begin + warp + s * warps;
-                if (t < tile_end) issue_tile(p, t, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
+            for (int s = 0; s < stages; ++s) {   // stages <= 3
+                const int t = s == 0 ? t0 : (s == 1 ? t1 : t2);
+                if (t >= 0) issue_tile(p, t, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
             }
         }
 
@@ -909,51 +930,36 @@ struct RowKernel {
                 p.trace[((int64_t)blockIdx.x * warps + warp) * kTraceWords + word] = global_timer_ns();
         };
         stamp(0);
+        // the kernel that follows in the stream may start its own prologue under this kernel's tail (PDL)
+        if (p.pdl_trigger == 1) grid_dep_launch_dependents();
 
-        if constexpr (NS > 0) {
-            const int n = NS * p.n_secondary * BT;
-            // theta[ti_s[slot]]: issue the index loads of four entries, then the four value loads
-            for (int k0 = threadIdx.x; k0 < n; k0 += 4 * blockDim.x) {
-                int element[4];
+        // Everything the warp needs before its first tile is two levels of dependent global loads (slot ->
+        // theta element -> value): all first-level loads are issued here, then all second-level ones, so
+        // the prologue costs two memory latencies instead of one pair per item.
+        // level 1: theta elements of the global terms, keys of the first two tiles, elements of the value table
+        int eg[NGa];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int k = k0 + u * blockDim.x;
-                    element[u] = k < n ? p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary] : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int k = k0 + u * blockDim.x;
-                    if (element[u] >= 0) valS[k] = theta_at(p, k % BT, element[u]);
-                }
-            }
-            for (int k = threadIdx.x; k < n * warps; k += blockDim.x) gradS_all[k] = T(0);
-            __syncthreads();
-        }
-
-        // (after the barrier: the warps without prior work start on their tiles at once)
-        if (p.prior_family != nullptr) priors(p, warp, lane);
-
-        T vg[NGa][BT];
-#pragma unroll
-        for (int t = 0; t < NGa; ++t)
-#pragma unroll
-            for (int b = 0; b < BT; ++b) vg[t][b] = (NG > 0) ? theta_at(p, b, p.ti_g[t][0]) : T(0);
-
-        double accG64[NG + 1][BT];
-#pragma unroll
-        for (int t = 0; t <= NG; ++t)
-#pragma unroll
-            for (int b = 0; b < BT; ++b) accG64[t][b] = 0.0;
-
-        // software prefetch of the tile keys (two tiles ahead) and primary values (one ahead)
-        int tile = tile_begin + warp;
+        for (int t = 0; t < NGa; ++t) eg[t] = (NG > 0 && t < NG) ? p.ti_g[t][0] : 0;
         int4 k0 = make_int4(0, 0, 0, 0), k1 = make_int4(0, 0, 0, 0);
-        T vp0[NPa][BT];
+        int sp0 = -1, sp1 = -1;
         if constexpr (NP > 0) {
-            if (tile < tile_end) k0 = p.tile_meta[tile];
-            if (tile + warps < tile_end) k1 = p.tile_meta[tile + warps];
+            if (t0 >= 0) k0 = p.tile_meta[t0];
+            if (t1 >= 0) k1 = p.tile_meta[t1];
+            if constexpr (NS == 0) {
+                if (t0 >= 0) sp0 = p.tile_split[t0];
+                if (t1 >= 0) sp1 = p.tile_split[t1];
+            }
         }
-        load_vp(p, k0, vp0);
+        constexpr int kFillUnroll = 4;
+        const int n_sec = NS * p.n_secondary * BT;
+        int element[kFillUnroll];
+        if constexpr (NS > 0) {
+#pragma unroll
+            for (int u = 0; u < kFillUnroll; ++u) {
+                const int k = threadIdx.x + u * blockDim.x;
+                element[u] = k < n_sec ? p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary] : -1;
+            }
+        }
         // lane j of a straddling tile stages group kf + j: its theta elements are fetched one tile ahead
         auto staged_elements = [&](const int4 &meta, int (&out)[NPa]) {
 #pragma unroll
@@ -961,11 +967,51 @@ struct RowKernel {
                 out[t] = (NP > 0 && meta.x != meta.y && lane <= meta.y - meta.x && meta.y - meta.x < kStagedGroups)
                              ? p.ti_p[t][meta.x + lane] : 0;
         };
+        // level 2: the values
+        T vg[NGa][BT];
+#pragma unroll
+        for (int t = 0; t < NGa; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) vg[t][b] = (NG > 0) ? theta_at(p, b, eg[t]) : T(0);
+        T vp0[NPa][BT];
+        load_vp(p, k0, vp0);
         int se0[NPa], se1[NPa];
         staged_elements(k0, se0);
+        if constexpr (NS > 0) {
+#pragma unroll
+            for (int u = 0; u < kFillUnroll; ++u) {
+                const int k = threadIdx.x + u * blockDim.x;
+                if (element[u] >= 0) valS[k] = theta_at(p, k % BT, element[u]);
+            }
+            // (tables with more entries than one round of the CTA: the rest, four at a time as above)
+            for (int k0f = threadIdx.x + kFillUnroll * blockDim.x; k0f < n_sec; k0f += kFillUnroll * blockDim.x) {
+                int el[kFillUnroll];
+#pragma unroll
+                for (int u = 0; u < kFillUnroll; ++u) {
+                    const int k = k0f + u * blockDim.x;
+                    el[u] = k < n_sec ? p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < kFillUnroll; ++u) {
+                    const int k = k0f + u * blockDim.x;
+                    if (el[u] >= 0) valS[k] = theta_at(p, k % BT, el[u]);
+                }
+            }
+            for (int k = threadIdx.x; k < n_sec * warps; k += blockDim.x) gradS_all[k] = T(0);
+            __syncthreads();
+        }
+
+        // (after the barrier: the warps without prior work start on their tiles at once)
+        if (p.prior_family != nullptr) priors(p, warp, lane);
+
+        double accG64[NG + 1][BT];
+#pragma unroll
+        for (int t = 0; t <= NG; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) accG64[t][b] = 0.0;
+
         // tiles with exactly two groups (and no secondary level) take the two-group path: the split row
         // and the second group's values are fetched ahead like the first group's
-        int sp0 = -1, sp1 = -1;
         T vq0[NPa][BT], vq1[NPa][BT];
         auto load_second = [&](const int4 &meta, const int (&se)[NPa], T (&vq)[NPa][BT]) {
 #pragma unroll
@@ -976,32 +1022,34 @@ struct RowKernel {
                     vq[t][b] = (NP > 0 && NS == 0 && meta.y == meta.x + 1) ? theta_at(p, b, element) : T(0);
             }
         };
-        if constexpr (NP > 0 && NS == 0) {
-            if (tile < tile_end) sp0 = p.tile_split[tile];
-            if (tile + warps < tile_end) sp1 = p.tile_split[tile + warps];
-        }
         load_second(k0, se0, vq0);
 
         stamp(1);
-        if (p.trace != nullptr && tile < tile_end) {
+        if (p.trace != nullptr && t0 >= 0) {
             mbar_wait(bars, 0);  // (the loop's own wait on this phase then returns at once)
             stamp(2);
         }
         int s = 0;             // stage of the ring that holds the current tile, and the parity of its barrier
         uint32_t parity = 0;   // (counted, not derived from the iteration number: no integer division per tile)
-        for (; tile < tile_end; tile += warps) {
+        // the accumulator tables of the secondary level are fp32 for fp32 plans: every kFoldTiles tiles the CTA
+        // adds them into its fp64 partial (cta_sec) and clears them, so an entry never collects more than
+        // 2 * kFoldTiles + 1 rounded additions however long the shard is (n_folds is the same for all warps)
+        int pos = 0;
+        for (; t0 >= 0; ++pos) {
+            const int tile = t0;
             int4 k2 = make_int4(0, 0, 0, 0);
             T vp1[NPa][BT];
             if constexpr (NP > 0) {
-                if (tile + 2 * warps < tile_end) k2 = p.tile_meta[tile + 2 * warps];
+                if (t2 >= 0) k2 = p.tile_meta[t2];
             }
             load_vp(p, k1, vp1);
             staged_elements(k1, se1);
             load_second(k1, se1, vq1);
             int sp2 = -1;
             if constexpr (NP > 0 && NS == 0) {
-                if (tile + 2 * warps < tile_end) sp2 = p.tile_split[tile + 2 * warps];
+                if (t2 >= 0) sp2 = p.tile_split[t2];
             }
+            const int t4 = my_tiles[pos + 4];
 
             mbar_wait(bars + s, parity);
 
@@ -1032,8 +1080,8 @@ struct RowKernel {
             }
 
             __syncwarp();
-            const int next = tile + stages * warps;
-            if (next < tile_end) {
+            const int next = stages == 2 ? t2 : t3;   // the tile `stages` positions ahead takes over this slot
+            if (next >= 0) {
                 if (elect_one()) {
                     fence_proxy_async();
                     issue_tile(p, next, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
@@ -1042,6 +1090,14 @@ struct RowKernel {
             if (++s == stages) {
                 s = 0;
                 parity ^= 1u;
+            }
+            t0 = t1;
+            t1 = t2;
+            t2 = t3;
+            t3 = t4;
+            if constexpr (NS > 0) {
+                if (((pos + 1) & (kFoldTiles - 1)) == 0 && (pos + 1) / kFoldTiles <= p.sched_folds)
+                    fold_tables(p, gradS_all, warps, pos + 1 == kFoldTiles);
             }
             k0 = k1;
             k1 = k2;
@@ -1060,6 +1116,17 @@ struct RowKernel {
         }
 
         stamp(3);
+        if (p.pdl_trigger == 2) grid_dep_launch_dependents();
+        if (p.trace != nullptr && lane == 0) {
+            // tiles of this warp by class (one group / two groups / more), for tools/trace_rows.py
+            unsigned long long n_class[3] = {0, 0, 0};
+            for (int i = 0; my_tiles[i] >= 0; ++i) {
+                const int4 meta = p.tile_meta[my_tiles[i]];
+                const int groups = NP > 0 ? meta.y - meta.x : 0;
+                ++n_class[groups < 2 ? groups : 2];
+            }
+            for (int c = 0; c < 3; ++c) p.trace[((int64_t)blockIdx.x * warps + warp) * kTraceWords + 5 + c] = n_class[c];
+        }
         // ---- CTA epilogue: fixed-order reductions over lanes, then warps ---------------------------
         __syncthreads();  // all warps are done with their staging buffers; reuse the first one
         double *red = reinterpret_cast<double *>(smem + cl.stage_off);  // [warps][(NG+1)*BT]
@@ -1082,7 +1149,8 @@ struct RowKernel {
             for (int k = threadIdx.x; k < n; k += blockDim.x) {
                 double s = 0.0;
                 for (int w = 0; w < warps; ++w) s += (double)gradS_all[(int64_t)w * n + k];
-                p.cta_sec[(int64_t)blockIdx.x * n + k] = s;
+                double *dst = p.cta_sec + (int64_t)blockIdx.x * n + k;
+                *dst = p.sched_folds == 0 ? s : *dst + s;
             }
         }
         stamp(4);

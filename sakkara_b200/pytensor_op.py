@@ -60,7 +60,9 @@ def make_op(value_grad):
         __props__ = ()
 
         def make_node(self, theta):
-            theta = pt.as_tensor_variable(theta).astype(dtype)
+            theta = pt.as_tensor_variable(theta)
+            if str(theta.dtype) != dtype:
+                theta = theta.astype(dtype)
             return Apply(self, [theta], [pt.scalar(dtype=dtype), pt.vector(dtype=dtype)])
 
         def perform(self, node, inputs, outputs):

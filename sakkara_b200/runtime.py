@@ -55,7 +55,7 @@ class Stats(C.Structure):
 
 EXPORTS = ('skk_plan_create', 'skk_eval', 'skk_plan_destroy', 'skk_last_error', 'skk_comm_unique_id',
            'skk_comm_init', 'skk_comm_destroy', 'skk_peer_alloc', 'skk_peer_init', 'skk_stats', 'skk_stream',
-           'skk_trace_enable', 'skk_trace_read', 'skk_abi_version')
+           'skk_trace_enable', 'skk_trace_read', 'skk_alu_peak', 'skk_abi_version')
 
 _lib = None
 
@@ -96,12 +96,25 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.skk_trace_enable.restype = C.c_int
     lib.skk_trace_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.skk_trace_read.restype = C.c_int64
+    lib.skk_alu_peak.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    lib.skk_alu_peak.restype = C.c_int
     lib.skk_abi_version.argtypes = []
     lib.skk_abi_version.restype = C.c_int
     if lib.skk_abi_version() != ABI_VERSION:
         raise RuntimeError(f'libskk_b200.so has ABI {lib.skk_abi_version()}, binding expects {ABI_VERSION}')
     _lib = lib
     return lib
+
+
+def alu_peak(device: int = 0) -> dict:
+    """Measured thread-instruction rates of the device: fp64 FMA, fp32 FMA, MUFU.EX2 (per second)."""
+    lib = load_library()
+    out = {}
+    for kind, name in enumerate(('dfma_per_s', 'ffma_per_s', 'mufu_per_s')):
+        v = C.c_double()
+        _check(lib, lib.skk_alu_peak(device, kind, C.byref(v)))
+        out[name] = v.value
+    return out
 
 
 class SkkError(RuntimeError):

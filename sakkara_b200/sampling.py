@@ -120,12 +120,14 @@ def sample_hmc(model, chains: int = 64, draws: int = 500, tune: int = 500, n_lea
     gen.manual_seed(seed)
     stream = torch.cuda.ExternalStream(skk.stream, device=dev)
 
-    theta = init_scale * torch.randn(chains, P, dtype=tdt, device=dev, generator=gen)
-
     def evaluate(q, lp, g):
         skk.eval_device(q.data_ptr(), chains, lp.data_ptr(), g.data_ptr(), sync=False)
 
+    # everything -- the start positions included -- is created and consumed on the plan's stream: the library
+    # launches there, and torch's caching allocator then knows which stream uses the buffers
+    stream.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(stream):
+        theta = init_scale * torch.randn(chains, P, dtype=tdt, device=dev, generator=gen)
         kept, kept_logp, accepted, eps = hmc_chains(evaluate, theta, draws, tune, n_leapfrog, step_size,
                                                     target_accept, generator=gen)
     torch.cuda.synchronize()

@@ -32,7 +32,7 @@ class Variable:
         self.dtype, self.ndim, self.name = str(dtype), ndim, name
         self.owner, self.index, self.value = None, 0, value     # value: constants only
 
-    def astype(self, dtype): return Cast(dtype)(self)
+    def astype(self, dtype): return self if str(dtype) == self.dtype else Cast(dtype)(self)   # (a no-op cast returns the variable itself, as in PyTensor)
     def ravel(self): return Ravel()(self)
     def sum(self): return Sum()(self)
     def __add__(self, o): return Elemwise('add')(self, as_tensor_variable(o))

@@ -34,7 +34,7 @@ def main():
 
     def compile_one(src):
         base = os.path.basename(src)[:-3]
-        if only and base != 'skk_api' and not any(pat in base for pat in only.split(',')):
+        if only and base not in ('skk_api', 'skk_microbench') and not any(pat in base for pat in only.split(',')):
             if base.startswith('skk_row_'):
                 stub_names.append(('row', base[len('skk_row_'):]))
             else:

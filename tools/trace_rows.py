@@ -48,21 +48,6 @@ def main():
     grid, warps, wt = st['grid'], st['block'] // 32, st['rows_per_tile']
     kp = f.kernel_plan
     n_tiles = st['n_tiles']
-    # tile classes from the segment offsets
-    seg = kp.seg_offsets
-    cls = np.zeros(n_tiles, dtype=np.int64)
-    if kp.n_primary:
-        r0 = np.arange(n_tiles, dtype=np.int64) * wt
-        r1 = np.minimum(kp.n_rows, r0 + wt) - 1
-        kf = np.searchsorted(seg, r0, side='right') - 1
-        kl = np.searchsorted(seg, np.maximum(r0, r1), side='right') - 1
-        cls = np.minimum(kl - kf, 2)
-    per_warp = np.zeros((grid * warps, 3), dtype=np.int64)
-    for c in range(grid):
-        tb, te = n_tiles * c // grid, n_tiles * (c + 1) // grid
-        for w in range(warps):
-            t = np.arange(tb + w, te, warps)
-            per_warp[c * warps + w] = np.bincount(cls[t], minlength=3) if len(t) else 0
     runs = []
     for _ in range(a.evals):
         flush.zero_()
@@ -70,6 +55,8 @@ def main():
         f(theta)
         runs.append(skk.trace_read().astype(np.int64))
     tr = runs[-1]
+    per_warp = tr[:, 5:8]                      # tiles per class, counted by the kernel from the warp's schedule
+    cls_total = per_warp.sum(0)
     act = per_warp.sum(1) > 0
     t0, t1, t2, t3, t4 = (tr[:, k] for k in range(5))
     base = t0.min()
@@ -79,7 +66,7 @@ def main():
         x = x[act] if len(x) == len(act) else x
         return 'min %.1f  p50 %.1f  p90 %.1f  max %.1f us' % tuple(1e-3 * np.percentile(x, [0, 50, 90, 100]))
     print(f'{a.config} rows/gpu={kp.n_rows} grid={grid}x{warps} warps tiles={n_tiles} ({n_tiles / (grid * warps):.1f} per warp) '
-          f'classes 1/2/3+ groups: {np.bincount(cls, minlength=3).tolist()}')
+          f'classes 1/2/3+ groups: {cls_total.tolist()}; tiles per warp min {per_warp.sum(1).min()} max {per_warp.sum(1).max()}')
     print(f'kernel span (first entry -> last exit): {1e-3 * span:.1f} us; spans of {a.evals} runs: '
           + ', '.join('%.1f' % (1e-3 * (r[:, 4].max() - r[:, 0].min())) for r in runs))
     print('entry after first entry :', q(t0 - base))
