@@ -151,7 +151,9 @@ struct skk_plan {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::vector<void *> allocs;
     unsigned char *arena = nullptr;   // current arena of the small allocations
-    size_t arena_used = 0;
+    size_t arena_used = 0, arena_size = 0;
+    void *first_arena = nullptr;      // (the one with the persisting L2 window)
+    bool l2_window = false;
     size_t device_bytes = 0;
     bool use_graphs = true;
     std::vector<GraphEntry> graphs;
@@ -220,18 +222,25 @@ static size_t elt_size(int dtype) { return dtype == SKK_F64 ? 8 : 4; }
 // (descriptors, slot tables, partial sums, theta and the outputs) is carved out of shared 4 MiB arenas, so that
 // what an evaluation touches besides the rows lies in a handful of pages -- after the caches and TLBs have
 // been swept (the bench flushes L2 between steps) every separate allocation costs its own page walk.
-static const size_t kArenaBytes = 4u << 20, kArenaMaxItem = 1u << 20;
+// The first arena is larger and, unless SKK_L2_PERSIST=0, is given a persisting L2 access-policy window on the plan's
+// streams: the row data of one evaluation sweeps the whole L2 (c4: 700 MB per pass), and without the window every
+// evaluation would start by fetching its descriptors, schedules, theta and the previous partials' lines from HBM again
+// -- each a full memory latency on the dependent-load chains that the small kernels consist of.
+static const size_t kArenaBytes = 4u << 20, kArenaMaxItem = 4u << 20, kFirstArenaBytes = 24u << 20;
 
 template <typename U>
 static int dev_alloc(skk_plan *pl, U **out, size_t count, bool zero = false) {
     void *p = nullptr;
     const size_t bytes = (std::max<size_t>(count * sizeof(U), 16) + 255) & ~(size_t)255;
     if (bytes <= kArenaMaxItem) {
-        if (!pl->arena || pl->arena_used + bytes > kArenaBytes) {
-            CUDA_TRY(cudaMalloc(&p, kArenaBytes));
+        if (!pl->arena || pl->arena_used + bytes > pl->arena_size) {
+            const size_t size = pl->arena ? kArenaBytes : kFirstArenaBytes;
+            CUDA_TRY(cudaMalloc(&p, size));
             pl->allocs.push_back(p);
-            pl->device_bytes += kArenaBytes;
+            pl->device_bytes += size;
+            if (!pl->arena) pl->first_arena = p;
             pl->arena = static_cast<unsigned char *>(p);
+            pl->arena_size = size;
             pl->arena_used = 0;
         }
         p = pl->arena + pl->arena_used;
@@ -528,7 +537,10 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
                 const int64_t sl = (unit - first_p) % d->n_primary;
                 const int4 sd = slot_desc[sl];
                 if (sd.y < sd.x) continue;  // empty group
-                msrc.push_back((uint32_t)(t * d->n_primary + sl));
+                // (direct_p holds something only for a group that lies inside one tile and is either an inner
+                // group of it, or begins on the tile's first row -- such a group may start and end inside lane 0,
+                // which then stores it directly and leaves tile_head zero; everywhere else it is zero for good)
+                if (sd.x == sd.y && (sd.z == 0 || seg[sl] % WT == 0)) msrc.push_back((uint32_t)(t * d->n_primary + sl));
                 for (int tile = sd.x; tile <= sd.y; ++tile) {
                     const int kind = tile == sd.x ? sd.z : (tile == sd.y ? sd.w : 1);
                     if (kind) msrc.push_back(((uint32_t)kind << 30) | (uint32_t)(tile * pl->np + t));
@@ -972,6 +984,7 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
         rp.n_chunks = pl->n_chunks;
     }
     rp.trace = pl->trace;
+    rp.peer_seq = (pl->peer_ready && b0 == 0) ? pl->peer.seq : nullptr;  // the evaluation's first row kernel counts it
     rp.pdl_trigger = env_int("SKK_NO_PDL", 0) ? 0 : env_int("SKK_PDL_TRIGGER", 2);
     void *args[] = {&rp};
     if (timed) CUDA_TRY(cudaEventRecord(pl->evk0, pl->stream));
@@ -1118,6 +1131,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         rp.b_valid = b_valid;
         rp.grid = cfg.grid;
         rp.batch_total = batch;
+        rp.trace = pl->trace ? pl->trace + (size_t)std::max(pl->cfg1.grid, pl->cfg4.grid) * pl->warps * kTraceWords : nullptr;
         const unsigned slot_blocks = (unsigned)(rp.blocks_p + rp.blocks_s + 1);
         if (fused) {
             if (priors) {
@@ -1427,6 +1441,25 @@ int skk_plan_create(const skk_plan_desc *d, skk_plan **out) {
     if (rc != SKK_OK) return guard(rc);
     ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) return guard(fail(SKK_ERR_CUDA, "plan upload: %s", cudaGetErrorString(ce)));
+    if (pl->first_arena && env_int("SKK_L2_PERSIST", 1)) {
+        // best effort: a device without the feature (or with the set-aside taken) runs without the window
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, pl->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, 32u << 20);
+            size_t have = 0;
+            cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+            if (have < want) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = pl->first_arena;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(kFirstArenaBytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            pl->l2_window = cudaStreamSetAttribute(pl->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess &&
+                            cudaStreamSetAttribute(pl->side, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+        }
+        (void)cudaGetLastError();
+    }
 
     const size_t e = elt_size(pl->dtype);
     pl->stats.stored_bytes_per_row = (uint64_t)(pl->n_x * e + (pl->y_u8 ? 1 : e) + (pl->has_off ? e : 0) +
@@ -1540,9 +1573,8 @@ int skk_peer_init(skk_plan *pl, const void *handles, int32_t rank, int32_t nrank
     }
     pp.fed8 = reinterpret_cast<const unsigned long long *>(static_cast<uint4 *>(pl->peer_local) + fed8_line_offset);
     unsigned long long *words = nullptr;
-    if (int rc = dev_alloc(pl, &words, 2, true)) return rc;  // seq | done
+    if (int rc = dev_alloc(pl, &words, 2, true)) return rc;
     pp.seq = words;
-    pp.done = reinterpret_cast<unsigned int *>(words + 1);
     CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&pl->peer_status), sizeof(int), cudaHostAllocMapped));
     *pl->peer_status = 0;
     CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&pp.status), pl->peer_status, 0));
@@ -1594,7 +1626,7 @@ int skk_trace_enable(skk_plan *pl, int32_t on) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
     pl->graphs.clear();
     if (on && !pl->trace) {
-        pl->trace_words = (size_t)std::max(pl->cfg1.grid, pl->cfg4.grid) * pl->warps * kTraceWords;
+        pl->trace_words = ((size_t)std::max(pl->cfg1.grid, pl->cfg4.grid) * pl->warps + kFinishTraceCtas) * kTraceWords;
         if (int rc = dev_alloc(pl, &pl->trace, pl->trace_words, true)) return rc;
     }
     if (!on) pl->trace = nullptr;  // (the buffer stays with the plan's allocations)

@@ -18,7 +18,8 @@
 
 namespace skk {
 
-constexpr int kSerialLimit = 48;  // longer partial lists are summed by a whole warp
+constexpr int kSerialLimit = 48;
+constexpr int kSecInFlight = 40;  // CTA partials of a secondary slot that a thread of the finish kernel loads at once  // longer partial lists are summed by a whole warp
 
 // All 32 lanes cooperate on the long lists of the warp's lanes, one list at a time: lane-strided
 // partial sums + fixed shuffle tree.  `value(item, e, b)` is the e-th addend of chain b.
@@ -215,7 +216,12 @@ struct ReduceParams {
     const int64_t *multi_src_ptr;  // [n_multi + 1]
     const uint32_t *multi_src;
     const uint8_t *is_parent;      // [P] 1: the element is a hyper-parameter (has children in the priors)
+    // optional per-CTA timeline of the finish kernels (skk_trace_enable): [kFinishTraceCtas][kTraceWords], else null
+    //   0 %globaltimer at entry   1 ... when the row kernel's results are visible (after griddepcontrol.wait)
+    //   2 ... when the CTA's own sums are stored / pushed   3 ... at exit   4 CTA class
+    unsigned long long *trace;
 };
+constexpr int kFinishTraceCtas = 1024;
 
 // blockIdx.x in [0, blocks_p): primary slots, one per thread;  [blocks_p, blocks_p + blocks_s):
 // secondary slots, 32 per CTA x 8 ranges of row-kernel CTAs;  last CTA: global terms and logp.
@@ -319,21 +325,24 @@ __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_consta
 //            results.  Which ranks feed which element is static: every rank writes its own byte of
 //            fed8[j] into all peers when the exchange is set up (skk_peer_init).
 // A rank can be at most one evaluation ahead of a peer (it needs that peer's lines to finish), hence
-// two parities suffice.  Polls are bounded: on timeout a status word in mapped host memory is set
+// two parities suffice.  The evaluation number lives on the device (so that the exchange replays inside a CUDA
+// graph) and is advanced by the row kernel at the start of every evaluation.  Polls are bounded: on timeout a status word in mapped host memory is set
 // and the kernel carries on, so a lost peer can never hang the GPU.
 constexpr int kMaxPeers = 8;
 struct PeerParams {
     uint4 *peer_lines[kMaxPeers];             // peer_lines[r]: rank r's receive buffer as seen from this rank
     const unsigned long long *fed8;           // [P + 2] own buffer: byte r != 0 when rank r feeds the element
     unsigned long long *seq;                  // this rank's evaluation counter (device)
-    unsigned int *done;                       // CTAs of the combining kernel that have finished
     int *status;                              // mapped host word, != 0 after a timeout
     int64_t stride;                           // lines per slot
     int32_t rank, nranks;
 };
 
+// number of the current evaluation: advanced by the row kernel of the evaluation's first batch tile (one thread, at
+// its start), read by the kernels behind it in the stream once the row kernel's writes are visible -- nothing has
+// to close an evaluation, so the exchanging kernels end without a fence or a ticket
 __device__ __forceinline__ unsigned long long peer_seq(const PeerParams &pp) {
-    return *reinterpret_cast<volatile unsigned long long *>(pp.seq) + 1;
+    return *reinterpret_cast<volatile unsigned long long *>(pp.seq);
 }
 
 // stores `value` of evaluation `seq` at line `at` of this rank's slot in every peer
@@ -513,6 +522,16 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                                             T *__restrict__ out_logp, T *__restrict__ out_grad) {
     const int lane = threadIdx.x & 31;
     const int64_t P = rp.n_params;
+    auto stamp = [&](int word, unsigned long long value) {
+        if (rp.trace != nullptr && threadIdx.x == 0 && blockIdx.x < kFinishTraceCtas)
+            rp.trace[(int64_t)blockIdx.x * kTraceWords + word] = value;
+    };
+    stamp(0, global_timer_ns());
+    // descriptors are in flight; everything after this reads what the row kernel wrote
+    auto dep_wait = [&]() {
+        grid_dep_wait();
+        stamp(1, global_timer_ns());
+    };
     // 1 / sigma^2 of the Normal likelihood per chain (1 for the other families)
     double scale[BT];
 #pragma unroll
@@ -580,7 +599,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             single[t] = elem[t] >= 0 && (rp.multi_p[t] == 0 || rp.single_unit[elem[t]] != -2);
             if (!single[t]) elem[t] = -1;
         }
-        grid_dep_wait();  // descriptors are in flight; everything below reads what the row kernel wrote
+        dep_wait();
         double pg[kMaxTermsPerLevel][BT];
 #pragma unroll
         for (int t = 0; t < kMaxTermsPerLevel; ++t) prior_of(elem[t], pg[t]);
@@ -640,7 +659,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             elem[t] = (sub == 0 && valid && t < rp.ns && rp.multi_s[t] != 1) ? rp.ti_s[t][slot] : -1;
             if (elem[t] >= 0 && rp.multi_s[t] == 2 && rp.single_unit[elem[t]] == -2) elem[t] = -1;
         }
-        grid_dep_wait();
+        dep_wait();
         double pg[kMaxTermsPerLevel][BT];
 #pragma unroll
         for (int t = 0; t < kMaxTermsPerLevel; ++t) prior_of(elem[t], pg[t]);
@@ -653,8 +672,18 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 if (valid) {
                     const double *src = rp.cta_sec + ((int64_t)t * rp.n_secondary + slot) * BT + b;
                     const int64_t stride = (int64_t)rp.ns * rp.n_secondary * BT;
+                    if (per <= kSecInFlight) {
+                        // the usual grid (two CTAs per SM: 37 partials per sub-range): every load is issued before
+                        // the first addition, so the sub-range costs one memory latency; same order of additions
+                        double v[kSecInFlight];
+#pragma unroll
+                        for (int k = 0; k < kSecInFlight; ++k) v[k] = c0 + k < c1 ? src[(c0 + k) * stride] : 0.0;
+#pragma unroll
+                        for (int k = 0; k < kSecInFlight; ++k) acc += v[k];
+                    } else {
 #pragma unroll 8
-                    for (int c = c0; c < c1; ++c) acc += src[c * stride];
+                        for (int c = c0; c < c1; ++c) acc += src[c * stride];
+                    }
                 }
                 part[sub][lane] = acc;
                 __syncthreads();
@@ -671,7 +700,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         __shared__ double glob[(kMaxTermsPerLevel + 1) * BT];
         __shared__ double lp_part[8];
         const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-        grid_dep_wait();
+        dep_wait();
         for (int item = warp; item < (rp.ng + 1) * BT; item += warps) {
             double acc = 0.0;
             for (int c = lane; c < rp.grid; c += 32) acc += rp.cta_glob[(int64_t)c * (rp.ng + 1) * BT + item];
@@ -761,7 +790,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             hi = rp.chunk_ptr[q + 1];
             j = rp.parent[q];
         }
-        grid_dep_wait();
+        dep_wait();
         if (active) {
             prior_of(j, pg);
             const int64_t first = lo + (heavy ? threadIdx.x : lane), step = heavy ? blockDim.x : 32;
@@ -807,7 +836,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         // elements that no term feeds and that have no children: own prior term only
         const int64_t k = ((int64_t)blockIdx.x - b_none) * blockDim.x + threadIdx.x;
         const int64_t j = k < rp.n_none ? rp.none_elem[k] : -1;
-        grid_dep_wait();
+        dep_wait();
         if (j >= 0) {
             if (!(sigma_is_param && j == rp.sigma_theta_index)) {
                 double pg[BT];
@@ -825,30 +854,48 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         const int64_t lo2 = have ? rp.multi_src_ptr[m] : 0, hi2 = have ? rp.multi_src_ptr[m + 1] : 0;
         const int32_t j = have ? rp.multi_elem[m] : -1;
         constexpr uint32_t kNoSrc = 0xffffffffu;
-        uint32_t src0[4];
+        // the list of raw partials is static: its first kMultiAhead * 32 entries are fetched before the row kernel
+        // has finished, so that afterwards only the values remain (one memory latency for the usual lengths)
+        constexpr int kMultiAhead = BT == 1 ? 16 : 8;
+        uint32_t src0[kMultiAhead];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) src0[u] = lo2 + lane + 32 * u < hi2 ? rp.multi_src[lo2 + lane + 32 * u] : kNoSrc;
-        grid_dep_wait();
+        for (int u = 0; u < kMultiAhead; ++u) src0[u] = lo2 + lane + 32 * u < hi2 ? rp.multi_src[lo2 + lane + 32 * u] : kNoSrc;
+        dep_wait();
         double pg[BT], acc[BT];
         prior_of(j, pg);
 #pragma unroll
         for (int b = 0; b < BT; ++b) acc[b] = 0.0;
-        auto add_src = [&](uint32_t src) {
-            if (src == kNoSrc) return;
+        auto value_of = [&](uint32_t src, int b) -> double {
+            if (src == kNoSrc) return 0.0;
             const int kind = (int)(src >> 30);
             const int64_t at = (int64_t)(src & 0x3fffffffu) * BT;
             const double *base = kind == 0 ? rp.direct_p : (kind == 1 ? rp.tile_head : rp.tile_tail);
-#pragma unroll
-            for (int b = 0; b < BT; ++b) acc[b] += base[at + b];
+            return base[at + b];
         };
+        {
+            double v[kMultiAhead][BT];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) add_src(src0[u]);
-        for (int64_t e0 = lo2 + lane + 128; e0 < hi2; e0 += 128) {
+            for (int u = 0; u < kMultiAhead; ++u)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) v[u][b] = value_of(src0[u], b);
+#pragma unroll
+            for (int u = 0; u < kMultiAhead; ++u)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] += v[u][b];
+        }
+        for (int64_t e0 = lo2 + lane + 32 * kMultiAhead; e0 < hi2; e0 += 128) {
             uint32_t src[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) src[u] = e0 + 32 * u < hi2 ? rp.multi_src[e0 + 32 * u] : kNoSrc;
+            double v[4][BT];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) add_src(src[u]);
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) v[u][b] = value_of(src[u], b);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] += v[u][b];
         }
         const int64_t first_p = rp.ng + 1, first_s = first_p + (int64_t)rp.np * rp.n_primary;
         for (int64_t e = lo + lane; e < hi; e += 32) {
@@ -871,6 +918,9 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         for (int b = 0; b < BT; ++b) lik[b] = warp_sum(acc[b]);
         if (lane == 0 && have) store(j, lik, pg);
     }
+    stamp(2, global_timer_ns());
+    stamp(4, (unsigned long long)((int)blockIdx.x < rp.blocks_p ? 0 : (int)blockIdx.x < b_glob ? 1 : (int)blockIdx.x == b_glob ? 2
+                                  : (int)blockIdx.x < b_none ? 3 : (int)blockIdx.x < b_multi ? 4 : 5));
     if constexpr (MODE == 3) {
         // ---- combine a slice of theta from the R slots of the own buffer (rank order), as the lines arrive ----
         // (hyper-parameters were finished above: nothing feeds them on any rank)
@@ -911,17 +961,8 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 __syncthreads();
             }
         }
-        // the last CTA to finish closes the evaluation (the slots of this parity may be reused two
-        // evaluations later)
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            if (atomicAdd(pp.done, 1u) == gridDim.x - 1) {
-                *pp.done = 0;
-                *pp.seq = seq;
-            }
-        }
     }
+    stamp(3, global_timer_ns());
 }
 
 template <typename T, int BT>
@@ -1007,19 +1048,6 @@ __global__ void skk_final_kernel(const __grid_constant__ FinalParams fp, const _
             else
                 ll = lik_at(P);
             out_logp[b] = (T)(tot + ll + lik_at(P + 1));
-        }
-    }
-    if constexpr (PEER) {
-        // the last CTA to finish closes the evaluation (the slots of this parity may be reused two
-        // evaluations later)
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const unsigned int total = gridDim.x * gridDim.y;
-            if (atomicAdd(pp.done, 1u) == total - 1) {
-                *pp.done = 0;
-                *pp.seq = seq;
-            }
         }
     }
 }

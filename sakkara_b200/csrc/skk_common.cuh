@@ -74,6 +74,9 @@ struct RowParams {
     const double *link_a_const, *link_b_const;
     double *link_part;       // [b_valid][n_chunks]
     int64_t n_chunks;
+    // row-sharded runs over peer memory: the evaluation counter of the exchange, advanced by one thread of the
+    // evaluation's first row kernel (null otherwise); the kernels behind it in the stream read it
+    unsigned long long *peer_seq;
     // optional per-warp timeline (skk_trace_enable): [grid * warps][kTraceWords], null in normal operation
     unsigned long long *trace;
     // when the kernel that follows in the stream (launched with the PDL attribute) may start: 0 at this

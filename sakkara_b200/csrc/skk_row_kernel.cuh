@@ -930,6 +930,7 @@ struct RowKernel {
                 p.trace[((int64_t)blockIdx.x * warps + warp) * kTraceWords + word] = global_timer_ns();
         };
         stamp(0);
+        if (p.peer_seq != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *p.peer_seq = *p.peer_seq + 1;
         // the kernel that follows in the stream may start its own prologue under this kernel's tail (PDL)
         if (p.pdl_trigger == 1) grid_dep_launch_dependents();
 

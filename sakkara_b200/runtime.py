@@ -256,15 +256,23 @@ class SkkPlan:
         self._guard()
         _check(self.lib, self.lib.skk_trace_enable(self._handle, 1 if on else 0))
 
-    def trace_read(self) -> np.ndarray:
-        """``[grid * warps, 8]`` uint64: globaltimer ns at entry / prologue done / first tile / loop end / exit."""
+    def trace_read(self, finish: bool = False) -> np.ndarray:
+        """
+        ``[grid * warps, 8]`` uint64 of the row kernel: globaltimer ns at entry / prologue done / first tile / loop
+        end / exit (words 5-7: tiles per class).  ``finish=True``: the records of the kernel behind it instead,
+        one per CTA that ran -- entry / row kernel's results visible / own sums stored / exit / CTA class.
+        """
         self._guard()
         st = self.stats()
-        out = np.zeros((st['grid'] * (st['block'] // 32), 8), dtype=np.uint64)
+        n_rows = st['grid'] * (st['block'] // 32)
+        out = np.zeros((n_rows + 1024, 8), dtype=np.uint64)
         n = self.lib.skk_trace_read(self._handle, out.ctypes.data, out.size)
         if n < 0:
             _check(self.lib, int(n))
-        return out
+        if finish:
+            tail = out[n_rows:]
+            return tail[tail[:, 0] > 0]
+        return out[:n_rows]
 
     def _guard(self) -> None:
         if not self._handle:

@@ -54,6 +54,7 @@ def main():
         torch.cuda.synchronize()
         f(theta)
         runs.append(skk.trace_read().astype(np.int64))
+    fin = skk.trace_read(finish=True).astype(np.int64)
     tr = runs[-1]
     per_warp = tr[:, 5:8]                      # tiles per class, counted by the kernel from the warp's schedule
     cls_total = per_warp.sum(0)
@@ -87,6 +88,20 @@ def main():
         print(f'  slowest warp cta {i // warps} warp {i % warps}: tiles {per_warp[i].tolist()} entry +{1e-3 * (t0[i] - base):.1f} '
               f'prologue {1e-3 * (t1[i] - t0[i]):.1f} wait {1e-3 * (t2[i] - t1[i]):.1f} loop {1e-3 * (t3[i] - t2[i]):.1f} '
               f'end +{1e-3 * (t3[i] - base):.1f} us')
+    if len(fin):
+        # the kernel behind the row kernel (finish / finish+exchange), per CTA class, relative to the row kernel
+        last_exit = t4.max()
+        names = ['primary slots', 'secondary slots', 'global + logp', 'hyper-parameters', 'unfed elements', 'multi-slot elements']
+        print(f'finish kernel: {len(fin)} CTAs; first entry {1e-3 * (fin[:, 0].min() - base):+.1f} us after the row kernel\'s first entry, '
+              f'{1e-3 * (fin[:, 0].min() - last_exit):+.1f} us relative to its last exit; last exit '
+              f'{1e-3 * (fin[:, 3].max() - last_exit):+.1f} us after the row kernel\'s last exit')
+        for c in range(6):
+            sel = fin[fin[:, 4] == c]
+            if not len(sel):
+                continue
+            rel = lambda col: 1e-3 * (sel[:, col] - last_exit)
+            print(f'  {names[c]:20s} {len(sel):4d} CTAs: entry {rel(0).min():+6.1f}..{rel(0).max():+6.1f}  results visible {rel(1).min():+6.1f}..{rel(1).max():+6.1f}'
+                  f'  own sums done {rel(2).min():+6.1f}..{rel(2).max():+6.1f}  exit {rel(3).min():+6.1f}..{rel(3).max():+6.1f} us')
     if a.out:
         json.dump({'config': a.config, 'rows': int(kp.n_rows), 'span_us': 1e-3 * float(span),
                    'trace': tr[:, :5].tolist(), 'tiles': per_warp.tolist()}, open(a.out, 'w'))
