@@ -54,6 +54,15 @@ extern "C" {
 #define SKK_PRIOR_NORMAL 0       /* a = mu, b = sigma                       */
 #define SKK_PRIOR_HALFNORMAL 3   /* a = sigma; sampled as log, +log-Jacobian */
 #define SKK_PRIOR_EXPONENTIAL 4  /* a = lam;   sampled as log, +log-Jacobian */
+/* families with constant parameters only; the device evaluates the theta-dependent part, the
+ * normaliser (a function of a, b alone) belongs into skk_plan_desc.logp_const */
+#define SKK_PRIOR_HALFCAUCHY 5   /* a = beta;              log, +log-Jacobian */
+#define SKK_PRIOR_GAMMA 6        /* a = alpha, b = beta;   log, +log-Jacobian */
+#define SKK_PRIOR_INVGAMMA 7     /* a = alpha, b = beta;   log, +log-Jacobian */
+#define SKK_PRIOR_CAUCHY 8       /* a = alpha, b = beta                       */
+#define SKK_PRIOR_LAPLACE 9      /* a = mu,    b = b                          */
+#define SKK_PRIOR_LOGNORMAL 10   /* a = mu,    b = sigma;  log, +log-Jacobian */
+#define SKK_PRIOR_HALFSTUDENTT 11 /* a = nu,   b = sigma;  log, +log-Jacobian */
 
 /* where the group index of a linear-predictor term comes from */
 #define SKK_LEVEL_GLOBAL 0       /* one value for all rows                                    */
@@ -90,7 +99,10 @@ typedef struct {
  * Parameter a / b of the prior is a constant (x_const_len = 1 or size) or, per element, another
  * element of theta (x_index != NULL; the prior-level gather of
  * /root/reference/sakkara/model/composable/hierarchical/base.py:46-55).  A linked sigma refers to
- * a log-transformed element u and means exp(u).
+ * a log-transformed element u and means exp(u).  Both together (x_index != NULL, x_const != NULL,
+ * x_const_len = size): element g reads theta[x_index[g]], or the constant x_const[g] where
+ * x_index[g] is -1 -- the member-wise parameters of a GroupComponent
+ * (/root/reference/sakkara/model/composable/group.py:69-103).
  */
 typedef struct {
     int32_t family;             /* SKK_PRIOR_*                                   */

@@ -29,6 +29,8 @@ def _evaluate(node, env):
         value = _evaluate(node.value, env)
         fill = _evaluate(node.fill, env)
         return torch.where(torch.as_tensor(node.mask), fill, value)
+    if isinstance(node, sym.Concat):
+        return torch.cat([torch.as_tensor(_evaluate(piece, env), dtype=torch.float64).reshape(-1) for piece in node.pieces])
     if isinstance(node, sym.BinOp):
         left, right = _evaluate(node.left, env), _evaluate(node.right, env)
         return sym.BinOp.OPS[node.op](left, right)
@@ -59,6 +61,26 @@ def logp_dlogp_autograd(recorded: sym.Model, theta: np.ndarray):
             value = torch.exp(raw)
             env[id(rv)] = value
             total = total + (torch.distributions.Exponential(params['lam']).log_prob(value) + raw).sum()
+        elif rv.family in ('HalfCauchy', 'Gamma', 'InverseGamma', 'LogNormal', 'HalfStudentT'):
+            value = torch.exp(raw)
+            env[id(rv)] = value
+            if rv.family == 'HalfCauchy':
+                lp = torch.distributions.HalfCauchy(params['beta']).log_prob(value)
+            elif rv.family == 'Gamma':
+                lp = torch.distributions.Gamma(params['alpha'], params['beta']).log_prob(value)
+            elif rv.family == 'InverseGamma':
+                lp = torch.distributions.InverseGamma(params['alpha'], params['beta']).log_prob(value)
+            elif rv.family == 'LogNormal':
+                lp = torch.distributions.LogNormal(params['mu'], params['sigma']).log_prob(value)
+            else:   # a half Student-t is a Student-t folded at 0: twice the density on the positive side
+                lp = torch.distributions.StudentT(params['nu'], torch.zeros(()), params['sigma']).log_prob(value) + np.log(2.0)
+            total = total + (lp + raw).sum()
+        elif rv.family == 'Cauchy':
+            env[id(rv)] = raw
+            total = total + torch.distributions.Cauchy(params['alpha'], params['beta']).log_prob(raw).sum()
+        elif rv.family == 'Laplace':
+            env[id(rv)] = raw
+            total = total + torch.distributions.Laplace(params['mu'], params['b']).log_prob(raw).sum()
         else:
             raise NotImplementedError(rv.family)
     assert offset == theta_t.numel()

@@ -42,7 +42,9 @@ def likelihood_from_kernel_plan(kp, theta):
         mu = np.exp(eta)
         logp = np.sum(y * eta - mu)
         d = y - mu
-    logp += kp.logp_const    # -sum(lgamma(y + 1)) of a Poisson model; rows masked out for NaN observations
+    # -sum(lgamma(y + 1)) of a Poisson model; rows masked out for NaN observations (not the normalisers of the
+    # prior families that the plan's constant also carries: this function is the likelihood alone)
+    logp += kp.logp_const - kp.prior_logp_const
     for t, slot in zip(kp.terms, slot_rows):
         x = 1.0 if t.xcol < 0 else kp.xcols[t.xcol].astype(np.float64)
         np.add.at(grad, t.theta_index.astype(np.int64)[slot], d * x)

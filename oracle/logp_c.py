@@ -70,7 +70,7 @@ class COracle:
                 x = np.ascontiguousarray(term.x, dtype=self.dtype)
                 self.keep.append(x)
                 d.x[t] = x.ctypes.data
-            d.base[t] = plan.blocks[term.block].offset
+            d.base[t] = plan.term_base(term)
         y = np.ascontiguousarray(lik.y, dtype=self.dtype)
         self.keep.append(y)
         d.y = y.ctypes.data

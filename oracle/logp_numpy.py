@@ -54,6 +54,31 @@ def _block_value(plan, theta, number):
     return np.exp(raw) if b.transform == 'log' else raw
 
 
+def _is_log(plan) -> np.ndarray:
+    """Per element of theta: True where the element is sampled on the log scale."""
+    flags = np.zeros(plan.n_params + 1, dtype=bool)         # (+1: index -1 of a member-wise parameter reads False)
+    for b in plan.blocks:
+        flags[b.offset:b.offset + b.size] = b.transform == 'log'
+    return flags
+
+
+def _all_values(plan, theta):
+    """Constrained values of all of theta, block after block."""
+    return np.concatenate([_block_value(plan, theta, k) for k in range(len(plan.blocks))]) if plan.blocks else theta
+
+
+def _param_value(plan, theta, prm, dtype):
+    """Value of a prior parameter per element: constant, gathered, or (member-wise) one or the other."""
+    T = np.dtype(dtype).type
+    if prm.is_const:
+        return T(1) * prm.const.astype(dtype)
+    if prm.is_mixed:
+        values = _all_values(plan, theta)
+        gathered = values[np.maximum(prm.index, 0)]
+        return np.where(prm.index >= 0, gathered, np.broadcast_to(prm.const.astype(dtype), prm.index.shape))
+    return _block_value(plan, theta, prm.block)[prm.index]
+
+
 def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = False):
     """
     Joint log-posterior and gradient at one point.
@@ -86,25 +111,35 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
             np.add.at(view, index, values)                       # AdvancedIncSubtensor1
             np.add.at(mass[b.offset:b.offset + b.size], index, np.abs(values).astype(np.float64))
 
+    def acc_absolute(index, values):
+        np.add.at(grad, index, values)
+        np.add.at(mass, index, np.abs(values).astype(np.float64))
+
     # ---- priors, in creation order -----------------------------------------------------------
     for number, b in enumerate(plan.blocks):
         raw = theta[b.offset:b.offset + b.size]
         if b.family == 'Normal':
             mu_p, sd_p = b.params['mu'], b.params['sigma']
-            mu = T(1) * mu_p.const.astype(dtype) if mu_p.is_const else _block_value(plan, theta, mu_p.block)[mu_p.index]
-            sd = T(1) * sd_p.const.astype(dtype) if sd_p.is_const else _block_value(plan, theta, sd_p.block)[sd_p.index]
-            mu = np.broadcast_to(mu, raw.shape)
-            sd = np.broadcast_to(sd, raw.shape)
+            mu = np.broadcast_to(_param_value(plan, theta, mu_p, dtype), raw.shape)
+            sd = np.broadcast_to(_param_value(plan, theta, sd_p, dtype), raw.shape)
             z = (raw - mu) / sd
             terms = T(-0.5) * z * z - T(LOG_SQRT_2PI) - np.log(sd)
             logp += np.sum(terms, dtype=np.float64)
             logp_mass += np.sum(np.abs(terms), dtype=np.float64)
             acc(number, None, -z / sd)
-            if not mu_p.is_const:
+            if mu_p.is_mixed:
+                # member-wise parameter: per element a constant (index -1) or an element of theta
+                linked = mu_p.index >= 0
+                d_mu = z / sd
+                acc_absolute(mu_p.index[linked], np.where(_is_log(plan)[mu_p.index], d_mu * mu, d_mu)[linked])
+            elif not mu_p.is_const:
                 # a mu that is a positive variable is sampled as u = log(mu): chain rule d mu / d u = mu
                 d_mu = z / sd
                 acc(mu_p.block, mu_p.index, d_mu * mu if plan.blocks[mu_p.block].transform == 'log' else d_mu)
-            if not sd_p.is_const:
+            if sd_p.is_mixed:
+                linked = sd_p.index >= 0
+                acc_absolute(sd_p.index[linked], (z * z - T(1))[linked])
+            elif not sd_p.is_const:
                 # d/d sigma = (z^2 - 1)/sigma, times d sigma / d u = sigma
                 acc(sd_p.block, sd_p.index, z * z - T(1))
         elif b.family == 'HalfNormal':
@@ -122,6 +157,50 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
             logp += np.sum(terms, dtype=np.float64)
             logp_mass += np.sum(np.abs(terms), dtype=np.float64)
             acc(number, None, -lam * s + T(1))
+        elif b.family in ('HalfCauchy', 'Gamma', 'InverseGamma', 'Cauchy', 'Laplace', 'LogNormal', 'HalfStudentT'):
+            # constant parameters only; PyMC's logp of the family (pymc/distributions/continuous.py) at the
+            # back-transformed value, plus the log-Jacobian of the LogTransform (= raw) for the positive ones
+            def const(name):
+                return np.broadcast_to(b.params[name].const.astype(dtype), raw.shape)
+            if b.family == 'HalfCauchy':
+                beta = const('beta')
+                x = np.exp(raw)
+                terms = T(np.log(2.0 / np.pi)) - np.log(beta) - np.log1p((x / beta) ** 2) + raw
+                g = -T(2) * x * x / (beta * beta + x * x) + T(1)
+            elif b.family == 'Gamma':
+                alpha, beta = const('alpha'), const('beta')
+                x = np.exp(raw)
+                terms = alpha * np.log(beta) - gammaln(alpha).astype(dtype) + (alpha - T(1)) * raw - beta * x + raw
+                g = (alpha - T(1)) - beta * x + T(1)
+            elif b.family == 'InverseGamma':
+                alpha, beta = const('alpha'), const('beta')
+                x = np.exp(raw)
+                terms = alpha * np.log(beta) - gammaln(alpha).astype(dtype) - (alpha + T(1)) * raw - beta / x + raw
+                g = -(alpha + T(1)) + beta / x + T(1)
+            elif b.family == 'Cauchy':
+                loc, beta = const('alpha'), const('beta')
+                z = (raw - loc) / beta
+                terms = -T(np.log(np.pi)) - np.log(beta) - np.log1p(z * z)
+                g = -T(2) * z / (beta * (T(1) + z * z))
+            elif b.family == 'Laplace':
+                mu, scale = const('mu'), const('b')
+                terms = -np.log(T(2) * scale) - np.abs(raw - mu) / scale
+                g = -np.sign(raw - mu) / scale
+            elif b.family == 'LogNormal':
+                mu, sd = const('mu'), const('sigma')
+                z = (raw - mu) / sd                             # raw = log(x)
+                terms = T(-0.5) * z * z - T(LOG_SQRT_2PI) - np.log(sd) - raw + raw
+                g = -z / sd
+            else:                                               # HalfStudentT
+                nu, sd = const('nu'), const('sigma')
+                x = np.exp(raw)
+                q = (x / sd) ** 2 / nu
+                terms = (T(np.log(2.0)) + (gammaln((nu + 1) / 2) - gammaln(nu / 2)).astype(dtype)
+                         - T(0.5) * np.log(nu * T(np.pi) * sd * sd) - (nu + T(1)) / T(2) * np.log1p(q) + raw)
+                g = -(nu + T(1)) * q / (T(1) + q) + T(1)
+            logp += np.sum(terms, dtype=np.float64)
+            logp_mass += np.sum(np.abs(terms), dtype=np.float64)
+            acc(number, None, g.astype(dtype))
         else:
             raise NotImplementedError(b.family)
 
@@ -131,7 +210,10 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
     eta = np.zeros(plan.n_rows, dtype=dtype) if lik.offset is None else lik.offset.astype(dtype).copy()
     columns = []
     for t in plan.terms:
-        gathered = _block_value(plan, theta, t.block)[t.index]   # AdvancedSubtensor1
+        if t.block < 0:     # member-wise coefficient: absolute elements of theta, several blocks
+            gathered = _all_values(plan, theta)[t.index]
+        else:
+            gathered = _block_value(plan, theta, t.block)[t.index]   # AdvancedSubtensor1
         x = None if t.x is None else t.x.astype(dtype)
         columns.append(x)
         eta += gathered if x is None else gathered * x
@@ -162,6 +244,11 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
     logp_mass += np.sum(np.abs(terms), dtype=np.float64)
 
     for t, x in zip(plan.terms, columns):
+        if t.block < 0:
+            if _is_log(plan)[t.index].any():
+                raise NotImplementedError('positive blocks in the linear predictor')
+            acc_absolute(t.index, d_eta if x is None else d_eta * x)
+            continue
         if plan.blocks[t.block].transform != 'identity':
             raise NotImplementedError('positive blocks in the linear predictor')
         acc(t.block, t.index, d_eta if x is None else d_eta * x)

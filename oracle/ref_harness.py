@@ -44,6 +44,7 @@ def _fake_modules():
     ptt.Variable = sym.Var
     ptt.exp = sym.exp
     ptt.sigmoid = sym.sigmoid
+    ptt.stack = sym.stack                               # composable/group.py:100
     pt.tensor = ptt
     return {'pymc': pm, 'pymc.data': pm_data, 'pytensor': pt, 'pytensor.tensor': ptt}
 

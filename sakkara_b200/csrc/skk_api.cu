@@ -326,14 +326,17 @@ static int configure_launch(skk_plan *pl, int bt, LaunchCfg *cfg) {
 
 // Static schedule of the row kernel: which tiles every warp of the grid processes, and in which order.  Tiles are
 // handed out in index order to the warp with the least work so far -- measured per tile class (tools/trace_rows.py:
-// a tile with two groups costs ~1.85x a common one on models with a secondary level, the rolled generic path
+// a tile with two groups costs ~3x a common one on models with a secondary level -- two dependent loads of
+// the split row and the second group's value, cold after an L2 sweep --, the rolled generic path
 // more), and the warps that carry prior work in the prologue start with that much on their account.  A fixed
 // list per warp keeps every sum of the evaluation in a fixed order; the balance removes the tail in which a few
 // warps with several expensive tiles kept their SMs busy while all others had finished.
 static int build_schedule(skk_plan *pl, const std::vector<int2> &keys, int64_t n_rows, int64_t n_prior_groups,
                           int64_t n_chunks, LaunchCfg *cfg) {
     const int W = pl->warps, grid = cfg->grid, n_warps = grid * W, WT = pl->rows_per_tile;
-    const double cost_two = pl->ns > 0 ? 1.85 : 1.1, cost_generic = pl->ns > 0 ? 4.0 : 3.0, cost_prior = 1.0;
+    // (SKK_COST_TWO / SKK_COST_PRIOR, in hundredths: calibration runs)
+    const double cost_two = env_int("SKK_COST_TWO", pl->ns > 0 ? 300 : 110) / 100.0, cost_generic = pl->ns > 0 ? 4.0 : 3.0,
+                 cost_prior = env_int("SKK_COST_PRIOR", 100) / 100.0;
     std::vector<double> load(n_warps, 0.0);
     if (pl->fused_ok && pl->include_priors) {
         // (skk_row_kernel.cuh: priors(): group / chunk q -> CTA q % grid, warp W - 1 - (q / grid) % W)
@@ -567,11 +570,13 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     std::vector<Link> links;
     // family of the block every theta element belongs to (a linked parameter may refer to any other block)
     std::vector<int8_t> elem_family(Pn, -1);
+    bool any_extended = false;  // a family the row kernel's prologue does not evaluate
     for (int k = 0; k < d->n_blocks; ++k) {
         const skk_block_desc &bd = d->blocks[k];
         if (bd.offset < 0 || bd.size < 0 || bd.offset + bd.size > d->n_params)
             return fail(SKK_ERR_INVALID, "block %d outside theta", k);
-        if (bd.family != SKK_PRIOR_NORMAL && bd.family != SKK_PRIOR_HALFNORMAL && bd.family != SKK_PRIOR_EXPONENTIAL)
+        if (bd.family != SKK_PRIOR_NORMAL && bd.family != SKK_PRIOR_HALFNORMAL && bd.family != SKK_PRIOR_EXPONENTIAL &&
+            !(bd.family >= SKK_PRIOR_HALFCAUCHY && bd.family <= SKK_PRIOR_HALFSTUDENTT))
             return fail(SKK_ERR_UNSUPPORTED, "block %d: unknown prior family %d", k, bd.family);
         for (int64_t g = 0; g < bd.size; ++g) {
             if (elem_family[bd.offset + g] != -1)
@@ -582,31 +587,36 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     for (int k = 0; k < d->n_blocks; ++k) {
         const skk_block_desc &bd = d->blocks[k];
         const bool normal = bd.family == SKK_PRIOR_NORMAL;
+        // families with a second (constant) parameter
+        const bool two = normal || (prior_is_extended(bd.family) && bd.family != SKK_PRIOR_HALFCAUCHY);
+        if (prior_is_extended(bd.family)) any_extended = true;
         if (!normal && (bd.a_index || bd.b_index))
             return fail(SKK_ERR_UNSUPPORTED, "block %d: only Normal priors take random parameters", k);
-        if (!bd.a_index && bd.a_const_len != 1 && bd.a_const_len != bd.size)
+        // (index and constants together: per element the constant where the index is -1 -- the member-wise
+        // parameters of a GroupComponent, /root/reference/sakkara/model/composable/group.py:69-103)
+        if (bd.a_index ? (bd.a_const != nullptr && bd.a_const_len != bd.size) : (bd.a_const_len != 1 && bd.a_const_len != bd.size))
             return fail(SKK_ERR_INVALID, "block %d: bad a_const_len", k);
-        if (normal && !bd.b_index && bd.b_const_len != 1 && bd.b_const_len != bd.size)
+        if (two && (bd.b_index ? (bd.b_const != nullptr && bd.b_const_len != bd.size) : (bd.b_const_len != 1 && bd.b_const_len != bd.size)))
             return fail(SKK_ERR_INVALID, "block %d: bad b_const_len", k);
         for (int64_t g = 0; g < bd.size; ++g) {
             const int64_t j = bd.offset + g;
             fam[j] = (int8_t)bd.family;
-            if (bd.a_index) {
+            if (bd.a_index && (bd.a_index[g] >= 0 || bd.a_const == nullptr)) {
                 const int64_t src = bd.a_index[g];
                 if (src < 0 || src >= d->n_params) return fail(SKK_ERR_INVALID, "prior link outside theta");
                 // a mu that is a positive variable is sampled as its log: mu = exp(theta[src])
-                const bool mu_is_log = elem_family[src] != SKK_PRIOR_NORMAL;
+                const bool mu_is_log = prior_is_log(elem_family[src]);
                 if (mu_is_log) fam[j] = (int8_t)(fam[j] | kPriorMuIsLog);
                 a_src[j] = (int32_t)src;
                 links.push_back(Link{src, (int32_t)j, 0});
             } else {
                 a_const[j] = bd.a_const[bd.a_const_len == 1 ? 0 : g];
             }
-            if (normal) {
-                if (bd.b_index) {
+            if (two) {
+                if (bd.b_index && (bd.b_index[g] >= 0 || bd.b_const == nullptr)) {
                     const int64_t src = bd.b_index[g];
                     if (src < 0 || src >= d->n_params) return fail(SKK_ERR_INVALID, "prior link outside theta");
-                    if (elem_family[src] == SKK_PRIOR_NORMAL)
+                    if (!prior_is_log(elem_family[src]))
                         return fail(SKK_ERR_INVALID, "block %d: a linked sigma must be a positive (log-transformed) variable", k);
                     b_src[j] = (int32_t)src;
                     links.push_back(Link{src, (int32_t)j, 1});
@@ -673,7 +683,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     std::vector<int32_t> none_elem;
     {
         std::vector<char> is_parent(Pn, 0);
-        pl->fused_ok = true;
+        pl->fused_ok = !any_extended;
         for (const Parent &q : parents) {
             is_parent[q.element] = 1;
             if (single_unit[q.element] != -1 || (d->family == SKK_LIK_NORMAL && q.element == d->sigma_theta_index))

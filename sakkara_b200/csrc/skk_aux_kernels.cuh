@@ -356,26 +356,48 @@ __device__ __forceinline__ void peer_push(const PeerParams &pp, unsigned long lo
                      : "memory");
 }
 
-// sum over the ranks that feed line `at` (rank order), each polled until it shows evaluation `seq`
+// sum over the ranks that feed line `at` (rank order).  The lines of all those ranks are loaded at once and the
+// ones that do not show evaluation `seq` yet are loaded again, so the wait costs one memory latency after the last
+// arrival instead of one per rank.
 __device__ __forceinline__ double peer_combine(const PeerParams &pp, unsigned long long seq, int64_t at, unsigned long long fed) {
     const uint32_t flag = (uint32_t)seq;
     const uint4 *mine = pp.peer_lines[pp.rank] + (int64_t)(seq & 1) * pp.nranks * pp.stride + at;
-    double s = 0.0;
-    for (int r = 0; r < pp.nranks; ++r) {
-        if (((fed >> (8 * r)) & 0xffull) == 0) continue;
-        const uint4 *src = mine + (int64_t)r * pp.stride;
-        uint32_t lo, f1, hi, f2;
-        const long long t0 = clock64();
-        for (;;) {
-            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(src) : "memory");
-            if (f1 == flag && f2 == flag) break;
-            if (clock64() - t0 > (1ll << 36)) {  // ~35 s: report and go on
-                *pp.status = 1;
-                break;
-            }
-        }
-        s += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    uint32_t lo[kMaxPeers], hi[kMaxPeers];
+    unsigned wanted = 0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) {
+        lo[r] = hi[r] = 0u;
+        if (r < pp.nranks && ((fed >> (8 * r)) & 0xffull) != 0) wanted |= 1u << r;
     }
+    unsigned pending = wanted;
+    const long long t0 = clock64();
+    while (pending != 0) {
+        uint32_t l[kMaxPeers], f1[kMaxPeers], h[kMaxPeers], f2[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+            l[r] = f1[r] = h[r] = f2[r] = 0u;
+            if ((pending >> r) & 1u)
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(l[r]), "=r"(f1[r]), "=r"(h[r]), "=r"(f2[r])
+                             : "l"(mine + (int64_t)r * pp.stride)
+                             : "memory");
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)
+            if (((pending >> r) & 1u) && f1[r] == flag && f2[r] == flag) {
+                lo[r] = l[r];
+                hi[r] = h[r];
+                pending &= ~(1u << r);
+            }
+        if (pending != 0 && clock64() - t0 > (1ll << 36)) {  // ~35 s: report and go on
+            *pp.status = 1;
+            break;
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+        if ((wanted >> r) & 1u) s += __longlong_as_double((long long)(((unsigned long long)hi[r] << 32) | lo[r]));
     return s;
 }
 
@@ -700,6 +722,13 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         __shared__ double glob[(kMaxTermsPerLevel + 1) * BT];
         __shared__ double lp_part[8];
         const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+        // (static descriptors of the global terms: in flight before the row kernel's results are waited for)
+        int32_t jg = -1;
+        if ((int)threadIdx.x < rp.ng) {
+            jg = rp.ti_g[threadIdx.x][0];
+            const int multi = rp.multi_g[threadIdx.x];
+            if (multi == 1 || (multi == 2 && rp.single_unit[jg] == -2)) jg = -1;
+        }
         dep_wait();
         for (int item = warp; item < (rp.ng + 1) * BT; item += warps) {
             double acc = 0.0;
@@ -722,8 +751,7 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         __syncthreads();
         if ((int)threadIdx.x < rp.ng) {
             double lik[BT], pg[BT];
-            int32_t j = rp.ti_g[threadIdx.x][0];
-            if (rp.multi_g[threadIdx.x] == 1 || (rp.multi_g[threadIdx.x] == 2 && rp.single_unit[j] == -2)) j = -1;
+            const int32_t j = jg;
 #pragma unroll
             for (int b = 0; b < BT; ++b) lik[b] = glob[threadIdx.x * BT + b];
             prior_of(j, pg);
@@ -936,10 +964,12 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             }
             for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < P; j += (int64_t)gridDim.x * blockDim.x) {
                 if (rp.is_parent[j]) continue;
+                // (the element's own prior term travels next to the first poll, not behind the last)
+                const double own = rp.include_priors ? rp.prior_grad[row * P + j] : 0.0;
                 double g = peer_combine(pp, seq, base + j, pp.fed8[j]) * sc;
                 if (normal && j == rp.sigma_theta_index)
                     g += peer_combine(pp, seq, base + P, pp.fed8[P]) * sc - (double)rp.n_rows_total;
-                if (rp.include_priors) g += rp.prior_grad[row * P + j];
+                g += own;
                 out_grad[row * P + j] = (T)g;
             }
             if (blockIdx.x == gridDim.x - 1) {

@@ -237,6 +237,9 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// start fetching a line that a later load of this SM will want (no register, no dependency)
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
 // ---------------------------------------------------------------------------------------------
 // warp primitives (all reductions use a fixed tree => bit-reproducible)
 // ---------------------------------------------------------------------------------------------
@@ -317,9 +320,21 @@ __device__ __forceinline__ double prior_mu_of(int family_byte, double raw) {
     return (family_byte & kPriorMuIsLog) ? exp(raw) : raw;
 }
 
+// positive families: PyMC samples them on the log scale (value variable <name>_log__, LogTransform)
+__host__ __device__ __forceinline__ bool prior_is_log(int family) {
+    return family == SKK_PRIOR_HALFNORMAL || family == SKK_PRIOR_EXPONENTIAL || family == SKK_PRIOR_HALFCAUCHY ||
+           family == SKK_PRIOR_GAMMA || family == SKK_PRIOR_INVGAMMA || family == SKK_PRIOR_LOGNORMAL ||
+           family == SKK_PRIOR_HALFSTUDENTT;
+}
+// families >= SKK_PRIOR_HALFCAUCHY: constant parameters only, evaluated without their normaliser (which the plan
+// carries in logp_const); plans that contain one evaluate their priors in the separate prior kernels, so that the
+// row kernel's prologue keeps the three basic families only (EXT = false)
+__host__ __device__ __forceinline__ bool prior_is_extended(int family) { return family >= SKK_PRIOR_HALFCAUCHY; }
+
 // One prior term in fp64.  v: the (transformed) element; a, b: mu and sd (Normal) or the rate /
 // scale in a (Exponential, HalfNormal; sampled as log, the log-Jacobian v is included).
 // Returns logp; grad = d/dv; for the Normal also d/d mu and d/d log(sd).
+template <bool EXT = true>
 __device__ __forceinline__ double prior_term(int family, double v, double a, double b, double &grad, double &d_mu,
                                              double &d_log_sd) {
     d_mu = 0.0;
@@ -336,9 +351,53 @@ __device__ __forceinline__ double prior_term(int family, double v, double a, dou
         grad = -q * q + 1.0;
         return -0.5 * q * q + kLogSqrt2OverPi - log(a) + v;
     }
-    const double sv = exp(v);  // SKK_PRIOR_EXPONENTIAL
-    grad = -a * sv + 1.0;
-    return log(a) - a * sv + v;
+    if (!EXT || family == SKK_PRIOR_EXPONENTIAL) {
+        const double sv = exp(v);
+        grad = -a * sv + 1.0;
+        return log(a) - a * sv + v;
+    }
+    if constexpr (EXT) {
+        // theta-dependent parts only (see prior_is_extended); x = exp(v) for the positive families
+        switch (family) {
+            case SKK_PRIOR_HALFCAUCHY: {  // -log1p((x/beta)^2) + v
+                const double q = exp(v) / a, q2 = q * q;
+                grad = -2.0 * q2 / (1.0 + q2) + 1.0;
+                return -log1p(q2) + v;
+            }
+            case SKK_PRIOR_GAMMA: {  // (alpha - 1) v - beta x + v
+                const double x = exp(v);
+                grad = a - b * x;
+                return a * v - b * x;
+            }
+            case SKK_PRIOR_INVGAMMA: {  // -(alpha + 1) v - beta / x + v
+                const double r = b * exp(-v);
+                grad = -a + r;
+                return -a * v - r;
+            }
+            case SKK_PRIOR_CAUCHY: {  // -log1p(z^2)
+                const double z = (v - a) / b;
+                grad = -2.0 * z / (b * (1.0 + z * z));
+                return -log1p(z * z);
+            }
+            case SKK_PRIOR_LAPLACE: {  // -|v - mu| / b
+                const double e = v - a;
+                grad = e > 0.0 ? -1.0 / b : (e < 0.0 ? 1.0 / b : 0.0);
+                return -fabs(e) / b;
+            }
+            case SKK_PRIOR_LOGNORMAL: {  // -z^2 / 2 with z = (log x - mu) / sigma; -log x and the Jacobian cancel
+                const double z = (v - a) / b;
+                grad = -z / b;
+                return -0.5 * z * z;
+            }
+            default: {  // SKK_PRIOR_HALFSTUDENTT: -(nu + 1)/2 log1p(x^2 / (nu sigma^2)) + v
+                const double x = exp(v) / b, q = x * x / a;
+                grad = -(a + 1.0) * q / (1.0 + q) + 1.0;
+                return -0.5 * (a + 1.0) * log1p(q) + v;
+            }
+        }
+    }
+    grad = 0.0;
+    return 0.0;
 }
 
 template <>

@@ -825,7 +825,7 @@ struct RowKernel {
                 const double a = a_src >= 0 ? prior_mu_of(family, (double)th[a_src]) : a_c;
                 const double sd = b_src >= 0 ? exp((double)th[b_src]) : b_c;
                 double grad, d_mu, d_log_sd;
-                lp[b] += prior_term(family & kPriorFamilyMask, (double)th[j], a, sd, grad, d_mu, d_log_sd);
+                lp[b] += prior_term<false>(family & kPriorFamilyMask, (double)th[j], a, sd, grad, d_mu, d_log_sd);
                 p.prior_grad[(int64_t)b * p.n_params + j] = grad;
             }
         }
@@ -854,7 +854,7 @@ struct RowKernel {
                     const double a = a_src >= 0 ? (mu_is_log ? exp((double)th[a_src]) : (double)th[a_src]) : a_c;
                     const double sd = b_src >= 0 ? exp((double)th[b_src]) : b_c;
                     double grad, d_mu, d_log_sd;
-                    prior_term(SKK_PRIOR_NORMAL, (double)th[j], a, sd, grad, d_mu, d_log_sd);
+                    prior_term<false>(SKK_PRIOR_NORMAL, (double)th[j], a, sd, grad, d_mu, d_log_sd);
                     v = (kind & 3) == 0 ? (mu_is_log ? d_mu * a : d_mu) : d_log_sd;
                 }
                 v = warp_sum(v);
@@ -1051,6 +1051,15 @@ struct RowKernel {
                 if (t2 >= 0) sp2 = p.tile_split[t2];
             }
             const int t4 = my_tiles[pos + 4];
+            if constexpr (NP > 0 && NS > 0) {
+                // the next tile holds two groups: its split row and the slots of its second group are fetched now,
+                // so that the two dependent loads in front of that tile's rows find them on chip
+                if (t1 >= 0 && k1.y == k1.x + 1) {
+                    prefetch_l1(p.tile_split + t1);
+#pragma unroll
+                    for (int t = 0; t < NP; ++t) prefetch_l1(p.ti_p[t] + k1.y);
+                }
+            }
 
             mbar_wait(bars + s, parity);
 

@@ -26,10 +26,27 @@ class B200Model:
     evaluated by the sm_100a kernels through the C ABI.
     """
 
-    def __init__(self, recorded: sym.Model, groupset: GroupSet, plan: 'ModelPlan'):
+    def __init__(self, recorded: sym.Model, groupset: GroupSet, plan: Optional['ModelPlan'], unsupported=None):
         self.recorded = recorded
         self.groupset = groupset
-        self.plan = plan
+        self._plan = plan
+        self._unsupported = unsupported
+
+    @property
+    def plan(self) -> 'ModelPlan':
+        """
+        The lowered model.  A component graph the fused kernels cannot express (no observed likelihood, a predictor
+        that is not affine in theta, an unknown family ...) still builds -- like in the reference, where ``build()``
+        takes any component (``tests/components/test_group_component.py``) -- and raises here, when something asks
+        for its evaluation.
+        """
+        if self._plan is None:
+            raise self._unsupported
+        return self._plan
+
+    @property
+    def is_lowered(self) -> bool:
+        return self._plan is not None
 
     # pm.Model-like surface --------------------------------------------------------------------
     @property
@@ -68,7 +85,10 @@ class B200Model:
 
     def logp_dlogp_function(self, dtype: str = 'float64', max_batch: int = 1, device: Optional[int] = None,
                             **options):
-        from sakkara_b200.valuegrad import ValueGradFunction
+        from sakkara_b200.valuegrad import MinibatchValueGrad, ValueGradFunction
+        if self.plan.minibatch is not None:
+            # MinibatchLikelihood: a fresh random subset of the rows per call, scaled to the whole data set
+            return MinibatchValueGrad(self.plan, dtype=dtype, device=device, **options)
         return ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
 
     def to_pymc(self, dtype: str = 'float64', device: Optional[int] = None):
@@ -112,8 +132,14 @@ def build(df: pd.DataFrame, component: ModelComponent, backend: str = 'auto', dt
 
     with sym.Model(coords=groupset.coords()) as recorded:
         component.build(groupset)
-    model = B200Model(recorded, groupset, lower_model(recorded))
-    if backend == 'b200':
+    from sakkara_b200.plan.lower import UnsupportedModelError
+    try:
+        model = B200Model(recorded, groupset, lower_model(recorded))
+    except UnsupportedModelError as err:
+        if len(recorded.observed_RVs) == 1:
+            raise           # a likelihood the kernels cannot evaluate: say so at once
+        model = B200Model(recorded, groupset, None, err)    # a bare component: the recorded graph only
+    if backend == 'b200' or not model.is_lowered:
         return model
     from sakkara_b200.pytensor_op import pymc_available, to_pymc_model
     if backend == 'pymc' or pymc_available():

@@ -67,7 +67,8 @@ class ModelComponent:
         raise NotImplementedError
 
     def to_minibatch(self, batch_size: int, group: str) -> 'ModelComponent':
-        raise NotImplementedError('Minibatch ADVI is outside the logp+dlogp hot path (SURVEY.md §3.4)')
+        """The component's counterpart for mini-batches of ``group`` (reference ``base.py:65-70``)."""
+        raise NotImplementedError
 
     # -- life cycle ----------------------------------------------------------------------------
     def build(self, groupset: GroupSet) -> None:
@@ -172,6 +173,11 @@ class FunctionComponent(ModelComponent):
         args = tuple(c.representation.map(c.variable, target) for c in self.args)
         kwargs = {k: c.representation.map(c.variable, target) for k, c in self.kwargs.items()}
         self.variable = self.fct(*args, **kwargs)
+
+    def to_minibatch(self, batch_size: int, group: str) -> 'ModelComponent':
+        # the same function over the mini-batched operands (reference function/base.py:100-104)
+        return FunctionComponent(self.fct, self.output_group, *[c.to_minibatch(batch_size, group) for c in self.args],
+                                 **{k: c.to_minibatch(batch_size, group) for k, c in self.kwargs.items()})
 
     @staticmethod
     def math_op(fct: Callable, left: Any, right: Any) -> 'FunctionComponent':
@@ -280,6 +286,9 @@ class DataComponent(FixedValueComponent):
     def build_variable(self) -> None:
         self.variable = sym.ConstantData(self.name, self.values)
 
+    def to_minibatch(self, batch_size: int, group: str) -> 'ModelComponent':
+        return MinibatchComponent(self, batch_size, group)
+
 
 def data_components(df: pd.DataFrame, group: Union[str, Tuple[str, ...]] = 'obs') -> Dict[str, DataComponent]:
     """One :class:`DataComponent` per column of ``df`` (reference ``fixed/data.py:47-58``)."""
@@ -298,6 +307,9 @@ class Composable(ModelComponent):
         self.group = _as_group_tuple(group)
         self.subcomponents = subcomponents
         self._groups_cache: Optional[Set[str]] = None
+
+    def to_minibatch(self, batch_size: int, group: str) -> 'ModelComponent':
+        return MinibatchComponent(self, batch_size, group)
 
     def get_name(self) -> Optional[str]:
         return self.name
@@ -445,11 +457,24 @@ class Likelihood(DistributionComponent):
 
 
 class MinibatchLikelihood(Likelihood):
-    """Minibatch ADVI likelihood of the reference; outside the logp+dlogp hot path."""
+    """
+    Likelihood over mini-batches of iid rows (reference ``composable/hierarchical/likelihood.py:65-89``): every
+    parameter and the observations are replaced by their mini-batch counterparts -- ``batch_size`` rows redrawn at
+    every evaluation -- and the distribution is told the size of the whole data set (``total_size``), so that its
+    logp is scaled by ``total_size / batch_size``.
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError('MinibatchLikelihood (stochastic ADVI) is outside the B200 hot path '
-                                  '(SURVEY.md §3.4)')
+    :param batch_size: observations per evaluation.
+    """
+
+    def __init__(self, generator: Callable, observed: DataComponent, batch_size: int, name: str = 'likelihood',
+                 group: str = 'obs', nan_param_mask: Dict[str, Any] = None, nan_data_mask: Any = None, **kwargs: Any):
+        kwargs['total_size'] = len(observed.values)
+        super().__init__(generator, observed, name, group, nan_param_mask, nan_data_mask, **kwargs)
+        if self.nan_rows is not None:
+            raise NotImplementedError('NaN-masked observations in a MinibatchLikelihood')
+        self.batch_size = batch_size
+        for key, comp in self.subcomponents.items():
+            self.subcomponents[key] = comp.to_minibatch(batch_size, group)
 
 
 class Reshaper(HierarchicalComponent):
@@ -463,10 +488,75 @@ class Reshaper(HierarchicalComponent):
 
 
 class GroupComponent(Composable):
-    """Per-member heterogeneous components of the reference; not expressible as a flat plan."""
+    """
+    A component given member by member of a group (reference ``composable/group.py:15-103``): every member
+    (value of the data-frame column; a tuple for several groups) gets its own component or plain value.
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError('GroupComponent is outside the B200 hot path (SURVEY.md §2 row 11)')
+    The variable is the concatenation, in member order, of every member's component mapped to the joint
+    representation and restricted to the member's cells -- a :class:`sakkara_b200.model.sym.Concat` node, which the
+    lowering turns into gathers that read different parameter blocks (or constants) in different cells.
+
+    :param group: group(s) the component is defined for.
+    :param name: name of the resulting (deterministic) variable.
+    :param membercomponents: ``{member: component or value}``.
+    """
+
+    def __init__(self, group: Union[str, Tuple[str, ...]], name: Optional[str] = None,
+                 membercomponents: Optional[Dict[Any, Any]] = None):
+        super().__init__(name, group, dict())
+        self.base_representation = None
+        self.components_representation = None
+        if membercomponents is not None:
+            for member, component in membercomponents.items():
+                self.add(member, component)
+
+    def __getitem__(self, item: Any) -> ModelComponent:
+        return self.subcomponents[item if isinstance(item, tuple) else (item,)]
+
+    def add(self, member: Any, component: Any) -> None:
+        """Set the component (or plain value) of one member."""
+        if not isinstance(component, ModelComponent):
+            component = DataComponent(component, 'global')
+        self.subcomponents[member if isinstance(member, tuple) else (member,)] = component
+        self._groups_cache = None
+
+    def prebuild(self, groupset: GroupSet) -> None:
+        self.build_components(groupset)
+
+    def build_representation(self, groupset: GroupSet) -> None:
+        base = MinimalTensorRepresentation()
+        for g in self.group:
+            base.add_group(groupset[g])
+        parts = MinimalTensorRepresentation(groupset['global'])
+        for comp in self.subcomponents.values():
+            parts = MinimalTensorRepresentation(*comp.representation.get_groups(), *parts.get_groups())
+        joint = MinimalTensorRepresentation(*base.get_groups(), *parts.get_groups())
+        # the member-wise pieces are laid out member-major, so the component's own groups must stay the leading ones
+        if base.get_groups() != joint.get_groups()[:len(base.get_groups())]:
+            raise ValueError('The group value specified for this GroupComponent have children among the '
+                             'component groups')
+        self.base_representation, self.components_representation, self.representation = base, parts, joint
+
+    def build_variable(self) -> None:
+        base, joint = self.base_representation, self.representation
+        members = base.get_member_tuples()
+        if not all(m in self.subcomponents for m in members):
+            raise ValueError('All member of group component must be specified.')
+        shape = joint.get_shape()
+        # every base group's member per cell of the joint representation
+        member_of_cell = [np.asarray(base.map(m, joint)).reshape(-1) for m in base.get_members()]
+        pieces = []
+        for member in members:
+            comp = self.subcomponents[member]
+            on_joint = comp.representation.map(comp.variable, joint)
+            if not isinstance(on_joint, sym.Var):
+                on_joint = np.broadcast_to(np.asarray(on_joint, dtype=np.float64), shape)
+            mask = np.ones(int(np.prod(shape)), dtype=bool)
+            for axis, value in enumerate(member):
+                mask &= member_of_cell[axis] == value
+            pieces.append(on_joint.reshape(-1)[mask])
+        full = sym.stack(pieces).ravel().reshape(shape)
+        self.variable = sym.Deterministic(self.name, full, dims=self.dims())
 
 
 # =============================================================================================
@@ -498,6 +588,53 @@ class WrapperComponent(ModelComponent):
             self.component.build(groupset)
 
 
+class MinibatchComponent(WrapperComponent):
+    """
+    Mini-batch view of a component (reference ``minibatch.py:9-33``): the wrapped component is built in full, mapped
+    to ``group`` and indexed with the group's mini-batch variable.
+    """
+
+    def __init__(self, component: ModelComponent, batch_size: int, group: str):
+        super().__init__(component)
+        self.batch_size = batch_size
+        self.group = group
+        self.transformed_variable = None
+
+    def build_representation(self, groupset: GroupSet) -> None:
+        self.representation = MinimalTensorRepresentation(groupset[self.group])
+        self.transformed_variable = self.component.representation.map(self.component.variable, self.representation)
+
+    def to_minibatch(self, batch_size: int, group: str) -> 'ModelComponent':
+        return self.component.to_minibatch(batch_size, group)
+
+    def build_variable(self) -> None:
+        minibatch = self.representation.get_groups()[0].get_minibatch(self.batch_size)
+        value = self.transformed_variable
+        if not isinstance(value, sym.Var):
+            value = sym.DataVar(None, np.asarray(value))
+        self.variable = value[minibatch]
+
+
+class MinibatchDeterministic(WrapperComponent):
+    """Named alias of a mini-batched variable, without dims (reference ``deterministic.py:23-32``)."""
+
+    def __init__(self, name: str, component: ModelComponent):
+        super().__init__(component)
+        self.name = name
+
+    def get_name(self) -> Optional[str]:
+        return self.name
+
+    def build_representation(self, groupset: GroupSet) -> None:
+        self.representation = self.component.representation
+
+    def to_minibatch(self, batch_size: int, group: str) -> 'ModelComponent':
+        return self
+
+    def build_variable(self) -> None:
+        self.variable = sym.Deterministic(self.name, self.component.variable)
+
+
 class DeterministicComponent(WrapperComponent):
     """Named alias of a component's variable (reference ``deterministic.py:36-51``)."""
 
@@ -507,6 +644,9 @@ class DeterministicComponent(WrapperComponent):
 
     def build_representation(self, groupset: GroupSet) -> None:
         self.representation = self.component.representation
+
+    def to_minibatch(self, batch_size: int, group: str) -> 'ModelComponent':
+        return MinibatchDeterministic(self.name, self.component.to_minibatch(batch_size, group))
 
     def build_variable(self) -> None:
         self.variable = sym.Deterministic(self.name, self.component.variable,

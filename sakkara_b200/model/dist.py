@@ -30,7 +30,7 @@ class Family:
         self.discrete = discrete
 
     def __call__(self, name: str, *args, shape: Tuple[int, ...] = (), dims: Optional[Tuple[str, ...]] = None,
-                 observed: Any = None, **kwargs) -> sym.RandomVar:
+                 observed: Any = None, total_size: Any = None, **kwargs) -> sym.RandomVar:
         if args:
             # PyMC allows positional parameters in declaration order
             for key, value in zip(self.params, args):
@@ -55,7 +55,9 @@ class Family:
             raise TypeError(f'{self.name}: missing parameters {missing}')
         if isinstance(shape, int):
             shape = (shape,)
-        var = sym.RandomVar(self.name, name, params, tuple(shape), dims, observed)
+        if total_size is not None and observed is None:
+            raise TypeError(f'{self.name}: total_size is a property of observed variables')
+        var = sym.RandomVar(self.name, name, params, tuple(shape), dims, observed, total_size)
         return sym.Model.current().register(var)
 
     def __repr__(self):
@@ -65,11 +67,20 @@ class Family:
 Normal = Family('Normal', {'mu': 0.0, 'sigma': 1.0})
 HalfNormal = Family('HalfNormal', {'sigma': 1.0}, positive=True)
 Exponential = Family('Exponential', {'lam': None}, positive=True)
+# families with constant parameters only (theta-dependent part on the device, normaliser in the plan's constant)
+HalfCauchy = Family('HalfCauchy', {'beta': None}, positive=True)
+Gamma = Family('Gamma', {'alpha': None, 'beta': None}, positive=True)
+InverseGamma = Family('InverseGamma', {'alpha': None, 'beta': 1.0}, positive=True)
+Cauchy = Family('Cauchy', {'alpha': None, 'beta': None})
+Laplace = Family('Laplace', {'mu': None, 'b': None})
+LogNormal = Family('LogNormal', {'mu': 0.0, 'sigma': 1.0}, positive=True)
+HalfStudentT = Family('HalfStudentT', {'nu': None, 'sigma': 1.0}, positive=True)
 # exactly one of p / logit_p must be given (checked in Family.__call__)
 Bernoulli = Family('Bernoulli', {'p': None, 'logit_p': None}, discrete=True)
 Poisson = Family('Poisson', {'mu': None}, discrete=True)
 
-FAMILIES: Dict[str, Family] = {f.name: f for f in (Normal, HalfNormal, Exponential, Bernoulli, Poisson)}
+FAMILIES: Dict[str, Family] = {f.name: f for f in (Normal, HalfNormal, Exponential, HalfCauchy, Gamma, InverseGamma,
+                                                   Cauchy, Laplace, LogNormal, HalfStudentT, Bernoulli, Poisson)}
 
 
 def resolve_generator(generator: Callable) -> Family:

@@ -23,7 +23,32 @@ class Var:
     def __getitem__(self, index) -> 'Var':
         if not isinstance(index, tuple):
             index = (index,)
-        return Gather(self, tuple(np.asarray(i) for i in index))
+        if len(index) == 1 and isinstance(index[0], MinibatchIndex):
+            return MinibatchGather(self, index[0])
+        arrays = tuple(np.asarray(i) for i in index)
+        if len(arrays) == 1 and arrays[0].dtype == bool:
+            # boolean mask over the whole tensor (reference ``composable/group.py:93``: ``variable[mask]``)
+            if arrays[0].shape != tuple(self.shape):
+                raise IndexError(f'mask of shape {arrays[0].shape} for a tensor of shape {tuple(self.shape)}')
+            arrays = np.nonzero(arrays[0])
+        return Gather(self, tuple(np.asarray(i) for i in arrays))
+
+    # shape changes are gathers with the identity permutation (row-major, like PyTensor's)
+    def ravel(self) -> 'Var':
+        if len(self.shape) == 1:
+            return self
+        size = int(np.prod(self.shape)) if len(self.shape) else 1
+        return Gather(self, tuple(np.asarray(i) for i in np.unravel_index(np.arange(size), self.shape)))
+
+    def flatten(self) -> 'Var':
+        return self.ravel()
+
+    def reshape(self, *shape) -> 'Var':
+        if len(shape) == 1 and not isinstance(shape[0], (int, np.integer)):
+            shape = tuple(shape[0])
+        flat = self.ravel()
+        size = flat.shape[0]
+        return Gather(flat, (np.arange(size).reshape(shape),))
 
     # arithmetic -----------------------------------------------------------------------------
     def __add__(self, other): return BinOp('add', self, other)
@@ -100,6 +125,58 @@ class Masked(Var):
         self.shape = np.broadcast_shapes(shape_of(value), self.mask.shape)
 
 
+class Concat(Var):
+    """
+    One-dimensional concatenation of one-dimensional pieces: what ``pt.stack(pieces).ravel()`` is for
+    the equally long member-wise pieces of a ``GroupComponent`` (reference ``composable/group.py:95-100``).
+    A piece may be a ``Var`` or plain numbers.
+    """
+
+    def __init__(self, pieces):
+        self.pieces = list(pieces)
+        lengths = []
+        for piece in self.pieces:
+            shape = shape_of(piece)
+            if len(shape) != 1:
+                raise ValueError(f'Concat takes one-dimensional pieces, got shape {shape}')
+            lengths.append(int(shape[0]))
+        self.lengths = lengths
+        self.shape = (int(sum(lengths)),)
+
+
+def stack(pieces) -> Var:
+    """``pt.stack`` of equally long one-dimensional pieces: a ``[len(pieces), length]`` tensor."""
+    pieces = list(pieces)
+    cat = Concat(pieces)
+    if len(set(cat.lengths)) > 1:
+        raise ValueError(f'stack needs pieces of equal length, got {cat.lengths}')
+    return cat.reshape(len(pieces), cat.lengths[0] if cat.lengths else 0)
+
+
+class MinibatchIndex(Var):
+    """
+    ``batch_size`` row numbers drawn uniformly (with replacement) from ``range(n)``, redrawn at every evaluation:
+    what ``pymc.data.minibatch_index(0, n, size=(batch_size,))`` is in the reference
+    (``sakkara/relation/group.py:54-60``).
+    """
+
+    def __init__(self, n: int, batch_size: int):
+        self.n = int(n)
+        self.batch_size = int(batch_size)
+        self.shape = (self.batch_size,)
+
+
+class MinibatchGather(Var):
+    """``base[minibatch]``: the rows of the current minibatch (reference ``sakkara/model/minibatch.py:31-33``)."""
+
+    def __init__(self, base: Var, minibatch: MinibatchIndex):
+        if len(shape_of(base)) < 1 or shape_of(base)[0] != minibatch.n:
+            raise IndexError(f'minibatch over {minibatch.n} members for a tensor of shape {shape_of(base)}')
+        self.base = base
+        self.minibatch = minibatch
+        self.shape = (minibatch.batch_size,) + tuple(shape_of(base)[1:])
+
+
 class DataVar(Var):
     """Constant data registered in the model (reference: ``pm.ConstantData``, ``fixed/data.py:41``)."""
 
@@ -116,7 +193,8 @@ class RandomVar(Var):
     """
 
     def __init__(self, family: str, name: str, params: Dict[str, Any], shape: Tuple[int, ...],
-                 dims: Optional[Tuple[str, ...]], observed: Any = None):
+                 dims: Optional[Tuple[str, ...]], observed: Any = None, total_size: Optional[int] = None):
+        self.total_size = None if total_size is None else int(total_size)   # minibatch: rows of the whole data set
         self.family = family
         self.name = name
         self.params = params

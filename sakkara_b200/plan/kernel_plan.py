@@ -29,7 +29,7 @@ import pandas as pd
 from scipy.special import gammaln
 
 from sakkara_b200.plan.lower import UnsupportedModelError
-from sakkara_b200.plan.model_plan import FAMILY_IDS, ModelPlan
+from sakkara_b200.plan.model_plan import FAMILY_IDS, PRIOR_PARAMS, ModelPlan, prior_normaliser
 
 LEVEL_GLOBAL, LEVEL_PRIMARY, LEVEL_SECONDARY = 0, 1, 2
 MAX_TERMS_PER_LEVEL = 2
@@ -78,6 +78,7 @@ class KernelPlan:
     sigma_theta_index: int
     logp_const: float
     include_priors: bool = True
+    prior_logp_const: float = 0.0           # the part of logp_const that is normalisers of prior families
 
     @property
     def stored_bytes_per_row(self) -> int:
@@ -203,13 +204,20 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     column_of_term: Dict[int, int] = {}
     elem_of_term: Dict[int, np.ndarray] = {}    # block element per code, per term
     seen_arrays: Dict[int, int] = {}
+    positive = np.zeros(plan.n_params, dtype=bool)
+    for b in plan.blocks:
+        positive[b.offset:b.offset + b.size] = b.transform != 'identity'
     for number, term in enumerate(plan.terms):
-        block = plan.blocks[term.block]
-        if block.transform != 'identity':
-            raise UnsupportedModelError(f'{block.name}: positive variables cannot enter the linear predictor')
+        base = plan.term_base(term)
         index = take(term.index)
-        if n == 0 or block.size == 1 or index.min() == index.max():
-            global_terms[number] = block.offset + (int(index[0]) if n else 0)
+        if term.block >= 0:
+            block = plan.blocks[term.block]
+            if block.transform != 'identity':
+                raise UnsupportedModelError(f'{block.name}: positive variables cannot enter the linear predictor')
+        elif n and positive[np.unique(index)].any():
+            raise UnsupportedModelError('positive variables cannot enter the linear predictor')
+        if n == 0 or (term.block >= 0 and block.size == 1) or index.min() == index.max():
+            global_terms[number] = base + (int(index[0]) if n else 0)
             continue
         key = id(term.index)
         if key in seen_arrays:
@@ -326,7 +334,6 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     terms: List[KernelTerm] = []
     counts = {LEVEL_GLOBAL: 0, LEVEL_PRIMARY: 0, LEVEL_SECONDARY: 0}
     for number, term in enumerate(plan.terms):
-        block = plan.blocks[term.block]
         xc = xcol_of(term.x)
         if number in global_terms:
             level = LEVEL_GLOBAL
@@ -337,7 +344,7 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
             level = LEVEL_PRIMARY if fine == primary else LEVEL_SECONDARY
             code_of_slot = p_code_of_slot if fine == primary else s_code_of_slot
             own_codes = code_of_slot if c == fine else table[(fine, c)][code_of_slot]
-            theta_index = (block.offset + elem_of_term[number][own_codes]).astype(np.int32)
+            theta_index = (plan.term_base(term) + elem_of_term[number][own_codes]).astype(np.int32)
         counts[level] += 1
         terms.append(KernelTerm(level=level, xcol=xc, theta_index=theta_index, block=term.block))
     if counts[LEVEL_GLOBAL] > MAX_TERMS_PER_LEVEL or counts[LEVEL_PRIMARY] > MAX_TERMS_PER_LEVEL \
@@ -375,23 +382,34 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
 
     # ---- priors ---------------------------------------------------------------------------------------------------
     blocks: List[KernelBlock] = []
+    prior_logp_const = 0.0
     for b in plan.blocks:
         kb = KernelBlock(family=FAMILY_IDS[b.family], offset=b.offset, size=b.size)
-        names = {'Normal': ('mu', 'sigma'), 'HalfNormal': ('sigma', None), 'Exponential': ('lam', None)}[b.family]
+        names = PRIOR_PARAMS[b.family]
         for slot, pname in zip('ab', names):
             if pname is None:
                 continue
             prm = b.params[pname]
             if prm.is_const:
                 setattr(kb, slot + '_const', np.ascontiguousarray(np.atleast_1d(prm.const), dtype=np.float64))
+            elif prm.is_mixed:
+                # per element a constant or an element of theta (index -1: the constant)
+                setattr(kb, slot + '_const', np.ascontiguousarray(np.broadcast_to(prm.const, (b.size,)), dtype=np.float64))
+                setattr(kb, slot + '_index', np.ascontiguousarray(prm.index, dtype=np.int32))
             else:
                 src = plan.blocks[prm.block]
                 setattr(kb, slot + '_index', (src.offset + prm.index).astype(np.int32))
         blocks.append(kb)
+        if include_priors and FAMILY_IDS[b.family] >= FAMILY_IDS['HalfCauchy']:
+            # the device evaluates these families without their normaliser; like the constant of the masked
+            # rows every rank adds its share
+            norm = np.broadcast_to(prior_normaliser(b.family, kb.a_const, kb.b_const), (b.size,))
+            prior_logp_const += float(np.sum(norm, dtype=np.float64)) * (n / total if total else 1.0)
 
     return KernelPlan(dtype=dtype, family=FAMILY_IDS[lik.family], n_rows=n, n_rows_total=total,
                       n_params=plan.n_params, perm=perm, xcols=xcols, y=np.ascontiguousarray(y_store), y_kind=y_kind,
                       eta_offset=eta_offset, n_primary=n_primary, seg_offsets=seg_offsets, n_secondary=n_secondary,
                       sec_codes=None if sec_codes is None else np.ascontiguousarray(sec_codes), terms=terms,
                       blocks=blocks, sigma_const=sigma_const, sigma_theta_index=sigma_theta_index,
-                      logp_const=logp_const, include_priors=include_priors)
+                      logp_const=logp_const + prior_logp_const, include_priors=include_priors,
+                      prior_logp_const=prior_logp_const)

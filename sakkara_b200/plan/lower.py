@@ -16,7 +16,7 @@ arbitrary ``f_`` callables -- raises ``NotImplementedError``: there is no CPU fa
 path, the caller is told to use the stock PyMC graph.
 """
 from dataclasses import dataclass
-from typing import Any, List, Optional, Union
+from typing import Any, Dict, List, Optional, Union
 
 import numpy as np
 
@@ -34,6 +34,9 @@ class Monomial:
     coef: Union[float, np.ndarray]             # scalar or array broadcastable to the form's shape
     var: Optional[sym.RandomVar] = None        # free variable, None for the constant part
     index: Optional[np.ndarray] = None         # int64, flat element of `var` per cell, form-shaped
+    tag: Optional[int] = None                  # monomials that stem from the pieces of one Concat node: their
+                                               # supports (coef != 0) are disjoint, so they can be read as ONE
+                                               # gather over several blocks (_merge_pieces)
 
 
 class AffineForm:
@@ -51,6 +54,9 @@ class AffineForm:
             assert m.var is None
             total = total + m.coef
         return total
+
+
+_minibatches_seen: List[Any] = []      # MinibatchIndex nodes met by _lower since lower_model() started
 
 
 def _scale(coef, factor):
@@ -75,12 +81,32 @@ def _lower(node: Any) -> AffineForm:
             if isinstance(coef, np.ndarray) and coef.ndim > 0:
                 coef = np.broadcast_to(coef, base.shape)[node.indices]
             index = None if m.var is None else np.broadcast_to(m.index, base.shape)[node.indices]
-            out.append(Monomial(coef, m.var, index))
+            out.append(Monomial(coef, m.var, index, m.tag))
+        return AffineForm(node.shape, out)
+    if isinstance(node, sym.MinibatchGather):
+        # lowered over ALL rows: which rows an evaluation uses is decided when it runs (ModelPlan.minibatch)
+        _minibatches_seen.append(node.minibatch)
+        return _lower(node.base)
+    if isinstance(node, sym.Concat):
+        # piece by piece: the piece's monomials, zero outside the piece's range
+        total = node.shape[0]
+        out, start = [], 0
+        for piece, length in zip(node.pieces, node.lengths):
+            form = _lower(piece)
+            for m in form.monomials:
+                coef = np.zeros(total, dtype=np.float64)
+                coef[start:start + length] = np.broadcast_to(m.coef, (length,))
+                index = None
+                if m.var is not None:
+                    index = np.zeros(total, dtype=np.int64)
+                    index[start:start + length] = np.broadcast_to(m.index, (length,))
+                out.append(Monomial(coef, m.var, index, id(node) if m.var is not None else None))
+            start += length
         return AffineForm(node.shape, out)
     if isinstance(node, sym.UnaryOp):
         if node.op == 'neg':
             inner = _lower(node.arg)
-            return AffineForm(inner.shape, [Monomial(_scale(m.coef, -1.0), m.var, m.index) for m in inner.monomials])
+            return AffineForm(inner.shape, [Monomial(_scale(m.coef, -1.0), m.var, m.index, m.tag) for m in inner.monomials])
         raise UnsupportedModelError(f'{node.op}() may only wrap the whole linear predictor of the likelihood')
     if isinstance(node, sym.BinOp):
         left, right = _lower(node.left), _lower(node.right)
@@ -88,7 +114,7 @@ def _lower(node: Any) -> AffineForm:
         if node.op in ('add', 'sub'):
             sign = 1.0 if node.op == 'add' else -1.0
             monos = [_broadcast(m, left.shape, shape) for m in left.monomials]
-            monos += [_broadcast(Monomial(_scale(m.coef, sign), m.var, m.index), right.shape, shape)
+            monos += [_broadcast(Monomial(_scale(m.coef, sign), m.var, m.index, m.tag), right.shape, shape)
                       for m in right.monomials]
             return AffineForm(shape, monos)
         if node.op == 'mul':
@@ -97,14 +123,14 @@ def _lower(node: Any) -> AffineForm:
             const, other, other_shape = (left, right, right.shape) if left.is_const else (right, left, left.shape)
             factor = const.const_value()
             factor = float(factor) if factor.ndim == 0 else factor
-            return AffineForm(shape, [_broadcast(Monomial(_scale(m.coef, factor), m.var, m.index), other_shape, shape)
+            return AffineForm(shape, [_broadcast(Monomial(_scale(m.coef, factor), m.var, m.index, m.tag), other_shape, shape)
                                       for m in other.monomials])
         if node.op == 'truediv':
             if not right.is_const:
                 raise UnsupportedModelError('Division by a random variable is not affine in theta')
             factor = 1.0 / right.const_value()
             factor = float(factor) if factor.ndim == 0 else factor
-            return AffineForm(shape, [_broadcast(Monomial(_scale(m.coef, factor), m.var, m.index), left.shape, shape)
+            return AffineForm(shape, [_broadcast(Monomial(_scale(m.coef, factor), m.var, m.index, m.tag), left.shape, shape)
                                       for m in left.monomials])
         raise UnsupportedModelError(f'Operator {node.op} cannot be lowered to the fused GLM kernel')
     if isinstance(node, sym.Var):
@@ -117,7 +143,7 @@ def _broadcast(m: Monomial, from_shape, to_shape) -> Monomial:
     """Bring the index array of a monomial to the (broadcast) shape of the enclosing form."""
     if m.var is None or tuple(from_shape) == tuple(to_shape):
         return m
-    return Monomial(m.coef, m.var, np.broadcast_to(m.index, to_shape))
+    return Monomial(m.coef, m.var, np.broadcast_to(m.index, to_shape), m.tag)
 
 
 def _merge_constants(form: AffineForm) -> Optional[np.ndarray]:
@@ -130,7 +156,51 @@ def _merge_constants(form: AffineForm) -> Optional[np.ndarray]:
     return total
 
 
-def _prior_param(value: Any, block_of, size: int, what: str) -> PriorParam:
+@dataclass
+class _Gather:
+    """A merged monomial: ``coef * theta[absolute index]`` per cell, reading one block or several."""
+    coef: np.ndarray                           # float64, form-shaped
+    absolute: np.ndarray                       # int64, form-shaped: element of theta
+    blocks: List[int]                          # the blocks it reads, in order of appearance
+
+
+def _merge_pieces(form: AffineForm, block_of, blocks) -> List[_Gather]:
+    """
+    The non-constant monomials of ``form`` as gathers from theta.  Monomials that stem from the pieces of one
+    ``Concat`` (a ``GroupComponent``) and whose supports are disjoint are read as one gather with absolute
+    indices: ``c1 * a[i1] + c2 * b[i2] == (c1 + c2) * theta[where(c1 != 0, off_a + i1, off_b + i2)]``.
+    """
+    out: List[_Gather] = []
+    groups: Dict[int, List[int]] = {}
+    supports: Dict[int, np.ndarray] = {}
+    for m in form.monomials:
+        if m.var is None:
+            continue
+        number = block_of[id(m.var)]
+        coef = np.array(np.broadcast_to(np.asarray(m.coef, dtype=np.float64), form.shape))
+        absolute = blocks[number].offset + np.broadcast_to(m.index, form.shape).astype(np.int64)
+        if m.tag is not None:
+            support = coef != 0.0
+            target = None
+            for k in groups.get(m.tag, []):
+                if not (supports[k] & support).any():
+                    target = k
+                    break
+            if target is not None:
+                g = out[target]
+                g.absolute = np.where(support, absolute, g.absolute)
+                g.coef = g.coef + coef
+                supports[target] |= support
+                if number not in g.blocks:
+                    g.blocks.append(number)
+                continue
+            groups.setdefault(m.tag, []).append(len(out))
+            supports[len(out)] = support
+        out.append(_Gather(coef, np.array(absolute), [number]))
+    return out
+
+
+def _prior_param(value: Any, block_of, size: int, what: str, blocks=None) -> PriorParam:
     form = _lower(value)
     if form.is_const:
         const = np.asarray(form.const_value(), dtype=np.float64)
@@ -138,6 +208,22 @@ def _prior_param(value: Any, block_of, size: int, what: str) -> PriorParam:
             raise UnsupportedModelError(f'{what}: constant of size {const.size} for a block of size {size}')
         return PriorParam(const=const.reshape(-1) if const.size > 1 else const.reshape(()))
     monos = form.monomials
+    if any(m.tag is not None for m in monos):
+        # member-wise parameter (GroupComponent): per element either a constant or one element of theta
+        gathers = _merge_pieces(form, block_of, blocks)
+        const = _merge_constants(form)
+        const = np.zeros(form.shape) if const is None else np.broadcast_to(np.asarray(const, dtype=np.float64), form.shape)
+        if len(gathers) != 1 or not np.isin(gathers[0].coef, (0.0, 1.0)).all() or \
+                np.any((gathers[0].coef == 1.0) & (const != 0.0)):
+            raise UnsupportedModelError(f'{what}: every element must be a constant or a single variable')
+        g = gathers[0]
+        absolute = np.where(g.coef == 1.0, g.absolute, -1).reshape(-1)
+        const = np.array(const, dtype=np.float64).reshape(-1)
+        if absolute.size == 1 and size > 1:
+            absolute, const = np.repeat(absolute, size), np.repeat(const, size)
+        if absolute.size != size:
+            raise UnsupportedModelError(f'{what}: parameter of size {absolute.size} for a block of size {size}')
+        return PriorParam(const=const, block=-1, index=np.ascontiguousarray(absolute, dtype=np.int64))
     if len(monos) != 1 or not np.all(np.asarray(monos[0].coef) == 1.0):
         raise UnsupportedModelError(f'{what}: prior parameters must be constants or a single gathered variable')
     m = monos[0]
@@ -163,7 +249,7 @@ def _masked_likelihood(obs: sym.RandomVar, y: np.ndarray):
         raise UnsupportedModelError('Either all or none of the likelihood parameters carry a NaN mask')
     mask = None
     for node in wrapped.values():
-        rows = np.broadcast_to(node.mask, obs.shape).reshape(-1)
+        rows = np.broadcast_to(node.mask, obs.shape).reshape(-1)     # (never mini-batched: components.py)
         if mask is not None and not np.array_equal(mask, rows):
             raise UnsupportedModelError('Likelihood parameters are masked on different rows')
         mask = rows
@@ -215,21 +301,29 @@ def lower_model(model: sym.Model) -> ModelPlan:
 
     for rv, block in zip(model.free_RVs, blocks):
         for key, value in rv.params.items():
-            param = _prior_param(value, block_of, block.size, f'{rv.name}.{key}')
+            param = _prior_param(value, block_of, block.size, f'{rv.name}.{key}', blocks)
             if not param.is_const:
-                if param.block >= block_of[id(rv)]:
+                if param.is_mixed:
+                    absolute = param.index[param.index >= 0]
+                    sources = sorted({plan_block_of(blocks, int(j)) for j in np.unique(absolute)})
+                else:
+                    sources = [param.block]
+                if any(src >= block_of[id(rv)] for src in sources):
                     raise UnsupportedModelError(f'{rv.name}.{key}: parameter refers to a later variable')
                 if block.family != 'Normal':
                     raise UnsupportedModelError(f'{rv.name}.{key}: only Normal blocks may have random parameters')
-                if key == 'sigma' and blocks[param.block].transform != 'log':
+                if key == 'sigma' and any(blocks[src].transform != 'log' for src in sources):
                     raise UnsupportedModelError(f'{rv.name}.sigma must be a positive (HalfNormal/Exponential) variable')
             block.params[key] = param
 
     obs = model.observed_RVs[0]
+    del _minibatches_seen[:]
     y_form = _lower(obs.observed)
     if not y_form.is_const:
         raise UnsupportedModelError('Observed data must be constant')
-    y = np.ascontiguousarray(np.broadcast_to(y_form.const_value(), obs.shape), dtype=np.float64).reshape(-1)
+    # a mini-batched likelihood (MinibatchLikelihood) is lowered over the whole data set
+    obs_shape = obs.shape if obs.total_size is None else (obs.total_size,)
+    y = np.ascontiguousarray(np.broadcast_to(y_form.const_value(), obs_shape), dtype=np.float64).reshape(-1)
     n_rows = y.size
     # rows masked for NaN observations: lowered like all others (so that the indices stay the reference's),
     # then dropped from the plan; what they add to logp does not depend on theta
@@ -278,7 +372,7 @@ def lower_model(model: sym.Model) -> ModelPlan:
         raise UnsupportedModelError(f'Linear predictor of shape {eta.shape} for {n_rows} observations')
     terms: List[Term] = []
     for m in eta.monomials:
-        if m.var is None:
+        if m.var is None or m.tag is not None:
             continue
         index = np.ascontiguousarray(np.broadcast_to(m.index, eta.shape), dtype=np.int64).reshape(-1)
         if index.size == 1 and n_rows > 1:
@@ -291,12 +385,32 @@ def lower_model(model: sym.Model) -> ModelPlan:
             if x.size == 1 and n_rows > 1:
                 x = np.repeat(x, n_rows)
         terms.append(Term(block=block_of[id(m.var)], index=index, x=x))
+    # member-wise coefficients (GroupComponent): the pieces of one component become one term
+    tagged = AffineForm(eta.shape, [m for m in eta.monomials if m.var is not None and m.tag is not None])
+    for g in _merge_pieces(tagged, block_of, blocks):
+        absolute = np.ascontiguousarray(g.absolute, dtype=np.int64).reshape(-1)
+        coef = g.coef.reshape(-1)
+        if absolute.size == 1 and n_rows > 1:
+            absolute, coef = np.repeat(absolute, n_rows), np.repeat(coef, n_rows)
+        x = None if np.all(coef == 1.0) else np.ascontiguousarray(coef)
+        if len(g.blocks) == 1:
+            terms.append(Term(block=g.blocks[0], index=absolute - blocks[g.blocks[0]].offset, x=x))
+        else:
+            terms.append(Term(block=-1, index=absolute, x=x))     # different blocks in different rows
     const = _merge_constants(eta)
     if const is not None and np.any(np.asarray(const) != 0.0):
         spec.offset = np.ascontiguousarray(np.broadcast_to(const, (n_rows,)), dtype=np.float64)
 
     plan = ModelPlan(blocks=blocks, terms=terms, likelihood=spec, n_rows=n_rows,
                      coords={k: np.asarray(v) for k, v in model.coords.items()})
+    if obs.total_size is not None:
+        # (the observed variable itself keeps the shape of the whole group, reference test_minibatch.py:22; the size
+        # of the batch is that of the index variable its parameters and observations are gathered with)
+        if len({id(mb) for mb in _minibatches_seen}) != 1 or _minibatches_seen[0].n != n_rows:
+            raise UnsupportedModelError('A mini-batched likelihood needs one mini-batch variable over all observations')
+        plan.minibatch = int(_minibatches_seen[0].batch_size)
+    elif _minibatches_seen:
+        raise UnsupportedModelError('Mini-batched components outside a MinibatchLikelihood')
     if masked is not None:
         keep = ~masked
         spec.y = np.ascontiguousarray(spec.y[keep])
@@ -310,6 +424,14 @@ def lower_model(model: sym.Model) -> ModelPlan:
         plan.logp_const = masked_logp
         plan.n_masked_rows = int(masked.sum())
     return plan
+
+
+def plan_block_of(blocks: List[Block], element: int) -> int:
+    """Number of the block that holds element ``element`` of theta."""
+    for number, b in enumerate(blocks):
+        if b.offset <= element < b.offset + b.size:
+            return number
+    raise IndexError(element)
 
 
 def _unwrap_link(node: Any, link: str, what: str):

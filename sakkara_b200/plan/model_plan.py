@@ -13,15 +13,50 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-# likelihood / prior family ids shared with the C ABI (include/skk_b200.h)
-FAMILY_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'HalfNormal': 3, 'Exponential': 4}
 LOG_SQRT_2PI = 0.91893853320467274178032973640562
 LOG_SQRT_2_OVER_PI = -0.22579135264472743236309761494744
+
+# likelihood / prior family ids shared with the C ABI (include/skk_b200.h)
+FAMILY_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'HalfNormal': 3, 'Exponential': 4,
+              'HalfCauchy': 5, 'Gamma': 6, 'InverseGamma': 7, 'Cauchy': 8, 'Laplace': 9, 'LogNormal': 10,
+              'HalfStudentT': 11}
+# prior families: names of the parameters that travel as a / b through the C ABI (include/skk_b200.h)
+PRIOR_PARAMS = {'Normal': ('mu', 'sigma'), 'HalfNormal': ('sigma', None), 'Exponential': ('lam', None),
+                'HalfCauchy': ('beta', None), 'Gamma': ('alpha', 'beta'), 'InverseGamma': ('alpha', 'beta'),
+                'Cauchy': ('alpha', 'beta'), 'Laplace': ('mu', 'b'), 'LogNormal': ('mu', 'sigma'),
+                'HalfStudentT': ('nu', 'sigma')}
+
+
+def prior_normaliser(family: str, a, b):
+    """
+    theta-independent part of the log-density of the families whose device code evaluates the theta-dependent
+    part only (``SKK_PRIOR_HALFCAUCHY`` and later, include/skk_b200.h); elementwise, 0 for the basic families.
+    """
+    from scipy.special import gammaln
+    a = np.asarray(a, dtype=np.float64)
+    b = None if b is None else np.asarray(b, dtype=np.float64)
+    if family == 'HalfCauchy':
+        return np.log(2.0 / np.pi) - np.log(a)
+    if family in ('Gamma', 'InverseGamma'):
+        return a * np.log(b) - gammaln(a)
+    if family == 'Cauchy':
+        return -np.log(np.pi) - np.log(b) + 0.0 * a
+    if family == 'Laplace':
+        return -np.log(2.0 * b) + 0.0 * a
+    if family == 'LogNormal':
+        return -LOG_SQRT_2PI - np.log(b) + 0.0 * a
+    if family == 'HalfStudentT':
+        return np.log(2.0) + gammaln(0.5 * (a + 1.0)) - gammaln(0.5 * a) - 0.5 * np.log(a * np.pi * b * b)
+    return np.zeros_like(a)
 
 
 @dataclass
 class PriorParam:
-    """One parameter of a block's prior: a constant, or ``theta[block][index]``."""
+    """
+    One parameter of a block's prior: a constant, or ``theta[block][index]``, or -- member-wise parameters of a
+    ``GroupComponent`` -- per element one or the other: ``block == -1``, ``index`` is the absolute element of
+    theta or -1, and ``const[size]`` holds the values of the elements with -1.
+    """
     const: Optional[np.ndarray] = None        # float64, scalar or shape (size,)
     block: Optional[int] = None               # source block number
     index: Optional[np.ndarray] = None        # int64[size], element of the source block per element
@@ -30,12 +65,16 @@ class PriorParam:
     def is_const(self) -> bool:
         return self.block is None
 
+    @property
+    def is_mixed(self) -> bool:
+        return self.block is not None and self.block < 0
+
 
 @dataclass
 class Block:
     """One free random variable = one contiguous slice of theta."""
     name: str
-    family: str                                # Normal | HalfNormal | Exponential
+    family: str                                # a key of PRIOR_PARAMS
     offset: int
     size: int
     shape: Tuple[int, ...]
@@ -51,7 +90,10 @@ class Block:
 
 @dataclass
 class Term:
-    """``eta[row] += theta[block][index[row]] * x[row]`` (``x`` omitted = 1)."""
+    """
+    ``eta[row] += theta[block][index[row]] * x[row]`` (``x`` omitted = 1).  ``block == -1``: ``index`` holds
+    absolute elements of theta (a member-wise coefficient, ``GroupComponent``, reads several blocks).
+    """
     block: int
     index: np.ndarray                          # int64[N]
     x: Optional[np.ndarray] = None             # float64[N]
@@ -77,10 +119,26 @@ class ModelPlan:
     coords: Dict[str, np.ndarray] = field(default_factory=dict)
     logp_const: float = 0.0                    # constant added to logp: the rows masked out for NaN observations
     n_masked_rows: int = 0                     # how many rows those were (they are not in n_rows / the arrays)
+    minibatch: Optional[int] = None            # MinibatchLikelihood: rows per evaluation, drawn from all n_rows; the
+                                               # likelihood part is scaled by n_rows / minibatch
 
     @property
     def n_params(self) -> int:
         return sum(b.size for b in self.blocks)
+
+    def term_base(self, term: 'Term') -> int:
+        """Offset in theta that ``term.index`` counts from."""
+        return 0 if term.block < 0 else self.blocks[term.block].offset
+
+    def take_rows(self, rows) -> 'ModelPlan':
+        """The same model over a subset (or multiset) of the observation rows; ``rows=[]`` leaves the priors."""
+        import dataclasses
+        rows = np.asarray(rows, dtype=np.int64)
+        lik = dataclasses.replace(self.likelihood, y=self.likelihood.y[rows],
+                                  offset=None if self.likelihood.offset is None else self.likelihood.offset[rows])
+        terms = [Term(t.block, t.index[rows], None if t.x is None else t.x[rows]) for t in self.terms]
+        return dataclasses.replace(self, terms=terms, likelihood=lik, n_rows=int(rows.size), logp_const=0.0,
+                                   n_masked_rows=0, minibatch=None)
 
     def block_slices(self) -> Dict[str, slice]:
         return {b.name: slice(b.offset, b.offset + b.size) for b in self.blocks}
@@ -88,8 +146,9 @@ class ModelPlan:
     def describe(self) -> str:
         lines = [f'ModelPlan: N={self.n_rows} P={self.n_params} likelihood={self.likelihood.family}']
         for i, b in enumerate(self.blocks):
-            ps = ', '.join(f'{k}={"const" if p.is_const else "block%d[idx]" % p.block}' for k, p in b.params.items())
+            ps = ', '.join(f'{k}={"const" if p.is_const else ("member-wise" if p.is_mixed else "block%d[idx]" % p.block)}'
+                           for k, p in b.params.items())
             lines.append(f'  block {i}: {b.value_name} [{b.offset}:{b.offset + b.size}] {b.family}({ps})')
         for t in self.terms:
-            lines.append(f'  term: block {t.block}[idx] * {"x" if t.x is not None else "1"}')
+            lines.append(f'  term: {"theta" if t.block < 0 else "block %d" % t.block}[idx] * {"x" if t.x is not None else "1"}')
         return '\n'.join(lines)

@@ -67,7 +67,11 @@ class Group:
             raise ValueError(f'Group {other.name} is not a parent or twin of {self.name}')
 
     def get_minibatch(self, batch_size):
-        raise NotImplementedError('Minibatch ADVI is outside the logp+dlogp hot path (SURVEY.md §3.4)')
+        """The group's minibatch index variable, created at the first call (reference ``group.py:54-60``)."""
+        if getattr(self, 'minibatch', None) is None:
+            from sakkara_b200.model.sym import MinibatchIndex
+            self.minibatch = MinibatchIndex(len(self), batch_size)
+        return self.minibatch
 
     def clear_minibatch(self) -> None:
         self.minibatch = None

@@ -22,7 +22,8 @@ from sakkara_b200.plan.model_plan import ModelPlan
 
 class ValueGradFunction:
     def __init__(self, plan: ModelPlan, dtype: str = 'float64', max_batch: int = 1, device: Optional[int] = None,
-                 rows=None, n_rows_total: Optional[int] = None, narrow_y: bool = True):
+                 rows=None, n_rows_total: Optional[int] = None, narrow_y: bool = True, include_priors: bool = True):
+        self._include_priors = include_priors
         self.model_plan = plan
         self.dtype = np.dtype(dtype)
         self.max_batch = int(max_batch)
@@ -58,7 +59,8 @@ class ValueGradFunction:
     def kernel_plan(self) -> KernelPlan:
         if self._kernel_plan is None:
             self._kernel_plan = make_kernel_plan(self.model_plan, dtype=self.dtype, rows=self._rows,
-                                                 n_rows_total=self._n_rows_total, narrow_y=self._narrow_y)
+                                                 n_rows_total=self._n_rows_total, narrow_y=self._narrow_y,
+                                                 include_priors=self._include_priors)
         return self._kernel_plan
 
     @property
@@ -85,3 +87,65 @@ class ValueGradFunction:
         state['_skk'] = None
         state['_pid'] = None
         return state
+
+
+class MinibatchValueGrad:
+    """
+    Value and gradient of a model with a ``MinibatchLikelihood`` (reference
+    ``composable/hierarchical/likelihood.py:65-89``): every call draws ``plan.minibatch`` rows uniformly with
+    replacement (``pymc.data.minibatch_index`` semantics, ``sakkara/relation/group.py:59``), evaluates the
+    likelihood of those rows with the fused kernels and scales it by ``n_rows / minibatch`` (PyMC's ``total_size``);
+    the prior terms are evaluated once per call by a plan without rows.  The estimate is unbiased for the full
+    logp and gradient, which is what stochastic ADVI consumes.
+
+    The rows of a call form a new (tiny) kernel plan -- sorted, uploaded, evaluated, dropped -- so a call costs a
+    plan creation (about a millisecond), not a pass over the data set; nothing of the full data is touched.
+
+    :param seed: seed of the row draws (``numpy.random.default_rng``); ``last_rows`` holds the rows of the last call.
+    """
+
+    def __init__(self, plan: ModelPlan, dtype: str = 'float64', device: Optional[int] = None, seed=None):
+        if plan.minibatch is None:
+            raise ValueError('the model has no MinibatchLikelihood')
+        self.model_plan = plan
+        self.dtype = np.dtype(dtype)
+        self.device = device
+        self.batch_size = int(plan.minibatch)
+        self.scale = plan.n_rows / self.batch_size
+        self.rng = np.random.default_rng(seed)
+        self.last_rows: Optional[np.ndarray] = None
+        self._priors = ValueGradFunction(plan.take_rows([]), dtype=dtype, device=device)
+
+    @property
+    def size(self) -> int:
+        return self.model_plan.n_params
+
+    def set_extra_values(self, extra_vars) -> None:
+        pass
+
+    def draw_rows(self) -> np.ndarray:
+        return np.sort(self.rng.integers(0, self.model_plan.n_rows, size=self.batch_size))
+
+    def __call__(self, theta, grad_out=None, extra_vars=None, rows=None):
+        theta = np.asarray(theta, dtype=self.dtype)
+        if theta.ndim != 1:
+            raise ValueError('a mini-batched model evaluates one theta per call')
+        rows = self.draw_rows() if rows is None else np.asarray(rows, dtype=np.int64)
+        self.last_rows = rows
+        batch = ValueGradFunction(self.model_plan, dtype=self.dtype, device=self.device, rows=rows,
+                                  n_rows_total=len(rows), include_priors=False)
+        try:
+            lik_logp, lik_grad = batch(theta)
+        finally:
+            batch.close()
+        prior_logp, prior_grad = self._priors(theta)
+        scale = self.dtype.type(self.model_plan.n_rows / len(rows))
+        logp = self.dtype.type(prior_logp + scale * lik_logp)
+        grad = (prior_grad + scale * lik_grad).astype(self.dtype)
+        if grad_out is not None:
+            grad_out[...] = grad
+            return logp, grad_out
+        return logp, grad
+
+    def close(self) -> None:
+        self._priors.close()

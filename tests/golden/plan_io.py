@@ -13,6 +13,10 @@ def plan_to_arrays(plan) -> dict:
             if prm.is_const:
                 out[f'b{i}_{key}_const'] = np.asarray(prm.const, dtype=np.float64)
                 params[key] = 'const'
+            elif prm.is_mixed:
+                out[f'b{i}_{key}_const'] = np.asarray(prm.const, dtype=np.float64)
+                out[f'b{i}_{key}_index'] = np.asarray(prm.index, dtype=np.int64)
+                params[key] = 'member-wise'
             else:
                 out[f'b{i}_{key}_index'] = np.asarray(prm.index, dtype=np.int64)
                 params[key] = int(prm.block)

@@ -145,6 +145,46 @@ def positive_mu_likelihood(df):
     return make
 
 
+# ---------------------------------------------------------------------------------------------
+# the prior families with constant parameters (HalfCauchy, Gamma, InverseGamma, Cauchy, Laplace, LogNormal,
+# HalfStudentT) as hyper-priors of a random-slope / random-intercept regression
+# ---------------------------------------------------------------------------------------------
+def wide_priors_likelihood(df):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        k = DC(pm.Normal, name='k', group='group', mu=DC(pm.Cauchy, name='k_loc', alpha=0.1, beta=2.0),
+               sigma=DC(pm.HalfCauchy, name='k_scale', beta=1.5))
+        c = DC(pm.Normal, name='c', group='group', mu=DC(pm.LogNormal, name='c_level', mu=-0.5, sigma=0.8),
+               sigma=DC(pm.Gamma, name='c_scale', alpha=2.5, beta=2.0))
+        icpt = DC(pm.Normal, name='icpt', mu=DC(pm.Laplace, name='icpt_loc', mu=0.2, b=1.3),
+                  sigma=DC(pm.InverseGamma, name='icpt_scale', alpha=3.0, beta=2.0))
+        return api.Likelihood(pm.Normal, mu=k * data['x'] + c + icpt,
+                              sigma=DC(pm.HalfStudentT, name='noise', nu=4.0, sigma=1.2), observed=data['y'])
+    return make
+
+
+# ---------------------------------------------------------------------------------------------
+# GroupComponent (reference composable/group.py, tests/components/test_group_component.py): a coefficient and a
+# prior scale given member by member -- different parameter blocks, a scalar variable and a constant
+# ---------------------------------------------------------------------------------------------
+def member_wise_likelihood(df):
+    def make(api, pm, pt):
+        DC, GC = api.DistributionComponent, api.GroupComponent
+        data = api.data_components(df[['x', 'y']])
+        slope = GC('sensor', 'slope', {
+            's': DC(pm.Normal, name='slope_s', group='time', sigma=2.0),
+            't': DC(pm.Normal, name='slope_t', group='time', mu=DC(pm.Normal, name='slope_t_level')),
+            'u': DC(pm.Normal, name='slope_u'),
+            'v': 0.75})
+        spread = GC('sensor', 'spread', {'s': 0.5, 't': DC(pm.HalfNormal, name='spread_t', sigma=1.0),
+                                         'u': DC(pm.Exponential, name='spread_u', lam=2.0), 'v': 1.5})
+        level = DC(pm.Normal, name='level', group='sensor', mu=0.3, sigma=spread)
+        return api.Likelihood(pm.Normal, mu=slope * data['x'] + level, sigma=DC(pm.HalfNormal, name='noise', sigma=1.0),
+                              observed=data['y'])
+    return make
+
+
 def zoo():
     out = {}
     df = readme_df()
@@ -161,4 +201,8 @@ def zoo():
     out['tuple_group'] = (df, tuple_group_likelihood(df))
     df = shuffled_linreg_df(seed=5)
     out['positive_mu'] = (df, positive_mu_likelihood(df))
+    df = shuffled_linreg_df(seed=6)
+    out['wide_priors'] = (df, wide_priors_likelihood(df))
+    df = tuple_group_df()
+    out['member_wise'] = (df, member_wise_likelihood(df))
     return out

@@ -113,10 +113,6 @@ def test_unsupported_structures_raise(df):
         class StudentT:
             pass
         build(df, Likelihood(pm.Normal, mu=DC(StudentT, name='t'), sigma=1.0, observed=data['y']))
-    with pytest.raises(NotImplementedError):
-        api.GroupComponent('g1')
-    with pytest.raises(NotImplementedError):
-        api.MinibatchLikelihood(pm.Normal, data['y'], 4)
 
 
 def test_pymc_generators_are_accepted_by_name(df):
@@ -141,3 +137,100 @@ def test_poisson_needs_exp_link(df):
         c.clear()
     with pytest.raises(UnsupportedModelError):
         build(frame, Likelihood(pm.Poisson, mu=k * data['x'], observed=data['y']))
+
+
+# ---------------------------------------------------------------------------------------------
+# GroupComponent: the cases of /root/reference/tests/components/test_group_component.py.  The reference draws
+# from degenerate Uniform variables to read the member-wise values; here the members are constants (or
+# Normal variables evaluated at a theta that numbers them) and the recorded graph is evaluated.
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture
+def simple_df():
+    # /root/reference/tests/fixtures/simple_df.py:6-16
+    return pd.DataFrame({
+        'global': 'global',
+        'building': np.repeat(list('ab'), 10),
+        'sensor': np.repeat(list('stuv'), 5),
+        'time': np.tile(pd.date_range('2018-01-01 00:00:00', tz='utc', periods=5, freq='h'), 4),
+        'time_2': pd.date_range('2020-01-01 00:00:00', tz='utc', periods=20, freq='h'),
+        'obs': np.arange(20)})
+
+
+def _values(component, model, theta=None):
+    """The component's variable evaluated at theta (free variables in creation order)."""
+    from oracle.autograd_check import _evaluate
+    import torch
+    env, offset = {}, 0
+    for rv in model.recorded.free_RVs:
+        env[id(rv)] = torch.as_tensor(theta[offset:offset + rv.size], dtype=torch.float64).reshape(rv.shape)
+        offset += rv.size
+    return np.asarray(_evaluate(component.variable, env))
+
+
+def test_group_component_fixed_values(simple_df):
+    gc = api.GroupComponent('sensor', 'gc', {k: i for i, k in enumerate('stuv')})
+    x = DC(pm.Normal, name='x', mu=gc, sigma=gc + 1.0, group='sensor')
+    model = build(simple_df, x, backend='b200')
+    assert [str(g) for g in gc.representation.get_groups()] == ['sensor']
+    assert gc.variable.shape == (4,)
+    assert _values(gc, model, np.zeros(4)).tolist() == [0, 1, 2, 3]
+    assert not model.is_lowered                                    # no likelihood: the recorded graph only
+    with pytest.raises(UnsupportedModelError):
+        model.plan
+
+
+def test_group_component_unrelated_groups(simple_df):
+    members = {k: DC(pm.Normal, name=f'm{k}', group='time') for k in 'stuv'}
+    gc = api.GroupComponent('sensor', 'gc', members)
+    x = gc + DC(pm.Normal, 'x', group='building')
+    model = build(simple_df, x, backend='b200')
+    assert [str(g) for g in gc.representation.get_groups()] == ['sensor', 'time']
+    assert gc.variable.shape == (4, 5)
+    theta = np.concatenate([np.full(5, float(i)) for i in range(4)] + [np.zeros(2)])
+    got = _values(gc, model, theta)
+    assert all(got[i, j] == i for i in range(4) for j in range(5))
+
+
+def test_group_component_mixed_groups(simple_df):
+    gc = api.GroupComponent('sensor', 'gc', {k: DC(pm.Normal, name=f'm{k}', group='time') for k in 'st'})
+    gc.add('u', DC(pm.Normal, name='mu', group='global'))
+    gc.add('v', 3)
+    model = build(simple_df, gc, backend='b200')
+    assert [str(g) for g in gc.representation.get_groups()] == ['sensor', 'time']
+    assert gc.variable.shape == (4, 5)
+    theta = np.concatenate([np.zeros(5), np.ones(5), [2.0]])
+    got = _values(gc, model, theta)
+    assert all(got[i, j] == i for i in range(4) for j in range(5))
+    assert gc['u'].get_name() == 'mu' and isinstance(gc['v'], DataComponent)
+
+
+def test_group_component_parent_child(simple_df):
+    with pytest.raises(ValueError):
+        gc = api.GroupComponent('building', 'gc', {k: DC(pm.Normal, name=f'c{k}', group='sensor') for k in 'ab'})
+        build(simple_df, gc, backend='b200')
+    c = DC(pm.Normal, name='c', group='building')
+    gc = api.GroupComponent('sensor', 'gc', {k: c for k in 'stuv'})
+    model = build(simple_df, gc, backend='b200')
+    assert _values(gc, model, np.array([0.0, 1.0])).tolist() == [0, 0, 1, 1]
+
+
+def test_group_component_needs_every_member(simple_df):
+    with pytest.raises(ValueError):
+        gc = api.GroupComponent('sensor', 'gc', {k: DC(pm.Normal, name=f'm{k}', group='time') for k in 'st'})
+        build(simple_df, gc, backend='b200')
+
+
+def test_group_component_lowers_to_one_term(simple_df):
+    # different blocks, a scalar variable and a constant in different rows: one gather over theta + an offset
+    frame = simple_df.assign(x=np.linspace(-1, 1, 20), y=np.cos(np.arange(20.0)))
+    data = data_components(frame[['x', 'y']])
+    gc = api.GroupComponent('sensor', 'gc', {'s': DC(pm.Normal, name='ms', group='time'),
+                                            't': DC(pm.Normal, name='mt', group='time'),
+                                            'u': DC(pm.Normal, name='mu'), 'v': 3.0})
+    plan = build(frame, Likelihood(pm.Normal, mu=gc * data['x'], sigma=1.0, observed=data['y']), backend='b200').plan
+    assert len(plan.terms) == 1 and plan.terms[0].block == -1
+    t = plan.terms[0]
+    assert t.index[:5].tolist() == [0, 1, 2, 3, 4] and t.index[5:10].tolist() == [5, 6, 7, 8, 9]
+    assert (t.index[10:15] == 10).all()
+    assert np.array_equal(t.x[:15], frame['x'].values[:15]) and (t.x[15:] == 0).all()
+    assert np.allclose(plan.likelihood.offset[15:], 3.0 * frame['x'].values[15:]) and (plan.likelihood.offset[:15] == 0).all()
