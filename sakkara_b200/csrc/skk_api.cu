@@ -326,8 +326,8 @@ static int configure_launch(skk_plan *pl, int bt, LaunchCfg *cfg) {
 
 // Static schedule of the row kernel: which tiles every warp of the grid processes, and in which order.  Tiles are
 // handed out in index order to the warp with the least work so far -- measured per tile class (tools/trace_rows.py:
-// a tile with two groups costs ~3x a common one on models with a secondary level -- two dependent loads of
-// the split row and the second group's value, cold after an L2 sweep --, the rolled generic path
+// a tile with two groups costs ~3x a common one on models with a secondary level (two ordered table updates
+// per row; prefetching its split row and second group's slots a tile ahead changed nothing),, the rolled generic path
 // more), and the warps that carry prior work in the prologue start with that much on their account.  A fixed
 // list per warp keeps every sum of the evaluation in a fixed order; the balance removes the tail in which a few
 // warps with several expensive tiles kept their SMs busy while all others had finished.

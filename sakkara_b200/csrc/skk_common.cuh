@@ -237,9 +237,6 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// start fetching a line that a later load of this SM will want (no register, no dependency)
-__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
-
 // ---------------------------------------------------------------------------------------------
 // warp primitives (all reductions use a fixed tree => bit-reproducible)
 // ---------------------------------------------------------------------------------------------

@@ -1051,16 +1051,6 @@ struct RowKernel {
                 if (t2 >= 0) sp2 = p.tile_split[t2];
             }
             const int t4 = my_tiles[pos + 4];
-            if constexpr (NP > 0 && NS > 0) {
-                // the next tile holds two groups: its split row and the slots of its second group are fetched now,
-                // so that the two dependent loads in front of that tile's rows find them on chip
-                if (t1 >= 0 && k1.y == k1.x + 1) {
-                    prefetch_l1(p.tile_split + t1);
-#pragma unroll
-                    for (int t = 0; t < NP; ++t) prefetch_l1(p.ti_p[t] + k1.y);
-                }
-            }
-
             mbar_wait(bars + s, parity);
 
             Tile tl{stage0 + (int64_t)s * sl.bytes, sl, tile, k0.x, k0.y};

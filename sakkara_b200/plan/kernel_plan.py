@@ -204,10 +204,11 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     column_of_term: Dict[int, int] = {}
     elem_of_term: Dict[int, np.ndarray] = {}    # block element per code, per term
     seen_arrays: Dict[int, int] = {}
+    plan_terms = plan.terms if n else []     # a plan without rows (the priors alone) has no linear predictor
     positive = np.zeros(plan.n_params, dtype=bool)
     for b in plan.blocks:
         positive[b.offset:b.offset + b.size] = b.transform != 'identity'
-    for number, term in enumerate(plan.terms):
+    for number, term in enumerate(plan_terms):
         base = plan.term_base(term)
         index = take(term.index)
         if term.block >= 0:
@@ -333,7 +334,7 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     # ---- terms --------------------------------------------------------------------------------------------------
     terms: List[KernelTerm] = []
     counts = {LEVEL_GLOBAL: 0, LEVEL_PRIMARY: 0, LEVEL_SECONDARY: 0}
-    for number, term in enumerate(plan.terms):
+    for number, term in enumerate(plan_terms):
         xc = xcol_of(term.x)
         if number in global_terms:
             level = LEVEL_GLOBAL

@@ -330,6 +330,7 @@ def lower_model(model: sym.Model) -> ModelPlan:
     obs_params, masked, masked_logp = _masked_likelihood(obs, y)
 
     spec = LikelihoodSpec(family=obs.family, name=obs.name, y=y)
+    row_sigma = None
     if obs.family == 'Normal':
         eta_node = obs_params['mu']
         sigma = _lower(obs_params['sigma'])
@@ -337,10 +338,16 @@ def lower_model(model: sym.Model) -> ModelPlan:
             value = np.asarray(sigma.const_value(), dtype=np.float64)
             if masked is not None and value.size == n_rows:
                 value = value.reshape(-1)[~masked]
-            value = np.unique(value)
-            if value.size != 1:
-                raise UnsupportedModelError('Row-dependent constant sigma is not supported')
-            spec.sigma_const = float(value[0])
+            if np.unique(value).size != 1:
+                # known measurement errors, one per row (also: a GroupComponent of constants): the rows are
+                # standardised -- y, the offset and every data column divided by sigma_i -- which leaves a unit
+                # sigma, and sum(-log sigma_i) joins the plan's constant (applied below, once the terms exist)
+                if (value <= 0).any():
+                    raise ValueError('Normal sigma must be positive')
+                row_sigma = np.ascontiguousarray(np.broadcast_to(sigma.const_value(), obs_shape), dtype=np.float64).reshape(-1)
+                spec.sigma_const = 1.0
+            else:
+                spec.sigma_const = float(value.reshape(-1)[0])
         else:
             m = sigma.monomials
             if len(m) != 1 or not np.all(np.asarray(m[0].coef) == 1.0):
@@ -411,6 +418,13 @@ def lower_model(model: sym.Model) -> ModelPlan:
         plan.minibatch = int(_minibatches_seen[0].batch_size)
     elif _minibatches_seen:
         raise UnsupportedModelError('Mini-batched components outside a MinibatchLikelihood')
+    if row_sigma is not None:
+        weight = 1.0 / row_sigma
+        spec.y = spec.y * weight
+        spec.offset = None if spec.offset is None else spec.offset * weight
+        for t in terms:
+            t.x = weight.copy() if t.x is None else t.x * weight
+        plan.logp_const -= float(np.sum(np.log(row_sigma if masked is None else row_sigma[~masked]), dtype=np.float64))
     if masked is not None:
         keep = ~masked
         spec.y = np.ascontiguousarray(spec.y[keep])
@@ -421,7 +435,7 @@ def lower_model(model: sym.Model) -> ModelPlan:
             if t.x is not None:
                 t.x = np.ascontiguousarray(t.x[keep])
         plan.n_rows = int(keep.sum())
-        plan.logp_const = masked_logp
+        plan.logp_const += masked_logp
         plan.n_masked_rows = int(masked.sum())
     return plan
 

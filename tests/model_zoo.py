@@ -185,6 +185,28 @@ def member_wise_likelihood(df):
     return make
 
 
+# ---------------------------------------------------------------------------------------------
+# known measurement errors: sigma of the Normal likelihood is a data column (one value per row)
+# ---------------------------------------------------------------------------------------------
+def row_sigma_df(n: int = 150, groups: int = 5, seed: int = 8) -> pd.DataFrame:
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, groups, n)
+    x = rng.normal(size=n)
+    s = rng.uniform(0.2, 1.5, n)
+    return pd.DataFrame({'x': x, 's': s, 'group': [f'g{v}' for v in g],
+                         'y': x * rng.normal(0.7, 0.4, groups)[g] + 0.3 + s * rng.normal(size=n)})
+
+
+def row_sigma_likelihood(df):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y', 's']])
+        k = DC(pm.Normal, name='k', group='group', mu=DC(pm.Normal, name='k_mean'), sigma=DC(pm.HalfNormal, name='k_sd'))
+        return api.Likelihood(pm.Normal, mu=k * data['x'] + DC(pm.Normal, name='icpt'), sigma=data['s'],
+                              observed=data['y'])
+    return make
+
+
 def zoo():
     out = {}
     df = readme_df()
@@ -205,4 +227,6 @@ def zoo():
     out['wide_priors'] = (df, wide_priors_likelihood(df))
     df = tuple_group_df()
     out['member_wise'] = (df, member_wise_likelihood(df))
+    df = row_sigma_df()
+    out['row_sigma'] = (df, row_sigma_likelihood(df))
     return out
