@@ -160,6 +160,10 @@ struct skk_plan {
 
     void *x[kMaxXCols] = {nullptr};
     void *y = nullptr, *off = nullptr, *codes = nullptr;
+    // the same columns in row order for the chain kernel (the row kernel's copies are stored tile-transposed,
+    // skk_row_kernel.cuh: kStageTransposed); null when the plan has no chain path
+    void *x_rows[kMaxXCols] = {nullptr};
+    void *y_rows = nullptr, *off_rows = nullptr;
     int4 *tile_meta = nullptr;
     int32_t *tile_split = nullptr;
     int64_t *seg_off = nullptr;
@@ -268,6 +272,32 @@ static int upload_bytes(skk_plan *pl, void **out, const void *host, size_t bytes
     unsigned char *p = nullptr;
     int rc = dev_upload<unsigned char>(pl, &p, static_cast<const unsigned char *>(host), bytes, padded_bytes);
     *out = p;
+    return rc;
+}
+
+// A column of the row kernel: tile by tile (WT = 32 * R rows, lane l owns rows l * R ... l * R + R - 1 of the tile) the
+// lane's row i is stored at position i * 32 + l, so that the 32 lanes read consecutive elements at every step
+// (skk_row_kernel.cuh: kStageTransposed).  Rows behind the last one are zero.
+template <typename E>
+static int upload_tiled(skk_plan *pl, void **out, const void *host, size_t n, size_t padded, int R) {
+    E *dev = nullptr;
+    if (!kStageTransposed) return upload_bytes(pl, out, host, n * sizeof(E), padded * sizeof(E));
+    const E *src = static_cast<const E *>(host);
+    const size_t WT = 32 * (size_t)R;
+    std::vector<E> tmp(padded, E(0));
+    const size_t full_tiles = n / WT;
+    for (size_t t = 0; t < full_tiles; ++t) {
+        const E *in = src + t * WT;
+        E *o = tmp.data() + t * WT;
+        for (int l = 0; l < 32; ++l)
+            for (int i = 0; i < R; ++i) o[(size_t)i * 32 + l] = in[(size_t)l * R + i];
+    }
+    for (size_t q = full_tiles * WT; q < n; ++q) {
+        const size_t w = q - full_tiles * WT, l = w / R, i = w % R;
+        tmp[full_tiles * WT + i * 32 + l] = src[q];
+    }
+    int rc = dev_upload<E>(pl, &dev, tmp.data(), padded);
+    *out = dev;
     return rc;
 }
 
@@ -380,21 +410,28 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     const size_t n = (size_t)d->n_rows;
 
     // ---- row columns, padded to whole tiles ------------------------------------------------------
+    // (a plan with a chain path keeps a second copy in row order for the chain kernel)
+    const bool row_copy = kStageTransposed && pl->ns == 0 && pl->max_batch >= kChainMinBatch && env_int("SKK_NO_CHAIN", 0) == 0;
+    const int R = kRowsPerLane;
     for (int c = 0; c < d->n_xcols; ++c) {
-        int rc = upload_bytes(pl, &pl->x[c], d->xcols[c], n * sizeof(T), padded * sizeof(T));
+        int rc = upload_tiled<T>(pl, &pl->x[c], d->xcols[c], n, padded, R);
         if (rc) return rc;
+        if (row_copy && (rc = upload_bytes(pl, &pl->x_rows[c], d->xcols[c], n * sizeof(T), padded * sizeof(T)))) return rc;
     }
     {
         const size_t ye = pl->y_u8 ? 1 : sizeof(T);
-        int rc = upload_bytes(pl, &pl->y, d->y, n * ye, padded * ye);
+        int rc = pl->y_u8 ? upload_tiled<uint8_t>(pl, &pl->y, d->y, n, padded, R) : upload_tiled<T>(pl, &pl->y, d->y, n, padded, R);
         if (rc) return rc;
+        if (row_copy && (rc = upload_bytes(pl, &pl->y_rows, d->y, n * ye, padded * ye))) return rc;
     }
     if (d->eta_offset) {
-        int rc = upload_bytes(pl, &pl->off, d->eta_offset, n * sizeof(T), padded * sizeof(T));
+        int rc = upload_tiled<T>(pl, &pl->off, d->eta_offset, n, padded, R);
         if (rc) return rc;
+        if (row_copy && (rc = upload_bytes(pl, &pl->off_rows, d->eta_offset, n * sizeof(T), padded * sizeof(T)))) return rc;
     }
     if (pl->ns > 0) {
-        int rc = upload_bytes(pl, &pl->codes, d->sec_codes, n * pl->sec_code_bytes, padded * pl->sec_code_bytes);
+        int rc = pl->sec_code_bytes == 2 ? upload_tiled<uint16_t>(pl, &pl->codes, d->sec_codes, n, padded, R)
+                                         : upload_tiled<int32_t>(pl, &pl->codes, d->sec_codes, n, padded, R);
         if (rc) return rc;
     }
 
@@ -1070,10 +1107,13 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
     if (chain) {
         // K2: lane = chain; one pass over the rows for the whole batch
         ChainParams<T> cp{};
-        for (int c = 0; c < pl->n_x; ++c) cp.x[c] = static_cast<const T *>(pl->x[c]);
-        cp.y = pl->y_u8 ? nullptr : static_cast<const T *>(pl->y);
-        cp.y8 = pl->y_u8 ? static_cast<const uint8_t *>(pl->y) : nullptr;
-        cp.eta_offset = static_cast<const T *>(pl->off);
+        // (the chain kernel reads the columns in row order)
+        const bool rows = pl->y_rows != nullptr;
+        for (int c = 0; c < pl->n_x; ++c) cp.x[c] = static_cast<const T *>(rows ? pl->x_rows[c] : pl->x[c]);
+        const void *yy = rows ? pl->y_rows : pl->y;
+        cp.y = pl->y_u8 ? nullptr : static_cast<const T *>(yy);
+        cp.y8 = pl->y_u8 ? static_cast<const uint8_t *>(yy) : nullptr;
+        cp.eta_offset = static_cast<const T *>(rows ? pl->off_rows : pl->off);
         cp.n_x = pl->n_x;
         cp.n_rows = pl->n_rows;
         cp.n_tiles = pl->chain_tiles;

@@ -73,6 +73,17 @@ struct PipeRows {
         kPipeRows == 0 ? 0 : ((int)sizeof(T) * BT <= 4 ? kPipeRows : ((int)sizeof(T) * BT <= 8 ? 2 : 1));
 };
 
+// Layout of a staged tile.  The lane owns R consecutive rows of the tile (li = lane * R ...), but a column stores the
+// tile row-step major: the lane's row i at position i * 32 + lane.  At every step the 32 lanes then read 32 consecutive
+// elements -- one shared-memory wavefront whatever the element size -- where lane-contiguous storage costs two to
+// three (strides of 17 bytes / 34 bytes fold several lanes onto one bank: 65 % excess wavefronts in the c4 profile,
+// profiles/r02).  The library permutes the columns accordingly when the plan is created (skk_api.cu: transpose_tiles).
+#ifdef SKK_NATURAL_STAGE
+constexpr bool kStageTransposed = false;
+#else
+constexpr bool kStageTransposed = true;
+#endif
+
 constexpr int kFoldTiles = 128;    // (power of two) tiles of a warp between two folds of the fp32 accumulator tables into fp64
 constexpr int kStagedGroups = 32;  // straddling tiles with up to this many segments are handled on chip
 
@@ -230,6 +241,9 @@ struct RowKernel {
                                                    const T *__restrict__ valS, T *__restrict__ gradS, uint32_t gradS_addr,
                                                    unsigned char *scratch, int lane) {
         const int li = lane * R;
+        // where the lane's row i sits in every staged column: at0 + i * kLaneStep (see kStageTransposed)
+        const int at0 = kStageTransposed ? lane : li;
+        constexpr int kLaneStep = kStageTransposed ? 32 : 1;
         const int64_t row0 = (int64_t)tl.tile * WT + li;
         const int64_t left = p.n_rows - row0;
         const int nvalid = FULL ? R : (left >= R ? R : (left > 0 ? (int)left : 0));
@@ -239,20 +253,20 @@ struct RowKernel {
 #pragma unroll
         for (int t = 0; t < NGa; ++t)
             pxg[t] = (t < NG && Spec::xg(p, t))
-                         ? reinterpret_cast<const T *>(tl.stage + p.xcol_g[t] * tl.sl.x_stride) + li : nullptr;
+                         ? reinterpret_cast<const T *>(tl.stage + p.xcol_g[t] * tl.sl.x_stride) + at0 : nullptr;
 #pragma unroll
         for (int t = 0; t < NPa; ++t)
             pxp[t] = (t < NP && Spec::xp(p, t))
-                         ? reinterpret_cast<const T *>(tl.stage + p.xcol_p[t] * tl.sl.x_stride) + li : nullptr;
+                         ? reinterpret_cast<const T *>(tl.stage + p.xcol_p[t] * tl.sl.x_stride) + at0 : nullptr;
 #pragma unroll
         for (int t = 0; t < NSa; ++t)
             pxs[t] = (t < NS && Spec::xs(p, t))
-                         ? reinterpret_cast<const T *>(tl.stage + p.xcol_s[t] * tl.sl.x_stride) + li : nullptr;
-        const T *sy = reinterpret_cast<const T *>(tl.stage + tl.sl.y_off) + li;
-        const uint8_t *sy8 = reinterpret_cast<const uint8_t *>(tl.stage + tl.sl.y_off) + li;
-        const T *soff = reinterpret_cast<const T *>(tl.stage + tl.sl.off_off) + li;
-        const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(tl.stage + tl.sl.code_off) + li;
-        const int32_t *sc32 = reinterpret_cast<const int32_t *>(tl.stage + tl.sl.code_off) + li;
+                         ? reinterpret_cast<const T *>(tl.stage + p.xcol_s[t] * tl.sl.x_stride) + at0 : nullptr;
+        const T *sy = reinterpret_cast<const T *>(tl.stage + tl.sl.y_off) + at0;
+        const uint8_t *sy8 = reinterpret_cast<const uint8_t *>(tl.stage + tl.sl.y_off) + at0;
+        const T *soff = reinterpret_cast<const T *>(tl.stage + tl.sl.off_off) + at0;
+        const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(tl.stage + tl.sl.code_off) + at0;
+        const int32_t *sc32 = reinterpret_cast<const int32_t *>(tl.stage + tl.sl.code_off) + at0;
         const bool y_u8 = Spec::y_u8(p);
         const bool has_off = Spec::has_off(p);
         const bool code16 = Spec::code16(p);
@@ -370,19 +384,19 @@ struct RowKernel {
             constexpr int K = PipeRows<T, BT>::value;
             int code[R];
 #pragma unroll
-            for (int i = 0; i < R; ++i) code[i] = code16 ? (int)sc16[i] : sc32[i];
+            for (int i = 0; i < R; ++i) code[i] = code16 ? (int)sc16[i * kLaneStep] : sc32[i * kLaneStep];
             struct Raw {
                 T y, off, xg[NGa], xp[NPa], xs[NSa], vs[NSa][BT], tab[NSa][BT];
             };
             auto load_raw = [&](int i, Raw &r) {
-                r.y = y_u8 ? (T)sy8[i] : sy[i];
-                r.off = has_off ? soff[i] : T(0);
+                r.y = y_u8 ? (T)sy8[i * kLaneStep] : sy[i * kLaneStep];
+                r.off = has_off ? soff[i * kLaneStep] : T(0);
 #pragma unroll
-                for (int t = 0; t < NG; ++t) r.xg[t] = Spec::xg(p, t) ? pxg[t][i] : T(1);
+                for (int t = 0; t < NG; ++t) r.xg[t] = Spec::xg(p, t) ? pxg[t][i * kLaneStep] : T(1);
 #pragma unroll
-                for (int t = 0; t < NP; ++t) r.xp[t] = Spec::xp(p, t) ? pxp[t][i] : T(1);
+                for (int t = 0; t < NP; ++t) r.xp[t] = Spec::xp(p, t) ? pxp[t][i * kLaneStep] : T(1);
 #pragma unroll
-                for (int t = 0; t < NS; ++t) r.xs[t] = Spec::xs(p, t) ? pxs[t][i] : T(1);
+                for (int t = 0; t < NS; ++t) r.xs[t] = Spec::xs(p, t) ? pxs[t][i * kLaneStep] : T(1);
 #pragma unroll
                 for (int t = 0; t < NS; ++t)
 #pragma unroll
@@ -501,7 +515,7 @@ struct RowKernel {
             }
 
             if constexpr (NS > 0) {
-                const int c = code16 ? (int)sc16[i] : sc32[i];
+                const int c = code16 ? (int)sc16[i * kLaneStep] : sc32[i * kLaneStep];
                 const bool change = valid && (c != scur);
                 if constexpr (FASTP && MID) {
                     // Two groups in the tile: inside either one the codes ascend, so among the runs that
@@ -577,15 +591,15 @@ struct RowKernel {
             }
 
             // data of the row
-            const T yv = y_u8 ? (T)sy8[i] : sy[i];
+            const T yv = y_u8 ? (T)sy8[i * kLaneStep] : sy[i * kLaneStep];
             T xg[NGa], xp[NPa], xs[NSa];
 #pragma unroll
-            for (int t = 0; t < NG; ++t) xg[t] = Spec::xg(p, t) ? pxg[t][i] : T(1);
+            for (int t = 0; t < NG; ++t) xg[t] = Spec::xg(p, t) ? pxg[t][i * kLaneStep] : T(1);
 #pragma unroll
-            for (int t = 0; t < NP; ++t) xp[t] = Spec::xp(p, t) ? pxp[t][i] : T(1);
+            for (int t = 0; t < NP; ++t) xp[t] = Spec::xp(p, t) ? pxp[t][i * kLaneStep] : T(1);
 #pragma unroll
-            for (int t = 0; t < NS; ++t) xs[t] = Spec::xs(p, t) ? pxs[t][i] : T(1);
-            const T off = has_off ? soff[i] : T(0);
+            for (int t = 0; t < NS; ++t) xs[t] = Spec::xs(p, t) ? pxs[t][i * kLaneStep] : T(1);
+            const T off = has_off ? soff[i * kLaneStep] : T(0);
 
 #pragma unroll
             for (int b = 0; b < BT; ++b) {

@@ -1,0 +1,30 @@
+#!/bin/bash
+# round 2, call K: tile-transposed staging (main) against lane-contiguous staging (variant `natural`) on the same box;
+# the two default-off experiments of round 1 (value gather per run; hoisted term sum of the chain kernel)
+mkdir -p gpurun_out
+TAG=${TAG:-r2k}
+B="--no-cpu-baseline --no-sub"
+V=$PWD/sakkara_b200/lib/variants
+summ() { python - "$1" "$2" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    c=d.get('check') or {}
+    w=d.get('warm_l2',{}).get('ms_per_step')
+    print(sys.argv[1], 'step_us=%.1f'%(1e3*d['ms_per_step']), 'kernel_us=%.1f'%(1e3*d['roofline']['kernel_ms']), 'e2e_us=%.1f'%(1e3*d['e2e']['ms_per_step']), 'warm_us=%s'%(('%.1f'%(1e3*w)) if w else '-'), 'launches/step=%.1f'%(d['gpu_launches']/d['steps']), 'frac=%.3f'%d['roofline']['frac'], 'check_ok=%s err_g=%.1e'%(c.get('ok'), c.get('err_grad', float('nan'))))
+except Exception as e:
+    print(sys.argv[1], 'FAILED', e)
+PY
+}
+run() { name=$1; shift; timeout 300 python bench.py "$@" $B --steps 30 --warmup 5 > gpurun_out/${TAG}_$name.json 2> gpurun_out/${TAG}_$name.err; summ $name gpurun_out/${TAG}_$name.json; }
+( time timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -12 ) 2>&1 | tee gpurun_out/${TAG}_pytest.log
+for c in "c4" "c4 --emulate-world 8" "c3" "c2"; do
+  n=$(echo $c | tr -d ' -' )
+  run ${n} --config $c
+  SKK_B200_LIB=$V/libskk_b200_natural.so run ${n}_natural --config $c
+done
+run c4_again --config c4
+SKK_B200_LIB=$V/libskk_b200_predval.so run c4_predval --config c4
+run c5 --config c5
+SKK_B200_LIB=$V/libskk_b200_chainhoist.so run c5_chainhoist --config c5
+timeout 300 python tools/trace_rows.py --config c4 --emulate-world 8 2>&1 | tee gpurun_out/${TAG}_trace_c4_w8.txt
