@@ -135,41 +135,10 @@ __global__ void __launch_bounds__(kChainWarps * 32) skk_chain_kernel(const __gri
                 for (int t = 0; t < NGa; ++t) accG[t] = T(0);
 #pragma unroll
                 for (int t = 0; t < NPa; ++t) accP[t] = T(0);
-#ifdef SKK_CHAIN_HOIST
-                // experiment (off by default, not yet timed): the terms without a data column are the same for
-                // every row of the run -- add them once here instead of `0 + value` in every row
-                T base = T(0);
-                bool have_base = false;
-#pragma unroll
-                for (int t = 0; t < NG; ++t)
-                    if (!pxg[t]) {
-                        base = have_base ? base + vg[t] : vg[t];
-                        have_base = true;
-                    }
-#pragma unroll
-                for (int t = 0; t < NP; ++t)
-                    if (!pxp[t]) {
-                        base = have_base ? base + vp[t] : vp[t];
-                        have_base = true;
-                    }
-#endif
 #pragma unroll 4
                 for (; i < run_end; ++i) {
                     const T yv = y_u8 ? (T)sy8[i] : sy[i];
                     T xg[NGa], xp[NPa];
-#ifdef SKK_CHAIN_HOIST
-                    T eta = has_off ? soff[i] + base : base;
-#pragma unroll
-                    for (int t = 0; t < NG; ++t) {
-                        xg[t] = pxg[t] ? pxg[t][i] : T(1);
-                        if (pxg[t]) eta += vg[t] * xg[t];
-                    }
-#pragma unroll
-                    for (int t = 0; t < NP; ++t) {
-                        xp[t] = pxp[t] ? pxp[t][i] : T(1);
-                        if (pxp[t]) eta += vp[t] * xp[t];
-                    }
-#else
                     T eta = has_off ? soff[i] : T(0);
 #pragma unroll
                     for (int t = 0; t < NG; ++t) {
@@ -181,7 +150,6 @@ __global__ void __launch_bounds__(kChainWarps * 32) skk_chain_kernel(const __gri
                         xp[t] = pxp[t] ? pxp[t][i] : T(1);
                         eta += vp[t] * xp[t];
                     }
-#endif
                     T lp, d;
                     family_row<T, FAM>(yv, eta, lp, d);
                     accL += lp;

@@ -401,15 +401,7 @@ struct RowKernel {
                 for (int t = 0; t < NS; ++t)
 #pragma unroll
                     for (int b = 0; b < BT; ++b) {
-#ifdef SKK_PRED_VALUE_LOAD
-                        // experiment (off by default, not yet timed): gather the value once per run -- only
-                        // the lanes whose code changes at this row take part, the others keep their value
-                        r.vs[t][b] = i > 0 ? lds_free_if(code[i] != code[i - 1],
-                                                         smem_addr(valS) + (uint32_t)s_at(p, t, code[i], b) * (uint32_t)sizeof(T), T(0))
-                                           : valS[s_at(p, t, code[i], b)];
-#else
                         r.vs[t][b] = valS[s_at(p, t, code[i], b)];
-#endif
                         // (only the lanes whose run ends here take part in the gather: fewer bank conflicts)
                         r.tab[t][b] = i > 0 ? lds_free_if(code[i] != code[i - 1],
                                                           gradS_addr + (uint32_t)s_at(p, t, code[i - 1], b) * (uint32_t)sizeof(T), T(0))
@@ -449,16 +441,8 @@ struct RowKernel {
                             for (int t = 0; t < NGa; ++t) vgb[t] = vg[t][b];
 #pragma unroll
                             for (int t = 0; t < NPa; ++t) vpb[t] = vp[t][b];
-#ifdef SKK_PRED_VALUE_LOAD
-#pragma unroll
-                            for (int t = 0; t < NSa; ++t) {
-                                if (t < NS && (i == 0 || code[i] != code[i - 1])) vs[t][b] = r.vs[t][b];
-                                vsb[t] = vs[t][b];
-                            }
-#else
 #pragma unroll
                             for (int t = 0; t < NSa; ++t) vsb[t] = r.vs[t][b];
-#endif
                             const T eta = eta_of(p, r.off, vgb, r.xg, vpb, r.xp, vsb, r.xs);
                             T lp, d;
                             family_row<T, FAM>(r.y, eta, lp, d);
@@ -1015,9 +999,11 @@ struct RowKernel {
             for (int k = threadIdx.x; k < n_sec * warps; k += blockDim.x) gradS_all[k] = T(0);
             __syncthreads();
         }
+        stamp(8);
 
         // (after the barrier: the warps without prior work start on their tiles at once)
         if (p.prior_family != nullptr) priors(p, warp, lane);
+        stamp(9);
 
         double accG64[NG + 1][BT];
 #pragma unroll
@@ -1143,6 +1129,7 @@ struct RowKernel {
         }
         // ---- CTA epilogue: fixed-order reductions over lanes, then warps ---------------------------
         __syncthreads();  // all warps are done with their staging buffers; reuse the first one
+        stamp(10);
         double *red = reinterpret_cast<double *>(smem + cl.stage_off);  // [warps][(NG+1)*BT]
         constexpr int NV = (NG + 1) * BT;
 #pragma unroll
@@ -1158,6 +1145,7 @@ struct RowKernel {
             for (int w = 0; w < warps; ++w) s += red[w * NV + threadIdx.x];
             p.cta_glob[(int64_t)blockIdx.x * NV + threadIdx.x] = s;
         }
+        stamp(11);
         if constexpr (NS > 0) {
             const int n = NS * p.n_secondary * BT;
             for (int k = threadIdx.x; k < n; k += blockDim.x) {

@@ -72,9 +72,17 @@ def main():
           + ', '.join('%.1f' % (1e-3 * (r[:, 4].max() - r[:, 0].min())) for r in runs))
     print('entry after first entry :', q(t0 - base))
     print('prologue (entry->ready)  :', q(t1 - t0))
+    if tr.shape[1] >= 12 and tr[:, 8].max() > 0:
+        print('  tables filled (entry->) :', q(tr[:, 8] - t0))
+        print('  priors (->done)         :', q(tr[:, 9] - tr[:, 8]))
+        print('  rest (->ready)          :', q(t1 - tr[:, 9]))
     print('wait for the first tile  :', q(t2 - t1))
     print('tile loop                :', q(t3 - t2))
     print('epilogue (loop end->exit):', q(t4 - t3))
+    if tr.shape[1] >= 12 and tr[:, 10].max() > 0:
+        print('  wait for the CTA (loop end->) :', q(tr[:, 10] - t3))
+        print('  global partials (->stored)    :', q(tr[:, 11] - tr[:, 10]))
+        print('  secondary partials (->exit)   :', q(t4 - tr[:, 11]))
     print('loop end after first entry:', q(t3 - base))
     # least-squares cost per tile class
     A = per_warp[act].astype(np.float64)
