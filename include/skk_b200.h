@@ -48,6 +48,9 @@ extern "C" {
 #define SKK_LIK_NORMAL 0         /* pm.Normal(mu=eta, sigma=...)          */
 #define SKK_LIK_BERNOULLI_LOGIT 1 /* pm.Bernoulli(logit_p=eta)             */
 #define SKK_LIK_POISSON_LOG 2    /* pm.Poisson(mu=exp(eta))               */
+#define SKK_LIK_NEGBINOMIAL_LOG 3 /* pm.NegativeBinomial(mu=exp(eta), alpha=const): alpha travels in
+                                    skk_plan_desc.sigma_const; lgamma(y+alpha) - lgamma(alpha) - lgamma(y+1)
+                                    + alpha log(alpha) per row belongs into logp_const */
 
 /* prior families of parameter blocks: the generator given to DistributionComponent
  * (/root/reference/sakkara/model/composable/hierarchical/distribution.py:41-51) */
@@ -144,7 +147,7 @@ typedef struct {
     int32_t n_blocks;
     const skk_term_desc *terms;
     const skk_block_desc *blocks;
-    double sigma_const;         /* Normal likelihood: fixed sigma ...            */
+    double sigma_const;         /* Normal likelihood: fixed sigma ... (NegativeBinomial: alpha) */
     int64_t sigma_theta_index;  /* ... or index of log(sigma) in theta; -1: const */
     double logp_const;          /* theta-independent part of logp of this shard
                                    (Poisson: -sum lgamma(y+1); the rows masked for NaN

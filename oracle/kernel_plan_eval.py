@@ -38,10 +38,15 @@ def likelihood_from_kernel_plan(kp, theta):
     elif kp.family == 1:
         logp = np.sum(y * eta - softplus(eta))
         d = y - sigmoid(eta)
-    else:
+    elif kp.family == 2:
         mu = np.exp(eta)
         logp = np.sum(y * eta - mu)
         d = y - mu
+    else:
+        alpha = kp.sigma_const                                   # NegativeBinomial: alpha in the sigma field
+        log_sum = np.logaddexp(eta, np.log(alpha))
+        logp = np.sum(y * eta - (y + alpha) * log_sum)
+        d = y - (y + alpha) * np.exp(eta - log_sum)
     # -sum(lgamma(y + 1)) of a Poisson model; rows masked out for NaN observations (not the normalisers of the
     # prior families that the plan's constant also carries: this function is the likelihood alone)
     logp += kp.logp_const - kp.prior_logp_const

@@ -14,6 +14,7 @@
  *   Normal    : logp_i = -0.5 r_i^2 - log(sqrt(2 pi)) - log(sigma), r_i = (y_i - eta_i)/sigma, d_i = r_i/sigma
  *   Bernoulli : logp_i = y_i eta_i - softplus(eta_i),                 d_i = y_i - sigmoid(eta_i)
  *   Poisson   : logp_i = y_i eta_i - exp(eta_i) - lgamma(y_i + 1),    d_i = y_i - exp(eta_i)
+ *   NegBinomial: logp_i = y_i eta_i - (y_i + alpha) log(alpha + exp(eta_i)) + const_i,  d_i = y_i - (y_i + alpha) mu_i / (alpha + mu_i)
  *               (one observed distribution call, /root/reference/sakkara/model/composable/hierarchical/likelihood.py:58-62)
  *   dlogp[base_t + index_t[i]] += d_i * x_t[i]                        (scatter-add, AdvancedIncSubtensor1)
  *
@@ -34,7 +35,7 @@
 #define LOG_SQRT_2PI 0.91893853320467274178
 
 typedef struct {
-    int32_t family;      /* 0 Normal, 1 Bernoulli-logit, 2 Poisson-log */
+    int32_t family;      /* 0 Normal, 1 Bernoulli-logit, 2 Poisson-log, 3 NegativeBinomial-log (alpha in sigma) */
     int32_t n_terms;
     int64_t n_rows;
     int64_t n_params;
@@ -47,7 +48,7 @@ typedef struct {
     int64_t sigma_theta_index;         /* -1: constant */
 } glm_desc;
 
-#define DEFINE_LIKELIHOOD(NAME, REAL, EXP, LOG1P, FABS)                                                        \
+#define DEFINE_LIKELIHOOD(NAME, REAL, EXP, LOG1P, FABS, LOGF)                                                  \
     double NAME(const glm_desc *d, const REAL *theta, double *grad, int threads) {                            \
         const REAL *y = (const REAL *)d->y;                                                                    \
         const REAL *off = (const REAL *)d->offset;                                                             \
@@ -77,10 +78,15 @@ typedef struct {
                     const REAL inv = (REAL)1 / ((REAL)1 + e);                                                  \
                     l = y[i] * eta - ((eta > 0 ? eta : (REAL)0) + LOG1P(e));                                   \
                     dd = y[i] - (eta >= 0 ? inv : e * inv);                                                    \
-                } else {                                                                                       \
+                } else if (d->family == 2) {                                                                   \
                     const REAL mu = EXP(eta);                                                                  \
                     l = y[i] * eta - mu;                                                                       \
                     dd = y[i] - mu;                                                                            \
+                } else { /* NegativeBinomial(mu = exp(eta), alpha = d->sigma), constants added by the caller */ \
+                    const REAL alpha = sigma, mu = EXP(eta);                                                   \
+                    const REAL lam = eta > (REAL)30 ? eta + LOG1P(alpha * EXP(-eta)) : LOG1P(mu / alpha) + LOGF(alpha); \
+                    l = y[i] * eta - (y[i] + alpha) * lam;                                                     \
+                    dd = y[i] - (y[i] + alpha) * (eta > (REAL)30 ? (REAL)1 / ((REAL)1 + alpha * EXP(-eta)) : mu / (alpha + mu)); \
                 }                                                                                              \
                 lp += (double)l;                                                                               \
                 for (int t = 0; t < T; ++t)                                                                    \
@@ -108,8 +114,8 @@ typedef struct {
 static int omp_get_thread_num(void) { return 0; }
 #endif
 
-DEFINE_LIKELIHOOD(skk_oracle_likelihood_f64, double, exp, log1p, fabs)
-DEFINE_LIKELIHOOD(skk_oracle_likelihood_f32, float, expf, log1pf, fabsf)
+DEFINE_LIKELIHOOD(skk_oracle_likelihood_f64, double, exp, log1p, fabs, log)
+DEFINE_LIKELIHOOD(skk_oracle_likelihood_f32, float, expf, log1pf, fabsf, logf)
 
 int skk_oracle_max_threads(void) {
 #ifdef _OPENMP

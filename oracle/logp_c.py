@@ -58,7 +58,7 @@ class COracle:
         lik = plan.likelihood
         self.keep = []
         d = GlmDesc()
-        d.family = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2}[lik.family]
+        d.family = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3}[lik.family]
         d.n_terms = len(plan.terms)
         d.n_rows = plan.n_rows
         d.n_params = plan.n_params
@@ -83,6 +83,10 @@ class COracle:
             d.sigma_theta_index = plan.blocks[lik.sigma_block].offset + lik.sigma_index
         self.desc = d
         self.const = -float(np.sum(gammaln(lik.y + 1.0))) if lik.family == 'Poisson' else 0.0
+        if lik.family == 'NegativeBinomial':
+            a = float(lik.sigma_const)
+            d.sigma = a
+            self.const = float(np.sum(gammaln(lik.y + a) - gammaln(lik.y + 1.0))) + plan.n_rows * (a * np.log(a) - float(gammaln(a)))
         self.const += float(getattr(plan, 'logp_const', 0.0))   # rows masked out for NaN observations
         self.fn = self.lib.skk_oracle_likelihood_f64 if self.dtype == np.float64 else self.lib.skk_oracle_likelihood_f32
 

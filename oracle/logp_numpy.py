@@ -238,6 +238,14 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
         mu = np.exp(eta)
         terms = y * eta - mu - gammaln(lik.y + 1.0).astype(dtype)
         d_eta = y - mu
+    elif lik.family == 'NegativeBinomial':
+        # pymc NegativeBinomial(mu, alpha): binomln(y + alpha - 1, y) + y log(mu / (mu + alpha)) + alpha log(alpha / (mu + alpha))
+        alpha = T(lik.sigma_const)
+        mu = np.exp(eta)
+        log_sum = np.logaddexp(eta, np.log(alpha))                 # log(mu + alpha)
+        const = (gammaln(lik.y + float(alpha)) - gammaln(lik.y + 1.0) - gammaln(float(alpha))).astype(dtype)
+        terms = const + y * (eta - log_sum) + alpha * (np.log(alpha) - log_sum)
+        d_eta = y - (y + alpha) * mu / (mu + alpha)
     else:
         raise NotImplementedError(lik.family)
     logp += np.sum(terms, dtype=np.float64)

@@ -39,6 +39,10 @@ const void *row_kernel_f64_bernoulli_bt1(int, int, int, int);
 const void *row_kernel_f64_bernoulli_bt4(int, int, int, int);
 const void *row_kernel_f64_poisson_bt1(int, int, int, int);
 const void *row_kernel_f64_poisson_bt4(int, int, int, int);
+const void *row_kernel_f32_negbinomial_bt1(int, int, int, int);
+const void *row_kernel_f32_negbinomial_bt4(int, int, int, int);
+const void *row_kernel_f64_negbinomial_bt1(int, int, int, int);
+const void *row_kernel_f64_negbinomial_bt4(int, int, int, int);
 const void *chain_kernel_f32(int, int, int);
 const void *chain_kernel_f64(int, int, int);
 }  // namespace skk
@@ -199,6 +203,7 @@ struct skk_plan {
     double *chain_totals = nullptr, *chain_head = nullptr, *chain_tail = nullptr, *chain_glob = nullptr;
     ChainReduceParams chain_reduce{};
     int32_t *theta_index_dev[kMaxTerms] = {nullptr};
+    int32_t sec_theta_base = -1;  // >= 0: the secondary term reads theta[base + slot]
     int term_level[kMaxTerms] = {0}, term_slot_in_level[kMaxTerms] = {0};
     // one-shot all-reduce over peer memory
     PeerParams peer{};
@@ -303,14 +308,16 @@ static int upload_tiled(skk_plan *pl, void **out, const void *host, size_t n, si
 
 static const void *lookup_kernel(int dtype, int family, int bt, int ng, int np, int ns, int spec) {
     typedef const void *(*Lookup)(int, int, int, int);
-    static const Lookup table[2][3][2] = {
+    static const Lookup table[2][4][2] = {
         {{row_kernel_f32_normal_bt1, row_kernel_f32_normal_bt4},
          {row_kernel_f32_bernoulli_bt1, row_kernel_f32_bernoulli_bt4},
-         {row_kernel_f32_poisson_bt1, row_kernel_f32_poisson_bt4}},
+         {row_kernel_f32_poisson_bt1, row_kernel_f32_poisson_bt4},
+         {row_kernel_f32_negbinomial_bt1, row_kernel_f32_negbinomial_bt4}},
         {{row_kernel_f64_normal_bt1, row_kernel_f64_normal_bt4},
          {row_kernel_f64_bernoulli_bt1, row_kernel_f64_bernoulli_bt4},
-         {row_kernel_f64_poisson_bt1, row_kernel_f64_poisson_bt4}}};
-    if (family < 0 || family > 2 || (bt != 1 && bt != 4)) return nullptr;
+         {row_kernel_f64_poisson_bt1, row_kernel_f64_poisson_bt4},
+         {row_kernel_f64_negbinomial_bt1, row_kernel_f64_negbinomial_bt4}}};
+    if (family < 0 || family > 3 || (bt != 1 && bt != 4)) return nullptr;
     return table[dtype == SKK_F64 ? 1 : 0][family][bt == 4 ? 1 : 0](ng, np, ns, spec);
 }
 
@@ -377,15 +384,25 @@ static int build_schedule(skk_plan *pl, const std::vector<int2> &keys, int64_t n
     std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
     for (int w = 0; w < n_warps; ++w) heap.push(Item(load[w], w));
     std::vector<std::vector<int32_t>> lists(n_warps);
+    // longest processing time first: the expensive tiles are placed before the common ones (in index order within
+    // a class), so the granularity left at the end is one common tile; every warp then walks its tiles in index order
+    std::vector<double> cost_of(pl->n_tiles);
+    std::vector<int32_t> order(pl->n_tiles);
     for (int t = 0; t < pl->n_tiles; ++t) {
         const bool full = (int64_t)(t + 1) * WT <= n_rows;
         const int groups = pl->np > 0 ? keys[t].y - keys[t].x + 1 : 1;
-        const double cost = groups <= 1 ? (full ? 1.0 : 1.5) : (groups == 2 && full ? cost_two : cost_generic);
+        cost_of[t] = groups <= 1 ? (full ? 1.0 : 1.5) : (groups == 2 && full ? cost_two : cost_generic);
+        order[t] = t;
+    }
+    if (env_int("SKK_SCHED_INDEX_ORDER", 0) == 0)
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cost_of[a] > cost_of[b]; });
+    for (int t : order) {
         Item it = heap.top();
         heap.pop();
         lists[it.second].push_back(t);
-        heap.push(Item(it.first + cost, it.second));
+        heap.push(Item(it.first + cost_of[t], it.second));
     }
+    for (auto &l : lists) std::sort(l.begin(), l.end());
     size_t longest = 0, shortest = SIZE_MAX;
     for (const auto &l : lists) {
         longest = std::max(longest, l.size());
@@ -478,6 +495,12 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
         const int64_t slots = td.level == SKK_LEVEL_GLOBAL ? 1 : td.level == SKK_LEVEL_PRIMARY ? d->n_primary : d->n_secondary;
         (void)slots;
         if (td.level == SKK_LEVEL_PRIMARY) host_ti_p[t] = td.theta_index;
+        if (td.level == SKK_LEVEL_SECONDARY && t == 0) {
+            // slot -> theta is `base + slot`? (then the row kernel fills its value table straight from theta)
+            bool affine = td.n_slots > 0 && env_int("SKK_NO_AFFINE_TABLE", 0) == 0;
+            for (int64_t k = 0; affine && k < td.n_slots; ++k) affine = td.theta_index[k] == td.theta_index[0] + k;
+            pl->sec_theta_base = affine ? td.theta_index[0] : -1;
+        }
         pl->theta_index_dev[i] = ti;
         pl->term_level[i] = td.level;
         pl->term_slot_in_level[i] = t;
@@ -1000,6 +1023,9 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
         rp.xcol_s[t] = pl->xcol_s[t];
     }
     rp.theta = th;
+    rp.fam_a = (T)(pl->family == SKK_LIK_NEGBINOMIAL_LOG ? pl->sigma_const : 0.0);
+    rp.fam_b = (T)(pl->family == SKK_LIK_NEGBINOMIAL_LOG ? log(pl->sigma_const) : 0.0);
+    rp.sec_theta_base = pl->sec_theta_base;
     rp.n_params = pl->n_params;
     rp.b_valid = b_valid;
     for (int i = 0; i < pl->n_terms; ++i) {
@@ -1131,6 +1157,8 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             }
         }
         cp.theta = th;
+        cp.fam_a = (T)(pl->family == SKK_LIK_NEGBINOMIAL_LOG ? pl->sigma_const : 0.0);
+        cp.fam_b = (T)(pl->family == SKK_LIK_NEGBINOMIAL_LOG ? log(pl->sigma_const) : 0.0);
         cp.n_params = pl->n_params;
         cp.batch = batch;
         cp.bp = pl->chain_bp;
@@ -1411,7 +1439,8 @@ int skk_plan_create(const skk_plan_desc *d, skk_plan **out) {
     if (d->abi_version != SKK_ABI_VERSION)
         return fail(SKK_ERR_INVALID, "descriptor ABI %d, library ABI %d", d->abi_version, SKK_ABI_VERSION);
     if (d->dtype != SKK_F32 && d->dtype != SKK_F64) return fail(SKK_ERR_INVALID, "bad dtype %d", d->dtype);
-    if (d->family < SKK_LIK_NORMAL || d->family > SKK_LIK_POISSON_LOG) return fail(SKK_ERR_UNSUPPORTED, "bad family %d", d->family);
+    if (d->family < SKK_LIK_NORMAL || d->family > SKK_LIK_NEGBINOMIAL_LOG) return fail(SKK_ERR_UNSUPPORTED, "bad family %d", d->family);
+    if (d->family == SKK_LIK_NEGBINOMIAL_LOG && !(d->sigma_const > 0.0)) return fail(SKK_ERR_INVALID, "NegativeBinomial alpha must be positive");
     if (d->n_rows < 0 || d->n_rows >= (int64_t)1 << 40) return fail(SKK_ERR_INVALID, "bad n_rows");
     if ((d->n_rows + 32 * kRowsPerLane - 1) / (32 * kRowsPerLane) >= INT32_MAX) return fail(SKK_ERR_UNSUPPORTED, "too many rows");
     if (d->n_params < 0 || d->n_params > INT32_MAX - 2) return fail(SKK_ERR_INVALID, "bad n_params");

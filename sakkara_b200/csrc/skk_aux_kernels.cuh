@@ -954,6 +954,9 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
         // (hyper-parameters were finished above: nothing feeds them on any rank)
         const unsigned long long seq = peer_seq(pp);
         const bool normal = rp.family == SKK_LIK_NORMAL;
+        __shared__ double lp_tail[8];
+        __shared__ double lp_pair[2];
+        const bool last = blockIdx.x == gridDim.x - 1;  // this CTA also produces logp
         for (int b = 0; b < rp.b_valid; ++b) {
             const int64_t row = rp.b0 + b;
             const int64_t base = row * (P + 2);
@@ -961,6 +964,15 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             if (normal) {
                 sigma = rp.sigma_theta_index >= 0 ? exp((double)theta[row * P + rp.sigma_theta_index]) : rp.sigma_const;
                 sc = 1.0 / (sigma * sigma);
+            }
+            if (last) {
+                // the priors' part of logp needs nothing from the exchange: summed before the waits below
+                double s = 0.0;
+                if (rp.include_priors)
+                    for (int k = threadIdx.x; k < rp.prior_ctas; k += blockDim.x)
+                        s += rp.prior_lp_part[row * rp.prior_ctas + k];
+                s = warp_sum(s);
+                if (lane == 0) lp_tail[threadIdx.x >> 5] = s;
             }
             for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < P; j += (int64_t)gridDim.x * blockDim.x) {
                 if (rp.is_parent[j]) continue;
@@ -972,21 +984,17 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 g += own;
                 out_grad[row * P + j] = (T)g;
             }
-            if (blockIdx.x == gridDim.x - 1) {
-                __shared__ double lp_tail[8];
-                double s = 0.0;
-                if (rp.include_priors)
-                    for (int k = threadIdx.x; k < rp.prior_ctas; k += blockDim.x)
-                        s += rp.prior_lp_part[row * rp.prior_ctas + k];
-                s = warp_sum(s);
-                if (lane == 0) lp_tail[threadIdx.x >> 5] = s;
+            if (last) {
+                // the likelihood's logp partial and the constant: two threads poll side by side
+                if (threadIdx.x == 0) lp_pair[0] = peer_combine(pp, seq, base + P, pp.fed8[P]);
+                if (threadIdx.x == 32) lp_pair[1] = peer_combine(pp, seq, base + P + 1, pp.fed8[P + 1]);
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     double tot = 0.0;
                     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += lp_tail[w];
-                    const double L = peer_combine(pp, seq, base + P, pp.fed8[P]);
+                    const double L = lp_pair[0];
                     const double ll = normal ? -0.5 * L * sc - (double)rp.n_rows_total * (kLogSqrt2Pi + log(sigma)) : L;
-                    out_logp[row] = (T)(tot + ll + peer_combine(pp, seq, base + P + 1, pp.fed8[P + 1]));
+                    out_logp[row] = (T)(tot + ll + lp_pair[1]);
                 }
                 __syncthreads();
             }

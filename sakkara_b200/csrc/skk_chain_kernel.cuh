@@ -34,6 +34,7 @@ struct ChainParams {
     const int32_t *theta_index_g[kMaxTermsPerLevel];  // [1]
     const int32_t *theta_index_p[kMaxTermsPerLevel];  // [n_primary]
     const T *theta;              // [batch][P]
+    T fam_a, fam_b;              // constants of the likelihood family (NegativeBinomial: alpha, log(alpha))
     int64_t n_params;
     int32_t batch;
     int32_t bp;                  // batch rounded up to a multiple of 32: chain stride of all outputs
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kChainWarps * 32) skk_chain_kernel(const __gri
                         eta += vp[t] * xp[t];
                     }
                     T lp, d;
-                    family_row<T, FAM>(yv, eta, lp, d);
+                    family_row<T, FAM>(yv, eta, lp, d, FamilyConst<T>{p.fam_a, p.fam_b});
                     accL += lp;
 #pragma unroll
                     for (int t = 0; t < NG; ++t) accG[t] += d * xg[t];

@@ -74,6 +74,11 @@ struct RowParams {
     const double *link_a_const, *link_b_const;
     double *link_part;       // [b_valid][n_chunks]
     int64_t n_chunks;
+    // >= 0: the secondary term's slot -> theta table is `sec_theta_base + slot` (the planner numbers the slots that
+    // way when it can): the value table is filled straight from theta, without the gather through ti_s
+    int32_t sec_theta_base;
+    // constants of the likelihood family (NegativeBinomial: alpha and log(alpha))
+    T fam_a, fam_b;
     // row-sharded runs over peer memory: the evaluation counter of the exchange, advanced by one thread of the
     // evaluation's first row kernel (null otherwise); the kernels behind it in the stream read it
     unsigned long long *peer_seq;
@@ -430,8 +435,14 @@ struct Math<double> {
     static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
 };
 
+// constants of a likelihood family (NegativeBinomial: a = alpha, b = log(alpha); unused otherwise)
+template <typename T>
+struct FamilyConst {
+    T a, b;
+};
+
 template <typename T, int FAM>
-__device__ __forceinline__ void family_row(T y, T eta, T &lp, T &d) {
+__device__ __forceinline__ void family_row(T y, T eta, T &lp, T &d, const FamilyConst<T> &fc) {
     if constexpr (FAM == SKK_LIK_NORMAL) {
         d = y - eta;
         lp = d * d;
@@ -441,10 +452,21 @@ __device__ __forceinline__ void family_row(T y, T eta, T &lp, T &d) {
         const T sig = eta >= T(0) ? inv : t * inv;
         lp = y * eta - (Math<T>::max(eta, T(0)) + Math<T>::log1p_of_exp_neg(t));
         d = y - sig;
-    } else {
+    } else if constexpr (FAM == SKK_LIK_POISSON_LOG) {
         const T mu = Math<T>::exp(eta);
         lp = y * eta - mu;
         d = y - mu;
+    } else {
+        // NegativeBinomial(mu = exp(eta), alpha): with u = eta - log(alpha),
+        //   log(alpha + mu) = log(alpha) + softplus(u),   mu / (alpha + mu) = sigmoid(u)
+        //   lp = y eta - (y + alpha) log(alpha + mu)  (+ per-row constants in logp_const),  d = y - (y + alpha) sigmoid(u)
+        const T u = eta - fc.b;
+        const T t = Math<T>::exp(-Math<T>::abs(u));
+        const T inv = Math<T>::rcp(T(1) + t);
+        const T sig = u >= T(0) ? inv : t * inv;
+        const T ya = y + fc.a;
+        lp = y * eta - ya * (fc.b + Math<T>::max(u, T(0)) + Math<T>::log1p_of_exp_neg(t));
+        d = y - ya * sig;
     }
 }
 

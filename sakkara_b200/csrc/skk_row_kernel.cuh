@@ -240,6 +240,7 @@ struct RowKernel {
                                                    const T (&vg)[NGa][BT], double (&accG64)[NG + 1][BT],
                                                    const T *__restrict__ valS, T *__restrict__ gradS, uint32_t gradS_addr,
                                                    unsigned char *scratch, int lane) {
+        const FamilyConst<T> fc{p.fam_a, p.fam_b};
         const int li = lane * R;
         // where the lane's row i sits in every staged column: at0 + i * kLaneStep (see kStageTransposed)
         const int at0 = kStageTransposed ? lane : li;
@@ -445,7 +446,7 @@ struct RowKernel {
                             for (int t = 0; t < NSa; ++t) vsb[t] = r.vs[t][b];
                             const T eta = eta_of(p, r.off, vgb, r.xg, vpb, r.xp, vsb, r.xs);
                             T lp, d;
-                            family_row<T, FAM>(r.y, eta, lp, d);
+                            family_row<T, FAM>(r.y, eta, lp, d, fc);
                             accL[b] += lp;
 #pragma unroll
                             for (int t = 0; t < NG; ++t) accG[t][b] += d * r.xg[t];
@@ -596,7 +597,7 @@ struct RowKernel {
                 for (int t = 0; t < NSa; ++t) vsb[t] = vs[t][b];
                 const T eta = eta_of(p, off, vgb, xg, vpb, xp, vsb, xs);
                 T lp, d;
-                family_row<T, FAM>(yv, eta, lp, d);
+                family_row<T, FAM>(yv, eta, lp, d, fc);
                 if (!valid) {
                     lp = T(0);
                     d = T(0);
@@ -956,7 +957,9 @@ struct RowKernel {
 #pragma unroll
             for (int u = 0; u < kFillUnroll; ++u) {
                 const int k = threadIdx.x + u * blockDim.x;
-                element[u] = k < n_sec ? p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary] : -1;
+                element[u] = k >= n_sec ? -1
+                             : (NS == 1 && p.sec_theta_base >= 0) ? p.sec_theta_base + (k / BT) % p.n_secondary
+                                                                  : p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary];
             }
         }
         // lane j of a straddling tile stages group kf + j: its theta elements are fetched one tile ahead
@@ -988,7 +991,9 @@ struct RowKernel {
 #pragma unroll
                 for (int u = 0; u < kFillUnroll; ++u) {
                     const int k = k0f + u * blockDim.x;
-                    el[u] = k < n_sec ? p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary] : -1;
+                    el[u] = k >= n_sec ? -1
+                            : (NS == 1 && p.sec_theta_base >= 0) ? p.sec_theta_base + (k / BT) % p.n_secondary
+                                                                 : p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary];
                 }
 #pragma unroll
                 for (int u = 0; u < kFillUnroll; ++u) {

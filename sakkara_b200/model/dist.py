@@ -78,9 +78,11 @@ HalfStudentT = Family('HalfStudentT', {'nu': None, 'sigma': 1.0}, positive=True)
 # exactly one of p / logit_p must be given (checked in Family.__call__)
 Bernoulli = Family('Bernoulli', {'p': None, 'logit_p': None}, discrete=True)
 Poisson = Family('Poisson', {'mu': None}, discrete=True)
+NegativeBinomial = Family('NegativeBinomial', {'mu': None, 'alpha': None}, discrete=True)
 
 FAMILIES: Dict[str, Family] = {f.name: f for f in (Normal, HalfNormal, Exponential, HalfCauchy, Gamma, InverseGamma,
-                                                   Cauchy, Laplace, LogNormal, HalfStudentT, Bernoulli, Poisson)}
+                                                   Cauchy, Laplace, LogNormal, HalfStudentT, Bernoulli, Poisson,
+                                                   NegativeBinomial)}
 
 
 def resolve_generator(generator: Callable) -> Family:

@@ -29,7 +29,7 @@ import pandas as pd
 from scipy.special import gammaln
 
 from sakkara_b200.plan.lower import UnsupportedModelError
-from sakkara_b200.plan.model_plan import FAMILY_IDS, PRIOR_PARAMS, ModelPlan, prior_normaliser
+from sakkara_b200.plan.model_plan import FAMILY_IDS, LIKELIHOOD_IDS, PRIOR_PARAMS, ModelPlan, prior_normaliser
 
 LEVEL_GLOBAL, LEVEL_PRIMARY, LEVEL_SECONDARY = 0, 1, 2
 MAX_TERMS_PER_LEVEL = 2
@@ -292,6 +292,12 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
         p_slot_of_row = inv[columns[primary].codes]
     if secondary is not None:
         s_code_of_slot = slot_order(secondary)
+        own = [t for t in columns[secondary].terms]
+        if len(own) == 1 and not any(c != secondary and owner.get(c) == secondary for c in range(k)):
+            # the level's only term sits on the level itself: number the slots in the order of the term's theta
+            # elements, so that slot -> theta is `base + slot` and the kernel fills its value table with one
+            # coalesced read of theta instead of a gather through the slot table
+            s_code_of_slot = np.argsort(elem_of_term[own[0]], kind='stable')
         n_secondary = len(s_code_of_slot)
         inv = np.empty(n_secondary, dtype=np.int64)
         inv[s_code_of_slot] = np.arange(n_secondary)
@@ -310,7 +316,7 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
         sec_codes = arrange(s_slot_of_row).astype(np.uint16 if n_secondary <= 1 << 16 else np.int32)
 
     if structure_only:
-        return KernelPlan(dtype=dtype, family=FAMILY_IDS[lik.family], n_rows=n, n_rows_total=total,
+        return KernelPlan(dtype=dtype, family=LIKELIHOOD_IDS[lik.family], n_rows=n, n_rows_total=total,
                           n_params=plan.n_params, perm=perm, xcols=[], y=np.empty(0), y_kind=0, eta_offset=None,
                           n_primary=n_primary, seg_offsets=seg_offsets, n_secondary=n_secondary, sec_codes=sec_codes,
                           terms=[], blocks=[], sigma_const=1.0, sigma_theta_index=-1, logp_const=0.0)
@@ -358,7 +364,7 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     y_rows = take(lik.y)
     y_sorted = arrange(y_rows)
     y_kind = 0
-    if narrow_y and lik.family in ('Bernoulli', 'Poisson') and (n == 0 or y_rows.max() <= 255):
+    if narrow_y and lik.family in ('Bernoulli', 'Poisson', 'NegativeBinomial') and (n == 0 or y_rows.max() <= 255):
         y_store = y_sorted.astype(np.uint8)
         y_kind = 1
     else:
@@ -369,12 +375,20 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     logp_const = 0.0
     if lik.family == 'Poisson':
         logp_const = -float(np.sum(gammaln(y_rows + 1.0), dtype=np.float64))
+    elif lik.family == 'NegativeBinomial':
+        # per row: lgamma(y + alpha) - lgamma(alpha) - lgamma(y + 1) + alpha log(alpha); the kernel adds
+        # y eta - (y + alpha) log(alpha + exp(eta))
+        a = float(lik.sigma_const)
+        logp_const = float(np.sum(gammaln(y_rows + a) - gammaln(y_rows + 1.0), dtype=np.float64)) + \
+            n * (a * np.log(a) - float(gammaln(a)))
     if plan.logp_const:
         # rows masked out for NaN observations (ModelPlan.logp_const): every rank adds its share, so that
         # the all-reduced constant of a sharded run is the whole
         logp_const += float(plan.logp_const) * (n / total if total else 1.0)
 
     sigma_const, sigma_theta_index = 1.0, -1
+    if lik.family == 'NegativeBinomial':
+        sigma_const = float(lik.sigma_const)             # (its alpha travels in the same field of the C ABI)
     if lik.family == 'Normal':
         if lik.sigma_block is None:
             sigma_const = float(lik.sigma_const)
@@ -407,7 +421,7 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
             norm = np.broadcast_to(prior_normaliser(b.family, kb.a_const, kb.b_const), (b.size,))
             prior_logp_const += float(np.sum(norm, dtype=np.float64)) * (n / total if total else 1.0)
 
-    return KernelPlan(dtype=dtype, family=FAMILY_IDS[lik.family], n_rows=n, n_rows_total=total,
+    return KernelPlan(dtype=dtype, family=LIKELIHOOD_IDS[lik.family], n_rows=n, n_rows_total=total,
                       n_params=plan.n_params, perm=perm, xcols=xcols, y=np.ascontiguousarray(y_store), y_kind=y_kind,
                       eta_offset=eta_offset, n_primary=n_primary, seg_offsets=seg_offsets, n_secondary=n_secondary,
                       sec_codes=None if sec_codes is None else np.ascontiguousarray(sec_codes), terms=terms,

@@ -274,6 +274,9 @@ def _masked_likelihood(obs: sym.RandomVar, y: np.ndarray):
         from scipy.special import gammaln
         with np.errstate(divide='ignore', invalid='ignore'):
             terms = np.where(y0 > 0, y0 * np.log(fill['mu']), 0.0) - fill['mu'] - gammaln(y0 + 1.0)
+    elif obs.family == 'NegativeBinomial':
+        from scipy.stats import nbinom
+        terms = nbinom.logpmf(y0, fill['alpha'], fill['alpha'] / (fill['alpha'] + fill['mu']))
     else:
         raise UnsupportedModelError(f'Likelihood family {obs.family} is not supported')
     return {k: v.value for k, v in wrapped.items()}, mask, float(np.sum(terms, dtype=np.float64))
@@ -367,10 +370,16 @@ def lower_model(model: sym.Model) -> ModelPlan:
             eta_node = _unwrap_link(obs_params['p'], 'sigmoid', 'Bernoulli p')
         if not np.isin(y, (0.0, 1.0)).all():
             raise ValueError('Bernoulli observations must be 0 or 1')
-    elif obs.family == 'Poisson':
-        eta_node = _unwrap_link(obs_params['mu'], 'exp', 'Poisson mu')
+    elif obs.family in ('Poisson', 'NegativeBinomial'):
+        eta_node = _unwrap_link(obs_params['mu'], 'exp', f'{obs.family} mu')
         if (y < 0).any() or (y != np.floor(y)).any():
-            raise ValueError('Poisson observations must be non-negative integers')
+            raise ValueError(f'{obs.family} observations must be non-negative integers')
+        if obs.family == 'NegativeBinomial':
+            alpha = _lower(obs_params['alpha'])
+            value = np.unique(np.asarray(alpha.const_value(), dtype=np.float64)) if alpha.is_const else np.empty(0)
+            if value.size != 1 or not value[0] > 0:
+                raise UnsupportedModelError('NegativeBinomial alpha must be one positive constant')
+            spec.sigma_const = float(value[0])
     else:
         raise UnsupportedModelError(f'Likelihood family {obs.family} is not supported')
 

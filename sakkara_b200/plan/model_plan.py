@@ -20,6 +20,8 @@ LOG_SQRT_2_OVER_PI = -0.22579135264472743236309761494744
 FAMILY_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'HalfNormal': 3, 'Exponential': 4,
               'HalfCauchy': 5, 'Gamma': 6, 'InverseGamma': 7, 'Cauchy': 8, 'Laplace': 9, 'LogNormal': 10,
               'HalfStudentT': 11}
+# likelihood families (SKK_LIK_* of include/skk_b200.h; the first three share FAMILY_IDS' numbers)
+LIKELIHOOD_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3}
 # prior families: names of the parameters that travel as a / b through the C ABI (include/skk_b200.h)
 PRIOR_PARAMS = {'Normal': ('mu', 'sigma'), 'HalfNormal': ('sigma', None), 'Exponential': ('lam', None),
                 'HalfCauchy': ('beta', None), 'Gamma': ('alpha', 'beta'), 'InverseGamma': ('alpha', 'beta'),
@@ -101,11 +103,11 @@ class Term:
 
 @dataclass
 class LikelihoodSpec:
-    family: str                                # Normal | Bernoulli | Poisson
+    family: str                                # a key of LIKELIHOOD_IDS
     name: str
     y: np.ndarray                              # float64[N] (counts / 0-1 stored as floats too)
     offset: Optional[np.ndarray] = None        # float64[N] constant part of eta
-    sigma_const: Optional[float] = None        # Normal only: fixed sigma ...
+    sigma_const: Optional[float] = None        # Normal: fixed sigma ... (NegativeBinomial: its constant alpha)
     sigma_block: Optional[int] = None          # ... or a positive (log-transformed) block
     sigma_index: int = 0                       # element of that block
 

@@ -207,6 +207,20 @@ def row_sigma_likelihood(df):
     return make
 
 
+# ---------------------------------------------------------------------------------------------
+# over-dispersed counts: NegativeBinomial(mu = exp(eta), alpha) on the crossed frame
+# ---------------------------------------------------------------------------------------------
+def crossed_negbinomial_likelihood(df):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        a = DC(pm.Normal, name='a', group='A', sigma=DC(pm.HalfNormal, name='sigma_a', sigma=1.0))
+        b = DC(pm.Normal, name='b', group='B', sigma=DC(pm.HalfCauchy, name='sigma_b', beta=1.0))
+        eta = DC(pm.Normal, name='beta') * data['x'] + a + b
+        return api.Likelihood(pm.NegativeBinomial, mu=api.f_(pt.exp)(eta), alpha=2.5, observed=data['y'])
+    return make
+
+
 def zoo():
     out = {}
     df = readme_df()
@@ -229,4 +243,6 @@ def zoo():
     out['member_wise'] = (df, member_wise_likelihood(df))
     df = row_sigma_df()
     out['row_sigma'] = (df, row_sigma_likelihood(df))
+    df = crossed_df(seed=9)
+    out['crossed_negbinomial'] = (df, crossed_negbinomial_likelihood(df))
     return out

@@ -1,8 +1,8 @@
 #!/bin/bash
-# round 2, call M: timelines with the prologue / epilogue broken down (c4 shard of 8, c3, c2), parity suite,
-# schedule: expensive tiles first (default) against index order
+# round 2, call N: parity suite (NegativeBinomial likelihood); value table filled straight from theta (default) against
+# the gather through the slot table; logp tail of the exchange kernel polled side by side
 mkdir -p gpurun_out
-TAG=${TAG:-r2m}
+TAG=${TAG:-r2n}
 B="--no-cpu-baseline --no-sub"
 summ() { python - "$1" "$2" <<'PY'
 import json,sys
@@ -16,13 +16,11 @@ except Exception as e:
 PY
 }
 run() { name=$1; shift; timeout 300 python bench.py "$@" $B --steps 30 --warmup 5 > gpurun_out/${TAG}_$name.json 2> gpurun_out/${TAG}_$name.err; summ $name gpurun_out/${TAG}_$name.json; }
-( time timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 ) 2>&1 | tee gpurun_out/${TAG}_pytest.log
-for c in "c4 --emulate-world 8" c3 c4; do
+( time timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -8 ) 2>&1 | tee gpurun_out/${TAG}_pytest.log
+for c in "c4 --emulate-world 8" c4; do
   n=$(echo $c | tr -d ' -' )
-  run ${n}_lpt --config $c
-  SKK_SCHED_INDEX_ORDER=1 run ${n}_index --config $c
+  run ${n} --config $c
+  SKK_NO_AFFINE_TABLE=1 run ${n}_gathered --config $c
 done
-for c in "c4 --emulate-world 8" c3 c2; do
-  n=$(echo $c | tr -d ' -' )
-  timeout 300 python tools/trace_rows.py --config $c 2>&1 | grep -v "slowest warp" | tee gpurun_out/${TAG}_trace_$n.txt
-done
+run c4emulateworld8_again --config c4 --emulate-world 8
+timeout 300 python tools/trace_rows.py --config c4 --emulate-world 8 2>&1 | grep -v "slowest warp" | tee gpurun_out/${TAG}_trace_c4_w8.txt
