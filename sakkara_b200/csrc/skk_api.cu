@@ -368,8 +368,8 @@ static int configure_launch(skk_plan *pl, int bt, LaunchCfg *cfg) {
 // more), and the warps that carry prior work in the prologue start with that much on their account.  A fixed
 // list per warp keeps every sum of the evaluation in a fixed order; the balance removes the tail in which a few
 // warps with several expensive tiles kept their SMs busy while all others had finished.
-static int build_schedule(skk_plan *pl, const std::vector<int2> &keys, int64_t n_rows, int64_t n_prior_groups,
-                          int64_t n_chunks, LaunchCfg *cfg) {
+static int build_schedule(skk_plan *pl, const std::vector<int2> &keys, const std::vector<char> &two_fast, int64_t n_rows,
+                          int64_t n_prior_groups, int64_t n_chunks, LaunchCfg *cfg) {
     const int W = pl->warps, grid = cfg->grid, n_warps = grid * W, WT = pl->rows_per_tile;
     // (SKK_COST_TWO / SKK_COST_PRIOR, in hundredths: calibration runs)
     const double cost_two = env_int("SKK_COST_TWO", pl->ns > 0 ? 300 : 110) / 100.0, cost_generic = pl->ns > 0 ? 4.0 : 3.0,
@@ -391,7 +391,8 @@ static int build_schedule(skk_plan *pl, const std::vector<int2> &keys, int64_t n
     for (int t = 0; t < pl->n_tiles; ++t) {
         const bool full = (int64_t)(t + 1) * WT <= n_rows;
         const int groups = pl->np > 0 ? keys[t].y - keys[t].x + 1 : 1;
-        cost_of[t] = groups <= 1 ? (full ? 1.0 : 1.5) : (groups == 2 && full ? cost_two : cost_generic);
+        // (a two-group tile whose parts share no secondary code runs the pipelined path: skk_row_kernel.cuh, use_pipe)
+        cost_of[t] = groups <= 1 ? (full ? 1.0 : 1.5) : (groups == 2 && full ? (two_fast[t] ? 1.2 : cost_two) : cost_generic);
         order[t] = t;
     }
     if (env_int("SKK_SCHED_INDEX_ORDER", 0) == 0)
@@ -828,9 +829,9 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     const int grid_max = std::max(pl->cfg1.grid, pl->cfg4.grid);
     {
         const int64_t n_prior_groups = ((int64_t)d->n_params + 31) / 32;
-        if (int rc = build_schedule(pl, keys, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg1)) return rc;
+        if (int rc = build_schedule(pl, keys, two_fast, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg1)) return rc;
         if (bt_max == 4)
-            if (int rc = build_schedule(pl, keys, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg4)) return rc;
+            if (int rc = build_schedule(pl, keys, two_fast, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg4)) return rc;
     }
 
     // ---- work buffers --------------------------------------------------------------------------------------------

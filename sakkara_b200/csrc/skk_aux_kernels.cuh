@@ -984,10 +984,12 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 g += own;
                 out_grad[row * P + j] = (T)g;
             }
+            stamp(5, global_timer_ns());
             if (last) {
                 // the likelihood's logp partial and the constant: two threads poll side by side
                 if (threadIdx.x == 0) lp_pair[0] = peer_combine(pp, seq, base + P, pp.fed8[P]);
                 if (threadIdx.x == 32) lp_pair[1] = peer_combine(pp, seq, base + P + 1, pp.fed8[P + 1]);
+                stamp(6, global_timer_ns());
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     double tot = 0.0;

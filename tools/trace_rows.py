@@ -110,6 +110,11 @@ def main():
             rel = lambda col: 1e-3 * (sel[:, col] - last_exit)
             print(f'  {names[c]:20s} {len(sel):4d} CTAs: entry {rel(0).min():+6.1f}..{rel(0).max():+6.1f}  results visible {rel(1).min():+6.1f}..{rel(1).max():+6.1f}'
                   f'  own sums done {rel(2).min():+6.1f}..{rel(2).max():+6.1f}  exit {rel(3).min():+6.1f}..{rel(3).max():+6.1f} us')
+        if fin.shape[1] >= 7 and fin[:, 5].max() > 0:
+            slow = fin[np.argmax(fin[:, 3])]
+            r = lambda col: 1e-3 * (int(slow[col]) - last_exit)
+            print(f'  CTA that exits last (class {names[int(slow[4])]}): entry {r(0):+.1f}  results visible {r(1):+.1f}  own sums {r(2):+.1f}  '
+                  f'slice combined {r(5):+.1f}  logp lines polled {r(6) if slow[6] else float("nan"):+.1f}  exit {r(3):+.1f} us')
     if a.out:
         json.dump({'config': a.config, 'rows': int(kp.n_rows), 'span_us': 1e-3 * float(span),
                    'trace': tr[:, :5].tolist(), 'tiles': per_warp.tolist()}, open(a.out, 'w'))
