@@ -476,6 +476,19 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             keys[t] = make_int2(std::min<int>(kf, (int)d->n_primary - 1), std::min<int>(kl, (int)d->n_primary - 1));
         }
     }
+    // two-group tiles whose two parts share no secondary code (first code of the tile > its last code): the row
+    // kernel runs them on its pipelined path (skk_row_kernel.cuh: use_pipe), the schedule counts them as cheap
+    std::vector<char> two_fast(pl->n_tiles + 1, 0);
+    if (d->n_primary > 0 && pl->ns > 0 && d->sec_codes)
+        for (int t = 0; t < pl->n_tiles; ++t) {
+            const int64_t r0 = (int64_t)t * WT, r1 = r0 + WT - 1;
+            if (r1 >= d->n_rows || keys[t].y != keys[t].x + 1) continue;
+            const int64_t c0 = pl->sec_code_bytes == 2 ? (int64_t) static_cast<const uint16_t *>(d->sec_codes)[r0]
+                                                       : (int64_t) static_cast<const int32_t *>(d->sec_codes)[r0];
+            const int64_t c1 = pl->sec_code_bytes == 2 ? (int64_t) static_cast<const uint16_t *>(d->sec_codes)[r1]
+                                                       : (int64_t) static_cast<const int32_t *>(d->sec_codes)[r1];
+            two_fast[t] = c0 > c1;
+        }
 
     // ---- terms: value-table layout and the reduce CSR ------------------------------------------------
     struct Entry {

@@ -384,6 +384,9 @@ struct RowKernel {
                 const int c_first = __shfl_sync(kFull, code16 ? (int)sc16[0] : sc32[0], 0);
                 const int c_last = __shfl_sync(kFull, code16 ? (int)sc16[(R - 1) * kLaneStep] : sc32[(R - 1) * kLaneStep], 31);
                 use_pipe = c_first > c_last;
+#ifdef SKK_NO_MID_PIPE
+                use_pipe = false;  // (A/B build: two-group tiles always on the rolled loop)
+#endif
             }
         }
         if constexpr (NS > 0 && FASTP && FULL && PipeRows<T, BT>::value > 0) {
