@@ -293,7 +293,12 @@ def run_config(config, args, rank, world, local, steps, warmup, rows_override=0,
         batch = batch_total // world + (1 if rank < batch_total % world else 0)
     emulate = args.emulate_world if config == args.config else 1
     t0 = time.time()
-    if emulate > 1:
+    if emulate > 1 and chains_sharded:
+        if world != 1:
+            raise SystemExit('--emulate-world runs on one GPU')
+        batch = batch_total // emulate                   # rank 0's chains of a W-rank run; nothing to exchange
+        plan = make_plan(config, rows_total, 0, 1)
+    elif emulate > 1:
         if world != 1:
             raise SystemExit('--emulate-world runs on one GPU')
         os.environ['SKK_FORCE_PEER'] = '1'

@@ -368,8 +368,8 @@ static int configure_launch(skk_plan *pl, int bt, LaunchCfg *cfg) {
 // more), and the warps that carry prior work in the prologue start with that much on their account.  A fixed
 // list per warp keeps every sum of the evaluation in a fixed order; the balance removes the tail in which a few
 // warps with several expensive tiles kept their SMs busy while all others had finished.
-static int build_schedule(skk_plan *pl, const std::vector<int2> &keys, const std::vector<char> &two_fast, int64_t n_rows,
-                          int64_t n_prior_groups, int64_t n_chunks, LaunchCfg *cfg) {
+static int build_schedule(skk_plan *pl, const std::vector<int2> &keys, int64_t n_rows, int64_t n_prior_groups,
+                          int64_t n_chunks, LaunchCfg *cfg) {
     const int W = pl->warps, grid = cfg->grid, n_warps = grid * W, WT = pl->rows_per_tile;
     // (SKK_COST_TWO / SKK_COST_PRIOR, in hundredths: calibration runs)
     const double cost_two = env_int("SKK_COST_TWO", pl->ns > 0 ? 300 : 110) / 100.0, cost_generic = pl->ns > 0 ? 4.0 : 3.0,
@@ -391,8 +391,7 @@ static int build_schedule(skk_plan *pl, const std::vector<int2> &keys, const std
     for (int t = 0; t < pl->n_tiles; ++t) {
         const bool full = (int64_t)(t + 1) * WT <= n_rows;
         const int groups = pl->np > 0 ? keys[t].y - keys[t].x + 1 : 1;
-        // (a two-group tile whose parts share no secondary code runs the pipelined path: skk_row_kernel.cuh, use_pipe)
-        cost_of[t] = groups <= 1 ? (full ? 1.0 : 1.5) : (groups == 2 && full ? (two_fast[t] ? 1.2 : cost_two) : cost_generic);
+        cost_of[t] = groups <= 1 ? (full ? 1.0 : 1.5) : (groups == 2 && full ? cost_two : cost_generic);
         order[t] = t;
     }
     if (env_int("SKK_SCHED_INDEX_ORDER", 0) == 0)
@@ -476,20 +475,6 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
             keys[t] = make_int2(std::min<int>(kf, (int)d->n_primary - 1), std::min<int>(kl, (int)d->n_primary - 1));
         }
     }
-    // two-group tiles whose two parts share no secondary code (first code of the tile > its last code): the row
-    // kernel runs them on its pipelined path (skk_row_kernel.cuh: use_pipe), the schedule counts them as cheap
-    std::vector<char> two_fast(pl->n_tiles + 1, 0);
-    if (d->n_primary > 0 && pl->ns > 0 && d->sec_codes)
-        for (int t = 0; t < pl->n_tiles; ++t) {
-            const int64_t r0 = (int64_t)t * WT, r1 = r0 + WT - 1;
-            if (r1 >= d->n_rows || keys[t].y != keys[t].x + 1) continue;
-            const int64_t c0 = pl->sec_code_bytes == 2 ? (int64_t) static_cast<const uint16_t *>(d->sec_codes)[r0]
-                                                       : (int64_t) static_cast<const int32_t *>(d->sec_codes)[r0];
-            const int64_t c1 = pl->sec_code_bytes == 2 ? (int64_t) static_cast<const uint16_t *>(d->sec_codes)[r1]
-                                                       : (int64_t) static_cast<const int32_t *>(d->sec_codes)[r1];
-            two_fast[t] = c0 > c1;
-        }
-
     // ---- terms: value-table layout and the reduce CSR ------------------------------------------------
     struct Entry {
         int64_t theta;
@@ -842,9 +827,9 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     const int grid_max = std::max(pl->cfg1.grid, pl->cfg4.grid);
     {
         const int64_t n_prior_groups = ((int64_t)d->n_params + 31) / 32;
-        if (int rc = build_schedule(pl, keys, two_fast, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg1)) return rc;
+        if (int rc = build_schedule(pl, keys, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg1)) return rc;
         if (bt_max == 4)
-            if (int rc = build_schedule(pl, keys, two_fast, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg4)) return rc;
+            if (int rc = build_schedule(pl, keys, d->n_rows, n_prior_groups, pl->n_chunks, &pl->cfg4)) return rc;
     }
 
     // ---- work buffers --------------------------------------------------------------------------------------------
@@ -1121,8 +1106,8 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
     const bool fused_sharded = sharded && !chain && pl->fused_ok && batch <= 4 && env_int("SKK_SHARDED_FINISH", 1) == 1;
     const bool in_row = fused || fused_sharded;  // the prior terms ride in the row kernel
     const bool pdl = env_int("SKK_NO_PDL", 0) == 0;  // the finish kernel starts under the row kernel's tail
-    // (for large batches they are big enough to fill the GPU themselves: run them in line)
-    const bool fork = batch < kChainMinBatch;
+    // (the prior kernels run on a parallel branch, next to the rows; SKK_PRIORS_IN_LINE=1: behind each other)
+    const bool fork = batch < kChainMinBatch || env_int("SKK_PRIORS_IN_LINE", 0) == 0;
     cudaStream_t ps = fork ? pl->side : st;
     if (priors && !in_row) {
         if (fork) {
@@ -1195,6 +1180,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         skk_chain_slot_kernel<<<dim3((unsigned)std::max<int64_t>(pl->ng + 1, std::min<int64_t>(std::max<int64_t>(1, pl->n_primary), 2048)), 2),
                                 threads, 0, st>>>(cr);
         ++launches;
+        if (priors && fork) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));  // the final kernel adds the prior terms
         skk_chain_final_kernel<T><<<(unsigned)std::min<size_t>(std::max<size_t>(1, P), 2048), threads, 0, st>>>(cr, th, out_logp, out_grad);
         ++launches;
         CUDA_TRY(cudaGetLastError());

@@ -47,6 +47,21 @@ __device__ __forceinline__ void warp_cooperative_lists(bool heavy, int64_t first
     }
 }
 
+// sum_{k = first, first + step, ... < n} at(k), in that order, with the loads issued eight at a time: the chain of
+// dependent memory latencies is n / (8 step) long instead of n / step (a thread of the finish kernels is latency-bound)
+template <typename F>
+__device__ __forceinline__ double strided_sum(int64_t first, int64_t step, int64_t n, F at) {
+    double s = 0.0;
+    for (int64_t k0 = first; k0 < n; k0 += 8 * step) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = k0 + u * step < n ? at(k0 + u * step) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    return s;
+}
+
 constexpr int kMaxTerms = 3 * kMaxTermsPerLevel;
 
 // ---- K3 -------------------------------------------------------------------------------------
@@ -303,8 +318,7 @@ __global__ void __launch_bounds__(256) skk_slot_total_kernel(const __grid_consta
         // global terms and the logp partial: one warp per (term, chain)
         const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
         for (int item = warp; item < (rp.ng + 1) * BT; item += warps) {
-            double acc = 0.0;
-            for (int c = lane; c < rp.grid; c += 32) acc += rp.cta_glob[(int64_t)c * (rp.ng + 1) * BT + item];
+            double acc = strided_sum(lane, 32, rp.grid, [&](int64_t c) { return rp.cta_glob[c * (rp.ng + 1) * BT + item]; });
             acc = warp_sum(acc);
             if (lane == 0) rp.totals[item] = acc;
         }
@@ -743,8 +757,8 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             const int chain = warp / WPC, sub = warp % WPC;
             double s = 0.0;
             if (rp.include_priors && chain < rp.b_valid)
-                for (int k = sub * 32 + lane; k < rp.n_lp_parts; k += WPC * 32)
-                    s += rp.prior_lp_part[(int64_t)(rp.b0 + chain) * rp.prior_ctas + k];
+                s = strided_sum(sub * 32 + lane, WPC * 32, rp.n_lp_parts,
+                                [&](int64_t k) { return rp.prior_lp_part[(int64_t)(rp.b0 + chain) * rp.prior_ctas + k]; });
             s = warp_sum(s);
             if (lane == 0) lp_part[warp] = s;
         }
@@ -969,8 +983,8 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
                 // the priors' part of logp needs nothing from the exchange: summed before the waits below
                 double s = 0.0;
                 if (rp.include_priors)
-                    for (int k = threadIdx.x; k < rp.prior_ctas; k += blockDim.x)
-                        s += rp.prior_lp_part[row * rp.prior_ctas + k];
+                    s = strided_sum(threadIdx.x, blockDim.x, rp.prior_ctas,
+                                    [&](int64_t k) { return rp.prior_lp_part[row * rp.prior_ctas + k]; });
                 s = warp_sum(s);
                 if (lane == 0) lp_tail[threadIdx.x >> 5] = s;
             }

@@ -372,25 +372,7 @@ struct RowKernel {
 
         uint32_t table_token = 0;  // ties the in-loop stores to the accumulator table to the fence after the loop
         // ---- the rows ---------------------------------------------------------------------------
-        // A tile with two groups takes the pipelined path as well when no code can end a run on both sides of the
-        // split: codes ascend inside either group, so the first group's part holds codes >= the tile's first code
-        // and the second group's part codes <= the tile's last code -- first > last means the two sets are disjoint,
-        // every run that ends inside a lane has no other writer, and the open runs at the span ends are still
-        // sorted runs per side.  (Otherwise: the rolled loop below with its two ordered table updates per row.)
-        bool use_pipe = false;
-        if constexpr (NS > 0 && FASTP && FULL && PipeRows<T, BT>::value > 0) {
-            use_pipe = true;
-            if constexpr (MID) {
-                const int c_first = __shfl_sync(kFull, code16 ? (int)sc16[0] : sc32[0], 0);
-                const int c_last = __shfl_sync(kFull, code16 ? (int)sc16[(R - 1) * kLaneStep] : sc32[(R - 1) * kLaneStep], 31);
-                use_pipe = c_first > c_last;
-#ifdef SKK_NO_MID_PIPE
-                use_pipe = false;  // (A/B build: two-group tiles always on the rolled loop)
-#endif
-            }
-        }
-        if constexpr (NS > 0 && FASTP && FULL && PipeRows<T, BT>::value > 0) {
-          if (use_pipe) {
+        if constexpr (NS > 0 && FASTP && FULL && !MID && PipeRows<T, BT>::value > 0) {
             // The common tile of a model with a secondary level (whole tile inside one primary segment,
             // all rows valid), software-pipelined by hand.  The hardware keeps shared-memory accesses in
             // program order and the assembler cannot prove that the accumulator table aliases nothing
@@ -458,9 +440,8 @@ struct RowKernel {
                             T vgb[NGa], vpb[NPa], vsb[NSa];
 #pragma unroll
                             for (int t = 0; t < NGa; ++t) vgb[t] = vg[t][b];
-                            const bool second = MID && li + i >= split;   // (two groups: the row lies in the second)
 #pragma unroll
-                            for (int t = 0; t < NPa; ++t) vpb[t] = second ? vp_second[t][b] : vp[t][b];
+                            for (int t = 0; t < NPa; ++t) vpb[t] = vp[t][b];
 #pragma unroll
                             for (int t = 0; t < NSa; ++t) vsb[t] = r.vs[t][b];
                             const T eta = eta_of(p, r.off, vgb, r.xg, vpb, r.xp, vsb, r.xs);
@@ -470,15 +451,7 @@ struct RowKernel {
 #pragma unroll
                             for (int t = 0; t < NG; ++t) accG[t][b] += d * r.xg[t];
 #pragma unroll
-                            for (int t = 0; t < NP; ++t) {
-                                if constexpr (MID) {
-                                    const T v = d * r.xp[t];
-                                    accP[t][b] += second ? T(0) : v;
-                                    accP2[t][b] += second ? v : T(0);
-                                } else {
-                                    accP[t][b] += d * r.xp[t];
-                                }
-                            }
+                            for (int t = 0; t < NP; ++t) accP[t][b] += d * r.xp[t];
 #pragma unroll
                             for (int t = 0; t < NS; ++t) accS[t][b] += d * r.xs[t];
                         }
@@ -488,11 +461,11 @@ struct RowKernel {
                 for (int k = 0; k < K; ++k) cur[k] = nxt[k];
             }
             scur = code[R - 1];
-          }
-        }
+        } else
         // Only the common path (tile inside one segment, all rows valid) is unrolled; the other
-        // variants stay rolled to keep the kernel inside the instruction cache.
-        if (!use_pipe)
+        // variants stay rolled to keep the kernel inside the instruction cache.  (Round 2: two-group tiles whose
+        // parts share no secondary code were tried on the pipelined path as well -- 150.1 vs 149.2 us on c4, same
+        // box, profiles/r02/p_ab_two_group_pipe.log -- and stay here.)
 #pragma unroll(FASTP && FULL && !(MID && NS > 0) ? R : 1)
         for (int i = 0; i < R; ++i) {
             const bool valid = FULL || i < nvalid;
