@@ -1106,8 +1106,9 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
     const bool fused_sharded = sharded && !chain && pl->fused_ok && batch <= 4 && env_int("SKK_SHARDED_FINISH", 1) == 1;
     const bool in_row = fused || fused_sharded;  // the prior terms ride in the row kernel
     const bool pdl = env_int("SKK_NO_PDL", 0) == 0;  // the finish kernel starts under the row kernel's tail
-    // (the prior kernels run on a parallel branch, next to the rows; SKK_PRIORS_IN_LINE=1: behind each other)
-    const bool fork = batch < kChainMinBatch || env_int("SKK_PRIORS_IN_LINE", 0) == 0;
+    // (for large batches they are big enough to fill the GPU themselves: run them in line -- on a parallel branch they
+    // take SMs from the chain kernel: c5 509 -> 1012 us, 128 chains 119 -> 138 us, profiles/r02/q_all.log)
+    const bool fork = batch < kChainMinBatch;
     cudaStream_t ps = fork ? pl->side : st;
     if (priors && !in_row) {
         if (fork) {

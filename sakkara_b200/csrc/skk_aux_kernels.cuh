@@ -1000,9 +1000,8 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
             }
             stamp(5, global_timer_ns());
             if (last) {
-                // the likelihood's logp partial and the constant: two threads poll side by side
-                if (threadIdx.x == 0) lp_pair[0] = peer_combine(pp, seq, base + P, pp.fed8[P]);
-                if (threadIdx.x == 32) lp_pair[1] = peer_combine(pp, seq, base + P + 1, pp.fed8[P + 1]);
+                // the likelihood's logp partial and the constant: two lanes of one warp poll side by side
+                if (threadIdx.x < 2) lp_pair[threadIdx.x] = peer_combine(pp, seq, base + P + threadIdx.x, pp.fed8[P + threadIdx.x]);
                 stamp(6, global_timer_ns());
                 __syncthreads();
                 if (threadIdx.x == 0) {
