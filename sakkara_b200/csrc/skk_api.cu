@@ -1177,9 +1177,9 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
         pl->stats.row_kernel_launches++;
         ChainReduceParams cr = pl->chain_reduce;
         cr.batch = batch;
-        const int threads = std::min(256, (batch + 31) & ~31);
+        const int threads = std::max(128, std::min(256, (batch + 31) & ~31));  // (>= 4 warps share the ranges of a global term)
         skk_chain_slot_kernel<<<dim3((unsigned)std::max<int64_t>(pl->ng + 1, std::min<int64_t>(std::max<int64_t>(1, pl->n_primary), 2048)), 2),
-                                threads, 0, st>>>(cr);
+                                256, 0, st>>>(cr);
         ++launches;
         if (priors && fork) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));  // the final kernel adds the prior terms
         skk_chain_final_kernel<T><<<(unsigned)std::min<size_t>(std::max<size_t>(1, P), 2048), threads, 0, st>>>(cr, th, out_logp, out_grad);

@@ -99,7 +99,7 @@ class B200Model:
 
 
 def build(df: pd.DataFrame, component: ModelComponent, backend: str = 'auto', dtype: str = 'float64',
-          device: Optional[int] = None):
+          device: Optional[int] = None, strict: bool = True):
     """
     Build a model from a single component (typically a ``Likelihood``); all underlying components
     and their groups are traced from it.
@@ -115,6 +115,10 @@ def build(df: pd.DataFrame, component: ModelComponent, backend: str = 'auto', dt
     :param dtype: floating type of the evaluator behind the ``pm.Model`` (``pytensor.config.floatX`` on the
         reference side).
     :param device: CUDA device ordinal (default: ``LOCAL_RANK`` or 0).
+    :param strict: a likelihood the fused kernels cannot evaluate raises ``UnsupportedModelError`` here (default);
+        ``False`` returns the recorded model all the same -- variables, shapes, dims and the component tree can be
+        inspected -- and the error is raised when its plan or ``logp_dlogp_function()`` is asked for.  There is no CPU
+        fallback either way.
     """
     if backend not in ('auto', 'pymc', 'b200'):
         raise ValueError("backend must be 'auto', 'pymc' or 'b200'")
@@ -136,7 +140,7 @@ def build(df: pd.DataFrame, component: ModelComponent, backend: str = 'auto', dt
     try:
         model = B200Model(recorded, groupset, lower_model(recorded))
     except UnsupportedModelError as err:
-        if len(recorded.observed_RVs) == 1:
+        if len(recorded.observed_RVs) == 1 and strict:
             raise           # a likelihood the kernels cannot evaluate: say so at once
         model = B200Model(recorded, groupset, None, err)    # a bare component: the recorded graph only
     if backend == 'b200' or not model.is_lowered:

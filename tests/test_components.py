@@ -109,6 +109,14 @@ def test_unsupported_structures_raise(df):
         build(df, Likelihood(pm.Normal, mu=k ** 2, sigma=1.0, observed=data['y']))
     for c in (k, *data.values()):
         c.clear()
+    for c in (k, *data.values()):
+        c.clear()
+    model = build(df, Likelihood(pm.Normal, mu=k ** 2, sigma=1.0, observed=data['y']), strict=False)
+    assert not model.is_lowered and model['k'].shape == (2,)      # the recorded graph is there ...
+    with pytest.raises(UnsupportedModelError):                     # ... its evaluation is not
+        model.logp_dlogp_function()
+    for c in (k, *data.values()):
+        c.clear()
     with pytest.raises(NotImplementedError):            # unknown distribution
         class StudentT:
             pass
