@@ -111,3 +111,37 @@ def test_error_metric_uses_the_l1_mass_of_the_reduction():
     theta = np.zeros(plan.n_params)
     logp, grad, mass_l, mass_g = logp_dlogp(plan, theta, np.float64, True)
     assert (mass_g >= np.abs(grad) - 1e-12).all() and mass_l >= abs(logp) - 1e-12
+
+
+def test_round2_prior_families_against_scipy():
+    """HalfCauchy, Gamma, InverseGamma, Cauchy, Laplace, LogNormal, HalfStudentT: PyMC's parametrisation written out
+    with scipy.stats on the back-transformed value, plus the log-Jacobian of the LogTransform for the positive ones."""
+    model = build_model(ZOO['wide_priors'])
+    plan = model.plan
+    theta = theta_points(plan, 2, seed=11)[1]
+    v = {name: theta[s] for name, s in plan.block_slices().items()}
+    e = np.exp
+    expected = stats.cauchy.logpdf(v['k_loc'], 0.1, 2.0).sum()
+    expected += (stats.halfcauchy.logpdf(e(v['k_scale']), scale=1.5) + v['k_scale']).sum()
+    expected += stats.norm.logpdf(v['k'], v['k_loc'], e(v['k_scale'])).sum()
+    expected += (stats.lognorm.logpdf(e(v['c_level']), s=0.8, scale=e(-0.5)) + v['c_level']).sum()
+    expected += (stats.gamma.logpdf(e(v['c_scale']), a=2.5, scale=1 / 2.0) + v['c_scale']).sum()
+    expected += stats.norm.logpdf(v['c'], e(v['c_level']), e(v['c_scale'])).sum()
+    expected += stats.laplace.logpdf(v['icpt_loc'], 0.2, 1.3).sum()
+    expected += (stats.invgamma.logpdf(e(v['icpt_scale']), a=3.0, scale=2.0) + v['icpt_scale']).sum()
+    expected += stats.norm.logpdf(v['icpt'], v['icpt_loc'], e(v['icpt_scale'])).sum()
+    # a half Student-t is the positive half of a Student-t with twice the density
+    expected += (stats.t.logpdf(e(v['noise']), df=4.0, scale=1.2) + np.log(2.0) + v['noise']).sum()
+    eta = sum(theta[plan.term_base(t) + t.index] * (1.0 if t.x is None else t.x) for t in plan.terms)
+    expected += stats.norm.logpdf(plan.likelihood.y, eta, e(v['noise'])).sum()
+    assert abs(logp_dlogp(plan, theta)[0] - expected) < 1e-11 * abs(expected)
+
+
+def test_negative_binomial_against_scipy():
+    plan = build_model(ZOO['crossed_negbinomial']).plan
+    theta = theta_points(plan, 2, seed=12)[1]
+    eta = sum(theta[plan.term_base(t) + t.index] * (1.0 if t.x is None else t.x) for t in plan.terms)
+    alpha, mu = plan.likelihood.sigma_const, np.exp(eta)
+    lik = stats.nbinom.logpmf(plan.likelihood.y.astype(int), alpha, alpha / (alpha + mu)).sum()
+    from oracle.logp_c import priors_only
+    assert abs(logp_dlogp(plan, theta)[0] - (logp_dlogp(priors_only(plan), theta)[0] + lik)) < 1e-11 * abs(lik)
