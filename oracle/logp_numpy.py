@@ -218,7 +218,16 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
         columns.append(x)
         eta += gathered if x is None else gathered * x
 
-    if lik.family == 'Normal':
+    if lik.family == 'Normal' and getattr(lik, 'sigma_rows_element', None) is not None:
+        # sigma differs between rows: a constant, or exp(theta[element]) (sigma per group as a parameter)
+        element = lik.sigma_rows_element
+        linked = element >= 0
+        sigma = np.where(linked, np.exp(theta[np.maximum(element, 0)]), lik.sigma_rows_const.astype(dtype)).astype(dtype)
+        r = (y - eta) / sigma
+        terms = T(-0.5) * r * r - T(LOG_SQRT_2PI) - np.log(sigma)
+        d_eta = r / sigma
+        acc_absolute(element[linked], (r * r - T(1))[linked])       # d/d log(sigma) = r^2 - 1
+    elif lik.family == 'Normal':
         if lik.sigma_block is None:
             sigma = T(lik.sigma_const)
         else:

@@ -85,7 +85,12 @@ class B200Model:
 
     def logp_dlogp_function(self, dtype: str = 'float64', max_batch: int = 1, device: Optional[int] = None,
                             **options):
-        from sakkara_b200.valuegrad import MinibatchValueGrad, ValueGradFunction
+        from sakkara_b200.valuegrad import MinibatchValueGrad, SplitSigmaValueGrad, ValueGradFunction
+        if self.plan.likelihood.sigma_rows_element is not None:
+            if self.plan.minibatch is not None:
+                raise NotImplementedError('a mini-batched likelihood with a sigma that differs between rows')
+            # sigma per group as a parameter: one standard plan per sigma, added up
+            return SplitSigmaValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
         if self.plan.minibatch is not None:
             # MinibatchLikelihood: a fresh random subset of the rows per call, scaled to the whole data set
             return MinibatchValueGrad(self.plan, dtype=dtype, device=device, **options)

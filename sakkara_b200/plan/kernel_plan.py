@@ -184,6 +184,9 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     if dtype not in (np.dtype('float32'), np.dtype('float64')):
         raise ValueError('dtype must be float32 or float64')
     lik = plan.likelihood
+    if lik.sigma_rows_element is not None and plan.n_rows:
+        raise UnsupportedModelError('a plan whose likelihood sigma differs between rows is evaluated through '
+                                    'ModelPlan.split_by_sigma() (model.logp_dlogp_function() does that)')
 
     def take(a):
         if a is None or rows is None:

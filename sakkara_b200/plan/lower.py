@@ -25,6 +25,9 @@ from sakkara_b200.model.dist import FAMILIES
 from sakkara_b200.plan.model_plan import Block, LikelihoodSpec, ModelPlan, PriorParam, Term
 
 
+MAX_SIGMA_SOURCES = 16     # distinct theta elements (plus constants) a row-dependent likelihood sigma may take
+
+
 class UnsupportedModelError(NotImplementedError):
     """The model has a structure the fused GLM kernel cannot express."""
 
@@ -352,17 +355,34 @@ def lower_model(model: sym.Model) -> ModelPlan:
             else:
                 spec.sigma_const = float(value.reshape(-1)[0])
         else:
-            m = sigma.monomials
-            if len(m) != 1 or not np.all(np.asarray(m[0].coef) == 1.0):
-                raise UnsupportedModelError('Likelihood sigma must be a constant or a single positive variable')
-            element = np.unique(np.broadcast_to(m[0].index, sigma.shape).reshape(-1)[~masked]
-                                if masked is not None and np.size(m[0].index) == n_rows else m[0].index)
-            source = block_of[id(m[0].var)]
-            if element.size != 1:
-                raise UnsupportedModelError('Group-dependent likelihood sigma is not supported yet (SURVEY.md §8f.3)')
-            if blocks[source].transform != 'log':
-                raise UnsupportedModelError('Likelihood sigma must be a positive (HalfNormal/Exponential) variable')
-            spec.sigma_block, spec.sigma_index = source, int(element[0])
+            # per row: a constant, or one positive (log-transformed) element of theta
+            gathers = _merge_pieces(AffineForm(sigma.shape, [m for m in sigma.monomials if m.var is not None]),
+                                    block_of, blocks)
+            const = _merge_constants(sigma)
+            const = np.zeros(obs_shape) if const is None else \
+                np.array(np.broadcast_to(np.asarray(const, dtype=np.float64), sigma.shape))
+            if len(gathers) != 1 or not np.isin(gathers[0].coef, (0.0, 1.0)).all() or \
+                    np.any((gathers[0].coef == 1.0) & (const != 0.0)):
+                raise UnsupportedModelError('Likelihood sigma must be, per row, a constant or a single positive variable')
+            g = gathers[0]
+            element = np.broadcast_to(np.where(g.coef == 1.0, g.absolute, -1), obs_shape).reshape(-1)
+            const = np.broadcast_to(const, obs_shape).reshape(-1)
+            used = np.unique(element[~masked] if masked is not None else element)
+            if any(blocks[plan_block_of(blocks, int(e))].transform != 'log' for e in used if e >= 0):
+                raise UnsupportedModelError('Likelihood sigma must be a positive (HalfNormal/Exponential ...) variable')
+            if ((element < 0) & (const <= 0))[~masked if masked is not None else slice(None)].any():
+                raise ValueError('Normal sigma must be positive')
+            if used.size == 1 and used[0] >= 0:
+                source = plan_block_of(blocks, int(used[0]))
+                spec.sigma_block, spec.sigma_index = source, int(used[0]) - blocks[source].offset
+            else:
+                # sigma differs between rows (GroupComponent of parameters and constants, or a block gathered by
+                # group): kept per row; the evaluator splits the rows by their sigma (valuegrad.SplitSigmaValueGrad)
+                if used.size > MAX_SIGMA_SOURCES:
+                    raise UnsupportedModelError(f'Likelihood sigma takes {used.size} different values of theta; at most '
+                                                f'{MAX_SIGMA_SOURCES} are evaluated (one plan per value)')
+                spec.sigma_rows_element = np.ascontiguousarray(element, dtype=np.int64)
+                spec.sigma_rows_const = np.ascontiguousarray(const, dtype=np.float64)
     elif obs.family == 'Bernoulli':
         if 'logit_p' in obs_params:
             eta_node = obs_params['logit_p']
@@ -443,6 +463,9 @@ def lower_model(model: sym.Model) -> ModelPlan:
             t.index = np.ascontiguousarray(t.index[keep])
             if t.x is not None:
                 t.x = np.ascontiguousarray(t.x[keep])
+        if spec.sigma_rows_element is not None:
+            spec.sigma_rows_element = np.ascontiguousarray(spec.sigma_rows_element[keep])
+            spec.sigma_rows_const = np.ascontiguousarray(spec.sigma_rows_const[keep])
         plan.n_rows = int(keep.sum())
         plan.logp_const += masked_logp
         plan.n_masked_rows = int(masked.sum())

@@ -110,6 +110,11 @@ class LikelihoodSpec:
     sigma_const: Optional[float] = None        # Normal: fixed sigma ... (NegativeBinomial: its constant alpha)
     sigma_block: Optional[int] = None          # ... or a positive (log-transformed) block
     sigma_index: int = 0                       # element of that block
+    # Normal whose sigma differs between rows and depends on theta (sigma per group as a parameter): per row the
+    # element of theta that holds log(sigma), or -1 and the constant in sigma_rows_const.  Such a plan is evaluated
+    # as one standard plan per distinct sigma (ModelPlan.split_by_sigma)
+    sigma_rows_element: Optional[np.ndarray] = None   # int64[N]
+    sigma_rows_const: Optional[np.ndarray] = None     # float64[N]
 
 
 @dataclass
@@ -136,11 +141,50 @@ class ModelPlan:
         """The same model over a subset (or multiset) of the observation rows; ``rows=[]`` leaves the priors."""
         import dataclasses
         rows = np.asarray(rows, dtype=np.int64)
-        lik = dataclasses.replace(self.likelihood, y=self.likelihood.y[rows],
-                                  offset=None if self.likelihood.offset is None else self.likelihood.offset[rows])
+        spec = self.likelihood
+        lik = dataclasses.replace(spec, y=spec.y[rows], offset=None if spec.offset is None else spec.offset[rows],
+                                  sigma_rows_element=None if spec.sigma_rows_element is None else spec.sigma_rows_element[rows],
+                                  sigma_rows_const=None if spec.sigma_rows_const is None else spec.sigma_rows_const[rows])
         terms = [Term(t.block, t.index[rows], None if t.x is None else t.x[rows]) for t in self.terms]
         return dataclasses.replace(self, terms=terms, likelihood=lik, n_rows=int(rows.size), logp_const=0.0,
                                    n_masked_rows=0, minibatch=None)
+
+    def block_of_element(self, element: int) -> int:
+        for number, b in enumerate(self.blocks):
+            if b.offset <= element < b.offset + b.size:
+                return number
+        raise IndexError(element)
+
+    def split_by_sigma(self) -> List['ModelPlan']:
+        """
+        A plan whose Normal sigma differs between rows as standard plans over disjoint row sets, one per element of
+        theta that serves as sigma (a plan with that one sigma parameter) and one for the rows with constant sigmas
+        (standardised: y, offset and data columns divided by sigma_i, unit sigma, sum(-log sigma_i) in the constant).
+        Their likelihoods add up to this plan's; the priors are this plan's without rows.
+        """
+        import dataclasses
+        spec = self.likelihood
+        if spec.sigma_rows_element is None:
+            return [self]
+        out = []
+        for element in np.unique(spec.sigma_rows_element):
+            rows = np.flatnonzero(spec.sigma_rows_element == element)
+            part = self.take_rows(rows)
+            lik = part.likelihood
+            if element >= 0:
+                number = self.block_of_element(int(element))
+                lik = dataclasses.replace(lik, sigma_block=number, sigma_index=int(element) - self.blocks[number].offset,
+                                          sigma_const=None, sigma_rows_element=None, sigma_rows_const=None)
+                part = dataclasses.replace(part, likelihood=lik)
+            else:
+                weight = 1.0 / lik.sigma_rows_const
+                terms = [Term(t.block, t.index, weight.copy() if t.x is None else t.x * weight) for t in part.terms]
+                lik = dataclasses.replace(lik, y=lik.y * weight, offset=None if lik.offset is None else lik.offset * weight,
+                                          sigma_const=1.0, sigma_block=None, sigma_rows_element=None, sigma_rows_const=None)
+                part = dataclasses.replace(part, terms=terms, likelihood=lik,
+                                           logp_const=-float(np.sum(np.log(spec.sigma_rows_const[rows]), dtype=np.float64)))
+            out.append(part)
+        return out
 
     def block_slices(self) -> Dict[str, slice]:
         return {b.name: slice(b.offset, b.offset + b.size) for b in self.blocks}

@@ -149,3 +149,50 @@ class MinibatchValueGrad:
 
     def close(self) -> None:
         self._priors.close()
+
+
+class SplitSigmaValueGrad:
+    """
+    Value and gradient of a model whose Normal likelihood has a sigma that differs between rows and depends on theta
+    -- sigma per group as a parameter, e.g. a ``GroupComponent`` of positive variables and constants (reference
+    ``tests/workflows/test_state_space.py:64-82``).  The rows are split by the element of theta that is their sigma
+    (``ModelPlan.split_by_sigma``): every part is a standard plan with ONE sigma parameter (or, for the constant
+    sigmas, standardised rows) evaluated by the fused kernels without priors; the priors come from a plan without
+    rows; the parts are added on the host in a fixed order.
+    """
+
+    def __init__(self, plan: ModelPlan, dtype: str = 'float64', max_batch: int = 1, device: Optional[int] = None):
+        self.model_plan = plan
+        self.dtype = np.dtype(dtype)
+        self.parts = [ValueGradFunction(part, dtype=dtype, max_batch=max_batch, device=device, include_priors=False)
+                      for part in plan.split_by_sigma()]
+        self._priors = ValueGradFunction(plan.take_rows([]), dtype=dtype, max_batch=max_batch, device=device)
+
+    @property
+    def size(self) -> int:
+        return self.model_plan.n_params
+
+    def set_extra_values(self, extra_vars) -> None:
+        pass
+
+    def __call__(self, theta, grad_out=None, extra_vars=None):
+        theta = np.asarray(theta, dtype=self.dtype)
+        logp, grad = self._priors(theta)
+        logp, grad = np.array(logp, dtype=np.float64), np.array(grad, dtype=np.float64)
+        for part in self.parts:
+            lp, g = part(theta)
+            logp = logp + lp
+            grad = grad + g
+        logp = logp.astype(self.dtype) if logp.ndim else self.dtype.type(logp)
+        grad = grad.astype(self.dtype)
+        if grad_out is not None:
+            grad_out[...] = grad
+            return logp, grad_out
+        return logp, grad
+
+    def stats(self) -> dict:
+        return self.parts[0].stats()
+
+    def close(self) -> None:
+        for f in self.parts + [self._priors]:
+            f.close()

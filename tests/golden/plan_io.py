@@ -34,6 +34,9 @@ def plan_to_arrays(plan) -> dict:
         out['offset'] = np.asarray(lik.offset, dtype=np.float64)
     meta['likelihood'] = {'family': lik.family, 'name': lik.name, 'sigma_const': lik.sigma_const,
                           'sigma_block': lik.sigma_block, 'sigma_index': lik.sigma_index}
+    if getattr(lik, 'sigma_rows_element', None) is not None:
+        out['sigma_rows_element'] = np.asarray(lik.sigma_rows_element, dtype=np.int64)
+        out['sigma_rows_const'] = np.asarray(lik.sigma_rows_const, dtype=np.float64)
     out['meta'] = np.array(json.dumps(meta))
     return out
 

@@ -221,6 +221,29 @@ def crossed_negbinomial_likelihood(df):
     return make
 
 
+# ---------------------------------------------------------------------------------------------
+# sigma per group as a parameter: the measurement model of /root/reference/tests/workflows/test_state_space.py:64-82
+# (a GroupComponent of a constant and a positive variable as sigma of a Normal likelihood), on a regression
+# ---------------------------------------------------------------------------------------------
+def group_sigma_df(n: int = 160, seed: int = 10) -> pd.DataFrame:
+    rng = np.random.default_rng(seed)
+    group = rng.integers(0, 3, n)
+    x = rng.normal(size=n)
+    sd = np.array([1e-1, 0.6, 1.4])[group]
+    return pd.DataFrame({'x': x, 'group': group, 'y': 0.8 * x - 0.2 + sd * rng.normal(size=n)})
+
+
+def group_sigma_likelihood(df):
+    def make(api, pm, pt):
+        DC, GC = api.DistributionComponent, api.GroupComponent
+        data = api.data_components(df[['x', 'y']])
+        R = GC(name='R', group='group', membercomponents={0: 1e-1, 1: DC(pm.Exponential, name='R_1', lam=10),
+                                                           2: DC(pm.HalfNormal, name='R_2', sigma=2.0)})
+        k = DC(pm.Normal, name='k', group='group', sigma=DC(pm.HalfNormal, name='k_sd', sigma=1.0))
+        return api.Likelihood(pm.Normal, mu=k * data['x'] + DC(pm.Normal, name='icpt'), sigma=R, observed=data['y'])
+    return make
+
+
 def zoo():
     out = {}
     df = readme_df()
@@ -245,4 +268,6 @@ def zoo():
     out['row_sigma'] = (df, row_sigma_likelihood(df))
     df = crossed_df(seed=9)
     out['crossed_negbinomial'] = (df, crossed_negbinomial_likelihood(df))
+    df = group_sigma_df()
+    out['group_sigma'] = (df, group_sigma_likelihood(df))
     return out

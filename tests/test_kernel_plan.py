@@ -23,7 +23,7 @@ ZOO = zoo()
 
 
 def full_eval(plan, kplans, theta):
-    lp, gp = logp_dlogp(priors_only(plan), theta)
+    lp, gp = logp_dlogp(plan.take_rows([]), theta)
     for kp in kplans:
         l, g = likelihood_from_kernel_plan(kp, theta)
         lp, gp = lp + l, gp + g
@@ -34,10 +34,11 @@ def full_eval(plan, kplans, theta):
 @pytest.mark.parametrize('name', sorted(ZOO))
 def test_kernel_plan_reproduces_oracle(name, dtype):
     plan = build_model(ZOO[name]).plan
-    kp = make_kernel_plan(plan, dtype)
+    # (a sigma that differs between rows: one standard kernel plan per sigma, ModelPlan.split_by_sigma)
+    kps = [make_kernel_plan(part, dtype) for part in plan.split_by_sigma()]
     for theta in theta_points(plan, 3, seed=2):
         ref = logp_dlogp(plan, theta)
-        got = full_eval(plan, [kp], theta)
+        got = full_eval(plan, kps, theta)
         tol = 1e-11 if dtype == 'float64' else 1e-5
         assert abs(got[0] - ref[0]) <= tol * max(1.0, abs(ref[0]))
         assert np.allclose(got[1], ref[1], rtol=tol, atol=tol * max(1.0, np.abs(ref[1]).max()))
