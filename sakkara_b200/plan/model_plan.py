@@ -145,6 +145,9 @@ class ModelPlan:
         lik = dataclasses.replace(spec, y=spec.y[rows], offset=None if spec.offset is None else spec.offset[rows],
                                   sigma_rows_element=None if spec.sigma_rows_element is None else spec.sigma_rows_element[rows],
                                   sigma_rows_const=None if spec.sigma_rows_const is None else spec.sigma_rows_const[rows])
+        if rows.size == 0 and lik.sigma_rows_element is not None:
+            # no rows, no likelihood: the priors alone (any sigma will do)
+            lik = dataclasses.replace(lik, sigma_rows_element=None, sigma_rows_const=None, sigma_const=1.0)
         terms = [Term(t.block, t.index[rows], None if t.x is None else t.x[rows]) for t in self.terms]
         return dataclasses.replace(self, terms=terms, likelihood=lik, n_rows=int(rows.size), logp_const=0.0,
                                    n_masked_rows=0, minibatch=None)

@@ -44,6 +44,18 @@ def test_kernel_plan_reproduces_oracle(name, dtype):
         assert np.allclose(got[1], ref[1], rtol=tol, atol=tol * max(1.0, np.abs(ref[1]).max()))
 
 
+@pytest.mark.parametrize('name', sorted(ZOO))
+def test_plan_without_rows_and_sigma_parts_are_plannable(name):
+    # what the mini-batch and split-sigma evaluators hand to the planner
+    plan = build_model(ZOO[name]).plan
+    kp = make_kernel_plan(plan.take_rows([]), 'float64')
+    assert kp.n_rows == 0 and kp.terms == [] and len(kp.blocks) == len(plan.blocks)
+    parts = plan.split_by_sigma()
+    assert sum(p.n_rows for p in parts) == plan.n_rows
+    for part in parts:
+        assert make_kernel_plan(part, 'float32', include_priors=False).n_rows == part.n_rows
+
+
 def test_levels_and_storage():
     kp = make_kernel_plan(synth.poisson_plan(synth.poisson_columns(5000, 40, 7, seed=1)[0]), 'float32')
     assert [t.level for t in kp.terms] == [LEVEL_GLOBAL, LEVEL_PRIMARY, LEVEL_SECONDARY]
