@@ -52,6 +52,12 @@ extern "C" {
                                     skk_plan_desc.sigma_const; lgamma(y+alpha) - lgamma(alpha) - lgamma(y+1)
                                     + alpha log(alpha) per row belongs into logp_const */
 
+#define SKK_LIK_NORMAL_LOGSIGMA 4 /* pm.Normal(mu=eta, sigma=exp(zeta)): zeta = sum of the terms whose xcol is
+                                    SKK_XCOL_LOG_SIGMA (sigma per group as a parameter; every such term reads
+                                    log-transformed elements of theta).  -N log(sqrt(2 pi)) belongs into logp_const */
+/* skk_term_desc.xcol of a term of the log-scale predictor zeta of SKK_LIK_NORMAL_LOGSIGMA (no data column) */
+#define SKK_XCOL_LOG_SIGMA (-2)
+
 /* prior families of parameter blocks: the generator given to DistributionComponent
  * (/root/reference/sakkara/model/composable/hierarchical/distribution.py:41-51) */
 #define SKK_PRIOR_NORMAL 0       /* a = mu, b = sigma                       */
@@ -91,7 +97,7 @@ extern "C" {
  */
 typedef struct {
     int32_t level;              /* SKK_LEVEL_*                                   */
-    int32_t xcol;               /* index into skk_plan_desc.xcols, -1: x == 1     */
+    int32_t xcol;               /* index into skk_plan_desc.xcols, -1: x == 1, SKK_XCOL_LOG_SIGMA */
     int64_t n_slots;            /* 1, n_primary or n_secondary                   */
     const int32_t *theta_index; /* [n_slots] element of theta read by each slot  */
 } skk_term_desc;

@@ -15,6 +15,7 @@ def likelihood_from_kernel_plan(kp, theta):
     theta = np.asarray(theta, dtype=np.float64)
     n = kp.n_rows
     eta = np.zeros(n) if kp.eta_offset is None else kp.eta_offset.astype(np.float64).copy()
+    zeta = None
     slot_rows = []
     for t in kp.terms:
         if t.level == 0:
@@ -25,10 +26,20 @@ def likelihood_from_kernel_plan(kp, theta):
             slot = kp.sec_codes.astype(np.int64)
         slot_rows.append(slot)
         x = 1.0 if t.xcol < 0 else kp.xcols[t.xcol].astype(np.float64)
-        eta += theta[t.theta_index.astype(np.int64)[slot]] * x
+        if t.xcol == -2:            # a term of log(sigma) (SKK_XCOL_LOG_SIGMA, family 4)
+            zeta = (zeta if zeta is not None else 0.0) + theta[t.theta_index.astype(np.int64)[slot]]
+        else:
+            eta += theta[t.theta_index.astype(np.int64)[slot]] * x
     y = kp.y.astype(np.float64)
     grad = np.zeros(kp.n_params)
-    if kp.family == 0:
+    dz = None
+    if kp.family == 4:
+        sigma = np.exp(zeta)
+        r = (y - eta) / sigma
+        logp = np.sum(-0.5 * r * r - zeta)
+        d = r / sigma
+        dz = r * r - 1.0
+    elif kp.family == 0:
         sigma = np.exp(theta[kp.sigma_theta_index]) if kp.sigma_theta_index >= 0 else kp.sigma_const
         r = (y - eta) / sigma
         logp = np.sum(-0.5 * r * r) - n * (LOG_SQRT_2PI + np.log(sigma))
@@ -52,5 +63,5 @@ def likelihood_from_kernel_plan(kp, theta):
     logp += kp.logp_const - kp.prior_logp_const
     for t, slot in zip(kp.terms, slot_rows):
         x = 1.0 if t.xcol < 0 else kp.xcols[t.xcol].astype(np.float64)
-        np.add.at(grad, t.theta_index.astype(np.int64)[slot], d * x)
+        np.add.at(grad, t.theta_index.astype(np.int64)[slot], dz if t.xcol == -2 else d * x)
     return logp, grad

@@ -441,6 +441,17 @@ struct FamilyConst {
     T a, b;
 };
 
+// Normal with a log-scale predictor: sigma = exp(zeta).  lp = -r^2 / 2 - zeta, d lp / d eta = r / sigma,
+// d lp / d zeta = r^2 - 1, with r = (y - eta) / sigma
+template <typename T>
+__device__ __forceinline__ void normal_logsigma_row(T y, T eta, T zeta, T &lp, T &d, T &dz) {
+    const T inv = Math<T>::exp(-zeta);
+    const T r = (y - eta) * inv;
+    lp = T(-0.5) * r * r - zeta;
+    d = r * inv;
+    dz = r * r - T(1);
+}
+
 template <typename T, int FAM>
 __device__ __forceinline__ void family_row(T y, T eta, T &lp, T &d, const FamilyConst<T> &fc) {
     if constexpr (FAM == SKK_LIK_NORMAL) {
@@ -457,6 +468,7 @@ __device__ __forceinline__ void family_row(T y, T eta, T &lp, T &d, const Family
         lp = y * eta - mu;
         d = y - mu;
     } else {
+        static_assert(FAM == SKK_LIK_NEGBINOMIAL_LOG, "family without a row function");
         // NegativeBinomial(mu = exp(eta), alpha): with u = eta - log(alpha),
         //   log(alpha + mu) = log(alpha) + softplus(u),   mu / (alpha + mu) = sigmoid(u)
         //   lp = y eta - (y + alpha) log(alpha + mu)  (+ per-row constants in logp_const),  d = y - (y + alpha) sigmoid(u)

@@ -230,6 +230,58 @@ struct RowKernel {
         }
     }
 
+    // SKK_LIK_NORMAL_LOGSIGMA: a term whose xcol is SKK_XCOL_LOG_SIGMA belongs to zeta = log(sigma), the others to eta
+    static constexpr bool kLogSigma = FAM == SKK_LIK_NORMAL_LOGSIGMA;
+    static __device__ __forceinline__ bool zg(const RowParams<T> &p, int t) { return kLogSigma && p.xcol_g[t] == SKK_XCOL_LOG_SIGMA; }
+    static __device__ __forceinline__ bool zp(const RowParams<T> &p, int t) { return kLogSigma && p.xcol_p[t] == SKK_XCOL_LOG_SIGMA; }
+    static __device__ __forceinline__ bool zs(const RowParams<T> &p, int t) { return kLogSigma && p.xcol_s[t] == SKK_XCOL_LOG_SIGMA; }
+    static __device__ __forceinline__ T zeta_of(const RowParams<T> &p, const T (&vgb)[NGa], const T (&vpb)[NPa],
+                                                const T (&vsb)[NSa]) {
+        T zeta = T(0);
+#pragma unroll
+        for (int t = 0; t < NG; ++t) zeta += zg(p, t) ? vgb[t] : T(0);
+#pragma unroll
+        for (int t = 0; t < NP; ++t) zeta += zp(p, t) ? vpb[t] : T(0);
+#pragma unroll
+        for (int t = 0; t < NS; ++t) zeta += zs(p, t) ? vsb[t] : T(0);
+        return zeta;
+    }
+    // one row: eta (without the zeta terms), the family's logp term and the derivatives, accumulated per term
+    static __device__ __forceinline__ void row_terms(const RowParams<T> &p, const FamilyConst<T> &fc, T y, T off,
+                                                     const T (&vgb)[NGa], const T (&xg)[NGa], const T (&vpb)[NPa],
+                                                     const T (&xp)[NPa], const T (&vsb)[NSa], const T (&xs)[NSa],
+                                                     T &lp, T (&dg)[NGa], T (&dp)[NPa], T (&ds)[NSa]) {
+        if constexpr (kLogSigma) {
+            T eg[NGa], ep[NPa], es[NSa];   // values of the eta terms only
+#pragma unroll
+            for (int t = 0; t < NGa; ++t) eg[t] = (t < NG && zg(p, t)) ? T(0) : vgb[t];
+#pragma unroll
+            for (int t = 0; t < NPa; ++t) ep[t] = (t < NP && zp(p, t)) ? T(0) : vpb[t];
+#pragma unroll
+            for (int t = 0; t < NSa; ++t) es[t] = (t < NS && zs(p, t)) ? T(0) : vsb[t];
+            const T eta = eta_of(p, off, eg, xg, ep, xp, es, xs);
+            const T zeta = zeta_of(p, vgb, vpb, vsb);
+            T d, dz;
+            normal_logsigma_row<T>(y, eta, zeta, lp, d, dz);
+#pragma unroll
+            for (int t = 0; t < NGa; ++t) dg[t] = (t < NG && zg(p, t)) ? dz : d * xg[t];
+#pragma unroll
+            for (int t = 0; t < NPa; ++t) dp[t] = (t < NP && zp(p, t)) ? dz : d * xp[t];
+#pragma unroll
+            for (int t = 0; t < NSa; ++t) ds[t] = (t < NS && zs(p, t)) ? dz : d * xs[t];
+        } else {
+            const T eta = eta_of(p, off, vgb, xg, vpb, xp, vsb, xs);
+            T d;
+            family_row<T, FAM>(y, eta, lp, d, fc);
+#pragma unroll
+            for (int t = 0; t < NGa; ++t) dg[t] = d * xg[t];
+#pragma unroll
+            for (int t = 0; t < NPa; ++t) dp[t] = d * xp[t];
+#pragma unroll
+            for (int t = 0; t < NSa; ++t) ds[t] = d * xs[t];
+        }
+    }
+
     // -----------------------------------------------------------------------------------------
     // FASTP: no per-row segment bookkeeping (the tile lies in one segment, or -- MID -- in exactly two:
     // rows from `split` on belong to the second group, whose values are vp_second)
@@ -444,6 +496,17 @@ struct RowKernel {
                             for (int t = 0; t < NPa; ++t) vpb[t] = vp[t][b];
 #pragma unroll
                             for (int t = 0; t < NSa; ++t) vsb[t] = r.vs[t][b];
+                            if constexpr (kLogSigma) {
+                                T lp, dg[NGa], dp[NPa], ds[NSa];
+                                row_terms(p, fc, r.y, r.off, vgb, r.xg, vpb, r.xp, vsb, r.xs, lp, dg, dp, ds);
+                                accL[b] += lp;
+#pragma unroll
+                                for (int t = 0; t < NG; ++t) accG[t][b] += dg[t];
+#pragma unroll
+                                for (int t = 0; t < NP; ++t) accP[t][b] += dp[t];
+#pragma unroll
+                                for (int t = 0; t < NS; ++t) accS[t][b] += ds[t];
+                            } else {
                             const T eta = eta_of(p, r.off, vgb, r.xg, vpb, r.xp, vsb, r.xs);
                             T lp, d;
                             family_row<T, FAM>(r.y, eta, lp, d, fc);
@@ -454,6 +517,7 @@ struct RowKernel {
                             for (int t = 0; t < NP; ++t) accP[t][b] += d * r.xp[t];
 #pragma unroll
                             for (int t = 0; t < NS; ++t) accS[t][b] += d * r.xs[t];
+                            }
                         }
                     }
                 }
@@ -597,6 +661,26 @@ struct RowKernel {
                 for (int t = 0; t < NPa; ++t) vpb[t] = (MID && li + i >= split) ? vp_second[t][b] : vp[t][b];
 #pragma unroll
                 for (int t = 0; t < NSa; ++t) vsb[t] = vs[t][b];
+                if constexpr (kLogSigma) {
+                    T lp, dg[NGa], dp[NPa], ds[NSa];
+                    row_terms(p, fc, yv, off, vgb, xg, vpb, xp, vsb, xs, lp, dg, dp, ds);
+                    accL[b] += valid ? lp : T(0);
+#pragma unroll
+                    for (int t = 0; t < NG; ++t) accG[t][b] += valid ? dg[t] : T(0);
+#pragma unroll
+                    for (int t = 0; t < NP; ++t) {
+                        const T v = valid ? dp[t] : T(0);
+                        if constexpr (MID) {
+                            const bool second = li + i >= split;
+                            accP[t][b] += second ? T(0) : v;
+                            accP2[t][b] += second ? v : T(0);
+                        } else {
+                            accP[t][b] += v;
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < NS; ++t) accS[t][b] += valid ? ds[t] : T(0);
+                } else {
                 const T eta = eta_of(p, off, vgb, xg, vpb, xp, vsb, xs);
                 T lp, d;
                 family_row<T, FAM>(yv, eta, lp, d, fc);
@@ -619,6 +703,7 @@ struct RowKernel {
                 }
 #pragma unroll
                 for (int t = 0; t < NS; ++t) accS[t][b] += d * xs[t];
+                }
             }
         }
 

@@ -29,7 +29,8 @@ import pandas as pd
 from scipy.special import gammaln
 
 from sakkara_b200.plan.lower import UnsupportedModelError
-from sakkara_b200.plan.model_plan import FAMILY_IDS, LIKELIHOOD_IDS, PRIOR_PARAMS, ModelPlan, prior_normaliser
+from sakkara_b200.plan.model_plan import (FAMILY_IDS, LIKELIHOOD_IDS, PRIOR_PARAMS, XCOL_LOG_SIGMA, ModelPlan, Term,
+                                          prior_normaliser)
 
 LEVEL_GLOBAL, LEVEL_PRIMARY, LEVEL_SECONDARY = 0, 1, 2
 MAX_TERMS_PER_LEVEL = 2
@@ -184,9 +185,10 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     if dtype not in (np.dtype('float32'), np.dtype('float64')):
         raise ValueError('dtype must be float32 or float64')
     lik = plan.likelihood
-    if lik.sigma_rows_element is not None and plan.n_rows:
-        raise UnsupportedModelError('a plan whose likelihood sigma differs between rows is evaluated through '
-                                    'ModelPlan.split_by_sigma() (model.logp_dlogp_function() does that)')
+    log_sigma = lik.sigma_rows_element is not None and plan.n_rows > 0
+    if log_sigma and (lik.sigma_rows_element < 0).any():
+        raise UnsupportedModelError('rows with a constant sigma next to rows whose sigma is a parameter: evaluate the '
+                                    'parts of ModelPlan.split_by_sigma() (model.logp_dlogp_function() does that)')
 
     def take(a):
         if a is None or rows is None:
@@ -207,7 +209,12 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     column_of_term: Dict[int, int] = {}
     elem_of_term: Dict[int, np.ndarray] = {}    # block element per code, per term
     seen_arrays: Dict[int, int] = {}
-    plan_terms = plan.terms if n else []     # a plan without rows (the priors alone) has no linear predictor
+    plan_terms = list(plan.terms) if n else []     # a plan without rows (the priors alone) has no linear predictor
+    sigma_term = -1
+    if log_sigma and n:
+        # sigma per row = exp(theta[element]): log(sigma) is gathered like a term of the predictor (absolute elements)
+        sigma_term = len(plan_terms)
+        plan_terms.append(Term(block=-1, index=lik.sigma_rows_element, x=None))
     positive = np.zeros(plan.n_params, dtype=bool)
     for b in plan.blocks:
         positive[b.offset:b.offset + b.size] = b.transform != 'identity'
@@ -218,6 +225,9 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
             block = plan.blocks[term.block]
             if block.transform != 'identity':
                 raise UnsupportedModelError(f'{block.name}: positive variables cannot enter the linear predictor')
+        elif number == sigma_term:
+            if n and not positive[np.unique(index)].all():
+                raise UnsupportedModelError('a likelihood sigma must be a positive (log-transformed) variable')
         elif n and positive[np.unique(index)].any():
             raise UnsupportedModelError('positive variables cannot enter the linear predictor')
         if n == 0 or (term.block >= 0 and block.size == 1) or index.min() == index.max():
@@ -344,7 +354,7 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     terms: List[KernelTerm] = []
     counts = {LEVEL_GLOBAL: 0, LEVEL_PRIMARY: 0, LEVEL_SECONDARY: 0}
     for number, term in enumerate(plan_terms):
-        xc = xcol_of(term.x)
+        xc = XCOL_LOG_SIGMA if number == sigma_term else xcol_of(term.x)
         if number in global_terms:
             level = LEVEL_GLOBAL
             theta_index = np.array([global_terms[number]], dtype=np.int32)
@@ -390,9 +400,13 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
         logp_const += float(plan.logp_const) * (n / total if total else 1.0)
 
     sigma_const, sigma_theta_index = 1.0, -1
+    family = LIKELIHOOD_IDS[lik.family]
+    if log_sigma:
+        family = LIKELIHOOD_IDS['NormalLogSigma']
+        logp_const -= n * 0.91893853320467274178032973640562        # the kernel adds -r^2 / 2 - log(sigma) per row
     if lik.family == 'NegativeBinomial':
         sigma_const = float(lik.sigma_const)             # (its alpha travels in the same field of the C ABI)
-    if lik.family == 'Normal':
+    if lik.family == 'Normal' and not log_sigma:
         if lik.sigma_block is None:
             sigma_const = float(lik.sigma_const)
         else:
@@ -424,7 +438,7 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
             norm = np.broadcast_to(prior_normaliser(b.family, kb.a_const, kb.b_const), (b.size,))
             prior_logp_const += float(np.sum(norm, dtype=np.float64)) * (n / total if total else 1.0)
 
-    return KernelPlan(dtype=dtype, family=LIKELIHOOD_IDS[lik.family], n_rows=n, n_rows_total=total,
+    return KernelPlan(dtype=dtype, family=family, n_rows=n, n_rows_total=total,
                       n_params=plan.n_params, perm=perm, xcols=xcols, y=np.ascontiguousarray(y_store), y_kind=y_kind,
                       eta_offset=eta_offset, n_primary=n_primary, seg_offsets=seg_offsets, n_secondary=n_secondary,
                       sec_codes=None if sec_codes is None else np.ascontiguousarray(sec_codes), terms=terms,

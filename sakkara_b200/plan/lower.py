@@ -25,9 +25,6 @@ from sakkara_b200.model.dist import FAMILIES
 from sakkara_b200.plan.model_plan import Block, LikelihoodSpec, ModelPlan, PriorParam, Term
 
 
-MAX_SIGMA_SOURCES = 16     # distinct theta elements (plus constants) a row-dependent likelihood sigma may take
-
-
 class UnsupportedModelError(NotImplementedError):
     """The model has a structure the fused GLM kernel cannot express."""
 
@@ -377,10 +374,8 @@ def lower_model(model: sym.Model) -> ModelPlan:
                 spec.sigma_block, spec.sigma_index = source, int(used[0]) - blocks[source].offset
             else:
                 # sigma differs between rows (GroupComponent of parameters and constants, or a block gathered by
-                # group): kept per row; the evaluator splits the rows by their sigma (valuegrad.SplitSigmaValueGrad)
-                if used.size > MAX_SIGMA_SOURCES:
-                    raise UnsupportedModelError(f'Likelihood sigma takes {used.size} different values of theta; at most '
-                                                f'{MAX_SIGMA_SOURCES} are evaluated (one plan per value)')
+                # group): kept per row; the kernels gather log(sigma) like a term of the predictor, rows with constant
+                # sigmas form a standardised plan of their own (ModelPlan.split_by_sigma, valuegrad.SplitSigmaValueGrad)
                 spec.sigma_rows_element = np.ascontiguousarray(element, dtype=np.int64)
                 spec.sigma_rows_const = np.ascontiguousarray(const, dtype=np.float64)
     elif obs.family == 'Bernoulli':

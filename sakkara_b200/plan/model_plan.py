@@ -21,7 +21,8 @@ FAMILY_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'HalfNormal': 3, 'Expon
               'HalfCauchy': 5, 'Gamma': 6, 'InverseGamma': 7, 'Cauchy': 8, 'Laplace': 9, 'LogNormal': 10,
               'HalfStudentT': 11}
 # likelihood families (SKK_LIK_* of include/skk_b200.h; the first three share FAMILY_IDS' numbers)
-LIKELIHOOD_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3}
+LIKELIHOOD_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3, 'NormalLogSigma': 4}
+XCOL_LOG_SIGMA = -2      # xcol of a term of log(sigma) (SKK_XCOL_LOG_SIGMA)
 # prior families: names of the parameters that travel as a / b through the C ABI (include/skk_b200.h)
 PRIOR_PARAMS = {'Normal': ('mu', 'sigma'), 'HalfNormal': ('sigma', None), 'Exponential': ('lam', None),
                 'HalfCauchy': ('beta', None), 'Gamma': ('alpha', 'beta'), 'InverseGamma': ('alpha', 'beta'),
@@ -158,11 +159,16 @@ class ModelPlan:
                 return number
         raise IndexError(element)
 
-    def split_by_sigma(self) -> List['ModelPlan']:
+    def split_by_sigma(self, per_element: bool = False) -> List['ModelPlan']:
         """
-        A plan whose Normal sigma differs between rows as standard plans over disjoint row sets, one per element of
-        theta that serves as sigma (a plan with that one sigma parameter) and one for the rows with constant sigmas
-        (standardised: y, offset and data columns divided by sigma_i, unit sigma, sum(-log sigma_i) in the constant).
+        A plan whose Normal sigma differs between rows as plans the kernels evaluate, over disjoint row sets:
+
+        * the rows whose sigma is an element of theta: ONE plan whose kernel gathers log(sigma) per row like a term of
+          the linear predictor (``SKK_LIK_NORMAL_LOGSIGMA``; it keeps ``sigma_rows_element``, all >= 0) -- or, with
+          ``per_element`` (and always when there is a single such element), one standard plan per element;
+        * the rows with constant sigmas: a standardised plan (y, offset and data columns divided by sigma_i, unit
+          sigma, sum(-log sigma_i) in the constant).
+
         Their likelihoods add up to this plan's; the priors are this plan's without rows.
         """
         import dataclasses
@@ -170,7 +176,13 @@ class ModelPlan:
         if spec.sigma_rows_element is None:
             return [self]
         out = []
-        for element in np.unique(spec.sigma_rows_element):
+        elements = np.unique(spec.sigma_rows_element)
+        linked = elements[elements >= 0]
+        if linked.size > 1 and not per_element:
+            rows = np.flatnonzero(spec.sigma_rows_element >= 0)
+            out.append(self if rows.size == self.n_rows else self.take_rows(rows))
+            elements = elements[elements < 0]
+        for element in elements:
             rows = np.flatnonzero(spec.sigma_rows_element == element)
             part = self.take_rows(rows)
             lik = part.likelihood

@@ -155,17 +155,20 @@ class SplitSigmaValueGrad:
     """
     Value and gradient of a model whose Normal likelihood has a sigma that differs between rows and depends on theta
     -- sigma per group as a parameter, e.g. a ``GroupComponent`` of positive variables and constants (reference
-    ``tests/workflows/test_state_space.py:64-82``).  The rows are split by the element of theta that is their sigma
-    (``ModelPlan.split_by_sigma``): every part is a standard plan with ONE sigma parameter (or, for the constant
-    sigmas, standardised rows) evaluated by the fused kernels without priors; the priors come from a plan without
-    rows; the parts are added on the host in a fixed order.
+    ``tests/workflows/test_state_space.py:64-82``) or a positive block gathered by group.  The rows whose sigma is a
+    parameter form ONE plan whose row kernel gathers ``log(sigma)`` per row like a term of the linear predictor
+    (``SKK_LIK_NORMAL_LOGSIGMA``: lp = -r^2/2 - zeta, d/d eta = r / sigma, d/d zeta = r^2 - 1), so any number of
+    groups costs one pass; rows with constant sigmas, if any, form a standardised standard plan; the priors come from
+    a plan without rows; the parts are added on the host in a fixed order.  ``per_element=True`` evaluates one
+    standard plan per sigma parameter instead (the cross-check of the kernel family in the tests).
     """
 
-    def __init__(self, plan: ModelPlan, dtype: str = 'float64', max_batch: int = 1, device: Optional[int] = None):
+    def __init__(self, plan: ModelPlan, dtype: str = 'float64', max_batch: int = 1, device: Optional[int] = None,
+                 per_element: bool = False):
         self.model_plan = plan
         self.dtype = np.dtype(dtype)
         self.parts = [ValueGradFunction(part, dtype=dtype, max_batch=max_batch, device=device, include_priors=False)
-                      for part in plan.split_by_sigma()]
+                      for part in plan.split_by_sigma(per_element=per_element)]
         self._priors = ValueGradFunction(plan.take_rows([]), dtype=dtype, max_batch=max_batch, device=device)
 
     @property

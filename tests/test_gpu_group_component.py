@@ -65,3 +65,46 @@ def test_member_wise_model_parity(n, family, dtype):
         l, g = logp_dlogp_autograd(model.recorded, theta)
         err_l, err_g = parity_error(l, g, plan, theta)
         assert err_l < 1e-12 and err_g < 1e-12
+
+
+def sigma_frame(n, groups, seed=5):
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, groups, n)
+    x = rng.normal(size=n)
+    sd = rng.uniform(0.3, 1.5, groups)[g]
+    return pd.DataFrame({'group': g, 'x': x, 'y': 0.6 * x + 0.1 + sd * rng.normal(size=n)})
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+@pytest.mark.parametrize('n,groups', [(2_000, 7), (150_000, 300)])
+def test_sigma_per_group_as_a_parameter(n, groups, dtype):
+    """sigma of the Normal likelihood is a positive block gathered by group: the row kernel gathers log(sigma) per
+    row (SKK_LIK_NORMAL_LOGSIGMA); cross-checked with one standard plan per sigma on the small case."""
+    df = sigma_frame(n, groups)
+    DC = api.DistributionComponent
+
+    def lik():
+        data = api.data_components(df[['x', 'y']])
+        k = DC(pm.Normal, name='k', group='group', mu=DC(pm.Normal, name='k_mean'), sigma=DC(pm.HalfNormal, name='k_sd'))
+        sigma = DC(pm.HalfNormal, name='noise', group='group', sigma=1.0)
+        return api.Likelihood(pm.Normal, mu=k * data['x'] + DC(pm.Normal, name='icpt'), sigma=sigma, observed=data['y'])
+    model = api.build(df, lik(), backend='b200')
+    plan = model.plan
+    assert plan.likelihood.sigma_rows_element is not None
+    assert len(np.unique(plan.likelihood.sigma_rows_element)) == groups
+    f = model.logp_dlogp_function(dtype=dtype, device=0, max_batch=2)
+    assert f.parts[0].kernel_plan.family == 4 and len(f.parts) == 1
+    rng = np.random.default_rng(2)
+    theta = rng.normal(0, 0.2, (2, plan.n_params))
+    logp, grad = f(theta.astype(dtype))
+    for b in range(2):
+        assert_parity(logp[b], grad[b], plan, theta[b], dtype)
+    one, g_one = f(theta[0].astype(dtype))
+    assert_parity(one, g_one, plan, theta[0], dtype)
+    f.close()
+    if groups <= 16:
+        g = model.logp_dlogp_function(dtype=dtype, device=0, per_element=True)
+        assert len(g.parts) == groups and all(p.kernel_plan.family == 0 for p in g.parts)
+        logp2, grad2 = g(theta[0].astype(dtype))
+        assert_parity(logp2, grad2, plan, theta[0], dtype)
+        g.close()
