@@ -89,7 +89,11 @@ class B200Model:
         if self.plan.likelihood.sigma_rows_element is not None:
             if self.plan.minibatch is not None:
                 raise NotImplementedError('a mini-batched likelihood with a sigma that differs between rows')
-            # sigma per group as a parameter: one standard plan per sigma, added up
+            # sigma per group as a parameter: the row kernel gathers log(sigma) per row; rows with constant sigmas
+            # next to them (or per_element=True) make it a sum of plans
+            if (self.plan.likelihood.sigma_rows_element >= 0).all() and not options.get('per_element'):
+                options.pop('per_element', None)
+                return ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
             return SplitSigmaValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
         if self.plan.minibatch is not None:
             # MinibatchLikelihood: a fresh random subset of the rows per call, scaled to the whole data set
