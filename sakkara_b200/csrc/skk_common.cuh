@@ -93,7 +93,7 @@ struct RowParams {
 //   0 %globaltimer at kernel entry     1 ... when the prologue is done (before the first tile wait)
 //   2 ... when the first tile has arrived   3 ... at the end of the tile loop   4 ... at kernel exit
 //   5, 6, 7 tiles of the warp with one group / two groups / more
-constexpr int kTraceWords = 12;  // (row kernel: 0-4 timeline, 5-7 tiles per class, 8-11 inside prologue and epilogue)
+constexpr int kTraceWords = 16;  // (row kernel: 0-4 timeline, 5-7 tiles per class, 8-13 inside prologue and epilogue)
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;

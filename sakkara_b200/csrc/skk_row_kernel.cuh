@@ -994,39 +994,43 @@ struct RowKernel {
         // prior work some warps carry).  A fixed list per warp keeps every sum in a fixed order.
         // [sched_len + 4] entries per warp, -1 behind the last tile; sched_len is a multiple of 4.
         const int32_t *my_tiles = p.sched + ((int64_t)blockIdx.x * warps + warp) * (p.sched_len + 4);
-        const int4 first4 = *reinterpret_cast<const int4 *>(my_tiles);
-        int t0 = first4.x, t1 = first4.y, t2 = first4.z, t3 = first4.w;
-
-        if (lane == 0) {
-            for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
-            mbar_fence_init();
-        }
-        __syncwarp();
-        // start the pipeline before touching anything else
-        if (elect_one()) {
-            for (int s = 0; s < stages; ++s) {   // stages <= 3
-                const int t = s == 0 ? t0 : (s == 1 ? t1 : t2);
-                if (t >= 0) issue_tile(p, t, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
-            }
-        }
-
         // optional timeline of the warp (skk_trace_enable); nothing of it is carried through the tile loop
         auto stamp = [&](int word) {
             if (p.trace != nullptr && lane == 0)
                 p.trace[((int64_t)blockIdx.x * warps + warp) * kTraceWords + word] = global_timer_ns();
         };
         stamp(0);
-        if (p.peer_seq != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *p.peer_seq = *p.peer_seq + 1;
-        // the kernel that follows in the stream may start its own prologue under this kernel's tail (PDL)
-        if (p.pdl_trigger == 1) grid_dep_launch_dependents();
+        const int4 first4 = *reinterpret_cast<const int4 *>(my_tiles);
 
+        // The small loads of the prologue are requested BEFORE the pipeline starts: all warps of the grid start
+        // their rings at once (c4: 296 x 8 x 3 tiles = 27 MB), and a load issued behind that burst waits for it in the
+        // memory system -- the value table used to be complete 4.8 us after the kernel's entry, most of it queueing.
         // Everything the warp needs before its first tile is two levels of dependent global loads (slot ->
-        // theta element -> value): all first-level loads are issued here, then all second-level ones, so
-        // the prologue costs two memory latencies instead of one pair per item.
-        // level 1: theta elements of the global terms, keys of the first two tiles, elements of the value table
+        // theta element -> value): what needs no earlier result goes first.
+        // level 1: theta elements of the global terms, elements of the value table (none to load when the planner
+        // numbered the slots so that slot -> theta is `base + slot`), and the table's values themselves
         int eg[NGa];
 #pragma unroll
         for (int t = 0; t < NGa; ++t) eg[t] = (NG > 0 && t < NG) ? p.ti_g[t][0] : 0;
+        constexpr int kFillUnroll = 4;
+        const int n_sec = NS * p.n_secondary * BT;
+        int element[kFillUnroll];
+        T vfill[kFillUnroll];
+        if constexpr (NS > 0) {
+#pragma unroll
+            for (int u = 0; u < kFillUnroll; ++u) {
+                const int k = threadIdx.x + u * blockDim.x;
+                element[u] = k >= n_sec ? -1
+                             : (NS == 1 && p.sec_theta_base >= 0) ? p.sec_theta_base + (k / BT) % p.n_secondary
+                                                                  : p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary];
+            }
+#pragma unroll
+            for (int u = 0; u < kFillUnroll; ++u)
+                vfill[u] = element[u] >= 0 ? theta_at(p, (threadIdx.x + u * blockDim.x) % BT, element[u]) : T(0);
+        }
+
+        int t0 = first4.x, t1 = first4.y, t2 = first4.z, t3 = first4.w;
+        // keys of the first two tiles (their theta elements ride in the tile meta)
         int4 k0 = make_int4(0, 0, 0, 0), k1 = make_int4(0, 0, 0, 0);
         int sp0 = -1, sp1 = -1;
         if constexpr (NP > 0) {
@@ -1037,18 +1041,23 @@ struct RowKernel {
                 if (t1 >= 0) sp1 = p.tile_split[t1];
             }
         }
-        constexpr int kFillUnroll = 4;
-        const int n_sec = NS * p.n_secondary * BT;
-        int element[kFillUnroll];
-        if constexpr (NS > 0) {
-#pragma unroll
-            for (int u = 0; u < kFillUnroll; ++u) {
-                const int k = threadIdx.x + u * blockDim.x;
-                element[u] = k >= n_sec ? -1
-                             : (NS == 1 && p.sec_theta_base >= 0) ? p.sec_theta_base + (k / BT) % p.n_secondary
-                                                                  : p.ti_s[k / (BT * p.n_secondary)][(k / BT) % p.n_secondary];
+
+        if (lane == 0) {
+            for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        // start the pipeline
+        if (elect_one()) {
+            for (int s = 0; s < stages; ++s) {   // stages <= 3
+                const int t = s == 0 ? t0 : (s == 1 ? t1 : t2);
+                if (t >= 0) issue_tile(p, t, stage0 + (int64_t)s * sl.bytes, sl, bars + s);
             }
         }
+        if (p.peer_seq != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *p.peer_seq = *p.peer_seq + 1;
+        // the kernel that follows in the stream may start its own prologue under this kernel's tail (PDL)
+        if (p.pdl_trigger == 1) grid_dep_launch_dependents();
+
         // lane j of a straddling tile stages group kf + j: its theta elements are fetched one tile ahead
         auto staged_elements = [&](const int4 &meta, int (&out)[NPa]) {
 #pragma unroll
@@ -1056,21 +1065,17 @@ struct RowKernel {
                 out[t] = (NP > 0 && meta.x != meta.y && lane <= meta.y - meta.x && meta.y - meta.x < kStagedGroups)
                              ? p.ti_p[t][meta.x + lane] : 0;
         };
-        // level 2: the values
-        T vg[NGa][BT];
-#pragma unroll
-        for (int t = 0; t < NGa; ++t)
-#pragma unroll
-            for (int b = 0; b < BT; ++b) vg[t][b] = (NG > 0) ? theta_at(p, b, eg[t]) : T(0);
-        T vp0[NPa][BT];
-        load_vp(p, k0, vp0);
-        int se0[NPa], se1[NPa];
-        staged_elements(k0, se0);
+        // level 2.  A warp issues in order: the accumulator tables are cleared under the latency of the value-table
+        // loads requested above, then the values are stored; the values of the global terms and of the first tile's
+        // group -- whose theta elements are level-1 results, back by then -- are requested last and arrive under the
+        // barrier and the first wait for a tile.
         if constexpr (NS > 0) {
+            for (int k = threadIdx.x; k < n_sec * warps; k += blockDim.x) gradS_all[k] = T(0);
+            stamp(13);
 #pragma unroll
             for (int u = 0; u < kFillUnroll; ++u) {
                 const int k = threadIdx.x + u * blockDim.x;
-                if (element[u] >= 0) valS[k] = theta_at(p, k % BT, element[u]);
+                if (element[u] >= 0) valS[k] = vfill[u];
             }
             // (tables with more entries than one round of the CTA: the rest, four at a time as above)
             for (int k0f = threadIdx.x + kFillUnroll * blockDim.x; k0f < n_sec; k0f += kFillUnroll * blockDim.x) {
@@ -1088,9 +1093,18 @@ struct RowKernel {
                     if (el[u] >= 0) valS[k] = theta_at(p, k % BT, el[u]);
                 }
             }
-            for (int k = threadIdx.x; k < n_sec * warps; k += blockDim.x) gradS_all[k] = T(0);
-            __syncthreads();
+            stamp(12);  // (value table written)
         }
+        T vg[NGa][BT];
+#pragma unroll
+        for (int t = 0; t < NGa; ++t)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) vg[t][b] = (NG > 0) ? theta_at(p, b, eg[t]) : T(0);
+        T vp0[NPa][BT];
+        load_vp(p, k0, vp0);
+        int se0[NPa], se1[NPa];
+        staged_elements(k0, se0);
+        if constexpr (NS > 0) __syncthreads();
         stamp(8);
 
         // (after the barrier: the warps without prior work start on their tiles at once)

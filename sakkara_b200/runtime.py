@@ -258,7 +258,7 @@ class SkkPlan:
 
     def trace_read(self, finish: bool = False) -> np.ndarray:
         """
-        ``[grid * warps, 12]`` uint64 of the row kernel: globaltimer ns at entry / prologue done / first tile / loop
+        ``[grid * warps, 16]`` uint64 of the row kernel: globaltimer ns at entry / prologue done / first tile / loop
         end / exit (words 5-7: tiles per class; 8-11: value tables filled / priors done / all warps of the CTA done
         / global partials stored).  ``finish=True``: the records of the kernel behind it instead,
         one per CTA that ran -- entry / row kernel's results visible / own sums stored / exit / CTA class.
@@ -266,7 +266,7 @@ class SkkPlan:
         self._guard()
         st = self.stats()
         n_rows = st['grid'] * (st['block'] // 32)
-        out = np.zeros((n_rows + 1024, 12), dtype=np.uint64)
+        out = np.zeros((n_rows + 1024, 16), dtype=np.uint64)
         n = self.lib.skk_trace_read(self._handle, out.ctypes.data, out.size)
         if n < 0:
             _check(self.lib, int(n))

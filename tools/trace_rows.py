@@ -73,6 +73,10 @@ def main():
     print('entry after first entry :', q(t0 - base))
     print('prologue (entry->ready)  :', q(t1 - t0))
     if tr.shape[1] >= 12 and tr[:, 8].max() > 0:
+        if tr.shape[1] >= 14 and tr[:, 12].max() > 0:
+            print('    tables cleared (entry->):', q(tr[:, 13] - t0))
+            print('    values written (->)     :', q(tr[:, 12] - tr[:, 13]))
+            print('    first values requested, barrier (->):', q(tr[:, 8] - tr[:, 12]))
         print('  tables filled (entry->) :', q(tr[:, 8] - t0))
         print('  priors (->done)         :', q(tr[:, 9] - tr[:, 8]))
         print('  rest (->ready)          :', q(t1 - tr[:, 9]))
