@@ -652,10 +652,20 @@ __device__ __forceinline__ void finish_body(const ReduceParams &rp, const PeerPa
 #pragma unroll
                     for (int b = 0; b < BT; ++b)
                         acc[b] = rp.direct_p[((int64_t)t * rp.n_primary + slot) * BT + b] + addend(d, t_lo, t, b);
-#pragma unroll 4
-                    for (int64_t tile = t_lo + 1; tile < t_hi; ++tile)
+                    // (tiles in order, their loads requested sixteen at a time for a batch tile of one)
+                    constexpr int kAhead = BT == 1 ? 16 : 4;
+                    for (int64_t tile0 = t_lo + 1; tile0 < t_hi; tile0 += kAhead) {
+                        double v[kAhead][BT];
 #pragma unroll
-                        for (int b = 0; b < BT; ++b) acc[b] += rp.tile_head[(tile * rp.np + t) * BT + b];
+                        for (int u = 0; u < kAhead; ++u)
+#pragma unroll
+                            for (int b = 0; b < BT; ++b)
+                                v[u][b] = tile0 + u < t_hi ? rp.tile_head[((tile0 + u) * rp.np + t) * BT + b] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < kAhead; ++u)
+#pragma unroll
+                            for (int b = 0; b < BT; ++b) acc[b] += v[u][b];
+                    }
                     if (t_hi > t_lo)
 #pragma unroll
                         for (int b = 0; b < BT; ++b) acc[b] += addend(d, t_hi, t, b);
