@@ -15,6 +15,7 @@ gathers.  Anything that is not affine in the parameters -- products of two block
 arbitrary ``f_`` callables -- raises ``NotImplementedError``: there is no CPU fallback on this
 path, the caller is told to use the stock PyMC graph.
 """
+import threading
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Union
 
@@ -56,7 +57,14 @@ class AffineForm:
         return total
 
 
-_minibatches_seen: List[Any] = []      # MinibatchIndex nodes met by _lower since lower_model() started
+class _Seen(threading.local):
+    """MinibatchIndex nodes met by _lower since lower_model() started (per thread)."""
+
+    def __init__(self):
+        self.nodes: List[Any] = []
+
+
+_seen = _Seen()
 
 
 def _scale(coef, factor):
@@ -85,7 +93,7 @@ def _lower(node: Any) -> AffineForm:
         return AffineForm(node.shape, out)
     if isinstance(node, sym.MinibatchGather):
         # lowered over ALL rows: which rows an evaluation uses is decided when it runs (ModelPlan.minibatch)
-        _minibatches_seen.append(node.minibatch)
+        _seen.nodes.append(node.minibatch)
         return _lower(node.base)
     if isinstance(node, sym.Concat):
         # piece by piece: the piece's monomials, zero outside the piece's range
@@ -320,7 +328,7 @@ def lower_model(model: sym.Model) -> ModelPlan:
             block.params[key] = param
 
     obs = model.observed_RVs[0]
-    del _minibatches_seen[:]
+    _seen.nodes = []
     y_form = _lower(obs.observed)
     if not y_form.is_const:
         raise UnsupportedModelError('Observed data must be constant')
@@ -437,10 +445,10 @@ def lower_model(model: sym.Model) -> ModelPlan:
     if obs.total_size is not None:
         # (the observed variable itself keeps the shape of the whole group, reference test_minibatch.py:22; the size
         # of the batch is that of the index variable its parameters and observations are gathered with)
-        if len({id(mb) for mb in _minibatches_seen}) != 1 or _minibatches_seen[0].n != n_rows:
+        if len({id(mb) for mb in _seen.nodes}) != 1 or _seen.nodes[0].n != n_rows:
             raise UnsupportedModelError('A mini-batched likelihood needs one mini-batch variable over all observations')
-        plan.minibatch = int(_minibatches_seen[0].batch_size)
-    elif _minibatches_seen:
+        plan.minibatch = int(_seen.nodes[0].batch_size)
+    elif _seen.nodes:
         raise UnsupportedModelError('Mini-batched components outside a MinibatchLikelihood')
     if row_sigma is not None:
         weight = 1.0 / row_sigma
