@@ -55,7 +55,11 @@ extern "C" {
 #define SKK_LIK_NORMAL_LOGSIGMA 4 /* pm.Normal(mu=eta, sigma=exp(zeta)): zeta = sum of the terms whose xcol is
                                     SKK_XCOL_LOG_SIGMA (sigma per group as a parameter; every such term reads
                                     log-transformed elements of theta).  -N log(sqrt(2 pi)) belongs into logp_const */
-/* skk_term_desc.xcol of a term of the log-scale predictor zeta of SKK_LIK_NORMAL_LOGSIGMA (no data column) */
+#define SKK_LIK_STUDENTT_LOGSIGMA 5 /* pm.StudentT(nu=const, mu=eta, sigma=exp(zeta)): nu travels in
+                                    skk_plan_desc.sigma_const; zeta = sum of the SKK_XCOL_LOG_SIGMA terms (none: sigma = 1,
+                                    i.e. rows standardised by a constant sigma); the normaliser
+                                    N (lgamma((nu+1)/2) - lgamma(nu/2) - log(nu pi)/2) belongs into logp_const */
+/* skk_term_desc.xcol of a term of the log-scale predictor zeta of the *_LOGSIGMA families (no data column) */
 #define SKK_XCOL_LOG_SIGMA (-2)
 
 /* prior families of parameter blocks: the generator given to DistributionComponent
@@ -153,7 +157,7 @@ typedef struct {
     int32_t n_blocks;
     const skk_term_desc *terms;
     const skk_block_desc *blocks;
-    double sigma_const;         /* Normal likelihood: fixed sigma ... (NegativeBinomial: alpha) */
+    double sigma_const;         /* Normal likelihood: fixed sigma ... (NegativeBinomial: alpha; StudentT: nu) */
     int64_t sigma_theta_index;  /* ... or index of log(sigma) in theta; -1: const */
     double logp_const;          /* theta-independent part of logp of this shard
                                    (Poisson: -sum lgamma(y+1); the rows masked for NaN

@@ -97,6 +97,9 @@ def logp_dlogp_autograd(recorded: sym.Model, theta: np.ndarray):
             total = total + d.log_prob(y).sum()
         elif rv.family == 'Poisson':
             total = total + torch.distributions.Poisson(params['mu']).log_prob(y).sum()
+        elif rv.family == 'StudentT':
+            total = total + torch.distributions.StudentT(torch.as_tensor(params['nu'], dtype=torch.float64), params['mu'],
+                                                         params['sigma']).log_prob(y).sum()
         elif rv.family == 'NegativeBinomial':
             # torch: total_count failures r and success probability p of the counted event; mean r p / (1 - p)
             mu, alpha = params['mu'], torch.as_tensor(params['alpha'], dtype=torch.float64)

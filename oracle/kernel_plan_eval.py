@@ -33,7 +33,16 @@ def likelihood_from_kernel_plan(kp, theta):
     y = kp.y.astype(np.float64)
     grad = np.zeros(kp.n_params)
     dz = None
-    if kp.family == 4:
+    if kp.family == 5:              # StudentT, nu in the sigma field, sigma = exp(zeta) (1 without a zeta term)
+        nu = kp.sigma_const
+        zeta = np.zeros(n) if zeta is None else zeta
+        sigma = np.exp(zeta)
+        r = (y - eta) / sigma
+        w = (nu + 1.0) / (nu + r * r)
+        logp = np.sum(-0.5 * (nu + 1.0) * np.log1p(r * r / nu) - zeta)
+        d = w * r / sigma
+        dz = w * r * r - 1.0
+    elif kp.family == 4:
         sigma = np.exp(zeta)
         r = (y - eta) / sigma
         logp = np.sum(-0.5 * r * r - zeta)

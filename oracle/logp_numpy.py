@@ -240,6 +240,23 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
             contrib = r * r - T(1)
             grad[sb.offset + lik.sigma_index] += np.sum(contrib, dtype=np.float64)
             mass[sb.offset + lik.sigma_index] += np.sum(np.abs(contrib), dtype=np.float64)
+    elif lik.family == 'StudentT':
+        # pymc StudentT(nu, mu, sigma): lgamma((nu+1)/2) - lgamma(nu/2) - log(nu pi)/2 - log(sigma) - (nu+1)/2 log1p(r^2/nu)
+        nu = T(lik.nu)
+        element = getattr(lik, 'sigma_rows_element', None)
+        if element is None:
+            sigma = np.ones(plan.n_rows, dtype=dtype)            # rows standardised by their constant sigma
+            linked = np.zeros(plan.n_rows, dtype=bool)
+        else:
+            linked = element >= 0
+            sigma = np.where(linked, np.exp(theta[np.maximum(element, 0)]), lik.sigma_rows_const.astype(dtype)).astype(dtype)
+        r = (y - eta) / sigma
+        norm = T(gammaln(0.5 * (float(nu) + 1.0)) - gammaln(0.5 * float(nu)) - 0.5 * np.log(float(nu) * np.pi))
+        terms = norm - np.log(sigma) - T(0.5) * (nu + T(1)) * np.log1p(r * r / nu)
+        w = (nu + T(1)) / (nu + r * r)
+        d_eta = w * r / sigma
+        if element is not None:
+            acc_absolute(element[linked], (w * r * r - T(1))[linked])
     elif lik.family == 'Bernoulli':
         terms = y * eta - softplus(eta)
         d_eta = y - sigmoid(eta)

@@ -47,6 +47,10 @@ const void *row_kernel_f32_logsigma_bt1(int, int, int, int);
 const void *row_kernel_f32_logsigma_bt4(int, int, int, int);
 const void *row_kernel_f64_logsigma_bt1(int, int, int, int);
 const void *row_kernel_f64_logsigma_bt4(int, int, int, int);
+const void *row_kernel_f32_studentt_bt1(int, int, int, int);
+const void *row_kernel_f32_studentt_bt4(int, int, int, int);
+const void *row_kernel_f64_studentt_bt1(int, int, int, int);
+const void *row_kernel_f64_studentt_bt4(int, int, int, int);
 const void *chain_kernel_f32(int, int, int);
 const void *chain_kernel_f64(int, int, int);
 }  // namespace skk
@@ -312,18 +316,20 @@ static int upload_tiled(skk_plan *pl, void **out, const void *host, size_t n, si
 
 static const void *lookup_kernel(int dtype, int family, int bt, int ng, int np, int ns, int spec) {
     typedef const void *(*Lookup)(int, int, int, int);
-    static const Lookup table[2][5][2] = {
+    static const Lookup table[2][6][2] = {
         {{row_kernel_f32_normal_bt1, row_kernel_f32_normal_bt4},
          {row_kernel_f32_bernoulli_bt1, row_kernel_f32_bernoulli_bt4},
          {row_kernel_f32_poisson_bt1, row_kernel_f32_poisson_bt4},
          {row_kernel_f32_negbinomial_bt1, row_kernel_f32_negbinomial_bt4},
-         {row_kernel_f32_logsigma_bt1, row_kernel_f32_logsigma_bt4}},
+         {row_kernel_f32_logsigma_bt1, row_kernel_f32_logsigma_bt4},
+         {row_kernel_f32_studentt_bt1, row_kernel_f32_studentt_bt4}},
         {{row_kernel_f64_normal_bt1, row_kernel_f64_normal_bt4},
          {row_kernel_f64_bernoulli_bt1, row_kernel_f64_bernoulli_bt4},
          {row_kernel_f64_poisson_bt1, row_kernel_f64_poisson_bt4},
          {row_kernel_f64_negbinomial_bt1, row_kernel_f64_negbinomial_bt4},
-         {row_kernel_f64_logsigma_bt1, row_kernel_f64_logsigma_bt4}}};
-    if (family < 0 || family > 4 || (bt != 1 && bt != 4)) return nullptr;
+         {row_kernel_f64_logsigma_bt1, row_kernel_f64_logsigma_bt4},
+         {row_kernel_f64_studentt_bt1, row_kernel_f64_studentt_bt4}}};
+    if (family < 0 || family > 5 || (bt != 1 && bt != 4)) return nullptr;
     return table[dtype == SKK_F64 ? 1 : 0][family][bt == 4 ? 1 : 0](ng, np, ns, spec);
 }
 
@@ -435,7 +441,7 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     // ---- row columns, padded to whole tiles ------------------------------------------------------
     // (a plan with a chain path keeps a second copy in row order for the chain kernel)
     const bool row_copy = kStageTransposed && pl->ns == 0 && pl->max_batch >= kChainMinBatch && env_int("SKK_NO_CHAIN", 0) == 0 &&
-                          pl->family != SKK_LIK_NORMAL_LOGSIGMA;
+                          pl->family != SKK_LIK_NORMAL_LOGSIGMA && pl->family != SKK_LIK_STUDENTT_LOGSIGMA;
     const int R = kRowsPerLane;
     for (int c = 0; c < d->n_xcols; ++c) {
         int rc = upload_tiled<T>(pl, &pl->x[c], d->xcols[c], n, padded, R);
@@ -924,7 +930,8 @@ static int create_impl(const skk_plan_desc *d, skk_plan *pl) {
     pl->use_graphs = env_int("SKK_NO_GRAPH", 0) == 0;
 
     // ---- chain-per-lane path: batches of >= kChainMinBatch vectors, models without a secondary level ----------
-    if (pl->ns == 0 && pl->max_batch >= kChainMinBatch && env_int("SKK_NO_CHAIN", 0) == 0 && pl->family != SKK_LIK_NORMAL_LOGSIGMA) {
+    if (pl->ns == 0 && pl->max_batch >= kChainMinBatch && env_int("SKK_NO_CHAIN", 0) == 0 && pl->family != SKK_LIK_NORMAL_LOGSIGMA &&
+        pl->family != SKK_LIK_STUDENTT_LOGSIGMA) {
         pl->chain_fn = pl->dtype == SKK_F64 ? chain_kernel_f64(pl->family, pl->ng, pl->np)
                                             : chain_kernel_f32(pl->family, pl->ng, pl->np);
         if (!pl->chain_fn) return fail(SKK_ERR_UNSUPPORTED, "no chain kernel for this shape");
@@ -1029,7 +1036,7 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
         rp.xcol_s[t] = pl->xcol_s[t];
     }
     rp.theta = th;
-    rp.fam_a = (T)(pl->family == SKK_LIK_NEGBINOMIAL_LOG ? pl->sigma_const : 0.0);
+    rp.fam_a = (T)((pl->family == SKK_LIK_NEGBINOMIAL_LOG || pl->family == SKK_LIK_STUDENTT_LOGSIGMA) ? pl->sigma_const : 0.0);
     rp.fam_b = (T)(pl->family == SKK_LIK_NEGBINOMIAL_LOG ? log(pl->sigma_const) : 0.0);
     rp.sec_theta_base = pl->sec_theta_base;
     rp.n_params = pl->n_params;
@@ -1447,7 +1454,8 @@ int skk_plan_create(const skk_plan_desc *d, skk_plan **out) {
     if (d->abi_version != SKK_ABI_VERSION)
         return fail(SKK_ERR_INVALID, "descriptor ABI %d, library ABI %d", d->abi_version, SKK_ABI_VERSION);
     if (d->dtype != SKK_F32 && d->dtype != SKK_F64) return fail(SKK_ERR_INVALID, "bad dtype %d", d->dtype);
-    if (d->family < SKK_LIK_NORMAL || d->family > SKK_LIK_NORMAL_LOGSIGMA) return fail(SKK_ERR_UNSUPPORTED, "bad family %d", d->family);
+    if (d->family < SKK_LIK_NORMAL || d->family > SKK_LIK_STUDENTT_LOGSIGMA) return fail(SKK_ERR_UNSUPPORTED, "bad family %d", d->family);
+    if (d->family == SKK_LIK_STUDENTT_LOGSIGMA && !(d->sigma_const > 0.0)) return fail(SKK_ERR_INVALID, "StudentT nu must be positive");
     if (d->family == SKK_LIK_NEGBINOMIAL_LOG && !(d->sigma_const > 0.0)) return fail(SKK_ERR_INVALID, "NegativeBinomial alpha must be positive");
     if (d->n_rows < 0 || d->n_rows >= (int64_t)1 << 40) return fail(SKK_ERR_INVALID, "bad n_rows");
     if ((d->n_rows + 32 * kRowsPerLane - 1) / (32 * kRowsPerLane) >= INT32_MAX) return fail(SKK_ERR_UNSUPPORTED, "too many rows");
@@ -1490,7 +1498,7 @@ int skk_plan_create(const skk_plan_desc *d, skk_plan **out) {
     for (int i = 0; i < d->n_terms && rc == SKK_OK; ++i) {
         const skk_term_desc &td = d->terms[i];
         if (td.level < SKK_LEVEL_GLOBAL || td.level > SKK_LEVEL_SECONDARY) rc = fail(SKK_ERR_INVALID, "term %d: bad level", i);
-        else if ((td.xcol < -1 && !(td.xcol == SKK_XCOL_LOG_SIGMA && d->family == SKK_LIK_NORMAL_LOGSIGMA)) || td.xcol >= d->n_xcols)
+        else if ((td.xcol < -1 && !(td.xcol == SKK_XCOL_LOG_SIGMA && (d->family == SKK_LIK_NORMAL_LOGSIGMA || d->family == SKK_LIK_STUDENTT_LOGSIGMA))) || td.xcol >= d->n_xcols)
             rc = fail(SKK_ERR_INVALID, "term %d: bad xcol", i);
         else if (!td.theta_index) rc = fail(SKK_ERR_INVALID, "term %d: null theta_index", i);
         else if (td.level == SKK_LEVEL_GLOBAL) { if (td.n_slots != 1) rc = fail(SKK_ERR_INVALID, "term %d: global terms have one slot", i); ++pl->ng; }

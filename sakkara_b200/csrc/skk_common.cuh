@@ -418,6 +418,7 @@ struct Math<float> {
     static __device__ __forceinline__ float log1p_of_exp_neg(float t) {  // t in (0, 1]
         return lg2(1.0f + t) * 0.6931471805599453f;
     }
+    static __device__ __forceinline__ float log1p_pos(float x) { return ::log1pf(x); }  // x >= 0, any size
     static __device__ __forceinline__ float rcp(float x) {
         float r;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -430,6 +431,7 @@ template <>
 struct Math<double> {
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
     static __device__ __forceinline__ double log1p_of_exp_neg(double t) { return ::log1p(t); }
+    static __device__ __forceinline__ double log1p_pos(double x) { return ::log1p(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double abs(double x) { return fabs(x); }
     static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
@@ -450,6 +452,18 @@ __device__ __forceinline__ void normal_logsigma_row(T y, T eta, T zeta, T &lp, T
     lp = T(-0.5) * r * r - zeta;
     d = r * inv;
     dz = r * r - T(1);
+}
+
+// Student-t with a log-scale predictor (nu constant): lp = -(nu+1)/2 log(1 + r^2/nu) - zeta,
+// d lp / d eta = (nu+1) r / (nu + r^2) / sigma,  d lp / d zeta = (nu+1) r^2 / (nu + r^2) - 1
+template <typename T>
+__device__ __forceinline__ void studentt_logsigma_row(T y, T eta, T zeta, T nu, T &lp, T &d, T &dz) {
+    const T inv = Math<T>::exp(-zeta);
+    const T r = (y - eta) * inv;
+    const T w = (nu + T(1)) * Math<T>::rcp(nu + r * r);
+    lp = T(-0.5) * (nu + T(1)) * Math<T>::log1p_pos(r * r * Math<T>::rcp(nu)) - zeta;
+    d = w * r * inv;
+    dz = w * r * r - T(1);
 }
 
 template <typename T, int FAM>

@@ -1,0 +1,6 @@
+// Row-kernel instantiations: float data, Student-t likelihood with a log-sigma predictor, batch tile 4 (see skk_row_inst.cuh).
+#include "skk_row_inst.cuh"
+
+namespace skk {
+const void *row_kernel_f32_studentt_bt4(int ng, int np, int ns, int spec) { return row_kernel_lookup<float, SKK_LIK_STUDENTT_LOGSIGMA, 4>(ng, np, ns, spec); }
+}  // namespace skk

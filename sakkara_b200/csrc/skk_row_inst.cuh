@@ -23,11 +23,11 @@ const void *row_kernel_lookup(int ng, int np, int ns, int spec) {
 #define SKK_FIXED(NG, NP, NS, SPEC)                                      \
     if (ng == NG && np == NP && ns == NS && spec == (SPEC))              \
         return reinterpret_cast<const void *>(&skk_row_kernel<T, FAM, BT, NG, NP, NS, kRowsPerLane, (SPEC)>);
-    if constexpr (FAM != SKK_LIK_NORMAL_LOGSIGMA) {      // (sigma per group: the run-time kernels only)
+    if constexpr (FAM != SKK_LIK_NORMAL_LOGSIGMA && FAM != SKK_LIK_STUDENTT_LOGSIGMA) {  // (run-time kernels only)
     SKK_FIXED(1, 1, 0, kSpecXP0)                         // intercept + group slope * x (README / C2)
     SKK_FIXED(0, 2, 0, kSpecXP0)                         // nested: parent slope * x + child intercept (C3)
     }
-    if constexpr (FAM != SKK_LIK_NORMAL && FAM != SKK_LIK_NORMAL_LOGSIGMA) {
+    if constexpr (FAM != SKK_LIK_NORMAL && FAM != SKK_LIK_NORMAL_LOGSIGMA && FAM != SKK_LIK_STUDENTT_LOGSIGMA) {
         SKK_FIXED(1, 1, 0, kSpecXP0 | kSpecY8)
         SKK_FIXED(0, 2, 0, kSpecXP0 | kSpecY8)
         SKK_FIXED(1, 1, 1, kSpecXG0 | kSpecY8 | kSpecCode16)  // beta * x + a[A] + b[B] (C4)

@@ -231,7 +231,7 @@ struct RowKernel {
     }
 
     // SKK_LIK_NORMAL_LOGSIGMA: a term whose xcol is SKK_XCOL_LOG_SIGMA belongs to zeta = log(sigma), the others to eta
-    static constexpr bool kLogSigma = FAM == SKK_LIK_NORMAL_LOGSIGMA;
+    static constexpr bool kLogSigma = FAM == SKK_LIK_NORMAL_LOGSIGMA || FAM == SKK_LIK_STUDENTT_LOGSIGMA;
     static __device__ __forceinline__ bool zg(const RowParams<T> &p, int t) { return kLogSigma && p.xcol_g[t] == SKK_XCOL_LOG_SIGMA; }
     static __device__ __forceinline__ bool zp(const RowParams<T> &p, int t) { return kLogSigma && p.xcol_p[t] == SKK_XCOL_LOG_SIGMA; }
     static __device__ __forceinline__ bool zs(const RowParams<T> &p, int t) { return kLogSigma && p.xcol_s[t] == SKK_XCOL_LOG_SIGMA; }
@@ -262,7 +262,10 @@ struct RowKernel {
             const T eta = eta_of(p, off, eg, xg, ep, xp, es, xs);
             const T zeta = zeta_of(p, vgb, vpb, vsb);
             T d, dz;
-            normal_logsigma_row<T>(y, eta, zeta, lp, d, dz);
+            if constexpr (FAM == SKK_LIK_STUDENTT_LOGSIGMA)
+                studentt_logsigma_row<T>(y, eta, zeta, fc.a, lp, d, dz);
+            else
+                normal_logsigma_row<T>(y, eta, zeta, lp, d, dz);
 #pragma unroll
             for (int t = 0; t < NGa; ++t) dg[t] = (t < NG && zg(p, t)) ? dz : d * xg[t];
 #pragma unroll

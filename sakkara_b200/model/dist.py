@@ -19,7 +19,7 @@ class Family:
     :param params: accepted parameter names with their PyMC defaults (``None`` = required).
     :param positive: True when PyMC samples the variable on the log scale (LogTransform), i.e. the
         value variable is ``<name>_log__`` and the logp gains the log-Jacobian.
-    :param discrete: True for families that can only be observed (no gradient w.r.t. the value).
+    :param discrete: True for families that can only be observed here (discrete ones, and StudentT).
     """
 
     def __init__(self, name: str, params: Dict[str, Any], positive: bool = False, discrete: bool = False):
@@ -79,10 +79,12 @@ HalfStudentT = Family('HalfStudentT', {'nu': None, 'sigma': 1.0}, positive=True)
 Bernoulli = Family('Bernoulli', {'p': None, 'logit_p': None}, discrete=True)
 Poisson = Family('Poisson', {'mu': None}, discrete=True)
 NegativeBinomial = Family('NegativeBinomial', {'mu': None, 'alpha': None}, discrete=True)
+# (observed only: as a prior it would need three parameters)
+StudentT = Family('StudentT', {'nu': None, 'mu': 0.0, 'sigma': 1.0}, discrete=True)
 
 FAMILIES: Dict[str, Family] = {f.name: f for f in (Normal, HalfNormal, Exponential, HalfCauchy, Gamma, InverseGamma,
                                                    Cauchy, Laplace, LogNormal, HalfStudentT, Bernoulli, Poisson,
-                                                   NegativeBinomial)}
+                                                   NegativeBinomial, StudentT)}
 
 
 def resolve_generator(generator: Callable) -> Family:

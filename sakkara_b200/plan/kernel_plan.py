@@ -401,7 +401,12 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
 
     sigma_const, sigma_theta_index = 1.0, -1
     family = LIKELIHOOD_IDS[lik.family]
-    if log_sigma:
+    if lik.family == 'StudentT':
+        # the kernel adds -(nu + 1)/2 log(1 + r^2/nu) - log(sigma) per row (sigma = 1 without a zeta term)
+        nu = float(lik.nu)
+        sigma_const = nu                                             # (nu travels in the sigma field of the C ABI)
+        logp_const += n * float(gammaln(0.5 * (nu + 1.0)) - gammaln(0.5 * nu) - 0.5 * np.log(nu * np.pi))
+    elif log_sigma:
         family = LIKELIHOOD_IDS['NormalLogSigma']
         logp_const -= n * 0.91893853320467274178032973640562        # the kernel adds -r^2 / 2 - log(sigma) per row
     if lik.family == 'NegativeBinomial':

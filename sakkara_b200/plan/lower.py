@@ -285,6 +285,9 @@ def _masked_likelihood(obs: sym.RandomVar, y: np.ndarray):
     elif obs.family == 'NegativeBinomial':
         from scipy.stats import nbinom
         terms = nbinom.logpmf(y0, fill['alpha'], fill['alpha'] / (fill['alpha'] + fill['mu']))
+    elif obs.family == 'StudentT':
+        from scipy.stats import t as student_t
+        terms = student_t.logpdf(y0, fill['nu'], loc=fill['mu'], scale=fill['sigma'])
     else:
         raise UnsupportedModelError(f'Likelihood family {obs.family} is not supported')
     return {k: v.value for k, v in wrapped.items()}, mask, float(np.sum(terms, dtype=np.float64))
@@ -342,14 +345,21 @@ def lower_model(model: sym.Model) -> ModelPlan:
 
     spec = LikelihoodSpec(family=obs.family, name=obs.name, y=y)
     row_sigma = None
-    if obs.family == 'Normal':
+    if obs.family in ('Normal', 'StudentT'):
         eta_node = obs_params['mu']
         sigma = _lower(obs_params['sigma'])
+        student = obs.family == 'StudentT'
+        if student:
+            nu = _lower(obs_params['nu'])
+            value = np.unique(np.asarray(nu.const_value(), dtype=np.float64)) if nu.is_const else np.empty(0)
+            if value.size != 1 or not value[0] > 0:
+                raise UnsupportedModelError('StudentT nu must be one positive constant')
+            spec.nu = float(value[0])
         if sigma.is_const:
             value = np.asarray(sigma.const_value(), dtype=np.float64)
             if masked is not None and value.size == n_rows:
                 value = value.reshape(-1)[~masked]
-            if np.unique(value).size != 1:
+            if np.unique(value).size != 1 or student:   # (StudentT: always standardised, the kernel's sigma is exp(zeta))
                 # known measurement errors, one per row (also: a GroupComponent of constants): the rows are
                 # standardised -- y, the offset and every data column divided by sigma_i -- which leaves a unit
                 # sigma, and sum(-log sigma_i) joins the plan's constant (applied below, once the terms exist)
@@ -377,7 +387,7 @@ def lower_model(model: sym.Model) -> ModelPlan:
                 raise UnsupportedModelError('Likelihood sigma must be a positive (HalfNormal/Exponential ...) variable')
             if ((element < 0) & (const <= 0))[~masked if masked is not None else slice(None)].any():
                 raise ValueError('Normal sigma must be positive')
-            if used.size == 1 and used[0] >= 0:
+            if used.size == 1 and used[0] >= 0 and not student:
                 source = plan_block_of(blocks, int(used[0]))
                 spec.sigma_block, spec.sigma_index = source, int(used[0]) - blocks[source].offset
             else:

@@ -21,7 +21,7 @@ FAMILY_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'HalfNormal': 3, 'Expon
               'HalfCauchy': 5, 'Gamma': 6, 'InverseGamma': 7, 'Cauchy': 8, 'Laplace': 9, 'LogNormal': 10,
               'HalfStudentT': 11}
 # likelihood families (SKK_LIK_* of include/skk_b200.h; the first three share FAMILY_IDS' numbers)
-LIKELIHOOD_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3, 'NormalLogSigma': 4}
+LIKELIHOOD_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3, 'NormalLogSigma': 4, 'StudentT': 5}
 XCOL_LOG_SIGMA = -2      # xcol of a term of log(sigma) (SKK_XCOL_LOG_SIGMA)
 # prior families: names of the parameters that travel as a / b through the C ABI (include/skk_b200.h)
 PRIOR_PARAMS = {'Normal': ('mu', 'sigma'), 'HalfNormal': ('sigma', None), 'Exponential': ('lam', None),
@@ -111,6 +111,8 @@ class LikelihoodSpec:
     sigma_const: Optional[float] = None        # Normal: fixed sigma ... (NegativeBinomial: its constant alpha)
     sigma_block: Optional[int] = None          # ... or a positive (log-transformed) block
     sigma_index: int = 0                       # element of that block
+    nu: Optional[float] = None                 # StudentT: degrees of freedom (constant); its sigma is 1 (rows
+                                               # standardised) or per row in sigma_rows_*
     # Normal whose sigma differs between rows and depends on theta (sigma per group as a parameter): per row the
     # element of theta that holds log(sigma), or -1 and the constant in sigma_rows_const.  Such a plan is evaluated
     # as one standard plan per distinct sigma (ModelPlan.split_by_sigma)
@@ -178,7 +180,7 @@ class ModelPlan:
         out = []
         elements = np.unique(spec.sigma_rows_element)
         linked = elements[elements >= 0]
-        if linked.size > 1 and not per_element:
+        if (linked.size > 1 or (linked.size == 1 and spec.family == 'StudentT')) and not per_element:
             rows = np.flatnonzero(spec.sigma_rows_element >= 0)
             out.append(self if rows.size == self.n_rows else self.take_rows(rows))
             elements = elements[elements < 0]

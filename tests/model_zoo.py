@@ -244,6 +244,22 @@ def group_sigma_likelihood(df):
     return make
 
 
+# ---------------------------------------------------------------------------------------------
+# robust regression: StudentT likelihood, sigma per group as a parameter / one parameter / a constant
+# ---------------------------------------------------------------------------------------------
+def studentt_likelihood(df, sigma_kind):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        k = DC(pm.Normal, name='k', group='group', sigma=DC(pm.HalfNormal, name='k_sd', sigma=1.0))
+        sigma = {'group': lambda: DC(pm.HalfNormal, name='noise', group='group', sigma=1.0),
+                 'one': lambda: DC(pm.Exponential, name='noise', lam=2.0),
+                 'const': lambda: 0.7}[sigma_kind]()
+        return api.Likelihood(pm.StudentT, nu=4.0, mu=k * data['x'] + DC(pm.Normal, name='icpt'), sigma=sigma,
+                              observed=data['y'])
+    return make
+
+
 def zoo():
     out = {}
     df = readme_df()
@@ -270,4 +286,7 @@ def zoo():
     out['crossed_negbinomial'] = (df, crossed_negbinomial_likelihood(df))
     df = group_sigma_df()
     out['group_sigma'] = (df, group_sigma_likelihood(df))
+    out['studentt_group_sigma'] = (df, studentt_likelihood(df, 'group'))
+    out['studentt_one_sigma'] = (df, studentt_likelihood(df, 'one'))
+    out['studentt_const_sigma'] = (df, studentt_likelihood(df, 'const'))
     return out

@@ -118,9 +118,9 @@ def test_unsupported_structures_raise(df):
     for c in (k, *data.values()):
         c.clear()
     with pytest.raises(NotImplementedError):            # unknown distribution
-        class StudentT:
+        class Weibull:
             pass
-        build(df, Likelihood(pm.Normal, mu=DC(StudentT, name='t'), sigma=1.0, observed=data['y']))
+        build(df, Likelihood(pm.Normal, mu=DC(Weibull, name='t'), sigma=1.0, observed=data['y']))
 
 
 def test_pymc_generators_are_accepted_by_name(df):

@@ -30,8 +30,9 @@ def test_numpy_oracle_equals_autograd_on_recorded_graph(name):
 @pytest.mark.parametrize('name', sorted(ZOO))
 def test_c_oracle_equals_numpy_oracle(name, dtype, tol):
     model = build_model(ZOO[name])
-    if model.plan.likelihood.sigma_rows_element is not None:
-        pytest.skip('the C oracle (bench baseline) takes one sigma; row-dependent sigmas are covered by the NumPy and autograd oracles')
+    if model.plan.likelihood.sigma_rows_element is not None or model.plan.likelihood.family == 'StudentT':
+        pytest.skip('the C oracle (bench baseline) covers the four bench families with one sigma; row-dependent sigmas and StudentT '
+                    'are covered by the NumPy and autograd oracles')
     f = COracle(model.plan, dtype, threads=3)
     for theta in theta_points(model.plan, 3, seed=2):
         theta = theta.astype(dtype)
