@@ -148,3 +148,29 @@ def test_negative_binomial_against_scipy():
     lik = stats.nbinom.logpmf(plan.likelihood.y.astype(int), alpha, alpha / (alpha + mu)).sum()
     from oracle.logp_c import priors_only
     assert abs(logp_dlogp(plan, theta)[0] - (logp_dlogp(priors_only(plan), theta)[0] + lik)) < 1e-11 * abs(lik)
+
+
+@pytest.mark.parametrize('name', ['studentt_group_sigma', 'studentt_one_sigma', 'studentt_const_sigma', 'group_sigma'])
+def test_location_scale_likelihoods_against_scipy(name):
+    """StudentT / Normal with sigma per group, one sigma parameter or a constant: scipy.stats on the constrained scale."""
+    model = build_model(ZOO[name])
+    plan = model.plan
+    theta = theta_points(plan, 2, seed=13)[1]
+    sl = plan.block_slices()
+    eta = sum(theta[plan.term_base(t) + t.index] * (1.0 if t.x is None else t.x) for t in plan.terms)
+    df = ZOO[name][0]
+    group = df['group'].values
+    if name == 'studentt_const_sigma':
+        sigma = np.full(len(df), 0.7)
+        y, eta = df['y'].values, eta * 0.7            # (the plan's rows are standardised: undo it)
+    elif name == 'studentt_one_sigma':
+        sigma, y = np.full(len(df), np.exp(theta[sl['noise']][0])), df['y'].values
+    elif name == 'studentt_group_sigma':
+        members = list(plan.coords['group'])          # element k of the block belongs to the k-th member (first appearance)
+        sigma, y = np.exp(theta[sl['noise']])[[members.index(g) for g in group]], df['y'].values
+    else:
+        sigma = np.where(group == 0, 1e-1, np.where(group == 1, np.exp(theta[sl['R_1']][0]), np.exp(theta[sl['R_2']][0])))
+        y = df['y'].values
+    lik = (stats.norm.logpdf(y, eta, sigma) if name == 'group_sigma' else stats.t.logpdf(y, 4.0, loc=eta, scale=sigma)).sum()
+    prior = logp_dlogp(plan.take_rows([]), theta)[0]
+    assert abs(logp_dlogp(plan, theta)[0] - (prior + lik)) < 1e-11 * max(1.0, abs(lik))
