@@ -230,6 +230,19 @@ int skk_stats(skk_plan *plan, skk_stats_t *out);
 void *skk_stream(skk_plan *plan);
 
 /*
+ * Integrator update of a many-chain HMC / NUTS trajectory between two skk_eval calls, enqueued on the plan's
+ * stream (never synchronises): for every chain c < chains and element j < P
+ *     r[c][j] += a * eps[c] * grad[c][j];     q[c][j] += b * eps[c] * inv_mass[j] * r[c][j]    (b == 0: kick only)
+ * q, r, grad [chains, P], eps [chains] (signed: the direction of the chain's trajectory), inv_mass [P]: device
+ * pointers of the plan's dtype.  (a, b) = (0.5, 1) opens a leapfrog step, (0.5, 0) closes it, (1, 1) joins two.
+ * Replaces, for all chains at once, the momentum / position updates of pymc's leapfrog integrator
+ * (pymc/step_methods/hmc/integration.py, third-party; the reference reaches it through pm.sample(),
+ * README.md:34).  Used by sakkara_b200/sampling.py.
+ */
+int skk_leapfrog(skk_plan *plan, void *q, void *r, const void *grad, const void *eps, const void *inv_mass,
+                 int32_t chains, double a, double b);
+
+/*
  * Diagnostics: per-warp timeline of the row kernel (%globaltimer at entry, end of the prologue, arrival of
  * the first tile, end of the tile loop, exit).  skk_trace_read copies [grid * warps][8] words of the last
  * evaluation (at most `capacity` words) and returns the number of words, or a negative SKK_ERR_* code.

@@ -1714,6 +1714,26 @@ int skk_stats(skk_plan *pl, skk_stats_t *out) {
 
 void *skk_stream(skk_plan *pl) { return pl ? pl->stream : nullptr; }
 
+int skk_leapfrog(skk_plan *pl, void *q, void *r, const void *grad, const void *eps, const void *inv_mass, int32_t chains,
+                 double a, double b) {
+    if (!pl) return fail(SKK_ERR_INVALID, "null plan");
+    if (!q || !r || !grad || !eps || !inv_mass) return fail(SKK_ERR_INVALID, "null buffer");
+    if (chains < 1 || chains > 65535) return fail(SKK_ERR_INVALID, "chains %d outside [1, 65535]", chains);
+    CUDA_TRY(cudaSetDevice(pl->device));
+    const int n = (int)pl->n_params;
+    const dim3 grid((unsigned)std::min((n + 255) / 256, 64), (unsigned)chains);
+    if (pl->dtype == SKK_F64)
+        skk_leapfrog_kernel<double><<<grid, 256, 0, pl->stream>>>(
+            static_cast<double *>(q), static_cast<double *>(r), static_cast<const double *>(grad),
+            static_cast<const double *>(eps), static_cast<const double *>(inv_mass), n, a, b);
+    else
+        skk_leapfrog_kernel<float><<<grid, 256, 0, pl->stream>>>(
+            static_cast<float *>(q), static_cast<float *>(r), static_cast<const float *>(grad),
+            static_cast<const float *>(eps), static_cast<const float *>(inv_mass), n, (float)a, (float)b);
+    CUDA_TRY(cudaGetLastError());
+    return SKK_OK;
+}
+
 int skk_trace_enable(skk_plan *pl, int32_t on) {
     if (!pl) return fail(SKK_ERR_INVALID, "null plan");
     CUDA_TRY(cudaSetDevice(pl->device));

@@ -1126,4 +1126,23 @@ static __global__ void skk_peer_fed_kernel(const __grid_constant__ PeerParams pp
     }
 }
 
+
+// Integrator update of the many-chain samplers between two evaluations (sakkara_b200/sampling.py: kick_drift):
+//   r[c][j] += a * eps[c] * g[c][j];   q[c][j] += b * eps[c] * inv_mass[j] * r[c][j]      (b == 0: the kick only)
+// eps is signed per chain (NUTS extends every chain's trajectory in its own direction).  Elementwise over
+// [chains, P], HBM-bound (3 reads + 2 writes per element); blockIdx.y = chain, so no index division.
+template <typename T>
+__global__ void __launch_bounds__(256)
+skk_leapfrog_kernel(T *__restrict__ q, T *__restrict__ r, const T *__restrict__ g, const T *__restrict__ eps,
+                    const T *__restrict__ inv_mass, int n_params, T a, T b) {
+    const int64_t base = (int64_t)blockIdx.y * n_params;
+    const T e = eps[blockIdx.y];
+    const T ae = a * e, be = b * e;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_params; j += gridDim.x * blockDim.x) {
+        const T rn = r[base + j] + ae * g[base + j];
+        r[base + j] = rn;
+        if (b != T(0)) q[base + j] += be * inv_mass[j] * rn;
+    }
+}
+
 }  // namespace skk

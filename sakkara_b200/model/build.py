@@ -100,6 +100,17 @@ class B200Model:
             return MinibatchValueGrad(self.plan, dtype=dtype, device=device, **options)
         return ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
 
+    def sample(self, draws: int = 1000, tune: int = 1000, chains: int = 64, target_accept: float = 0.8,
+               random_seed: int = 0, max_treedepth: int = 8, dtype: str = 'float64', device: Optional[int] = None):
+        """
+        ``pm.sample``'s arguments on the many-chain NUTS of :mod:`sakkara_b200.sampling`: all chains advance in
+        lock-step on the device, one batched ``skk_eval`` per leapfrog step.  Returns an ``HMCResult`` (draws on the
+        unconstrained scale, ``constrained(plan)``, sampler statistics, ``summary(plan)`` with ESS and R-hat).
+        """
+        from sakkara_b200.sampling import sample_nuts
+        return sample_nuts(self, chains=chains, draws=draws, tune=tune, max_depth=max_treedepth,
+                           target_accept=target_accept, dtype=dtype, seed=random_seed, device=device)
+
     def to_pymc(self, dtype: str = 'float64', device: Optional[int] = None):
         """A ``pm.Model`` with the same free variables whose joint logp is one fused-kernel Op
         (needs PyMC; see sakkara_b200/pytensor_op.py)."""

@@ -55,7 +55,7 @@ class Stats(C.Structure):
 
 EXPORTS = ('skk_plan_create', 'skk_eval', 'skk_plan_destroy', 'skk_last_error', 'skk_comm_unique_id',
            'skk_comm_init', 'skk_comm_destroy', 'skk_peer_alloc', 'skk_peer_init', 'skk_stats', 'skk_stream',
-           'skk_trace_enable', 'skk_trace_read', 'skk_alu_peak', 'skk_abi_version')
+           'skk_trace_enable', 'skk_trace_read', 'skk_alu_peak', 'skk_abi_version', 'skk_leapfrog')
 
 _lib = None
 
@@ -92,6 +92,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.skk_stats.restype = C.c_int
     lib.skk_stream.argtypes = [C.c_void_p]
     lib.skk_stream.restype = C.c_void_p
+    lib.skk_leapfrog.argtypes = [C.c_void_p] * 6 + [C.c_int32, C.c_double, C.c_double]
+    lib.skk_leapfrog.restype = C.c_int
     lib.skk_trace_enable.argtypes = [C.c_void_p, C.c_int32]
     lib.skk_trace_enable.restype = C.c_int
     lib.skk_trace_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -206,6 +208,13 @@ class SkkPlan:
         flags = EVAL_DEVICE_IO | (0 if sync else EVAL_NO_SYNC) | (EVAL_TIME_KERNELS if time_kernels else 0)
         _check(self.lib, self.lib.skk_eval(self._handle, C.c_void_p(theta_ptr), batch, C.c_void_p(logp_ptr),
                                            C.c_void_p(grad_ptr), flags))
+
+    def leapfrog(self, q_ptr: int, r_ptr: int, grad_ptr: int, eps_ptr: int, inv_mass_ptr: int, chains: int,
+                 a: float, b: float) -> None:
+        """``r += a*eps*grad; q += b*eps*inv_mass*r`` for ``chains`` device-resident chains, enqueued on the plan's stream."""
+        self._guard()
+        _check(self.lib, self.lib.skk_leapfrog(self._handle, C.c_void_p(q_ptr), C.c_void_p(r_ptr), C.c_void_p(grad_ptr),
+                                               C.c_void_p(eps_ptr), C.c_void_p(inv_mass_ptr), chains, a, b))
 
     # -- multi-GPU -------------------------------------------------------------------------------
     def unique_id(self) -> bytes:
