@@ -59,6 +59,10 @@ extern "C" {
                                     skk_plan_desc.sigma_const; zeta = sum of the SKK_XCOL_LOG_SIGMA terms (none: sigma = 1,
                                     i.e. rows standardised by a constant sigma); the normaliser
                                     N (lgamma((nu+1)/2) - lgamma(nu/2) - log(nu pi)/2) belongs into logp_const */
+#define SKK_LIK_GAMMA_LOG 6      /* pm.Gamma(alpha=const, beta=alpha / exp(eta)), the Gamma GLM with mean exp(eta): alpha
+                                    travels in skk_plan_desc.sigma_const; the kernel adds -alpha (eta + y exp(-eta)) per
+                                    row, N (alpha log(alpha) - lgamma(alpha)) + (alpha - 1) sum log(y) belongs into
+                                    logp_const */
 /* skk_term_desc.xcol of a term of the log-scale predictor zeta of the *_LOGSIGMA families (no data column) */
 #define SKK_XCOL_LOG_SIGMA (-2)
 
@@ -157,7 +161,7 @@ typedef struct {
     int32_t n_blocks;
     const skk_term_desc *terms;
     const skk_block_desc *blocks;
-    double sigma_const;         /* Normal likelihood: fixed sigma ... (NegativeBinomial: alpha; StudentT: nu) */
+    double sigma_const;         /* Normal likelihood: fixed sigma ... (NegativeBinomial, Gamma: alpha; StudentT: nu) */
     int64_t sigma_theta_index;  /* ... or index of log(sigma) in theta; -1: const */
     double logp_const;          /* theta-independent part of logp of this shard
                                    (Poisson: -sum lgamma(y+1); the rows masked for NaN

@@ -104,6 +104,9 @@ def logp_dlogp_autograd(recorded: sym.Model, theta: np.ndarray):
             # torch: total_count failures r and success probability p of the counted event; mean r p / (1 - p)
             mu, alpha = params['mu'], torch.as_tensor(params['alpha'], dtype=torch.float64)
             total = total + torch.distributions.NegativeBinomial(alpha, probs=mu / (mu + alpha)).log_prob(y).sum()
+        elif rv.family == 'Gamma':
+            alpha = torch.as_tensor(params['alpha'], dtype=torch.float64)
+            total = total + torch.distributions.Gamma(alpha, params['beta']).log_prob(y).sum()
         else:
             raise NotImplementedError(rv.family)
     total.backward()

@@ -62,6 +62,11 @@ def likelihood_from_kernel_plan(kp, theta):
         mu = np.exp(eta)
         logp = np.sum(y * eta - mu)
         d = y - mu
+    elif kp.family == 6:
+        alpha = kp.sigma_const                                   # Gamma(alpha, beta = alpha / exp(eta)): alpha in the sigma field
+        w = y * np.exp(-eta)
+        logp = np.sum(-alpha * (eta + w))
+        d = alpha * (w - 1.0)
     else:
         alpha = kp.sigma_const                                   # NegativeBinomial: alpha in the sigma field
         log_sum = np.logaddexp(eta, np.log(alpha))

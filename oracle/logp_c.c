@@ -14,6 +14,7 @@
  *   Normal    : logp_i = -0.5 r_i^2 - log(sqrt(2 pi)) - log(sigma), r_i = (y_i - eta_i)/sigma, d_i = r_i/sigma
  *   Bernoulli : logp_i = y_i eta_i - softplus(eta_i),                 d_i = y_i - sigmoid(eta_i)
  *   Poisson   : logp_i = y_i eta_i - exp(eta_i) - lgamma(y_i + 1),    d_i = y_i - exp(eta_i)
+ *   Gamma     : logp_i = -alpha (eta_i + y_i exp(-eta_i)) + const_i,                    d_i = alpha (y_i exp(-eta_i) - 1)
  *   NegBinomial: logp_i = y_i eta_i - (y_i + alpha) log(alpha + exp(eta_i)) + const_i,  d_i = y_i - (y_i + alpha) mu_i / (alpha + mu_i)
  *               (one observed distribution call, /root/reference/sakkara/model/composable/hierarchical/likelihood.py:58-62)
  *   dlogp[base_t + index_t[i]] += d_i * x_t[i]                        (scatter-add, AdvancedIncSubtensor1)
@@ -35,7 +36,7 @@
 #define LOG_SQRT_2PI 0.91893853320467274178
 
 typedef struct {
-    int32_t family;      /* 0 Normal, 1 Bernoulli-logit, 2 Poisson-log, 3 NegativeBinomial-log (alpha in sigma) */
+    int32_t family;      /* 0 Normal, 1 Bernoulli-logit, 2 Poisson-log, 3 NegativeBinomial-log, 4 Gamma-log (alpha in sigma) */
     int32_t n_terms;
     int64_t n_rows;
     int64_t n_params;
@@ -82,6 +83,10 @@ typedef struct {
                     const REAL mu = EXP(eta);                                                                  \
                     l = y[i] * eta - mu;                                                                       \
                     dd = y[i] - mu;                                                                            \
+                } else if (d->family == 4) { /* Gamma(alpha = d->sigma, beta = alpha / exp(eta)), constants by the caller */ \
+                    const REAL alpha = sigma, w = y[i] * EXP(-eta);                                            \
+                    l = -alpha * (eta + w);                                                                    \
+                    dd = alpha * (w - (REAL)1);                                                                \
                 } else { /* NegativeBinomial(mu = exp(eta), alpha = d->sigma), constants added by the caller */ \
                     const REAL alpha = sigma, mu = EXP(eta);                                                   \
                     const REAL lam = eta > (REAL)30 ? eta + LOG1P(alpha * EXP(-eta)) : LOG1P(mu / alpha) + LOGF(alpha); \

@@ -58,7 +58,7 @@ class COracle:
         lik = plan.likelihood
         self.keep = []
         d = GlmDesc()
-        d.family = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3}[lik.family]
+        d.family = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3, 'Gamma': 4}[lik.family]
         d.n_terms = len(plan.terms)
         d.n_rows = plan.n_rows
         d.n_params = plan.n_params
@@ -87,6 +87,10 @@ class COracle:
             a = float(lik.sigma_const)
             d.sigma = a
             self.const = float(np.sum(gammaln(lik.y + a) - gammaln(lik.y + 1.0))) + plan.n_rows * (a * np.log(a) - float(gammaln(a)))
+        if lik.family == 'Gamma':
+            a = float(lik.sigma_const)
+            d.sigma = a
+            self.const = (a - 1.0) * float(np.sum(np.log(lik.y))) + plan.n_rows * (a * np.log(a) - float(gammaln(a)))
         self.const += float(getattr(plan, 'logp_const', 0.0))   # rows masked out for NaN observations
         self.fn = self.lib.skk_oracle_likelihood_f64 if self.dtype == np.float64 else self.lib.skk_oracle_likelihood_f32
 

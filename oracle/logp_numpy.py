@@ -272,6 +272,14 @@ def logp_dlogp(plan, theta: np.ndarray, dtype=np.float64, return_mass: bool = Fa
         const = (gammaln(lik.y + float(alpha)) - gammaln(lik.y + 1.0) - gammaln(float(alpha))).astype(dtype)
         terms = const + y * (eta - log_sum) + alpha * (np.log(alpha) - log_sum)
         d_eta = y - (y + alpha) * mu / (mu + alpha)
+    elif lik.family == 'Gamma':
+        # pymc Gamma(alpha, beta): alpha log(beta) - lgamma(alpha) + (alpha - 1) log(y) - beta y, with the rate of
+        # the log-link GLM beta = alpha / mu, mu = exp(eta)
+        alpha = T(lik.sigma_const)
+        w = y * np.exp(-eta)                                       # y / mu
+        const = ((float(alpha) - 1.0) * np.log(lik.y) + float(alpha) * np.log(float(alpha)) - gammaln(float(alpha))).astype(dtype)
+        terms = const - alpha * (eta + w)
+        d_eta = alpha * (w - T(1))
     else:
         raise NotImplementedError(lik.family)
     logp += np.sum(terms, dtype=np.float64)

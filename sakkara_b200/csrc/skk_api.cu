@@ -43,6 +43,10 @@ const void *row_kernel_f32_negbinomial_bt1(int, int, int, int);
 const void *row_kernel_f32_negbinomial_bt4(int, int, int, int);
 const void *row_kernel_f64_negbinomial_bt1(int, int, int, int);
 const void *row_kernel_f64_negbinomial_bt4(int, int, int, int);
+const void *row_kernel_f32_gamma_bt1(int, int, int, int);
+const void *row_kernel_f32_gamma_bt4(int, int, int, int);
+const void *row_kernel_f64_gamma_bt1(int, int, int, int);
+const void *row_kernel_f64_gamma_bt4(int, int, int, int);
 const void *row_kernel_f32_logsigma_bt1(int, int, int, int);
 const void *row_kernel_f32_logsigma_bt4(int, int, int, int);
 const void *row_kernel_f64_logsigma_bt1(int, int, int, int);
@@ -316,20 +320,22 @@ static int upload_tiled(skk_plan *pl, void **out, const void *host, size_t n, si
 
 static const void *lookup_kernel(int dtype, int family, int bt, int ng, int np, int ns, int spec) {
     typedef const void *(*Lookup)(int, int, int, int);
-    static const Lookup table[2][6][2] = {
+    static const Lookup table[2][7][2] = {
         {{row_kernel_f32_normal_bt1, row_kernel_f32_normal_bt4},
          {row_kernel_f32_bernoulli_bt1, row_kernel_f32_bernoulli_bt4},
          {row_kernel_f32_poisson_bt1, row_kernel_f32_poisson_bt4},
          {row_kernel_f32_negbinomial_bt1, row_kernel_f32_negbinomial_bt4},
          {row_kernel_f32_logsigma_bt1, row_kernel_f32_logsigma_bt4},
-         {row_kernel_f32_studentt_bt1, row_kernel_f32_studentt_bt4}},
+         {row_kernel_f32_studentt_bt1, row_kernel_f32_studentt_bt4},
+         {row_kernel_f32_gamma_bt1, row_kernel_f32_gamma_bt4}},
         {{row_kernel_f64_normal_bt1, row_kernel_f64_normal_bt4},
          {row_kernel_f64_bernoulli_bt1, row_kernel_f64_bernoulli_bt4},
          {row_kernel_f64_poisson_bt1, row_kernel_f64_poisson_bt4},
          {row_kernel_f64_negbinomial_bt1, row_kernel_f64_negbinomial_bt4},
          {row_kernel_f64_logsigma_bt1, row_kernel_f64_logsigma_bt4},
-         {row_kernel_f64_studentt_bt1, row_kernel_f64_studentt_bt4}}};
-    if (family < 0 || family > 5 || (bt != 1 && bt != 4)) return nullptr;
+         {row_kernel_f64_studentt_bt1, row_kernel_f64_studentt_bt4},
+         {row_kernel_f64_gamma_bt1, row_kernel_f64_gamma_bt4}}};
+    if (family < 0 || family > 6 || (bt != 1 && bt != 4)) return nullptr;
     return table[dtype == SKK_F64 ? 1 : 0][family][bt == 4 ? 1 : 0](ng, np, ns, spec);
 }
 
@@ -1036,7 +1042,8 @@ static int launch_rows(skk_plan *pl, const LaunchCfg &cfg, bool timed, const T *
         rp.xcol_s[t] = pl->xcol_s[t];
     }
     rp.theta = th;
-    rp.fam_a = (T)((pl->family == SKK_LIK_NEGBINOMIAL_LOG || pl->family == SKK_LIK_STUDENTT_LOGSIGMA) ? pl->sigma_const : 0.0);
+    rp.fam_a = (T)((pl->family == SKK_LIK_NEGBINOMIAL_LOG || pl->family == SKK_LIK_STUDENTT_LOGSIGMA || pl->family == SKK_LIK_GAMMA_LOG)
+                       ? pl->sigma_const : 0.0);
     rp.fam_b = (T)(pl->family == SKK_LIK_NEGBINOMIAL_LOG ? log(pl->sigma_const) : 0.0);
     rp.sec_theta_base = pl->sec_theta_base;
     rp.n_params = pl->n_params;
@@ -1171,7 +1178,7 @@ static int enqueue_eval(skk_plan *pl, const T *th, int batch, T *out_logp, T *ou
             }
         }
         cp.theta = th;
-        cp.fam_a = (T)(pl->family == SKK_LIK_NEGBINOMIAL_LOG ? pl->sigma_const : 0.0);
+        cp.fam_a = (T)((pl->family == SKK_LIK_NEGBINOMIAL_LOG || pl->family == SKK_LIK_GAMMA_LOG) ? pl->sigma_const : 0.0);
         cp.fam_b = (T)(pl->family == SKK_LIK_NEGBINOMIAL_LOG ? log(pl->sigma_const) : 0.0);
         cp.n_params = pl->n_params;
         cp.batch = batch;
@@ -1454,9 +1461,10 @@ int skk_plan_create(const skk_plan_desc *d, skk_plan **out) {
     if (d->abi_version != SKK_ABI_VERSION)
         return fail(SKK_ERR_INVALID, "descriptor ABI %d, library ABI %d", d->abi_version, SKK_ABI_VERSION);
     if (d->dtype != SKK_F32 && d->dtype != SKK_F64) return fail(SKK_ERR_INVALID, "bad dtype %d", d->dtype);
-    if (d->family < SKK_LIK_NORMAL || d->family > SKK_LIK_STUDENTT_LOGSIGMA) return fail(SKK_ERR_UNSUPPORTED, "bad family %d", d->family);
+    if (d->family < SKK_LIK_NORMAL || d->family > SKK_LIK_GAMMA_LOG) return fail(SKK_ERR_UNSUPPORTED, "bad family %d", d->family);
     if (d->family == SKK_LIK_STUDENTT_LOGSIGMA && !(d->sigma_const > 0.0)) return fail(SKK_ERR_INVALID, "StudentT nu must be positive");
     if (d->family == SKK_LIK_NEGBINOMIAL_LOG && !(d->sigma_const > 0.0)) return fail(SKK_ERR_INVALID, "NegativeBinomial alpha must be positive");
+    if (d->family == SKK_LIK_GAMMA_LOG && !(d->sigma_const > 0.0)) return fail(SKK_ERR_INVALID, "Gamma alpha must be positive");
     if (d->n_rows < 0 || d->n_rows >= (int64_t)1 << 40) return fail(SKK_ERR_INVALID, "bad n_rows");
     if ((d->n_rows + 32 * kRowsPerLane - 1) / (32 * kRowsPerLane) >= INT32_MAX) return fail(SKK_ERR_UNSUPPORTED, "too many rows");
     if (d->n_params < 0 || d->n_params > INT32_MAX - 2) return fail(SKK_ERR_INVALID, "bad n_params");

@@ -437,7 +437,7 @@ struct Math<double> {
     static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
 };
 
-// constants of a likelihood family (NegativeBinomial: a = alpha, b = log(alpha); unused otherwise)
+// constants of a likelihood family (NegativeBinomial: a = alpha, b = log(alpha); Gamma, StudentT: a = alpha / nu)
 template <typename T>
 struct FamilyConst {
     T a, b;
@@ -481,6 +481,12 @@ __device__ __forceinline__ void family_row(T y, T eta, T &lp, T &d, const Family
         const T mu = Math<T>::exp(eta);
         lp = y * eta - mu;
         d = y - mu;
+    } else if constexpr (FAM == SKK_LIK_GAMMA_LOG) {
+        // Gamma(alpha, beta = alpha / mu), mu = exp(eta): lp = -alpha (eta + y / mu) (+ constants in logp_const),
+        // d lp / d eta = alpha (y / mu - 1)
+        const T w = y * Math<T>::exp(-eta);
+        lp = -fc.a * (eta + w);
+        d = fc.a * (w - T(1));
     } else {
         static_assert(FAM == SKK_LIK_NEGBINOMIAL_LOG, "family without a row function");
         // NegativeBinomial(mu = exp(eta), alpha): with u = eta - log(alpha),

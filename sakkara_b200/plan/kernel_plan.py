@@ -394,6 +394,10 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
         a = float(lik.sigma_const)
         logp_const = float(np.sum(gammaln(y_rows + a) - gammaln(y_rows + 1.0), dtype=np.float64)) + \
             n * (a * np.log(a) - float(gammaln(a)))
+    elif lik.family == 'Gamma':
+        # per row: alpha log(alpha) - lgamma(alpha) + (alpha - 1) log(y); the kernel adds -alpha (eta + y exp(-eta))
+        a = float(lik.sigma_const)
+        logp_const = (a - 1.0) * float(np.sum(np.log(y_rows), dtype=np.float64)) + n * (a * np.log(a) - float(gammaln(a)))
     if plan.logp_const:
         # rows masked out for NaN observations (ModelPlan.logp_const): every rank adds its share, so that
         # the all-reduced constant of a sharded run is the whole
@@ -409,7 +413,7 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     elif log_sigma:
         family = LIKELIHOOD_IDS['NormalLogSigma']
         logp_const -= n * 0.91893853320467274178032973640562        # the kernel adds -r^2 / 2 - log(sigma) per row
-    if lik.family == 'NegativeBinomial':
+    if lik.family in ('NegativeBinomial', 'Gamma'):
         sigma_const = float(lik.sigma_const)             # (its alpha travels in the same field of the C ABI)
     if lik.family == 'Normal' and not log_sigma:
         if lik.sigma_block is None:

@@ -288,6 +288,9 @@ def _masked_likelihood(obs: sym.RandomVar, y: np.ndarray):
     elif obs.family == 'StudentT':
         from scipy.stats import t as student_t
         terms = student_t.logpdf(y0, fill['nu'], loc=fill['mu'], scale=fill['sigma'])
+    elif obs.family == 'Gamma':
+        from scipy.stats import gamma as gamma_dist
+        terms = gamma_dist.logpdf(y0, fill['alpha'], scale=1.0 / fill['beta'])
     else:
         raise UnsupportedModelError(f'Likelihood family {obs.family} is not supported')
     return {k: v.value for k, v in wrapped.items()}, mask, float(np.sum(terms, dtype=np.float64))
@@ -413,6 +416,16 @@ def lower_model(model: sym.Model) -> ModelPlan:
             if value.size != 1 or not value[0] > 0:
                 raise UnsupportedModelError('NegativeBinomial alpha must be one positive constant')
             spec.sigma_const = float(value[0])
+    elif obs.family == 'Gamma':
+        # the Gamma GLM with a log link: a constant shape alpha and the rate beta = alpha / mu, mu = exp(eta)
+        alpha = _lower(obs_params['alpha'])
+        value = np.unique(np.asarray(alpha.const_value(), dtype=np.float64)) if alpha.is_const else np.empty(0)
+        if value.size != 1 or not value[0] > 0:
+            raise UnsupportedModelError('Gamma alpha must be one positive constant')
+        spec.sigma_const = float(value[0])
+        eta_node = _gamma_rate_predictor(obs_params['beta'], spec.sigma_const)
+        if not (y if masked is None else y[~masked] > 0).all() or not (y if masked is None else y[~masked]).min(initial=1.0) > 0:
+            raise ValueError('Gamma observations must be positive')
     else:
         raise UnsupportedModelError(f'Likelihood family {obs.family} is not supported')
 
@@ -491,6 +504,46 @@ def plan_block_of(blocks: List[Block], element: int) -> int:
         if b.offset <= element < b.offset + b.size:
             return number
     raise IndexError(element)
+
+
+def _gamma_rate_predictor(node: Any, alpha: float):
+    """
+    The linear predictor eta of a Gamma likelihood's rate ``beta = alpha / exp(eta)``: accepts ``c / exp(L)`` and
+    ``c * exp(L)`` (either order) with a positive constant ``c``; a ``c`` other than alpha becomes a constant of eta
+    (``beta = alpha / exp(eta)`` with ``eta = L + log(alpha / c)``, resp. ``-L + log(alpha / c)``).
+    """
+    while isinstance(node, sym.DeterministicVar):
+        node = node.var
+    what = 'Gamma beta must be alpha / exp(linear predictor) for the fused kernel'
+    if not isinstance(node, sym.BinOp) or node.op not in ('truediv', 'mul'):
+        raise UnsupportedModelError(what)
+
+    def exp_arg(n):
+        while isinstance(n, sym.DeterministicVar):
+            n = n.var
+        return n.arg if isinstance(n, sym.UnaryOp) and n.op == 'exp' else None
+
+    def constant(n):
+        try:
+            form = _lower(n)
+        except UnsupportedModelError:
+            return None
+        if not form.is_const:
+            return None
+        value = np.unique(np.asarray(form.const_value(), dtype=np.float64))
+        return float(value[0]) if value.size == 1 and value[0] > 0 else None
+
+    if node.op == 'truediv':
+        c, inner, sign = constant(node.left), exp_arg(node.right), 1.0
+    else:
+        c, inner, sign = constant(node.left), exp_arg(node.right), -1.0
+        if c is None or inner is None:
+            c, inner = constant(node.right), exp_arg(node.left)
+    if c is None or inner is None:
+        raise UnsupportedModelError(what)
+    eta = inner if sign > 0 else sym.UnaryOp('neg', inner)
+    shift = float(np.log(alpha / c))
+    return eta if shift == 0.0 else sym.BinOp('add', eta, shift)
 
 
 def _unwrap_link(node: Any, link: str, what: str):

@@ -21,7 +21,8 @@ FAMILY_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'HalfNormal': 3, 'Expon
               'HalfCauchy': 5, 'Gamma': 6, 'InverseGamma': 7, 'Cauchy': 8, 'Laplace': 9, 'LogNormal': 10,
               'HalfStudentT': 11}
 # likelihood families (SKK_LIK_* of include/skk_b200.h; the first three share FAMILY_IDS' numbers)
-LIKELIHOOD_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3, 'NormalLogSigma': 4, 'StudentT': 5}
+LIKELIHOOD_IDS = {'Normal': 0, 'Bernoulli': 1, 'Poisson': 2, 'NegativeBinomial': 3, 'NormalLogSigma': 4, 'StudentT': 5,
+                  'Gamma': 6}
 XCOL_LOG_SIGMA = -2      # xcol of a term of log(sigma) (SKK_XCOL_LOG_SIGMA)
 # prior families: names of the parameters that travel as a / b through the C ABI (include/skk_b200.h)
 PRIOR_PARAMS = {'Normal': ('mu', 'sigma'), 'HalfNormal': ('sigma', None), 'Exponential': ('lam', None),
@@ -108,7 +109,7 @@ class LikelihoodSpec:
     name: str
     y: np.ndarray                              # float64[N] (counts / 0-1 stored as floats too)
     offset: Optional[np.ndarray] = None        # float64[N] constant part of eta
-    sigma_const: Optional[float] = None        # Normal: fixed sigma ... (NegativeBinomial: its constant alpha)
+    sigma_const: Optional[float] = None        # Normal: fixed sigma ... (NegativeBinomial, Gamma: the constant alpha)
     sigma_block: Optional[int] = None          # ... or a positive (log-transformed) block
     sigma_index: int = 0                       # element of that block
     nu: Optional[float] = None                 # StudentT: degrees of freedom (constant); its sigma is 1 (rows

@@ -222,6 +222,43 @@ def crossed_negbinomial_likelihood(df):
 
 
 # ---------------------------------------------------------------------------------------------
+# positive continuous observations: the Gamma GLM with a log link, Gamma(alpha, beta = alpha / exp(eta)), in the three
+# spellings the lowering accepts (alpha / exp(eta); alpha * exp(-eta); a constant other than alpha over exp(eta))
+# ---------------------------------------------------------------------------------------------
+def gamma_df(crossed: bool, seed: int = 11) -> pd.DataFrame:
+    df = crossed_df(seed=seed) if crossed else shuffled_linreg_df(seed=seed)
+    rng = np.random.default_rng(seed + 100)
+    mean = np.exp(0.3 * df['x'].values)
+    df['y'] = rng.gamma(3.0, mean / 3.0)
+    return df
+
+
+def crossed_gamma_likelihood(df):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        a = DC(pm.Normal, name='a', group='A', sigma=DC(pm.HalfNormal, name='sigma_a', sigma=1.0))
+        b = DC(pm.Normal, name='b', group='B', sigma=DC(pm.HalfNormal, name='sigma_b', sigma=1.0))
+        eta = DC(pm.Normal, name='beta') * data['x'] + a + b
+        return api.Likelihood(pm.Gamma, alpha=3.0, beta=3.0 / api.f_(pt.exp)(eta), observed=data['y'])
+    return make
+
+
+def grouped_gamma_likelihood(df, spelling):
+    def make(api, pm, pt):
+        DC = api.DistributionComponent
+        data = api.data_components(df[['x', 'y']])
+        k = DC(pm.Normal, name='k', group='group', sigma=DC(pm.HalfNormal, name='k_sd', sigma=1.0))
+        eta = k * data['x'] + DC(pm.Normal, name='icpt')
+        if spelling == 'times':
+            beta = 2.0 * api.f_(pt.exp)(-eta)               # alpha * exp(-eta)
+        else:
+            beta = 0.5 / api.f_(pt.exp)(eta)                # mean alpha / beta = 4 exp(eta): a constant of the predictor
+        return api.Likelihood(pm.Gamma, alpha=2.0, beta=beta, observed=data['y'])
+    return make
+
+
+# ---------------------------------------------------------------------------------------------
 # sigma per group as a parameter: the measurement model of /root/reference/tests/workflows/test_state_space.py:64-82
 # (a GroupComponent of a constant and a positive variable as sigma of a Normal likelihood), on a regression
 # ---------------------------------------------------------------------------------------------
@@ -284,6 +321,11 @@ def zoo():
     out['row_sigma'] = (df, row_sigma_likelihood(df))
     df = crossed_df(seed=9)
     out['crossed_negbinomial'] = (df, crossed_negbinomial_likelihood(df))
+    df = gamma_df(True)
+    out['crossed_gamma'] = (df, crossed_gamma_likelihood(df))
+    df = gamma_df(False)
+    out['grouped_gamma_times'] = (df, grouped_gamma_likelihood(df, 'times'))
+    out['grouped_gamma_shifted'] = (df, grouped_gamma_likelihood(df, 'shifted'))
     df = group_sigma_df()
     out['group_sigma'] = (df, group_sigma_likelihood(df))
     out['studentt_group_sigma'] = (df, studentt_likelihood(df, 'group'))

@@ -82,3 +82,27 @@ def test_alternative_paths_parity(name, switch, dtype, monkeypatch):
     if switch == 'SKK_NO_GRAPH':   # same kernels, same order: bit-identical
         assert np.array_equal(base_batch[0], logp_b) and np.array_equal(base_batch[1], grad_b)
     g.close()
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+@pytest.mark.parametrize('name,batch', [('crossed_gamma', 1), ('crossed_gamma', 6), ('grouped_gamma_times', 3),
+                                        ('grouped_gamma_shifted', 40)])
+def test_gamma_glm_batches(name, batch, dtype):
+    """The Gamma-log family through the row kernel (batch tiles of 1 and 4) and the chain-per-lane kernel (>= 32
+    vectors, no crossed factor), on a frame repeated to a few ragged tiles."""
+    import pandas as pd
+    df, make = ZOO[name]
+    big = pd.concat([df] * 9, ignore_index=True).iloc[:-7]
+    from model_zoo import crossed_gamma_likelihood, grouped_gamma_likelihood
+    make = crossed_gamma_likelihood(big) if name == 'crossed_gamma' else \
+        grouped_gamma_likelihood(big, 'times' if name.endswith('times') else 'shifted')
+    model = build_model((big, make))
+    f = model.logp_dlogp_function(dtype=dtype, max_batch=max(batch, 1))
+    thetas = theta_points(model.plan, max(batch, 2), seed=6, scale=0.3)[:batch]
+    logp, grad = f(thetas if batch > 1 else thetas[0])
+    logp, grad = np.atleast_1d(logp), np.atleast_2d(grad)
+    for b in sorted({0, batch // 2, batch - 1}):
+        assert_parity(logp[b], grad[b], model.plan, thetas[b], dtype)
+    if batch >= 32:
+        assert f.stats()['kernel_variant'] == 2              # chain-per-lane
+    f.close()

@@ -150,6 +150,29 @@ def test_negative_binomial_against_scipy():
     assert abs(logp_dlogp(plan, theta)[0] - (logp_dlogp(priors_only(plan), theta)[0] + lik)) < 1e-11 * abs(lik)
 
 
+@pytest.mark.parametrize('name,alpha,scale', [('crossed_gamma', 3.0, 1.0), ('grouped_gamma_times', 2.0, 1.0),
+                                              ('grouped_gamma_shifted', 2.0, 4.0)])
+def test_gamma_glm_against_scipy(name, alpha, scale):
+    """Gamma(alpha, beta = alpha / mu): scipy's density with shape alpha and scale mu / alpha, mu = scale * exp(eta) with
+    eta written out from the frame and the blocks of theta (not from the plan's terms)."""
+    model = build_model(ZOO[name])
+    plan, df = model.plan, ZOO[name][0]
+    assert plan.likelihood.family == 'Gamma' and plan.likelihood.sigma_const == alpha
+    theta = theta_points(plan, 2, seed=14)[1]
+    sl = plan.block_slices()
+    if name == 'crossed_gamma':
+        ia = [list(plan.coords['A']).index(v) for v in df['A']]
+        ib = [list(plan.coords['B']).index(v) for v in df['B']]
+        eta = theta[sl['beta']][0] * df['x'].values + theta[sl['a']][ia] + theta[sl['b']][ib]
+    else:
+        ig = [list(plan.coords['group']).index(v) for v in df['group']]
+        eta = theta[sl['k']][ig] * df['x'].values + theta[sl['icpt']][0]
+    mu = scale * np.exp(eta)
+    lik = stats.gamma.logpdf(df['y'].values, alpha, scale=mu / alpha).sum()
+    from oracle.logp_c import priors_only
+    assert abs(logp_dlogp(plan, theta)[0] - (logp_dlogp(priors_only(plan), theta)[0] + lik)) < 1e-11 * abs(lik)
+
+
 @pytest.mark.parametrize('name', ['studentt_group_sigma', 'studentt_one_sigma', 'studentt_const_sigma', 'group_sigma'])
 def test_location_scale_likelihoods_against_scipy(name):
     """StudentT / Normal with sigma per group, one sigma parameter or a constant: scipy.stats on the constrained scale."""
