@@ -29,6 +29,7 @@ import pandas as pd
 from scipy.special import gammaln
 
 from sakkara_b200.plan.lower import UnsupportedModelError
+from sakkara_b200.relation.groupset import first_rows
 from sakkara_b200.plan.model_plan import (FAMILY_IDS, LIKELIHOOD_IDS, PRIOR_PARAMS, XCOL_LOG_SIGMA, ModelPlan, Term,
                                           prior_normaliser)
 
@@ -107,8 +108,7 @@ def dense_codes(index: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """First-appearance factorisation: ``(codes[N] int64, elements[G] int64, first_row[G])``."""
     codes, elements = pd.factorize(index, sort=False)
     codes = codes.astype(np.int64, copy=False)
-    first_row = np.flatnonzero(~pd.Series(codes).duplicated(keep='first').values)
-    return codes, np.asarray(elements, dtype=np.int64), first_row
+    return codes, np.asarray(elements, dtype=np.int64), first_rows(codes, len(elements))
 
 
 def determines(codes_c: np.ndarray, first_row_c: np.ndarray, codes_d: np.ndarray) -> Optional[np.ndarray]:
@@ -139,12 +139,11 @@ def sort_rows(primary: Optional[np.ndarray], n_primary: int, secondary: Optional
 
     def is_sorted() -> bool:
         if primary is not None and secondary is not None:
-            dp = np.diff(primary)
-            if (dp < 0).any():
+            if (primary[1:] < primary[:-1]).any():
                 return False
-            return not ((dp == 0) & (np.diff(secondary) < 0)).any()
+            return not ((primary[1:] == primary[:-1]) & (secondary[1:] < secondary[:-1])).any()
         keys = primary if primary is not None else secondary
-        return not (np.diff(keys) < 0).any()
+        return not (keys[1:] < keys[:-1]).any()
 
     if is_sorted():
         return None

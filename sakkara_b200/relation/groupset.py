@@ -36,6 +36,13 @@ class GroupSet:
         return {name: group.members for name, group in self.groups.items()}
 
 
+def first_rows(codes: np.ndarray, n_members: int) -> np.ndarray:
+    """Row of the first appearance of every code: one reversed scatter (the last write of a slot wins)."""
+    first_row = np.empty(n_members, dtype=np.int64)
+    first_row[codes[::-1]] = np.arange(len(codes) - 1, -1, -1, dtype=np.int64)
+    return first_row
+
+
 def factorize_column(values) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """
     First-appearance factorisation of one column.
@@ -43,15 +50,18 @@ def factorize_column(values) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     :return: ``(codes[N] int64, members[G], first_row[G] int64)`` where ``first_row[g]`` is the
         row on which member ``g`` appears for the first time.
     """
+    n = len(values)
+    if n and isinstance(values, np.ndarray) and values.dtype.kind in 'iu' and values[0] == 0 and values[-1] == n - 1:
+        # the ``obs`` column build() adds (and any other row counter): its own factorisation, no hashing
+        counter = np.arange(n, dtype=np.int64)
+        if np.array_equal(values, counter):
+            return counter, values, counter
     codes, members = pd.factorize(values, sort=False)
     if (codes < 0).any():
         raise ValueError('Group columns must not contain missing values')
     codes = codes.astype(np.int64, copy=False)
-    # members are numbered in first-appearance order, so the k-th non-duplicated row is the
-    # first row of member k
-    first_row = np.flatnonzero(~pd.Series(codes).duplicated(keep='first').values).astype(np.int64)
     members = np.asarray(members) if not isinstance(members, np.ndarray) else members
-    return codes, members, first_row
+    return codes, members, first_rows(codes, len(members))
 
 
 def _determines(codes_i: np.ndarray, first_row_i: np.ndarray, codes_j: np.ndarray) -> bool:
@@ -62,12 +72,25 @@ def _determines(codes_i: np.ndarray, first_row_i: np.ndarray, codes_j: np.ndarra
 
 def functional_matrix(columns: List[str], codes: Dict[str, np.ndarray],
                       first_row: Dict[str, np.ndarray]) -> np.ndarray:
-    """``F[i, j]`` = column i determines column j (diagonal False)."""
+    """
+    ``F[i, j]`` = column i determines column j (diagonal False).  Decided from the member counts where they
+    suffice -- a function from the members of i onto those of j needs at least as many members in i; a column with one
+    member per row determines every column; every column determines a constant one -- and by one pass over the rows
+    otherwise.
+    """
     n = len(columns)
+    n_rows = len(codes[columns[0]]) if columns else 0
+    sizes = [len(first_row[c]) for c in columns]
     out = np.zeros((n, n), dtype=bool)
     for i, ci in enumerate(columns):
         for j, cj in enumerate(columns):
-            if i != j:
+            if i == j:
+                continue
+            if sizes[i] < sizes[j]:
+                out[i, j] = False
+            elif sizes[i] == n_rows or sizes[j] <= 1:
+                out[i, j] = True
+            else:
                 out[i, j] = _determines(codes[ci], first_row[ci], codes[cj])
     return out
 
