@@ -242,3 +242,37 @@ def test_group_component_lowers_to_one_term(simple_df):
     assert (t.index[10:15] == 10).all()
     assert np.array_equal(t.x[:15], frame['x'].values[:15]) and (t.x[15:] == 0).all()
     assert np.allclose(plan.likelihood.offset[15:], 3.0 * frame['x'].values[15:]) and (plan.likelihood.offset[:15] == 0).all()
+
+
+def test_gamma_glm_spellings_and_rejections():
+    """Gamma(alpha, beta = alpha / exp(eta)): the three accepted spellings give the same terms (a constant other than
+    alpha becomes an offset of eta); anything else raises."""
+    import pandas as pd
+    rng = np.random.default_rng(0)
+    frame = pd.DataFrame({'g': rng.integers(0, 3, 50), 'x': rng.normal(size=50), 'y': rng.gamma(2.0, 1.0, 50)})
+
+    def plan_of(beta_of, alpha=2.0, y='y'):
+        data = api.data_components(frame)
+        k = api.DistributionComponent(pm.Normal, name='k', group='g')
+        eta = k * data['x'] + api.DistributionComponent(pm.Normal, name='icpt')
+        return api.build(frame, api.Likelihood(pm.Gamma, alpha=alpha, beta=beta_of(eta), observed=data[y]),
+                         backend='b200').plan
+
+    exp = api.f_(sym.exp)
+    over = plan_of(lambda eta: 2.0 / exp(eta))
+    times = plan_of(lambda eta: exp(-eta) * 2.0)
+    shifted = plan_of(lambda eta: 0.5 / exp(eta))
+    assert over.likelihood.family == 'Gamma' and over.likelihood.sigma_const == 2.0 and over.likelihood.offset is None
+    for a, b in zip(over.terms, times.terms):
+        assert a.block == b.block and np.array_equal(a.index, b.index)
+        assert (a.x is None and b.x is None) or np.allclose(a.x, b.x)
+    assert np.allclose(shifted.likelihood.offset, np.log(2.0 / 0.5))
+    with pytest.raises(UnsupportedModelError):
+        plan_of(lambda eta: exp(eta) + 1.0)                           # not a rate of the log-link GLM
+    with pytest.raises(UnsupportedModelError):
+        plan_of(lambda eta: 2.0 / eta)                                # no link
+    with pytest.raises(UnsupportedModelError):
+        plan_of(lambda eta: 2.0 / exp(eta), alpha=api.DistributionComponent(pm.Exponential, name='shape', lam=1.0))
+    frame['y0'] = frame['y'].where(frame.index != 3, 0.0)
+    with pytest.raises(ValueError):
+        plan_of(lambda eta: 2.0 / exp(eta), y='y0')                   # observations must be positive
