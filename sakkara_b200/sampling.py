@@ -65,6 +65,41 @@ def kick_drift_torch(q, r, g, eps, inv_mass, a: float, b: float) -> None:
         q.add_(eps * inv_mass * r, alpha=b)
 
 
+class ChainPool:
+    """
+    What the chains of one process share with the chains of the other processes of a chain-sharded run (one process
+    per GPU, every GPU holds all rows and its share of the chains): nothing on the evaluation path,
+    only the adaptation statistics -- the mean acceptance behind the common step size and the moment sums behind
+    the common mass matrix -- so that all ranks adapt as one ensemble.  The default is a single process.
+    """
+
+    def mean(self, value):
+        """Mean over all chains of all ranks of a per-rank mean (0-d tensor) -> float."""
+        return float(value)
+
+    def sum_(self, tensor, count: int) -> int:
+        """In-place sum of ``tensor`` over the ranks; returns the summed ``count``."""
+        return count
+
+
+class DistributedChainPool(ChainPool):
+    """``torch.distributed`` all-reduces (NCCL on the GPUs, gloo in the CPU tests); equal chain counts per rank."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+
+    def mean(self, value):
+        v = value.detach().clone().reshape(1)
+        self.dist.all_reduce(v, group=self.group)
+        return float(v) / self.world
+
+    def sum_(self, tensor, count: int) -> int:
+        self.dist.all_reduce(tensor, group=self.group)
+        return count * self.world
+
+
 class _DualAveraging:
     """Step-size adaptation of Hoffman & Gelman (2014), one step size for all chains."""
 
@@ -119,11 +154,11 @@ def warmup_windows(tune: int):
 class _MassAdapt:
     """Pooled (all chains) running variance of theta inside a warm-up window, regularised like Stan's."""
 
-    def __init__(self, P, dev):
+    def __init__(self, P, dev, pool: Optional['ChainPool'] = None):
         import torch
-        self.torch = torch
-        self.s1 = torch.zeros(P, dtype=torch.float64, device=dev)
-        self.s2 = torch.zeros(P, dtype=torch.float64, device=dev)
+        self.pool = pool or ChainPool()
+        self.sums = torch.zeros(2, P, dtype=torch.float64, device=dev)      # sum of theta, sum of theta^2
+        self.s1, self.s2 = self.sums[0], self.sums[1]
         self.n = 0
 
     def add(self, theta) -> None:
@@ -133,11 +168,10 @@ class _MassAdapt:
         self.n += theta.shape[0]
 
     def variance(self, dtype):
-        n = self.n
+        n = self.pool.sum_(self.sums, self.n)
         var = (self.s2 - self.s1 * self.s1 / n) / (n - 1)
         var = (n / (n + 5.0)) * var + 1e-3 * (5.0 / (n + 5.0))
-        self.s1.zero_()
-        self.s2.zero_()
+        self.sums.zero_()
         self.n = 0
         return var.clamp(min=1e-10).to(dtype)
 
@@ -146,7 +180,7 @@ def _kinetic(r, inv_mass):
     return 0.5 * (r * r * inv_mass).sum(1)
 
 
-def _reasonable_step_size(evaluate, kd, theta, logp, grad, inv_mass, eps, work, generator):
+def _reasonable_step_size(evaluate, kd, theta, logp, grad, inv_mass, eps, work, generator, pool):
     """Doubles / halves the step until the mean acceptance of one leapfrog step crosses 0.8 (Hoffman & Gelman, alg. 4)."""
     import torch
     q, r, g, lp, eps_c = work
@@ -161,7 +195,7 @@ def _reasonable_step_size(evaluate, kd, theta, logp, grad, inv_mass, eps, work, 
         evaluate(q, lp, g)
         kd(q, r, g, eps_c, inv_mass, 0.5, 0.0)
         delta = torch.nan_to_num(-lp + _kinetic(r, inv_mass) - h0, nan=float('inf'))
-        accept = float((-delta).clamp(max=0).exp().mean())
+        accept = pool.mean((-delta).clamp(max=0).exp().mean())
         d = 1 if accept > 0.8 else -1
         if direction == 0:
             direction = d
@@ -176,7 +210,7 @@ def _reasonable_step_size(evaluate, kd, theta, logp, grad, inv_mass, eps, work, 
 
 
 def hmc_chains(evaluate, theta, draws: int, tune: int, n_leapfrog: int, step_size: float, target_accept: float,
-               generator=None, kick_drift=None):
+               generator=None, kick_drift=None, pool: Optional[ChainPool] = None):
     """
     Fixed-length HMC for all chains at once on whatever device ``theta`` lives, one
     ``evaluate(q, logp_out, grad_out)`` call per leapfrog step for the whole batch.
@@ -191,6 +225,7 @@ def hmc_chains(evaluate, theta, draws: int, tune: int, n_leapfrog: int, step_siz
     import torch
 
     kd = kick_drift or kick_drift_torch
+    pool = pool or ChainPool()
     chains, P = theta.shape
     dev, tdt = theta.device, theta.dtype
     logp = torch.empty(chains, dtype=tdt, device=dev)
@@ -206,7 +241,7 @@ def hmc_chains(evaluate, theta, draws: int, tune: int, n_leapfrog: int, step_siz
     kept = torch.empty(chains, draws, P, dtype=tdt, device=dev)
     kept_logp = torch.empty(chains, draws, dtype=tdt, device=dev)
     accepted = torch.zeros(chains, dtype=torch.float64, device=dev)
-    mass = _MassAdapt(P, dev)
+    mass = _MassAdapt(P, dev, pool)
     windows = warmup_windows(tune)
     in_window = {it for a, b in windows for it in range(a, b)}
     window_end = {b - 1 for _, b in windows}
@@ -233,7 +268,7 @@ def hmc_chains(evaluate, theta, draws: int, tune: int, n_leapfrog: int, step_siz
         logp.copy_(torch.where(take, prop_logp, logp))
         grad.copy_(torch.where(take[:, None], prop_grad, grad))
         if it < tune:
-            adapt.update(float(log_alpha.clamp(max=0).exp().mean()))
+            adapt.update(pool.mean(log_alpha.clamp(max=0).exp().mean()))
             if it in in_window:
                 mass.add(theta)
             if it in window_end:
@@ -273,7 +308,7 @@ def _turning(ra, rb, rsum, inv_mass):
 
 def nuts_chains(evaluate, theta, draws: int, tune: int, max_depth: int = 8, step_size: float = 0.1,
                 target_accept: float = 0.8, generator=None, kick_drift=None, max_delta_energy: float = 1000.0,
-                check_every: int = 4):
+                check_every: int = 4, pool: Optional[ChainPool] = None):
     """
     The No-U-Turn sampler with multinomial sampling of the trajectory (Betancourt 2017; what ``pm.sample`` runs per
     chain) for all chains in lock-step, one ``evaluate`` call per leapfrog step for the whole batch.
@@ -292,6 +327,7 @@ def nuts_chains(evaluate, theta, draws: int, tune: int, max_depth: int = 8, step
     import torch
 
     kd = kick_drift or kick_drift_torch
+    pool = pool or ChainPool()
     chains, P = theta.shape
     dev, tdt = theta.device, theta.dtype
 
@@ -325,7 +361,7 @@ def nuts_chains(evaluate, theta, draws: int, tune: int, max_depth: int = 8, step
              'diverging': torch.zeros(chains, draws, dtype=torch.bool, device=dev),
              'accept': torch.zeros(chains, draws, dtype=tdt, device=dev),
              'energy': torch.zeros(chains, draws, dtype=tdt, device=dev)}
-    mass = _MassAdapt(P, dev)
+    mass = _MassAdapt(P, dev, pool)
     windows = warmup_windows(tune)
     in_window = {it for a, b in windows for it in range(a, b)}
     window_end = {b - 1 for _, b in windows}
@@ -333,7 +369,7 @@ def nuts_chains(evaluate, theta, draws: int, tune: int, max_depth: int = 8, step
     evaluate(theta, logp, grad)
     if tune > 0:
         step_size = _reasonable_step_size(evaluate, kd, theta, logp, grad, inv_mass, step_size,
-                                          (q, r, g, lp, eps_c), generator)
+                                          (q, r, g, lp, eps_c), generator, pool)
     adapt = _DualAveraging(step_size, target_accept)
 
     for it in range(tune + draws):
@@ -417,13 +453,13 @@ def nuts_chains(evaluate, theta, draws: int, tune: int, max_depth: int = 8, step
         grad.copy_(g_prop)
         accept = sum_accept / n_steps.clamp(min=1).to(tdt)
         if it < tune:
-            adapt.update(float(accept.mean()))
+            adapt.update(pool.mean(accept.mean()))
             if it in in_window:
                 mass.add(theta)
             if it in window_end:
                 inv_mass = mass.variance(tdt)
                 adapt.restart(_reasonable_step_size(evaluate, kd, theta, logp, grad, inv_mass, adapt.eps,
-                                                    (q, r, g, lp, eps_c), generator))
+                                                    (q, r, g, lp, eps_c), generator, pool))
         else:
             k = it - tune
             kept[:, k] = theta
@@ -438,6 +474,24 @@ def nuts_chains(evaluate, theta, draws: int, tune: int, max_depth: int = 8, step
 
 # ---------------------------------------------------------------------------------------------------------------
 # drivers on the CUDA evaluator
+
+
+def chain_pool(chains: int):
+    """
+    ``(pool, chains of this process, rank)``: under ``torch.distributed`` with more than one rank (``torchrun``, one
+    process per GPU) the chains are split evenly over the ranks -- every GPU holds all rows, no collective on the
+    evaluation path (chains) -- and the ranks adapt step size and mass matrix as one ensemble.
+    """
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            if chains % world:
+                raise ValueError(f'{chains} chains do not split evenly over {world} ranks')
+            return DistributedChainPool(), chains // world, dist.get_rank()
+    except ImportError:      # pragma: no cover
+        pass
+    return ChainPool(), chains, 0
 
 
 def _device_setup(model, chains, dtype, device, seed):
@@ -469,14 +523,15 @@ def sample_hmc(model, chains: int = 64, draws: int = 500, tune: int = 500, n_lea
     """
     import torch
 
-    f, skk, dev, tdt, gen, stream, evaluate, kick_drift = _device_setup(model, chains, dtype, device, seed)
+    pool, chains, rank = chain_pool(chains)
+    f, skk, dev, tdt, gen, stream, evaluate, kick_drift = _device_setup(model, chains, dtype, device, seed + 7919 * rank)
     # everything -- the start positions included -- is created and consumed on the plan's stream: the library
     # launches there, and torch's caching allocator then knows which stream uses the buffers
     stream.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(stream):
         theta = init_scale * torch.randn(chains, f.size, dtype=tdt, device=dev, generator=gen)
         kept, kept_logp, accepted, eps = hmc_chains(evaluate, theta, draws, tune, n_leapfrog, step_size,
-                                                    target_accept, generator=gen,
+                                                    target_accept, generator=gen, pool=pool,
                                                     kick_drift=kick_drift if fused_leapfrog else None)
     torch.cuda.synchronize()
     result = HMCResult(draws=kept.cpu().numpy(), logp=kept_logp.cpu().numpy(),
@@ -496,13 +551,14 @@ def sample_nuts(model, chains: int = 64, draws: int = 500, tune: int = 500, max_
     """
     import torch
 
-    f, skk, dev, tdt, gen, stream, evaluate, kick_drift = _device_setup(model, chains, dtype, device, seed)
+    pool, chains, rank = chain_pool(chains)
+    f, skk, dev, tdt, gen, stream, evaluate, kick_drift = _device_setup(model, chains, dtype, device, seed + 7919 * rank)
     stream.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(stream):
         theta = init_scale * torch.randn(chains, f.size, dtype=tdt, device=dev, generator=gen)
         kept, kept_logp, stats, eps = nuts_chains(evaluate, theta, draws, tune, max_depth=max_depth,
                                                   step_size=step_size, target_accept=target_accept, generator=gen,
-                                                  kick_drift=kick_drift if fused_leapfrog else None)
+                                                  pool=pool, kick_drift=kick_drift if fused_leapfrog else None)
     torch.cuda.synchronize()
     stats = {k: v.cpu().numpy() for k, v in stats.items()}
     result = HMCResult(draws=kept.cpu().numpy(), logp=kept_logp.cpu().numpy(),

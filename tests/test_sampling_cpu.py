@@ -195,3 +195,43 @@ def test_diagnostics_on_known_processes():
     assert split_rhat(ar) < 1.05
     drift = iid + np.linspace(0, 3, 1000)[None, :]              # every chain drifts: the halves disagree
     assert split_rhat(drift) > 1.15
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# chain-sharded run: two processes (gloo), every rank its own chains, adaptation pooled
+
+
+def _sharded_nuts_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    from sakkara_b200.sampling import chain_pool, nuts_chains
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        pool, chains, r = chain_pool(16)
+        assert chains == 8 and r == rank and type(pool).__name__ == 'DistributedChainPool'
+        P = 5
+        sd = torch.linspace(0.2, 3.0, P, dtype=torch.float64)
+        mu = torch.arange(P, dtype=torch.float64)
+        gen = torch.Generator().manual_seed(100 + rank)
+        theta = 0.1 * torch.randn(chains, P, dtype=torch.float64, generator=gen)
+        kept, _, stats, eps = nuts_chains(_gaussian(mu, sd), theta, 250, 250, max_depth=7, generator=gen, pool=pool)
+        torch.save({'kept': kept, 'eps': eps, 'accept': float(stats['accept'].mean())}, os.path.join(out, f'r{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chain_sharded_nuts_adapts_as_one_ensemble(tmp_path):
+    import os
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_sharded_nuts_worker, args=(world, 29100 + os.getpid() % 700, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), f'r{r}.pt')) for r in range(world)]
+    assert res[0]['eps'] == res[1]['eps']                        # one step size for the whole ensemble
+    assert not torch.equal(res[0]['kept'], res[1]['kept'])       # ... but different chains
+    k = torch.cat([r['kept'] for r in res]).numpy()
+    P = k.shape[2]
+    sd = np.linspace(0.2, 3.0, P)
+    assert np.all(np.abs(k.mean((0, 1)) - np.arange(P)) < 0.1 * sd)
+    assert np.allclose(k.reshape(-1, P).std(0) / sd, 1.0, atol=0.06)
+    assert all(abs(r['accept'] - 0.8) < 0.1 for r in res)
