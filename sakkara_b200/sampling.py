@@ -497,6 +497,9 @@ def chain_pool(chains: int):
 def _device_setup(model, chains, dtype, device, seed):
     import torch
     f = model.logp_dlogp_function(dtype=dtype, max_batch=chains, device=device)
+    if not hasattr(f, 'skk'):
+        raise NotImplementedError(f'the many-chain samplers need a model that is one device plan; this one evaluates as '
+                                  f'{type(f).__name__} (a sum of plans added on the host)')
     skk = f.skk
     dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
     tdt = torch.float64 if dtype == 'float64' else torch.float32

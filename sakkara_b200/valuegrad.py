@@ -199,3 +199,85 @@ class SplitSigmaValueGrad:
     def close(self) -> None:
         for f in self.parts + [self._priors]:
             f.close()
+
+
+def secondary_chunk_groups(dtype, max_batch: int) -> int:
+    """
+    Largest secondary level one plan should carry: the row kernel keeps one table of the level's values and one
+    accumulator table per warp in shared memory -- ``(warps + 1) * groups * batch tile * sizeof(T)`` next to the warps'
+    staging rings -- and gives up pipeline stages and then warps to make a larger level fit, until it cannot
+    (``skk_plan_create``: "does not fit in shared memory").  With tables of up to 16 KB a CTA of eight warps still
+    fits an SM (9 x 16 KB + rings < 227 KB); beyond that the level is split over several plans instead.
+    """
+    tile = 4 if max_batch > 1 else 1
+    return max(256, (16 * 1024) // (np.dtype(dtype).itemsize * tile))
+
+
+class ChunkedSecondaryValueGrad:
+    """
+    Value and gradient of a crossed model whose smaller (secondary) factor is too large for the row kernel's
+    shared-memory tables: the rows are split by ranges of secondary groups into parts with at most
+    ``chunk_groups`` of them each; every part is an ordinary plan over its rows (same theta, its own sort, segments
+    and tables) evaluated by the same kernels, the priors come from a plan without rows, and the parts are added on
+    the host in a fixed order.  The likelihood is a sum over rows, so the result is the whole model's; every row is
+    still read once per evaluation.
+    """
+
+    def __init__(self, plan: ModelPlan, dtype: str = 'float64', max_batch: int = 1, device: Optional[int] = None,
+                 chunk_groups: Optional[int] = None):
+        self.model_plan = plan
+        self.dtype = np.dtype(dtype)
+        self.chunk_groups = int(chunk_groups or secondary_chunk_groups(dtype, max_batch))
+        self.part_rows = split_rows_by_secondary(plan, self.chunk_groups)
+        self.part_plans = [plan.take_rows(rows) for rows in self.part_rows]
+        self.parts = [ValueGradFunction(part, dtype=dtype, max_batch=max_batch, device=device, include_priors=False)
+                      for part in self.part_plans]
+        self._priors = ValueGradFunction(plan.take_rows([]), dtype=dtype, max_batch=max_batch, device=device)
+
+    @property
+    def size(self) -> int:
+        return self.model_plan.n_params
+
+    def set_extra_values(self, extra_vars) -> None:
+        pass
+
+    def __call__(self, theta, grad_out=None, extra_vars=None):
+        theta = np.asarray(theta, dtype=self.dtype)
+        logp, grad = self._priors(theta)
+        logp = np.array(logp, dtype=np.float64) + float(self.model_plan.logp_const)     # (rows masked for NaN)
+        grad = np.array(grad, dtype=np.float64)
+        for part in self.parts:
+            lp, g = part(theta)
+            logp = logp + lp
+            grad = grad + g
+        logp = logp.astype(self.dtype) if logp.ndim else self.dtype.type(logp)
+        grad = grad.astype(self.dtype)
+        if grad_out is not None:
+            grad_out[...] = grad
+            return logp, grad_out
+        return logp, grad
+
+    def stats(self) -> dict:
+        return self.parts[0].stats()
+
+    def close(self) -> None:
+        for f in self.parts + [self._priors]:
+            f.close()
+
+
+def split_rows_by_secondary(plan: ModelPlan, chunk_groups: int):
+    """
+    Row numbers of the parts of :class:`ChunkedSecondaryValueGrad`: part k holds the rows whose secondary group (in
+    the slot order of the whole model's kernel plan) lies in ``[k * size, (k + 1) * size)``, ``size`` = the level's
+    groups spread evenly over the fewest parts of at most ``chunk_groups``.  One part (all rows) when the level fits.
+    """
+    structure = make_kernel_plan(plan, dtype='float64', structure_only=True)
+    if structure.n_secondary <= chunk_groups:
+        return [np.arange(plan.n_rows)]
+    n_parts = -(-structure.n_secondary // chunk_groups)
+    size = -(-structure.n_secondary // n_parts)
+    part_of_sorted_row = structure.sec_codes.astype(np.int64) // size
+    original = np.arange(plan.n_rows) if structure.perm is None else structure.perm
+    order = np.argsort(part_of_sorted_row, kind='stable')
+    bounds = np.searchsorted(part_of_sorted_row[order], np.arange(n_parts + 1))
+    return [np.sort(original[order[bounds[k]:bounds[k + 1]]]) for k in range(n_parts)]

@@ -50,3 +50,33 @@ def test_a_plan_is_bound_to_its_process(plan):
 def test_row_shards(plan):
     f = ValueGradFunction(plan, rows=slice(0, 200), n_rows_total=500)
     assert f.kernel_plan.n_rows == 200 and f.kernel_plan.n_rows_total == 500
+
+
+def test_chunked_secondary_parts_add_up_to_the_model():
+    """A crossed model whose secondary factor is split over several plans (valuegrad.ChunkedSecondaryValueGrad): the
+    parts partition the rows, every part's secondary level respects the limit, and priors + parts -- each evaluated
+    from its KERNEL plan, i.e. what the device would compute -- add up to the oracle of the whole model."""
+    from oracle.kernel_plan_eval import likelihood_from_kernel_plan
+    from oracle.logp_numpy import logp_dlogp
+    from sakkara_b200 import synth
+    from sakkara_b200.plan.kernel_plan import make_kernel_plan
+    from sakkara_b200.valuegrad import secondary_chunk_groups, split_rows_by_secondary
+    cols, _ = synth.poisson_columns(6000, 90, 50, seed=4)
+    plan = synth.poisson_plan(cols)
+    assert len(split_rows_by_secondary(plan, 64)) == 1              # fits: one part, all rows
+    parts = split_rows_by_secondary(plan, 16)
+    assert len(parts) == 4                                          # 50 groups -> 4 parts of <= 13
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(plan.n_rows))
+    theta = synth.start_point(plan, 1, seed=3, scale=0.3)[0].astype(np.float64)
+    logp, grad = logp_dlogp(plan.take_rows([]), theta)              # the priors
+    grad = np.array(grad, dtype=np.float64)
+    for rows in parts:
+        kp = make_kernel_plan(plan.take_rows(rows), dtype='float64', include_priors=False)
+        assert 0 < kp.n_secondary <= 13 and kp.n_rows == len(rows)
+        lp, g = likelihood_from_kernel_plan(kp, theta)
+        logp, grad = logp + lp, grad + g
+    ref_logp, ref_grad = logp_dlogp(plan, theta)
+    assert abs(logp - ref_logp) < 1e-10 * abs(ref_logp)
+    assert np.allclose(grad, ref_grad, rtol=1e-10, atol=1e-10)
+    # the limits: tables of up to 16 KB, so that a CTA of eight warps still fits an SM
+    assert secondary_chunk_groups('float32', 1) == 4096 and secondary_chunk_groups('float64', 4) == 512
