@@ -98,14 +98,16 @@ class B200Model:
         if self.plan.minibatch is not None:
             # MinibatchLikelihood: a fresh random subset of the rows per call, scaled to the whole data set
             return MinibatchValueGrad(self.plan, dtype=dtype, device=device, **options)
-        from sakkara_b200.valuegrad import ChunkedSecondaryValueGrad, secondary_chunk_groups, split_rows_by_secondary
+        from sakkara_b200.valuegrad import PartitionedValueGrad, partition_rows, secondary_chunk_groups
         chunk = options.pop('chunk_groups', None) or secondary_chunk_groups(dtype, max_batch)
-        # (the secondary level is the smaller of two crossed factors: only a model with two gathers over more than
-        #  `chunk` elements can have one that large -- everything else skips the structure pass)
-        wide = sum(1 for t in self.plan.terms if t.block < 0 or self.plan.blocks[t.block].size > chunk)
-        if not options and wide >= 2 and len(split_rows_by_secondary(self.plan, chunk)) > 1:
-            # a crossed model whose smaller factor does not fit the row kernel's shared-memory tables: a sum of plans
-            return ChunkedSecondaryValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device, chunk_groups=chunk)
+        # (only a model with two gathers over more than `chunk` elements can have a secondary level -- the smaller of two
+        #  crossed factors -- that large, and only one with three non-constant gathers can have three crossed factors:
+        #  everything else skips the structure pass)
+        gathers = [t for t in self.plan.terms if t.block < 0 or self.plan.blocks[t.block].size > 1]
+        wide = sum(1 for t in gathers if t.block < 0 or self.plan.blocks[t.block].size > chunk)
+        if not options and (wide >= 2 or len(gathers) >= 3) and len(partition_rows(self.plan, chunk)) > 1:
+            # more than one plan: a secondary level too large for the shared-memory tables, or a third crossed factor
+            return PartitionedValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device, chunk_groups=chunk)
         return ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
 
     def sample(self, draws: int = 1000, tune: int = 1000, chains: int = 64, target_accept: float = 0.8,

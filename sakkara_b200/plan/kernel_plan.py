@@ -34,6 +34,19 @@ from sakkara_b200.plan.model_plan import (FAMILY_IDS, LIKELIHOOD_IDS, PRIOR_PARA
                                           prior_normaliser)
 
 LEVEL_GLOBAL, LEVEL_PRIMARY, LEVEL_SECONDARY = 0, 1, 2
+
+
+class CrossedFactorsError(UnsupportedModelError):
+    """
+    More crossed grouping factors than one plan sorts by.  Carries the smallest of them -- ``codes[N]``, the factor's
+    group of every row of the plan, and its ``size`` -- because inside one group of a factor its term is a single
+    element of theta: rows split by that factor are plans with one crossed factor less
+    (``valuegrad.PartitionedValueGrad``).
+    """
+
+    def __init__(self, message: str, codes: np.ndarray, size: int):
+        super().__init__(message)
+        self.codes, self.size = codes, int(size)
 MAX_TERMS_PER_LEVEL = 2
 MAX_SECONDARY_TERMS = 1
 MAX_XCOLS = 6
@@ -266,7 +279,9 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
               if not any((d, c) in table and (c, d) not in table for d in range(k) if d != c)]
     # twins cannot occur here (identical partitions were merged above)
     if len(finest) > 2:
-        raise UnsupportedModelError(f'{len(finest)} crossed grouping factors; the fused kernel handles at most two')
+        smallest = min(finest, key=lambda c: columns[c].size)
+        raise CrossedFactorsError(f'{len(finest)} crossed grouping factors; the fused kernel handles at most two',
+                                  codes=columns[smallest].codes, size=columns[smallest].size)
     primary = secondary = None
     if len(finest) == 1:
         primary = finest[0]

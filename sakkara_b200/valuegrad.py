@@ -17,6 +17,7 @@ from typing import Optional
 import numpy as np
 
 from sakkara_b200.plan.kernel_plan import KernelPlan, make_kernel_plan
+from sakkara_b200.plan.lower import UnsupportedModelError
 from sakkara_b200.plan.model_plan import ModelPlan
 
 
@@ -213,22 +214,26 @@ def secondary_chunk_groups(dtype, max_batch: int) -> int:
     return max(256, (16 * 1024) // (np.dtype(dtype).itemsize * tile))
 
 
-class ChunkedSecondaryValueGrad:
+class PartitionedValueGrad:
     """
-    Value and gradient of a crossed model whose smaller (secondary) factor is too large for the row kernel's
-    shared-memory tables: the rows are split by ranges of secondary groups into parts with at most
-    ``chunk_groups`` of them each; every part is an ordinary plan over its rows (same theta, its own sort, segments
-    and tables) evaluated by the same kernels, the priors come from a plan without rows, and the parts are added on
-    the host in a fixed order.  The likelihood is a sum over rows, so the result is the whole model's; every row is
-    still read once per evaluation.
+    Value and gradient of a model that one plan of the fused kernels cannot hold, as a sum of plans over disjoint
+    sets of rows (the likelihood is a sum over rows; every row is still read once per evaluation):
+
+    * a crossed model whose smaller (secondary) factor is too large for the row kernel's shared-memory tables is
+      split by ranges of secondary groups into parts with at most ``chunk_groups`` of them each;
+    * a model with more than two crossed factors is split by the groups of its smallest crossed factor -- inside one
+      group that factor's term is a single element of theta, a global term of the part -- until two are left.
+
+    Every part is an ordinary plan over its rows (same theta, its own sort, segments and tables) evaluated by the
+    same kernels; the priors come from a plan without rows; the parts are added on the host in a fixed order.
     """
 
     def __init__(self, plan: ModelPlan, dtype: str = 'float64', max_batch: int = 1, device: Optional[int] = None,
-                 chunk_groups: Optional[int] = None):
+                 chunk_groups: Optional[int] = None, max_parts: int = 256):
         self.model_plan = plan
         self.dtype = np.dtype(dtype)
         self.chunk_groups = int(chunk_groups or secondary_chunk_groups(dtype, max_batch))
-        self.part_rows = split_rows_by_secondary(plan, self.chunk_groups)
+        self.part_rows = partition_rows(plan, self.chunk_groups, max_parts)
         self.part_plans = [plan.take_rows(rows) for rows in self.part_rows]
         self.parts = [ValueGradFunction(part, dtype=dtype, max_batch=max_batch, device=device, include_priors=False)
                       for part in self.part_plans]
@@ -265,11 +270,14 @@ class ChunkedSecondaryValueGrad:
             f.close()
 
 
+ChunkedSecondaryValueGrad = PartitionedValueGrad      # (the first of the two cases, under its first name)
+
+
 def split_rows_by_secondary(plan: ModelPlan, chunk_groups: int):
     """
-    Row numbers of the parts of :class:`ChunkedSecondaryValueGrad`: part k holds the rows whose secondary group (in
-    the slot order of the whole model's kernel plan) lies in ``[k * size, (k + 1) * size)``, ``size`` = the level's
-    groups spread evenly over the fewest parts of at most ``chunk_groups``.  One part (all rows) when the level fits.
+    Rows of a plannable model split so that no part's secondary level exceeds ``chunk_groups``: part k holds the rows
+    whose secondary group (in the slot order of the whole model's kernel plan) lies in ``[k * size, (k + 1) * size)``,
+    ``size`` = the level's groups spread evenly over the fewest parts.  One part (all rows) when the level fits.
     """
     structure = make_kernel_plan(plan, dtype='float64', structure_only=True)
     if structure.n_secondary <= chunk_groups:
@@ -281,3 +289,32 @@ def split_rows_by_secondary(plan: ModelPlan, chunk_groups: int):
     order = np.argsort(part_of_sorted_row, kind='stable')
     bounds = np.searchsorted(part_of_sorted_row[order], np.arange(n_parts + 1))
     return [np.sort(original[order[bounds[k]:bounds[k + 1]]]) for k in range(n_parts)]
+
+
+def partition_rows(plan: ModelPlan, chunk_groups: int, max_parts: int = 256):
+    """
+    Row numbers of the parts of :class:`PartitionedValueGrad` (ascending inside a part; one part = all rows when a
+    single plan does).  More than two crossed factors: split by the smallest one, part by part, until the planner
+    accepts; then every part by ranges of its secondary level.
+    """
+    from sakkara_b200.plan.kernel_plan import CrossedFactorsError
+
+    def recurse(rows):
+        sub = plan if rows is None else plan.take_rows(rows)
+        base = np.arange(plan.n_rows) if rows is None else rows
+        try:
+            return [base[p] for p in split_rows_by_secondary(sub, chunk_groups)]
+        except CrossedFactorsError as err:
+            if err.size > max_parts:
+                raise
+            order = np.argsort(err.codes, kind='stable')
+            bounds = np.searchsorted(err.codes[order], np.arange(err.size + 1))
+            out = []
+            for k in range(err.size):
+                out += recurse(base[np.sort(order[bounds[k]:bounds[k + 1]])])
+            return out
+
+    parts = recurse(None)
+    if len(parts) > max_parts:
+        raise UnsupportedModelError(f'the model would take {len(parts)} plans (at most {max_parts})')
+    return parts

@@ -80,3 +80,68 @@ def test_chunked_secondary_parts_add_up_to_the_model():
     assert np.allclose(grad, ref_grad, rtol=1e-10, atol=1e-10)
     # the limits: tables of up to 16 KB, so that a CTA of eight warps still fits an SM
     assert secondary_chunk_groups('float32', 1) == 4096 and secondary_chunk_groups('float64', 4) == 512
+
+
+def _crossed3_model(n=4000, seed=1, four=False):
+    """beta * x + a[A] + b[B] + c[C] (+ d[D]) with independently drawn factors, through the DSL."""
+    import pandas as pd
+    import sakkara_b200.model as api
+    from sakkara_b200.model import dist as pm, sym as pt
+    rng = np.random.default_rng(seed)
+    df = pd.DataFrame({'x': rng.standard_normal(n), 'A': rng.integers(0, 40, n), 'B': rng.integers(0, 9, n),
+                       'C': rng.integers(0, 4, n), 'D': rng.integers(0, 3, n)})
+    df['y'] = rng.poisson(np.exp(0.2 * df['x'] + 0.1 * (df['C'] - 1.5))).astype(float)
+    DC = api.DistributionComponent
+    data = api.data_components(df[['x', 'y']])
+    eta = DC(pm.Normal, name='beta') * data['x']
+    for name in ('A', 'B', 'C') + (('D',) if four else ()):
+        eta = eta + DC(pm.Normal, name=name.lower(), group=name, sigma=DC(pm.HalfNormal, name='sd_' + name, sigma=1.0))
+    return api.build(df, api.Likelihood(pm.Poisson, mu=api.f_(pt.exp)(eta), observed=data['y']), backend='b200'), df
+
+
+def test_more_than_two_crossed_factors_become_a_sum_of_plans(four=False):
+    """Three crossed factors: rows split by the smallest factor; inside a part that factor's term is a single element
+    of theta.  Parts evaluated from their kernel plans + priors = the oracle of the whole model."""
+    from oracle.kernel_plan_eval import likelihood_from_kernel_plan
+    from oracle.logp_numpy import logp_dlogp
+    from sakkara_b200.plan.kernel_plan import CrossedFactorsError, make_kernel_plan
+    from sakkara_b200.valuegrad import partition_rows
+    model, df = _crossed3_model(four=four)
+    plan = model.plan
+    with pytest.raises(CrossedFactorsError) as info:
+        make_kernel_plan(plan, 'float64')
+    assert info.value.size == (3 if four else 4) and len(info.value.codes) == plan.n_rows
+    parts = partition_rows(plan, chunk_groups=4096)
+    assert len(parts) == (12 if four else 4)
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(plan.n_rows))
+    for rows in parts:                                               # a part = one group of C (and of D)
+        assert df['C'].values[rows].min() == df['C'].values[rows].max()
+        assert not four or df['D'].values[rows].min() == df['D'].values[rows].max()
+    theta = np.random.default_rng(3).normal(0, 0.3, plan.n_params)
+    logp, grad = logp_dlogp(plan.take_rows([]), theta)
+    grad = np.array(grad, dtype=np.float64)
+    for rows in parts:
+        kp = make_kernel_plan(plan.take_rows(rows), dtype='float64', include_priors=False)
+        assert kp.n_primary <= 40 and kp.n_secondary <= 9
+        lp, g = likelihood_from_kernel_plan(kp, theta)
+        logp, grad = logp + lp, grad + g
+    ref_logp, ref_grad = logp_dlogp(plan, theta)
+    assert abs(logp - ref_logp) < 1e-10 * abs(ref_logp)
+    assert np.allclose(grad, ref_grad, rtol=1e-10, atol=1e-10)
+    # the model hands out the sum of plans (constructed lazily: no device needed to get this far)
+    f = model.logp_dlogp_function()
+    assert type(f).__name__ == 'PartitionedValueGrad' and len(f.parts) == len(parts)
+    with pytest.raises(Exception):
+        partition_rows(plan, chunk_groups=4096, max_parts=2)
+
+
+def test_four_crossed_factors_next_to_a_covariate_exceed_the_kernels():
+    """Two peeled factors and beta * x are three terms that are global inside a part; the kernels take two."""
+    from sakkara_b200.plan.kernel_plan import make_kernel_plan
+    from sakkara_b200.plan.lower import UnsupportedModelError
+    from sakkara_b200.valuegrad import partition_rows
+    model, _ = _crossed3_model(four=True)
+    parts = partition_rows(model.plan, chunk_groups=4096)
+    assert len(parts) == 12
+    with pytest.raises(UnsupportedModelError, match='3 global'):
+        make_kernel_plan(model.plan.take_rows(parts[0]), dtype='float64', include_priors=False)

@@ -1,7 +1,8 @@
 """
-A crossed model whose secondary factor is split over several plans (valuegrad.ChunkedSecondaryValueGrad) on the GPU.
-(The composition is pinned on CPU in tests/test_valuegrad.py; this file was written after the round's GPU budget
-was spent and sorts last so that it cannot mask another file's result under ``-x``.)
+Models that take several plans (valuegrad.PartitionedValueGrad) on the GPU: a crossed model whose secondary factor is
+split by ranges of groups, and a model with three crossed factors split by the smallest one.
+(The composition is pinned on CPU in tests/test_valuegrad.py from the parts' kernel plans; this file was written
+after the round's GPU budget was spent and sorts last so that it cannot mask another file's result under ``-x``.)
 """
 import numpy as np
 import pytest
@@ -39,4 +40,17 @@ def test_secondary_level_too_large_for_one_plan():
     theta = synth.start_point(plan, 1, seed=2, scale=0.2, dtype='float64')[0]
     logp, grad = f(theta)
     assert_parity(logp, grad, plan, theta, 'float64')
+    f.close()
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+def test_three_crossed_factors(dtype):
+    from helpers import theta_points
+    from test_valuegrad import _crossed3_model
+    model, _ = _crossed3_model()
+    f = model.logp_dlogp_function(dtype=dtype)
+    assert type(f).__name__ == 'PartitionedValueGrad' and len(f.parts) == 4
+    for theta in theta_points(model.plan, 3, seed=4, scale=0.3):
+        logp, grad = f(theta)
+        assert_parity(logp, grad, model.plan, theta, dtype)
     f.close()
