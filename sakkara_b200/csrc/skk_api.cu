@@ -1335,6 +1335,9 @@ static int eval_impl(skk_plan *pl, const void *theta, int batch, void *logp_out,
         return fail(SKK_ERR_NCCL, "peer all-reduce timed out waiting for another rank; destroy the plans of all ranks "
                                   "and connect again");
 
+    // (which kernels this evaluation takes: the same test as in enqueue_eval)
+    pl->stats.kernel_variant = (pl->chain_ready && batch >= kChainMinBatch && !(pl->comm != nullptr || pl->peer_ready)) ? 2 : 1;
+
     const T *th = dev_io ? static_cast<const T *>(theta) : static_cast<const T *>(pl->theta_dev);
     T *out_grad = dev_io ? static_cast<T *>(grad_out) : static_cast<T *>(pl->out_dev);
     T *out_logp = dev_io ? static_cast<T *>(logp_out) : static_cast<T *>(pl->out_dev) + (size_t)batch * P;

@@ -54,3 +54,17 @@ def test_three_crossed_factors(dtype):
         logp, grad = f(theta)
         assert_parity(logp, grad, model.plan, theta, dtype)
     f.close()
+
+
+def test_stats_name_the_kernels_of_the_last_evaluation():
+    """skk_stats_t.kernel_variant: 2 when the chain-per-lane kernels evaluated the batch, 1 for the row kernel."""
+    from sakkara_b200.valuegrad import ValueGradFunction
+    cols, _ = synth.linreg_columns(20_000, 50, seed=3)
+    plan = synth.linreg_plan(cols)
+    f = ValueGradFunction(plan, dtype='float64', max_batch=40)
+    theta = synth.start_point(plan, 40, seed=2, scale=0.3, dtype='float64')
+    f(theta)
+    assert f.stats()['kernel_variant'] == 2 and f.stats()['row_kernel_launches'] == 1
+    f(theta[:3])
+    assert f.stats()['kernel_variant'] == 1
+    f.close()
