@@ -494,12 +494,54 @@ def chain_pool(chains: int):
     return ChainPool(), chains, 0
 
 
+def _host_setup(f, dtype, seed):
+    """
+    A model that is not one device plan -- a sum of plans added on the host (``PartitionedValueGrad``,
+    ``SplitSigmaValueGrad``): the chains live in host memory and every leapfrog step is one batched call of the
+    evaluator with host buffers (the rows are still read by the kernels; theta and the gradients cross PCIe).
+    """
+    import torch
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    gen = torch.Generator()
+    gen.manual_seed(seed)
+
+    def evaluate(q, lp, g):
+        logp, grad = f(q.numpy())
+        lp.copy_(torch.from_numpy(np.ascontiguousarray(logp)))
+        g.copy_(torch.from_numpy(np.ascontiguousarray(grad)))
+
+    return f, None, torch.device('cpu'), tdt, gen, None, evaluate, None
+
+
+class _OnStream:
+    """The plan's stream as torch's current one (device-resident chains); nothing for host-resident chains."""
+
+    def __init__(self, stream, dev):
+        self.stream, self.dev, self.ctx = stream, dev, None
+
+    def __enter__(self):
+        if self.stream is not None:
+            import torch
+            # everything -- the start positions included -- is created and consumed on the plan's stream: the library
+            # launches there, and torch's caching allocator then knows which stream uses the buffers
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+            self.ctx = torch.cuda.stream(self.stream)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            import torch
+            self.ctx.__exit__(*exc)
+            torch.cuda.synchronize()
+        return False
+
+
 def _device_setup(model, chains, dtype, device, seed):
     import torch
     f = model.logp_dlogp_function(dtype=dtype, max_batch=chains, device=device)
     if not hasattr(f, 'skk'):
-        raise NotImplementedError(f'the many-chain samplers need a model that is one device plan; this one evaluates as '
-                                  f'{type(f).__name__} (a sum of plans added on the host)')
+        return _host_setup(f, dtype, seed)
     skk = f.skk
     dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
     tdt = torch.float64 if dtype == 'float64' else torch.float32
@@ -528,15 +570,11 @@ def sample_hmc(model, chains: int = 64, draws: int = 500, tune: int = 500, n_lea
 
     pool, chains, rank = chain_pool(chains)
     f, skk, dev, tdt, gen, stream, evaluate, kick_drift = _device_setup(model, chains, dtype, device, seed + 7919 * rank)
-    # everything -- the start positions included -- is created and consumed on the plan's stream: the library
-    # launches there, and torch's caching allocator then knows which stream uses the buffers
-    stream.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(stream):
+    with _OnStream(stream, dev):
         theta = init_scale * torch.randn(chains, f.size, dtype=tdt, device=dev, generator=gen)
         kept, kept_logp, accepted, eps = hmc_chains(evaluate, theta, draws, tune, n_leapfrog, step_size,
                                                     target_accept, generator=gen, pool=pool,
                                                     kick_drift=kick_drift if fused_leapfrog else None)
-    torch.cuda.synchronize()
     result = HMCResult(draws=kept.cpu().numpy(), logp=kept_logp.cpu().numpy(),
                        accept_rate=(accepted / max(draws, 1)).cpu().numpy(), step_size=eps,
                        value_var_names=[b.value_name for b in model.plan.blocks])
@@ -556,13 +594,11 @@ def sample_nuts(model, chains: int = 64, draws: int = 500, tune: int = 500, max_
 
     pool, chains, rank = chain_pool(chains)
     f, skk, dev, tdt, gen, stream, evaluate, kick_drift = _device_setup(model, chains, dtype, device, seed + 7919 * rank)
-    stream.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(stream):
+    with _OnStream(stream, dev):
         theta = init_scale * torch.randn(chains, f.size, dtype=tdt, device=dev, generator=gen)
         kept, kept_logp, stats, eps = nuts_chains(evaluate, theta, draws, tune, max_depth=max_depth,
                                                   step_size=step_size, target_accept=target_accept, generator=gen,
                                                   pool=pool, kick_drift=kick_drift if fused_leapfrog else None)
-    torch.cuda.synchronize()
     stats = {k: v.cpu().numpy() for k, v in stats.items()}
     result = HMCResult(draws=kept.cpu().numpy(), logp=kept_logp.cpu().numpy(),
                        accept_rate=stats['accept'].mean(1), step_size=eps,

@@ -235,3 +235,36 @@ def test_chain_sharded_nuts_adapts_as_one_ensemble(tmp_path):
     assert np.all(np.abs(k.mean((0, 1)) - np.arange(P)) < 0.1 * sd)
     assert np.allclose(k.reshape(-1, P).std(0) / sd, 1.0, atol=0.06)
     assert all(abs(r['accept'] - 0.8) < 0.1 for r in res)
+
+
+def test_samplers_run_host_resident_for_models_that_are_a_sum_of_plans():
+    """sample_nuts / sample_hmc with an evaluator that is not one device plan (no ``skk``): chains in host memory, one
+    batched call with host buffers per leapfrog step -- here a stand-in evaluator with a Gaussian target."""
+    from types import SimpleNamespace
+    from sakkara_b200.sampling import sample_hmc, sample_nuts
+    P = 4
+    mu, sd = np.arange(P, dtype=np.float64), np.array([0.5, 1.0, 2.0, 4.0])
+    calls = []
+
+    class Evaluator:
+        size = P
+        dtype = np.dtype('float64')
+
+        def __call__(self, theta):
+            calls.append(theta.shape)
+            z = (theta - mu) / sd
+            return -0.5 * (z * z).sum(1), -z / sd
+
+        def close(self):
+            calls.append('closed')
+
+    model = SimpleNamespace(plan=SimpleNamespace(blocks=[SimpleNamespace(value_name='v', name='v', offset=0, size=P,
+                                                                         transform='identity')]),
+                            logp_dlogp_function=lambda **kw: Evaluator())
+    res = sample_nuts(model, chains=16, draws=200, tune=200, seed=3)
+    assert res.draws.shape == (16, 200, P) and calls[-1] == 'closed' and set(calls[:-1]) == {(16, P)}
+    assert np.allclose(res.draws.reshape(-1, P).std(0) / sd, 1.0, atol=0.08)
+    assert np.all(np.abs(res.draws.mean((0, 1)) - mu) < 0.15 * sd)
+    assert res.constrained(model.plan)['v'].shape == (16, 200, P)
+    res = sample_hmc(model, chains=8, draws=50, tune=80, n_leapfrog=5, step_size=0.2, seed=1)
+    assert res.draws.shape == (8, 50, P) and 0.3 < res.accept_rate.mean() <= 1.0
