@@ -121,6 +121,18 @@ class B200Model:
         return sample_nuts(self, chains=chains, draws=draws, tune=tune, max_depth=max_treedepth,
                            target_accept=target_accept, dtype=dtype, seed=random_seed, device=device)
 
+    def fit(self, n: int = 10_000, method: str = 'advi', learning_rate: float = 1e-3, random_seed: int = 0,
+            dtype: str = 'float64', device: Optional[int] = None, **kwargs):
+        """
+        ``pm.fit``'s arguments on the mean-field ADVI of :mod:`sakkara_b200.variational` (a model with a
+        ``MinibatchLikelihood`` evaluates a fresh random subset of the rows per step).  Returns the approximation
+        (``mean``, ``sd``, ``elbo``, ``sample()``).
+        """
+        if method != 'advi':
+            raise NotImplementedError(f"method {method!r}: only mean-field 'advi' is built here")
+        from sakkara_b200.variational import fit_advi
+        return fit_advi(self, n=n, learning_rate=learning_rate, seed=random_seed, dtype=dtype, device=device, **kwargs)
+
     def to_pymc(self, dtype: str = 'float64', device: Optional[int] = None):
         """A ``pm.Model`` with the same free variables whose joint logp is one fused-kernel Op
         (needs PyMC; see sakkara_b200/pytensor_op.py)."""

@@ -68,3 +68,28 @@ def test_stats_name_the_kernels_of_the_last_evaluation():
     f(theta[:3])
     assert f.stats()['kernel_variant'] == 1
     f.close()
+
+
+def test_advi_on_a_minibatched_model():
+    """model.fit(): mean-field ADVI whose every step evaluates a fresh mini-batch of rows with the fused kernels."""
+    import pandas as pd
+    import sakkara_b200.model as api
+    from sakkara_b200.model import dist as pm
+    rng = np.random.default_rng(1)
+    n = 3000
+    group = rng.integers(0, 2, n)
+    x = rng.standard_normal(n)
+    df = pd.DataFrame({'x': x, 'g': group, 'y': np.array([-1.0, 1.0])[group] * x + 0.2 + 0.4 * rng.standard_normal(n)})
+    data = api.data_components(df)
+    DC = api.DistributionComponent
+    k = DC(pm.Normal, name='k', group='g')
+    lik = api.MinibatchLikelihood(pm.Normal, observed=data['y'], batch_size=256, mu=k * data['x'] + DC(pm.Normal, name='icpt'),
+                                  sigma=DC(pm.Exponential, name='noise', lam=1.0))
+    model = api.build(df, lik, backend='b200')
+    assert model.plan.minibatch == 256
+    approx = model.fit(n=1500, learning_rate=0.02, random_seed=3, start_sigma=0.1)
+    post = approx.constrained(model.plan, approx.sample(2000))
+    order = list(model.plan.coords['g'])
+    assert np.allclose(post['k'].mean(0), np.array([-1.0, 1.0])[order], atol=0.15)
+    assert abs(post['icpt'].mean() - 0.2) < 0.1 and abs(post['noise'].mean() - 0.4) < 0.1
+    assert approx.elbo[-200:].mean() > approx.elbo[:200].mean()
