@@ -234,7 +234,9 @@ class PartitionedValueGrad:
         self.dtype = np.dtype(dtype)
         self.chunk_groups = int(chunk_groups or secondary_chunk_groups(dtype, max_batch))
         self.part_rows = partition_rows(plan, self.chunk_groups, max_parts)
-        self.part_plans = [plan.take_rows(rows) for rows in self.part_rows]
+        merged = [merge_constant_terms(plan.take_rows(rows)) for rows in self.part_rows]
+        self.part_plans = [part for part, _ in merged]
+        self.aliases = [alias for _, alias in merged]
         self.parts = [ValueGradFunction(part, dtype=dtype, max_batch=max_batch, device=device, include_priors=False)
                       for part in self.part_plans]
         self._priors = ValueGradFunction(plan.take_rows([]), dtype=dtype, max_batch=max_batch, device=device)
@@ -251,10 +253,10 @@ class PartitionedValueGrad:
         logp, grad = self._priors(theta)
         logp = np.array(logp, dtype=np.float64) + float(self.model_plan.logp_const)     # (rows masked for NaN)
         grad = np.array(grad, dtype=np.float64)
-        for part in self.parts:
-            lp, g = part(theta)
+        for part, alias in zip(self.parts, self.aliases):
+            lp, g = part(alias_theta(theta, alias))
             logp = logp + lp
-            grad = grad + g
+            grad = grad + alias_grad(g, alias)
         logp = logp.astype(self.dtype) if logp.ndim else self.dtype.type(logp)
         grad = grad.astype(self.dtype)
         if grad_out is not None:
@@ -268,6 +270,59 @@ class PartitionedValueGrad:
     def close(self) -> None:
         for f in self.parts + [self._priors]:
             f.close()
+
+
+def merge_constant_terms(part: ModelPlan):
+    """
+    Terms without a data column whose gather is constant over the part's rows -- the peeled crossed factors, a global
+    intercept -- each add one element of theta to every row's predictor and each receive the same gradient, the sum
+    of d over the rows.  The kernels take two global terms; any number of these is evaluated as ONE: the part keeps the
+    first such term and is evaluated at a theta whose kept element holds the sum of all of them
+    (:func:`alias_theta`; the priors are not evaluated by the parts, so nothing else reads the element), and its
+    gradient is copied to the others (:func:`alias_grad`).  Returns ``(part, None)`` when there is nothing to merge,
+    else ``(part without the merged terms, (kept element, merged elements))``.
+    """
+    import dataclasses
+    kept_terms, first, others = [], None, []
+    for t in part.terms:
+        if t.x is None and part.n_rows and t.index.min() == t.index.max():
+            element = part.term_base(t) + int(t.index[0])
+            if first is None:
+                first = element
+                kept_terms.append(t)
+            else:
+                others.append(element)
+        else:
+            kept_terms.append(t)
+    if not others:
+        return part, None
+    for t in kept_terms:
+        # (the kept element must be read by its own term only: the part is evaluated with another value in it)
+        position = first - part.term_base(t)
+        if not (t.x is None and t.index.min() == t.index.max()) and (t.index == position).any():
+            return part, None
+    return dataclasses.replace(part, terms=kept_terms), (first, others)
+
+
+def alias_theta(theta: np.ndarray, alias) -> np.ndarray:
+    if alias is None:
+        return theta
+    first, others = alias
+    out = np.array(theta, copy=True)
+    for element in others:
+        out[..., first] += theta[..., element]
+    return out
+
+
+def alias_grad(grad: np.ndarray, alias) -> np.ndarray:
+    if alias is None:
+        return grad
+    first, others = alias
+    out = np.array(grad, dtype=np.float64, copy=True)
+    shared = out[..., first].copy()
+    for element in others:
+        out[..., element] += shared
+    return out
 
 
 ChunkedSecondaryValueGrad = PartitionedValueGrad      # (the first of the two cases, under its first name)

@@ -135,13 +135,35 @@ def test_more_than_two_crossed_factors_become_a_sum_of_plans(four=False):
         partition_rows(plan, chunk_groups=4096, max_parts=2)
 
 
-def test_four_crossed_factors_next_to_a_covariate_exceed_the_kernels():
-    """Two peeled factors and beta * x are three terms that are global inside a part; the kernels take two."""
+def test_four_crossed_factors_next_to_a_covariate():
+    """Two peeled factors and beta * x are three terms that are global inside a part, the kernels take two: the terms
+    without a data column are evaluated as one (the kept element holds their sum, its gradient is copied to the others)."""
+    from oracle.kernel_plan_eval import likelihood_from_kernel_plan
+    from oracle.logp_numpy import logp_dlogp
     from sakkara_b200.plan.kernel_plan import make_kernel_plan
     from sakkara_b200.plan.lower import UnsupportedModelError
-    from sakkara_b200.valuegrad import partition_rows
+    from sakkara_b200.valuegrad import alias_grad, alias_theta, merge_constant_terms, partition_rows
     model, _ = _crossed3_model(four=True)
-    parts = partition_rows(model.plan, chunk_groups=4096)
+    plan = model.plan
+    parts = partition_rows(plan, chunk_groups=4096)
     assert len(parts) == 12
     with pytest.raises(UnsupportedModelError, match='3 global'):
-        make_kernel_plan(model.plan.take_rows(parts[0]), dtype='float64', include_priors=False)
+        make_kernel_plan(plan.take_rows(parts[0]), dtype='float64', include_priors=False)
+    theta = np.random.default_rng(5).normal(0, 0.3, plan.n_params)
+    logp, grad = logp_dlogp(plan.take_rows([]), theta)
+    grad = np.array(grad, dtype=np.float64)
+    sl = plan.block_slices()
+    for rows in parts:
+        part, alias = merge_constant_terms(plan.take_rows(rows))
+        first, others = alias
+        assert sl['c'].start <= first < sl['c'].stop and len(others) == 1 and sl['d'].start <= others[0] < sl['d'].stop
+        kp = make_kernel_plan(part, dtype='float64', include_priors=False)
+        lp, g = likelihood_from_kernel_plan(kp, alias_theta(theta, alias))
+        logp, grad = logp + lp, grad + alias_grad(g, alias)
+    ref_logp, ref_grad = logp_dlogp(plan, theta)
+    assert abs(logp - ref_logp) < 1e-10 * abs(ref_logp)
+    assert np.allclose(grad, ref_grad, rtol=1e-10, atol=1e-10)
+    # batches: the aliasing acts on the last axis
+    batch = np.stack([theta, theta + 0.1])
+    assert np.array_equal(alias_theta(batch, alias)[0], alias_theta(theta, alias))
+    assert alias_theta(theta, None) is theta and alias_grad(grad, None) is grad

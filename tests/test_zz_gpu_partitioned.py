@@ -93,3 +93,16 @@ def test_advi_on_a_minibatched_model():
     assert np.allclose(post['k'].mean(0), np.array([-1.0, 1.0])[order], atol=0.15)
     assert abs(post['icpt'].mean() - 0.2) < 0.1 and abs(post['noise'].mean() - 0.4) < 0.1
     assert approx.elbo[-200:].mean() > approx.elbo[:200].mean()
+
+
+def test_four_crossed_factors_next_to_a_covariate():
+    """Two peeled factors are evaluated as one global term of a part (valuegrad.merge_constant_terms)."""
+    from helpers import theta_points
+    from test_valuegrad import _crossed3_model
+    model, _ = _crossed3_model(four=True)
+    f = model.logp_dlogp_function(dtype='float64')
+    assert type(f).__name__ == 'PartitionedValueGrad' and len(f.parts) == 12 and all(a is not None for a in f.aliases)
+    for theta in theta_points(model.plan, 2, seed=6, scale=0.3):
+        logp, grad = f(theta)
+        assert_parity(logp, grad, model.plan, theta, 'float64')
+    f.close()
