@@ -73,3 +73,42 @@ def test_advi_on_the_regression_posterior():
     assert abs(post['intercept'].mean() - 0.3) < 0.1
     assert abs(post['sigma_est'].mean() - 0.5) < 0.08
     assert np.all(approx.sd[sl['k']] < 0.2)                 # the data are informative: tight factors
+
+
+def _reference_minibatch_model():
+    """The model of /root/reference/tests/workflows/test_minibatch_vi.py:8-16 on its fixtures (udf / xdf)."""
+    from sakkara_b200.model import (DeterministicComponent, DistributionComponent as DC, MinibatchLikelihood, build,
+                                    data_components, dist as pm)
+    udf = pd.DataFrame({'time': np.arange(30), 'u': np.random.default_rng(100).normal(0, 1, 30)})
+    xdf = pd.DataFrame({'g': ['a', 'b'], 'k': [-1, 1]}).merge(udf, how='cross')
+    xdf['y'] = xdf['u'] * xdf['k']
+    xdf['obs'] = np.arange(len(xdf))
+    udc, xdc = data_components(udf, 'time'), data_components(xdf)
+    k = DC(pm.Normal, name='k', group='g')
+    predicted = DeterministicComponent('predicted', k * udc['u'])
+    mbl = MinibatchLikelihood(pm.Normal, observed=xdc['y'], batch_size=10, mu=predicted, sigma=1e-15)
+    return build(xdf, mbl, backend='b200')
+
+
+def test_hierarchical_minibatch_workflow_of_the_reference():
+    """The reference's own mini-batch VI workflow (tests/workflows/test_minibatch_vi.py:8-24): ``pm.fit(n=10000,
+    random_seed=100)``, 10,000 draws, posterior means of k within 1e-2 of -1 / +1.  Here the loop is fit_advi and the
+    evaluator is the oracle on a fresh mini-batch per step, composed exactly like valuegrad.MinibatchValueGrad
+    composes the kernels' results (priors + n_rows / batch x likelihood of the drawn rows)."""
+    plan = _reference_minibatch_model().plan
+    assert plan.minibatch == 10 and plan.n_rows == 60 and list(plan.coords['g']) == ['a', 'b']
+
+    class MiniBatchOracle:
+        size = plan.n_params
+        rng = np.random.default_rng(100)
+
+        def __call__(self, theta):
+            rows = np.sort(self.rng.integers(0, plan.n_rows, plan.minibatch))
+            prior_l, prior_g = logp_dlogp(plan.take_rows([]), theta)
+            sub_l, sub_g = logp_dlogp(plan.take_rows(rows), theta)
+            scale = plan.n_rows / plan.minibatch
+            return prior_l + scale * (sub_l - prior_l), prior_g + scale * (sub_g - prior_g)
+
+    approx = fit_advi(MiniBatchOracle(), n=10000, seed=100)
+    k = approx.constrained(plan, approx.sample(10000, seed=100))['k']
+    assert abs(k[:, 0].mean() + 1.0) < 1e-2 and abs(k[:, 1].mean() - 1.0) < 1e-2

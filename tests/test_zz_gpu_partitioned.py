@@ -106,3 +106,13 @@ def test_four_crossed_factors_next_to_a_covariate():
         logp, grad = f(theta)
         assert_parity(logp, grad, model.plan, theta, 'float64')
     f.close()
+
+
+def test_minibatch_vi_workflow_of_the_reference():
+    """/root/reference/tests/workflows/test_minibatch_vi.py:8-24 with model.fit() on the mini-batched evaluator (fewer,
+    larger steps than the reference's 10,000 x 1e-3: every step creates a plan for its ten rows)."""
+    from test_variational import _reference_minibatch_model
+    model = _reference_minibatch_model()
+    approx = model.fit(n=4000, learning_rate=3e-3, random_seed=100)
+    k = approx.constrained(model.plan, approx.sample(10000, seed=100))['k']
+    assert abs(k[:, 0].mean() + 1.0) < 2e-2 and abs(k[:, 1].mean() - 1.0) < 2e-2
