@@ -182,7 +182,9 @@ class SplitSigmaValueGrad:
     def __call__(self, theta, grad_out=None, extra_vars=None):
         theta = np.asarray(theta, dtype=self.dtype)
         logp, grad = self._priors(theta)
-        logp, grad = np.array(logp, dtype=np.float64), np.array(grad, dtype=np.float64)
+        # (the parts are taken with ModelPlan.take_rows, which leaves the constant of the rows masked for NaN behind)
+        logp = np.array(logp, dtype=np.float64) + float(self.model_plan.logp_const)
+        grad = np.array(grad, dtype=np.float64)
         for part in self.parts:
             lp, g = part(theta)
             logp = logp + lp

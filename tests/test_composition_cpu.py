@@ -105,3 +105,38 @@ def test_host_resident_nuts_on_a_sum_of_plans():
     lp, _ = logp_dlogp(model.plan, res.draws[1, 7])
     assert res.logp[1, 7] == pytest.approx(lp, rel=1e-9)
     assert res.stats['depth'].max() <= 5 and res.accept_rate.mean() > 0.3
+
+
+def test_nan_masked_rows_next_to_sigma_parameters():
+    """A NaN-masked Normal likelihood whose sigma is a GroupComponent of a constant and two parameters: the evaluator is
+    a sum of plans (SplitSigmaValueGrad), and the constant of the masked rows is added once (it used to be dropped)."""
+    import warnings
+    import pandas as pd
+    import sakkara_b200.model as api
+    from oracle.autograd_check import logp_dlogp_autograd
+    from sakkara_b200.model import dist as pm
+    rng = np.random.default_rng(0)
+    n = 200
+    g = rng.integers(0, 3, n)
+    x = rng.normal(size=n)
+    df = pd.DataFrame({'x': x, 'group': g, 'y': 0.8 * x - 0.2 + np.array([0.1, 0.6, 1.4])[g] * rng.normal(size=n)})
+    df.loc[[3, 17, 50], 'y'] = np.nan
+    DC, GC = api.DistributionComponent, api.GroupComponent
+    data = api.data_components(df)
+    R = GC(name='R', group='group', membercomponents={0: 1e-1, 1: DC(pm.Exponential, name='R_1', lam=10),
+                                                       2: DC(pm.HalfNormal, name='R_2', sigma=2.0)})
+    k = DC(pm.Normal, name='k', group='group', sigma=DC(pm.HalfNormal, name='k_sd', sigma=1.0))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', UserWarning)
+        lik = api.Likelihood(pm.Normal, mu=k * data['x'] + DC(pm.Normal, name='icpt'), sigma=R, observed=data['y'],
+                             nan_param_mask={'mu': 0.5, 'sigma': 2.0}, nan_data_mask=0)
+        model = api.build(df, lik, backend='b200')
+    plan = model.plan
+    assert plan.n_masked_rows == 3 and plan.logp_const != 0.0
+    f = model.logp_dlogp_function()
+    assert type(f).__name__ == 'SplitSigmaValueGrad'
+    theta = np.random.default_rng(1).normal(0, 0.3, plan.n_params)
+    logp, grad = f(theta)
+    ref_logp, ref_grad = logp_dlogp_autograd(model.recorded, theta)            # all rows, where(mask, fill, value)
+    assert logp == pytest.approx(ref_logp, rel=1e-12)
+    assert np.allclose(grad, ref_grad, rtol=1e-9, atol=1e-9)
