@@ -95,6 +95,7 @@ class B200Model:
                 options.pop('per_element', None)
                 return ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
             return SplitSigmaValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
+        options.pop('per_element', None)      # (only a sigma that differs between rows has elements to split by)
         if self.plan.minibatch is not None:
             # MinibatchLikelihood: a fresh random subset of the rows per call, scaled to the whole data set
             return MinibatchValueGrad(self.plan, dtype=dtype, device=device, **options)

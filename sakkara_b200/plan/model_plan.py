@@ -181,7 +181,9 @@ class ModelPlan:
         out = []
         elements = np.unique(spec.sigma_rows_element)
         linked = elements[elements >= 0]
-        if (linked.size > 1 or (linked.size == 1 and spec.family == 'StudentT')) and not per_element:
+        # (StudentT has no standard plan with sigma as one element of theta: its sigma parameters always go through the
+        #  log-sigma kernels, whatever ``per_element`` says)
+        if linked.size and (spec.family == 'StudentT' or (linked.size > 1 and not per_element)):
             rows = np.flatnonzero(spec.sigma_rows_element >= 0)
             out.append(self if rows.size == self.n_rows else self.take_rows(rows))
             elements = elements[elements < 0]

@@ -140,3 +140,17 @@ def test_nan_masked_rows_next_to_sigma_parameters():
     ref_logp, ref_grad = logp_dlogp_autograd(model.recorded, theta)            # all rows, where(mask, fill, value)
     assert logp == pytest.approx(ref_logp, rel=1e-12)
     assert np.allclose(grad, ref_grad, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize('name', ['group_sigma', 'studentt_group_sigma', 'studentt_one_sigma', 'studentt_const_sigma',
+                                  'row_sigma', 'readme'])
+def test_per_element_option_never_changes_the_result(name):
+    """``per_element=True`` (one standard plan per sigma parameter: the cross-check of the log-sigma kernels) applies
+    to Normal sigmas; StudentT sigma parameters keep the log-sigma plan (there is no standard StudentT plan with a
+    sigma element -- it used to be evaluated with sigma = 1), other models ignore the option."""
+    model = build_model(ZOO[name])
+    f = model.logp_dlogp_function(per_element=True)
+    theta = theta_points(model.plan, 2, seed=1)[1]
+    logp, grad = f(theta)
+    ref_logp, ref_grad = logp_dlogp(model.plan, theta)
+    assert abs(logp - ref_logp) <= 1e-10 * abs(ref_logp) and np.allclose(grad, ref_grad, rtol=1e-9, atol=1e-9)
