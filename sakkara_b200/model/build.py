@@ -109,7 +109,18 @@ class B200Model:
         if not options and (wide >= 2 or len(gathers) >= 3) and len(partition_rows(self.plan, chunk)) > 1:
             # more than one plan: a secondary level too large for the shared-memory tables, or a third crossed factor
             return PartitionedValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device, chunk_groups=chunk)
-        return ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
+        f = ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
+        if not options and len(self.plan.terms) > 3:
+            # (2 global + 2 primary-level + 1 secondary-level terms is what one plan takes: with four terms or more ask the
+            #  planner now; what exceeds it is evaluated with terms folded into each other, priors from a plan of their own)
+            from sakkara_b200.plan.lower import UnsupportedModelError
+            try:
+                f.kernel_plan
+            except UnsupportedModelError as err:
+                if 'compiled kernels cover' not in str(err):
+                    raise
+                return PartitionedValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device, chunk_groups=chunk)
+        return f
 
     def sample(self, draws: int = 1000, tune: int = 1000, chains: int = 64, target_accept: float = 0.8,
                random_seed: int = 0, max_treedepth: int = 8, dtype: str = 'float64', device: Optional[int] = None):

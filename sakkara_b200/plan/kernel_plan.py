@@ -308,9 +308,23 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
         keys = [np.arange(col.size)] + [table[(fine, a)] for a in reversed(ancestors)]
         return np.lexsort(tuple(keys)) if ancestors else np.arange(col.size)
 
+    # ---- more global terms than the kernels take -------------------------------------------------------------------
+    # A global term is a term on the ancestor of every level: like any term on a parent of the sorted level it can ride on
+    # the primary segments with a slot -> theta table that names its one element for every slot (the finish kernel adds
+    # the slots of such an element in fixed order).  The surplus moves there while the primary level has room; a model
+    # without any grouping level gets a primary level of one segment.
+    promoted = set()
+    primary_terms = sum(1 for c in column_of_term.values() if primary is not None and owner[c] == primary)
+    surplus, room = len(global_terms) - MAX_TERMS_PER_LEVEL, MAX_TERMS_PER_LEVEL - primary_terms
+    if n and surplus > 0 and room > 0:
+        promoted = set(sorted(global_terms)[len(global_terms) - min(surplus, room):])
+
     n_primary = n_secondary = 0
     p_slot_of_row = s_slot_of_row = None
     p_code_of_slot = s_code_of_slot = None
+    if primary is None and promoted:
+        n_primary = 1
+        p_slot_of_row = np.zeros(n, dtype=np.int64)
     if primary is not None:
         p_code_of_slot = slot_order(primary)
         n_primary = len(p_code_of_slot)
@@ -336,7 +350,7 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
         return a if perm is None else a[perm]
 
     seg_offsets = np.zeros(n_primary + 1, dtype=np.int64)
-    if primary is not None:
+    if p_slot_of_row is not None:
         np.cumsum(np.bincount(p_slot_of_row, minlength=n_primary), out=seg_offsets[1:])
     sec_codes = None
     if secondary is not None:
@@ -369,7 +383,10 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
     counts = {LEVEL_GLOBAL: 0, LEVEL_PRIMARY: 0, LEVEL_SECONDARY: 0}
     for number, term in enumerate(plan_terms):
         xc = XCOL_LOG_SIGMA if number == sigma_term else xcol_of(term.x)
-        if number in global_terms:
+        if number in promoted:
+            level = LEVEL_PRIMARY
+            theta_index = np.full(n_primary, global_terms[number], dtype=np.int32)
+        elif number in global_terms:
             level = LEVEL_GLOBAL
             theta_index = np.array([global_terms[number]], dtype=np.int32)
         else:

@@ -224,7 +224,9 @@ class PartitionedValueGrad:
     * a crossed model whose smaller (secondary) factor is too large for the row kernel's shared-memory tables is
       split by ranges of secondary groups into parts with at most ``chunk_groups`` of them each;
     * a model with more than two crossed factors is split by the groups of its smallest crossed factor -- inside one
-      group that factor's term is a single element of theta, a global term of the part -- until two are left.
+      group that factor's term is a single element of theta, a global term of the part -- until two are left;
+    * a model (or part) with more terms on a level than the kernels take is evaluated with the terms that have no data
+      column folded into the finest of them (:func:`fold_terms`) -- possibly as a single part.
 
     Every part is an ordinary plan over its rows (same theta, its own sort, segments and tables) evaluated by the
     same kernels; the priors come from a plan without rows; the parts are added on the host in a fixed order.
@@ -236,11 +238,23 @@ class PartitionedValueGrad:
         self.dtype = np.dtype(dtype)
         self.chunk_groups = int(chunk_groups or secondary_chunk_groups(dtype, max_batch))
         self.part_rows = partition_rows(plan, self.chunk_groups, max_parts)
-        merged = [merge_constant_terms(plan.take_rows(rows)) for rows in self.part_rows]
-        self.part_plans = [part for part, _ in merged]
-        self.aliases = [alias for _, alias in merged]
-        self.parts = [ValueGradFunction(part, dtype=dtype, max_batch=max_batch, device=device, include_priors=False)
-                      for part in self.part_plans]
+        self.part_plans, self.aliases, self.parts = [], [], []
+        for rows in self.part_rows:
+            whole = plan.take_rows(rows)
+            part, folds = fold_terms(whole, only_constant=True)
+            f = ValueGradFunction(part, dtype=dtype, max_batch=max_batch, device=device, include_priors=False)
+            try:
+                f.kernel_plan
+            except UnsupportedModelError as err:
+                if 'compiled kernels cover' not in str(err):
+                    raise
+                # more terms on a level than the kernels take: fold every term the finest one determines
+                part, folds = fold_terms(whole, only_constant=False)
+                f = ValueGradFunction(part, dtype=dtype, max_batch=max_batch, device=device, include_priors=False)
+                f.kernel_plan
+            self.part_plans.append(part)
+            self.aliases.append(folds)
+            self.parts.append(f)
         self._priors = ValueGradFunction(plan.take_rows([]), dtype=dtype, max_batch=max_batch, device=device)
 
     @property
@@ -274,56 +288,82 @@ class PartitionedValueGrad:
             f.close()
 
 
-def merge_constant_terms(part: ModelPlan):
+def fold_terms(part: ModelPlan, only_constant: bool = True):
     """
-    Terms without a data column whose gather is constant over the part's rows -- the peeled crossed factors, a global
-    intercept -- each add one element of theta to every row's predictor and each receive the same gradient, the sum
-    of d over the rows.  The kernels take two global terms; any number of these is evaluated as ONE: the part keeps the
-    first such term and is evaluated at a theta whose kept element holds the sum of all of them
-    (:func:`alias_theta`; the priors are not evaluated by the parts, so nothing else reads the element), and its
-    gradient is copied to the others (:func:`alias_grad`).  Returns ``(part, None)`` when there is nothing to merge,
-    else ``(part without the merged terms, (kept element, merged elements))``.
+    Terms without a data column add elements of theta to the predictor; when the gather of one is a function of the
+    gather of another -- a global intercept or a peeled crossed factor (constant inside the part) next to anything, a
+    term on a parent level next to a term on its child level -- the two are one term of the finer level evaluated at
+    ``theta'[child element] = theta[child element] + theta[parent element]``, and the coarser term's gradient is the
+    sum of the finer one's over its children.  The kernels take 2 global, 2 primary-level and 1 secondary-level terms;
+    folding evaluates models beyond that with the same kernels.  It needs the part's priors evaluated elsewhere
+    (nothing else may read the modified elements): parts are plans without priors.
+
+    ``only_constant``: fold only terms that are constant inside the part, into the first of them (what a part of a
+    peeled crossed factor needs); otherwise every term that the finest one determines is folded into that.
+
+    Returns ``(part, None)`` when nothing folds, else ``(part without the folded terms, folds)`` with ``folds`` a list
+    of ``(host elements[G], folded elements[G])``, absolute positions in theta (:func:`alias_theta`, :func:`alias_grad`).
     """
     import dataclasses
-    kept_terms, first, others = [], None, []
-    for t in part.terms:
-        if t.x is None and part.n_rows and t.index.min() == t.index.max():
-            element = part.term_base(t) + int(t.index[0])
-            if first is None:
-                first = element
-                kept_terms.append(t)
-            else:
-                others.append(element)
-        else:
-            kept_terms.append(t)
-    if not others:
+    import pandas as pd
+    from sakkara_b200.relation.groupset import first_rows
+    free = [i for i, t in enumerate(part.terms) if t.x is None] if part.n_rows else []
+    if len(free) < 2:
         return part, None
-    for t in kept_terms:
-        # (the kept element must be read by its own term only: the part is evaluated with another value in it)
-        position = first - part.term_base(t)
-        if not (t.x is None and t.index.min() == t.index.max()) and (t.index == position).any():
+    absolute = {i: part.term_base(part.terms[i]) + np.asarray(part.terms[i].index, dtype=np.int64) for i in free}
+    distinct = {i: 1 if a.min() == a.max() else len(np.unique(a)) for i, a in absolute.items()}
+    if only_constant:
+        free = [i for i in free if distinct[i] == 1]
+        if len(free) < 2:
             return part, None
-    return dataclasses.replace(part, terms=kept_terms), (first, others)
+        host = free[0]
+    else:
+        host = max(free, key=lambda i: distinct[i])            # the finest (the first among equals)
+    codes, elements = pd.factorize(absolute[host], sort=False)
+    elements = np.asarray(elements, dtype=np.int64)
+    first = first_rows(codes.astype(np.int64, copy=False), len(elements))
+    folds, dropped = [], set()
+    for i in free:
+        if i == host:
+            continue
+        table = absolute[i][first]
+        if distinct[i] == 1 or np.array_equal(table[codes], absolute[i]):
+            folds.append((elements, table))
+            dropped.add(i)
+    if not folds:
+        return part, None
+    for j, t in enumerate(part.terms):
+        # (the host's elements must be read by the host term only: the part is evaluated with other values in them)
+        if j != host and j not in dropped and np.isin(part.term_base(t) + t.index, elements).any():
+            return part, None
+    return dataclasses.replace(part, terms=[t for j, t in enumerate(part.terms) if j not in dropped]), folds
 
 
-def alias_theta(theta: np.ndarray, alias) -> np.ndarray:
-    if alias is None:
+def merge_constant_terms(part: ModelPlan):
+    """:func:`fold_terms` restricted to the terms that are constant inside the part."""
+    return fold_terms(part, only_constant=True)
+
+
+def alias_theta(theta: np.ndarray, folds) -> np.ndarray:
+    """The point a folded part is evaluated at: ``theta[host] += theta[folded]`` for every fold."""
+    if folds is None:
         return theta
-    first, others = alias
     out = np.array(theta, copy=True)
-    for element in others:
-        out[..., first] += theta[..., element]
+    for host, folded in folds:
+        out[..., host] += theta[..., folded]
     return out
 
 
-def alias_grad(grad: np.ndarray, alias) -> np.ndarray:
-    if alias is None:
+def alias_grad(grad: np.ndarray, folds) -> np.ndarray:
+    """The gradient of the unfolded model: every folded element receives the sum of its hosts' gradients."""
+    if folds is None:
         return grad
-    first, others = alias
     out = np.array(grad, dtype=np.float64, copy=True)
-    shared = out[..., first].copy()
-    for element in others:
-        out[..., element] += shared
+    flat = out.reshape(-1, out.shape[-1])
+    source = np.array(grad, dtype=np.float64).reshape(-1, out.shape[-1])
+    for host, folded in folds:
+        for row in range(flat.shape[0]):
+            np.add.at(flat[row], folded, source[row, host])
     return out
 
 

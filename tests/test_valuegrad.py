@@ -147,16 +147,18 @@ def test_four_crossed_factors_next_to_a_covariate():
     plan = model.plan
     parts = partition_rows(plan, chunk_groups=4096)
     assert len(parts) == 12
-    with pytest.raises(UnsupportedModelError, match='3 global'):
-        make_kernel_plan(plan.take_rows(parts[0]), dtype='float64', include_priors=False)
+    # (as it stands a part has three global terms; the planner moves one to the primary level, the sum of plans folds
+    #  the two without a data column into one before it gets there)
+    unfolded = make_kernel_plan(plan.take_rows(parts[0]), dtype='float64', include_priors=False)
+    assert sorted(t.level for t in unfolded.terms) == [0, 0, 1, 1, 2]
     theta = np.random.default_rng(5).normal(0, 0.3, plan.n_params)
     logp, grad = logp_dlogp(plan.take_rows([]), theta)
     grad = np.array(grad, dtype=np.float64)
     sl = plan.block_slices()
     for rows in parts:
         part, alias = merge_constant_terms(plan.take_rows(rows))
-        first, others = alias
-        assert sl['c'].start <= first < sl['c'].stop and len(others) == 1 and sl['d'].start <= others[0] < sl['d'].stop
+        (host, folded), = alias                                     # one fold: d's element into c's
+        assert len(host) == 1 and sl['c'].start <= host[0] < sl['c'].stop and sl['d'].start <= folded[0] < sl['d'].stop
         kp = make_kernel_plan(part, dtype='float64', include_priors=False)
         lp, g = likelihood_from_kernel_plan(kp, alias_theta(theta, alias))
         logp, grad = logp + lp, grad + alias_grad(g, alias)
@@ -167,3 +169,46 @@ def test_four_crossed_factors_next_to_a_covariate():
     batch = np.stack([theta, theta + 0.1])
     assert np.array_equal(alias_theta(batch, alias)[0], alias_theta(theta, alias))
     assert alias_theta(theta, None) is theta and alias_grad(grad, None) is grad
+
+
+def test_terms_beyond_the_kernels_limits_are_folded():
+    """beta1 x1 + beta2 x2 + icpt + a[A] + s[A] x2 + p[parent of A] + b[B]: 3 global / 3 primary-level / 1 secondary-level
+    terms.  One global term moves to the primary level in the planner; the intercept and the parent-level term -- no
+    data column, determined by A -- fold into a[A].  Parts from their kernel plans + priors = the oracle."""
+    import pandas as pd
+    import sakkara_b200.model as api
+    from oracle.kernel_plan_eval import likelihood_from_kernel_plan
+    from oracle.logp_numpy import logp_dlogp
+    from sakkara_b200.model import dist as pm
+    from sakkara_b200.plan.kernel_plan import make_kernel_plan
+    from sakkara_b200.plan.lower import UnsupportedModelError
+    from sakkara_b200.valuegrad import alias_grad, alias_theta, fold_terms
+    rng = np.random.default_rng(3)
+    n = 900
+    A = rng.integers(0, 12, n)
+    df = pd.DataFrame({'x1': rng.standard_normal(n), 'x2': rng.standard_normal(n), 'A': A, 'PA': A // 3,
+                       'B': rng.integers(0, 5, n)})
+    df['y'] = 0.4 * df['x1'] - 0.2 * df['x2'] + 0.1 * df['PA'] + 0.5 * rng.standard_normal(n)
+    DC = api.DistributionComponent
+    data = api.data_components(df[['x1', 'x2', 'y']])
+    eta = (DC(pm.Normal, name='beta1') * data['x1'] + DC(pm.Normal, name='beta2') * data['x2'] + DC(pm.Normal, name='icpt')
+           + DC(pm.Normal, name='a', group='A', sigma=DC(pm.HalfNormal, name='a_sd')) + DC(pm.Normal, name='s', group='A') * data['x2']
+           + DC(pm.Normal, name='p', group='PA') + DC(pm.Normal, name='b', group='B'))
+    model = api.build(df, api.Likelihood(pm.Normal, mu=eta, sigma=DC(pm.Exponential, name='noise', lam=1.0),
+                                         observed=data['y']), backend='b200')
+    plan = model.plan
+    with pytest.raises(UnsupportedModelError, match='compiled kernels cover'):
+        make_kernel_plan(plan, 'float64')
+    part, folds = fold_terms(plan, only_constant=False)
+    assert len(part.terms) == len(plan.terms) - 2 and len(folds) == 2
+    kp = make_kernel_plan(part, dtype='float64', include_priors=False)
+    assert sorted(t.level for t in kp.terms) == [0, 0, 1, 1, 2]          # 2 global / 2 primary / 1 secondary
+    theta = np.random.default_rng(4).normal(0, 0.3, plan.n_params)
+    logp, grad = logp_dlogp(plan.take_rows([]), theta)
+    lp, g = likelihood_from_kernel_plan(kp, alias_theta(theta, folds))
+    logp, grad = logp + lp, np.array(grad, dtype=np.float64) + alias_grad(g, folds)
+    ref_logp, ref_grad = logp_dlogp(plan, theta)
+    assert abs(logp - ref_logp) < 1e-10 * abs(ref_logp)
+    assert np.allclose(grad, ref_grad, rtol=1e-10, atol=1e-10)
+    f = model.logp_dlogp_function()
+    assert type(f).__name__ == 'PartitionedValueGrad' and len(f.parts) == 1 and f.aliases[0] is not None

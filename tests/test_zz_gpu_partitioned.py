@@ -116,3 +116,39 @@ def test_minibatch_vi_workflow_of_the_reference():
     approx = model.fit(n=4000, learning_rate=3e-3, random_seed=100)
     k = approx.constrained(model.plan, approx.sample(10000, seed=100))['k']
     assert abs(k[:, 0].mean() + 1.0) < 2e-2 and abs(k[:, 1].mean() - 1.0) < 2e-2
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+def test_more_terms_than_one_level_takes(dtype):
+    """Two covariates + intercept + a[A] + b[B] (three global terms: the planner moves one to the primary level), and
+    the seven-term model of tests/test_valuegrad.py::test_terms_beyond_the_kernels_limits_are_folded."""
+    import pandas as pd
+    import sakkara_b200.model as api
+    from helpers import theta_points
+    from sakkara_b200.model import dist as pm
+    rng = np.random.default_rng(3)
+    n = 20_000
+    A = rng.integers(0, 120, n)
+    df = pd.DataFrame({'x1': rng.standard_normal(n), 'x2': rng.standard_normal(n), 'A': A, 'PA': A // 3,
+                       'B': rng.integers(0, 5, n)})
+    df['y'] = 0.4 * df['x1'] - 0.2 * df['x2'] + 0.1 * (df['PA'] % 3) + 0.5 * rng.standard_normal(n)
+    DC = api.DistributionComponent
+
+    def model_of(seven):
+        data = api.data_components(df[['x1', 'x2', 'y']])
+        eta = (DC(pm.Normal, name='beta1') * data['x1'] + DC(pm.Normal, name='beta2') * data['x2']
+               + DC(pm.Normal, name='icpt') + DC(pm.Normal, name='a', group='A', sigma=DC(pm.HalfNormal, name='a_sd'))
+               + DC(pm.Normal, name='b', group='B'))
+        if seven:
+            eta = eta + DC(pm.Normal, name='s', group='A') * data['x2'] + DC(pm.Normal, name='p', group='PA')
+        return api.build(df, api.Likelihood(pm.Normal, mu=eta, sigma=DC(pm.Exponential, name='noise', lam=1.0),
+                                            observed=data['y']), backend='b200')
+
+    for seven, kind in ((False, 'ValueGradFunction'), (True, 'PartitionedValueGrad')):
+        model = model_of(seven)
+        f = model.logp_dlogp_function(dtype=dtype)
+        assert type(f).__name__ == kind
+        for theta in theta_points(model.plan, 2, seed=8, scale=0.3):
+            logp, grad = f(theta)
+            assert_parity(logp, grad, model.plan, theta, dtype)
+        f.close()
