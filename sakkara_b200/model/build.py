@@ -93,7 +93,18 @@ class B200Model:
             # next to them (or per_element=True) make it a sum of plans
             if (self.plan.likelihood.sigma_rows_element >= 0).all() and not options.get('per_element'):
                 options.pop('per_element', None)
-                return ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
+                f = ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
+                if not options and len(self.plan.terms) >= 3:
+                    # (log(sigma) per row is one more term on its level: see the end of this function)
+                    from sakkara_b200.plan.lower import UnsupportedModelError
+                    from sakkara_b200.valuegrad import PartitionedValueGrad
+                    try:
+                        f.kernel_plan
+                    except UnsupportedModelError as err:
+                        if 'compiled kernels cover' not in str(err):
+                            raise
+                        return PartitionedValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device)
+                return f
             return SplitSigmaValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
         options.pop('per_element', None)      # (only a sigma that differs between rows has elements to split by)
         if self.plan.minibatch is not None:
@@ -110,8 +121,8 @@ class B200Model:
             # more than one plan: a secondary level too large for the shared-memory tables, or a third crossed factor
             return PartitionedValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device, chunk_groups=chunk)
         f = ValueGradFunction(self.plan, dtype=dtype, max_batch=max_batch, device=device, **options)
-        if not options and len(self.plan.terms) > 3:
-            # (2 global + 2 primary-level + 1 secondary-level terms is what one plan takes: with four terms or more ask the
+        if not options and len(self.plan.terms) >= 3:
+            # (2 global + 2 primary-level + 1 secondary-level terms is what one plan takes: with three terms or more ask the
             #  planner now; what exceeds it is evaluated with terms folded into each other, priors from a plan of their own)
             from sakkara_b200.plan.lower import UnsupportedModelError
             try:

@@ -514,6 +514,10 @@ def _gamma_rate_predictor(node: Any, alpha: float):
     """
     while isinstance(node, sym.DeterministicVar):
         node = node.var
+    if isinstance(node, sym.Gather):
+        # (a rate without any observation-level term is formed on the dense tensor of its factors and gathered to the
+        #  observations afterwards, see _unwrap_link: the elementwise expression commutes with the gather)
+        return sym.Gather(_gamma_rate_predictor(node.base, alpha), node.indices)
     what = 'Gamma beta must be alpha / exp(linear predictor) for the fused kernel'
     if not isinstance(node, sym.BinOp) or node.op not in ('truediv', 'mul'):
         raise UnsupportedModelError(what)
@@ -551,4 +555,13 @@ def _unwrap_link(node: Any, link: str, what: str):
         node = node.var
     if isinstance(node, sym.UnaryOp) and node.op == link:
         return node.arg
+    if isinstance(node, sym.Gather):
+        # A predictor without any observation-level term (``f_(exp)(a + b)`` with a, b on crossed factors) is evaluated
+        # on the dense [A, B] tensor and only then gathered to the observations (the reference's minimal representations,
+        # sakkara/relation/representation.py:277-290): an elementwise link commutes with the gather
+        base = node.base
+        while isinstance(base, sym.DeterministicVar):
+            base = base.var
+        if isinstance(base, sym.UnaryOp) and base.op == link:
+            return sym.Gather(base.arg, node.indices)
     raise UnsupportedModelError(f'{what} must be {link}(linear predictor) for the fused kernel')

@@ -302,12 +302,19 @@ def fold_terms(part: ModelPlan, only_constant: bool = True):
     peeled crossed factor needs); otherwise every term that the finest one determines is folded into that.
 
     Returns ``(part, None)`` when nothing folds, else ``(part without the folded terms, folds)`` with ``folds`` a list
-    of ``(host elements[G], folded elements[G])``, absolute positions in theta (:func:`alias_theta`, :func:`alias_grad`).
+    of ``(host elements[G], folded elements[G], ratio of the two terms' constant coefficients)``, absolute positions in theta (:func:`alias_theta`, :func:`alias_grad`).
     """
     import dataclasses
     import pandas as pd
     from sakkara_b200.relation.groupset import first_rows
-    free = [i for i, t in enumerate(part.terms) if t.x is None] if part.n_rows else []
+    # (a term whose data column is one constant c counts as well: c * theta_a + c' * theta_p = c * (theta_a + c'/c * theta_p))
+    coef = {}
+    for i, t in enumerate(part.terms if part.n_rows else []):
+        if t.x is None:
+            coef[i] = 1.0
+        elif t.x.min() == t.x.max() and t.x[0] != 0.0:
+            coef[i] = float(t.x[0])
+    free = sorted(coef)
     if len(free) < 2:
         return part, None
     absolute = {i: part.term_base(part.terms[i]) + np.asarray(part.terms[i].index, dtype=np.int64) for i in free}
@@ -328,7 +335,7 @@ def fold_terms(part: ModelPlan, only_constant: bool = True):
             continue
         table = absolute[i][first]
         if distinct[i] == 1 or np.array_equal(table[codes], absolute[i]):
-            folds.append((elements, table))
+            folds.append((elements, table, coef[i] / coef[host]))
             dropped.add(i)
     if not folds:
         return part, None
@@ -345,12 +352,12 @@ def merge_constant_terms(part: ModelPlan):
 
 
 def alias_theta(theta: np.ndarray, folds) -> np.ndarray:
-    """The point a folded part is evaluated at: ``theta[host] += theta[folded]`` for every fold."""
+    """The point a folded part is evaluated at: ``theta[host] += ratio * theta[folded]`` for every fold."""
     if folds is None:
         return theta
     out = np.array(theta, copy=True)
-    for host, folded in folds:
-        out[..., host] += theta[..., folded]
+    for host, folded, ratio in folds:
+        out[..., host] += ratio * theta[..., folded]
     return out
 
 
@@ -361,9 +368,9 @@ def alias_grad(grad: np.ndarray, folds) -> np.ndarray:
     out = np.array(grad, dtype=np.float64, copy=True)
     flat = out.reshape(-1, out.shape[-1])
     source = np.array(grad, dtype=np.float64).reshape(-1, out.shape[-1])
-    for host, folded in folds:
+    for host, folded, ratio in folds:
         for row in range(flat.shape[0]):
-            np.add.at(flat[row], folded, source[row, host])
+            np.add.at(flat[row], folded, ratio * source[row, host])
     return out
 
 

@@ -157,7 +157,8 @@ def test_four_crossed_factors_next_to_a_covariate():
     sl = plan.block_slices()
     for rows in parts:
         part, alias = merge_constant_terms(plan.take_rows(rows))
-        (host, folded), = alias                                     # one fold: d's element into c's
+        (host, folded, ratio), = alias                              # one fold: d's element into c's
+        assert ratio == 1.0
         assert len(host) == 1 and sl['c'].start <= host[0] < sl['c'].stop and sl['d'].start <= folded[0] < sl['d'].stop
         kp = make_kernel_plan(part, dtype='float64', include_priors=False)
         lp, g = likelihood_from_kernel_plan(kp, alias_theta(theta, alias))
