@@ -101,7 +101,7 @@ class B200Model:
                     try:
                         f.kernel_plan
                     except UnsupportedModelError as err:
-                        if 'compiled kernels cover' not in str(err):
+                        if 'compiled kernels cover' not in str(err) and 'crossed grouping factors' not in str(err):
                             raise
                         return PartitionedValueGrad(self.plan, dtype=dtype, max_batch=max_batch, device=device)
                 return f
