@@ -289,16 +289,31 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
         a, b = finest
         # the smaller factor goes to the shared-memory table, the larger one is sorted
         primary, secondary = (a, b) if columns[a].size >= columns[b].size else (b, a)
-    owner: Dict[int, int] = {}
-    for c in range(k):
-        if c == primary or c == secondary:
-            owner[c] = c
-        elif primary is not None and (primary, c) in table:
-            owner[c] = primary
-        elif secondary is not None and (secondary, c) in table:
-            owner[c] = secondary
-        else:
-            raise UnsupportedModelError('a grouping column is determined by neither sorted level')
+
+    def assign_owners() -> Dict[int, int]:
+        out: Dict[int, int] = {}
+        for c in range(k):
+            if c == primary or c == secondary:
+                out[c] = c
+            elif primary is not None and (primary, c) in table:
+                out[c] = primary
+            elif secondary is not None and (secondary, c) in table:
+                out[c] = secondary
+            else:
+                raise UnsupportedModelError('a grouping column is determined by neither sorted level')
+        return out
+
+    def level_terms(fine) -> int:
+        return sum(1 for c in column_of_term.values() if owner[c] == fine)
+
+    owner = assign_owners()
+    if secondary is not None and level_terms(secondary) > MAX_SECONDARY_TERMS and \
+            level_terms(primary) <= MAX_SECONDARY_TERMS:
+        # the smaller factor carries more terms than the secondary level takes and the larger one few enough: they
+        # change places (the secondary level's tables are then the larger ones; valuegrad.PartitionedValueGrad splits a
+        # level that does not fit)
+        primary, secondary = secondary, primary
+        owner = assign_owners()
 
     def slot_order(fine: int) -> np.ndarray:
         """codes of `fine` ordered so that the groups of one ancestor are adjacent"""
