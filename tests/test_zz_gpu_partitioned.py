@@ -152,3 +152,29 @@ def test_more_terms_than_one_level_takes(dtype):
             logp, grad = f(theta)
             assert_parity(logp, grad, model.plan, theta, dtype)
         f.close()
+
+
+@pytest.mark.parametrize('seed', [0, 3, 5, 6, 9, 14, 16, 22, 24, 37, 41, 49, 57, 63])
+def test_random_models_on_the_device(seed):
+    """Models of tests/test_composition_cpu.py's generator that one plan did not take before the planner moved terms
+    between levels / the evaluator folded terms / summed plans (and a few ordinary ones), on the real device."""
+    import warnings
+    import sakkara_b200.model as api
+    from sakkara_b200.plan.lower import UnsupportedModelError
+    from test_composition_cpu import random_model
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            df, lik, description = random_model(seed)
+            model = api.build(df, lik, backend='b200')
+            f = model.logp_dlogp_function(dtype='float64')
+            theta = np.random.default_rng(seed).normal(0, 0.4, model.plan.n_params)
+            logp, grad = f(theta)
+    except (UnsupportedModelError, NotImplementedError) as err:
+        pytest.skip(f'outside the supported class: {err}')
+    except ValueError as err:
+        if 'minimal' in str(err):
+            pytest.skip('the random frame made a parent column a twin')
+        raise
+    assert_parity(logp, grad, model.plan, theta, 'float64')
+    f.close()
