@@ -82,3 +82,55 @@ def test_both_crossed_spellings_lower_to_the_same_gathers():
     assert ta.keys() == tb.keys() == {'beta', 'a', 'b'}
     for name in ta:
         assert np.array_equal(ta[name].index, tb[name].index)
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason='reference sources not present')
+@pytest.mark.parametrize('seed', range(0, 60))
+def test_random_models_match_live_reference(seed):
+    """The random models of tests/test_composition_cpu.py built by the reference's own ``build()`` (recording fake PyMC)
+    and by ours: the lowered plans -- theta layout, every gather index, data columns -- are identical.  A NaN-masked
+    likelihood is the one designed difference (the reference keeps the masked rows with constant parameters through a
+    per-row GroupComponent, we drop them and keep their constant): there logp and gradient must agree instead."""
+    import warnings
+    import numpy as np
+    from oracle.logp_numpy import logp_dlogp
+    from sakkara_b200.model import build
+    from sakkara_b200.plan.lower import UnsupportedModelError
+    from test_composition_cpu import random_model
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            frame, likelihood, description = random_model(seed)
+            ours = build(frame, likelihood, backend='b200').plan
+            ref = ref_harness.reference_plan(lambda api, pm, pt: random_model(seed, api, pm, pt)[1], frame)
+    except (UnsupportedModelError, NotImplementedError) as err:
+        pytest.skip(f'outside the supported class: {err}')
+    except ValueError as err:
+        if 'minimal' in str(err):
+            pytest.skip('the random frame made a parent column a twin (both implementations raise)')
+        raise
+    if 'nan' not in description.split('+'):
+        assert_same(plan_to_arrays(ref), plan_to_arrays(ours))
+        return
+    theta = np.random.default_rng(seed).normal(0, 0.4, ours.n_params)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        (ref_logp, ref_grad), (logp, grad) = logp_dlogp(ref, theta), logp_dlogp(ours, theta)
+    assert logp == pytest.approx(ref_logp, rel=1e-10)
+    assert np.allclose(grad, ref_grad, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 3, 5, 6, 10, 14, 16, 19, 22, 28, 35])
+def test_random_models_match_golden(seed):
+    """Twelve of the random models, pinned by fixtures the reference's own ``build()`` produced
+    (tests/golden/make_golden.py: random_models) -- the same check where /root/reference is not present."""
+    import warnings
+    import numpy as np
+    from sakkara_b200.model import build
+    from test_composition_cpu import random_model
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        frame, likelihood, _ = random_model(seed)
+        ours = build(frame, likelihood, backend='b200').plan
+    golden = dict(np.load(os.path.join(GOLDEN, f'random_{seed:02d}.npz'), allow_pickle=False))
+    assert_same(golden, plan_to_arrays(ours))

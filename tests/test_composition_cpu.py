@@ -166,7 +166,10 @@ def test_per_element_option_never_changes_the_result(name):
 # parent-level / crossed / cell (A x B) terms in random order, random prior families for the group-level scales, NaN masks
 
 
-def random_model(seed):
+def random_model(seed, api=api, pm=pm, pt=pt):
+    """A random model on a random frame, written against the DSL modules it is given (ours by default; the reference's,
+    through oracle/ref_harness.py, in tests/test_build_parity.py).  Returns ``(frame, likelihood, description)``."""
+    _DC = api.DistributionComponent
     rng=np.random.default_rng(seed)
     n=int(rng.integers(40,400))
     nA=int(rng.integers(2,12)); per=int(rng.integers(2,4)); nB=int(rng.integers(2,7)); nC=int(rng.integers(2,4))
