@@ -95,7 +95,7 @@ def test_minibatch_evaluator_and_fit():
     assert logp == pytest.approx(prior_l + 6.0 * (sub_l - prior_l), rel=1e-10)
     assert np.allclose(grad, prior_g + 6.0 * (sub_g - prior_g), rtol=1e-10)
     f.close()
-    approx = model.fit(n=4000, learning_rate=3e-3, random_seed=100)            # the GPU test's call
+    approx = model.fit(n=1500, learning_rate=8e-3, random_seed=100)            # the GPU test's call
     k = approx.constrained(plan, approx.sample(10000, seed=100))['k']
     assert abs(k[:, 0].mean() + 1.0) < 2e-2 and abs(k[:, 1].mean() - 1.0) < 2e-2
 
