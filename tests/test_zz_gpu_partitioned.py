@@ -11,7 +11,7 @@ from helpers import assert_parity
 from sakkara_b200 import synth
 from sakkara_b200.valuegrad import ChunkedSecondaryValueGrad
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]      # (pytest-timeout, where installed: a stuck test fails alone)
 
 
 @pytest.mark.parametrize('dtype', ['float64', 'float32'])
