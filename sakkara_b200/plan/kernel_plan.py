@@ -314,6 +314,26 @@ def make_kernel_plan(plan: ModelPlan, dtype='float64', rows: Optional[np.ndarray
         # level that does not fit)
         primary, secondary = secondary, primary
         owner = assign_owners()
+    if primary is not None and secondary is None and level_terms(primary) > MAX_TERMS_PER_LEVEL:
+        # One grouping factor (with its parents) carries more terms than the primary level takes -- an intercept and two
+        # random slopes by the same group -- and there is no crossed factor: the secondary level is free.  The last of the
+        # terms moves there, on a copy of its own column (the rows are sorted by the primary level, so a level it determines
+        # is constant inside every segment: trivially sorted inside it)
+        number = max(t for t, c in column_of_term.items() if owner[c] == primary)
+        c = column_of_term[number]
+        src = columns[c]
+        src.terms.remove(number)
+        columns.append(_Column(src.codes, src.elements, src.first_row, [number]))
+        secondary = len(columns) - 1
+        column_of_term[number] = secondary
+        for (a, b), t in list(table.items()):
+            if b == c:
+                table[(a, secondary)] = t
+            if a == c:
+                table[(secondary, b)] = t
+        table[(c, secondary)] = table[(secondary, c)] = np.arange(src.size)
+        k = len(columns)
+        owner = assign_owners()
 
     def slot_order(fine: int) -> np.ndarray:
         """codes of `fine` ordered so that the groups of one ancestor are adjacent"""

@@ -174,3 +174,50 @@ def test_two_rank_gloo_allreduce():
         out = manager.dict()
         mp.spawn(_gloo_worker, args=(world, 29533 + os.getpid() % 500, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _mixed_model_plan(n=2500, groups=37, covariates=2, seed=4):
+    """intercept + a[g] + s1[g] x1 + s2[g] x2 (+ beta_k x_k): more terms than one level takes."""
+    import pandas as pd
+    import sakkara_b200.model as api
+    from sakkara_b200.model import dist as pm
+    rng = np.random.default_rng(seed)
+    df = pd.DataFrame({'x1': rng.standard_normal(n), 'x2': rng.standard_normal(n), 'x3': rng.standard_normal(n),
+                       'g': rng.integers(0, groups, n)})
+    df['y'] = 0.3 * df['x1'] - 0.2 * df['x2'] + 0.5 * rng.standard_normal(n)
+    DC = api.DistributionComponent
+    data = api.data_components(df[['x1', 'x2', 'x3', 'y']])
+    eta = DC(pm.Normal, name='a', group='g', sigma=DC(pm.HalfNormal, name='a_sd')) \
+        + DC(pm.Normal, name='s1', group='g') * data['x1'] + DC(pm.Normal, name='s2', group='g') * data['x2']
+    for k in range(covariates):
+        eta = eta + DC(pm.Normal, name=f'beta{k + 1}') * data[f'x{k + 1}']
+    if covariates == 3:
+        eta = eta + DC(pm.Normal, name='icpt')
+    lik = api.Likelihood(pm.Normal, mu=eta, sigma=DC(pm.Exponential, name='noise', lam=1.0), observed=data['y'])
+    return api.build(df, lik, backend='b200').plan
+
+
+@pytest.mark.parametrize('covariates,levels', [(2, [0, 0, 1, 1, 2]), (3, [0, 0, 1, 1, 1, 2])])
+def test_terms_move_between_levels(covariates, levels):
+    """An intercept and two random slopes by one group are three primary-level terms: the third moves to the free
+    secondary level on a copy of the group's column.  A third covariate and a global intercept next to them are four
+    global terms: two would have to ride on the primary level, which is full -- still more than one plan takes."""
+    from oracle.kernel_plan_eval import likelihood_from_kernel_plan
+    plan = _mixed_model_plan(covariates=covariates)
+    if covariates == 3:
+        with pytest.raises(UnsupportedModelError, match='compiled kernels cover'):
+            make_kernel_plan(plan, 'float64')
+        return
+    kp = make_kernel_plan(plan, 'float64', include_priors=False)
+    assert sorted(t.level for t in kp.terms) == levels
+    assert kp.n_secondary == kp.n_primary == 37 and kp.sec_codes.dtype == np.uint16
+    # the copy is sorted inside every primary segment: it is constant there
+    for k in range(kp.n_primary):
+        segment = kp.sec_codes[kp.seg_offsets[k]:kp.seg_offsets[k + 1]]
+        assert segment.min() == segment.max()
+    theta = np.random.default_rng(2).normal(0, 0.3, plan.n_params)
+    logp, grad = likelihood_from_kernel_plan(kp, theta)
+    prior_logp, prior_grad = logp_dlogp(plan.take_rows([]), theta)
+    ref_logp, ref_grad = logp_dlogp(plan, theta)
+    assert abs(logp + prior_logp - ref_logp) < 1e-10 * abs(ref_logp)
+    assert np.allclose(grad + prior_grad, ref_grad, rtol=1e-10, atol=1e-10)

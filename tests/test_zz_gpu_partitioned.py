@@ -178,3 +178,17 @@ def test_random_models_on_the_device(seed):
         raise
     assert_parity(logp, grad, model.plan, theta, 'float64')
     f.close()
+
+
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+def test_intercept_and_two_random_slopes_by_one_group(dtype):
+    """Three primary-level terms: the planner moves one to the free secondary level (tests/test_kernel_plan.py)."""
+    from sakkara_b200.valuegrad import ValueGradFunction
+    from test_kernel_plan import _mixed_model_plan
+    plan = _mixed_model_plan(n=60_000, groups=300)
+    f = ValueGradFunction(plan, dtype=dtype)
+    assert f.kernel_plan.n_secondary == 300
+    theta = np.random.default_rng(2).normal(0, 0.3, plan.n_params)
+    logp, grad = f(theta)
+    assert_parity(logp, grad, plan, theta, dtype)
+    f.close()
