@@ -213,3 +213,16 @@ def test_terms_beyond_the_kernels_limits_are_folded():
     assert np.allclose(grad, ref_grad, rtol=1e-10, atol=1e-10)
     f = model.logp_dlogp_function()
     assert type(f).__name__ == 'PartitionedValueGrad' and len(f.parts) == 1 and f.aliases[0] is not None
+
+
+def test_sum_of_plans_pickles_without_device_state():
+    """PyMC hands the evaluator to its worker processes: a PartitionedValueGrad travels as its plans (no device needed
+    to build or to unpickle it), like ValueGradFunction."""
+    import pickle
+    model, _ = _crossed3_model(n=400)
+    f = model.logp_dlogp_function()
+    assert type(f).__name__ == 'PartitionedValueGrad'
+    g = pickle.loads(pickle.dumps(f))
+    assert len(g.parts) == len(f.parts) and g.size == f.size and g.dtype == f.dtype
+    assert all(p._skk is None for p in g.parts)
+    assert all(np.array_equal(a.kernel_plan.seg_offsets, b.kernel_plan.seg_offsets) for a, b in zip(f.parts, g.parts))
