@@ -260,3 +260,45 @@ def test_random_models_equal_autograd_over_the_recorded_graph(seed):
         ref_logp, ref_grad = logp_dlogp_autograd(model.recorded, theta)
     assert abs(logp - ref_logp) <= 1e-9 * max(1.0, abs(ref_logp)), description
     assert np.abs(grad - ref_grad).max() <= 1e-8 * max(1.0, np.abs(ref_grad).max()), description
+
+
+@pytest.mark.parametrize('name', ['readme', 'crossed_poisson', 'group_sigma', 'crossed_gamma'])
+def test_pymc_model_over_the_real_evaluators(name):
+    """``build(df, likelihood)`` as the reference's user writes it, with PyMC importable (tests/pymc_stub.py evaluates
+    the PyMC / PyTensor interfaces the glue uses): the returned ``pm.Model``'s logp_dlogp_function -- value variables
+    in PyMC's raveled order, Jacobians removed from the Potential and re-added by the transforms -- over the repo's own
+    evaluator classes (here on the stand-in device) equals the oracle."""
+    import pymc_stub
+    import sakkara_b200.model as api_
+    pymc_stub.install()
+    try:
+        df, make = ZOO[name]
+        model = api_.build(df, make(api_, api_.dist, api_.sym))
+        assert type(model).__name__ == 'Model' and hasattr(model, 'b200')       # a pm.Model, not the B200Model
+        f = model.logp_dlogp_function()
+        plan = model.b200.plan
+        for theta in theta_points(plan, 2, seed=4, scale=0.3):
+            logp, grad = f(theta)
+            ref_logp, ref_grad = logp_dlogp(plan, theta)
+            assert abs(logp - ref_logp) <= 1e-10 * max(1.0, abs(ref_logp))
+            assert np.allclose(grad, ref_grad, rtol=1e-9, atol=1e-9)
+    finally:
+        pymc_stub.uninstall()
+
+
+def test_pymc_model_over_a_sum_of_plans():
+    import pymc_stub
+    from test_valuegrad import _crossed3_model
+    pymc_stub.install()
+    try:
+        b200, _ = _crossed3_model(n=500)
+        from sakkara_b200.pytensor_op import to_pymc_model
+        model = to_pymc_model(b200)
+        assert type(model.b200_value_grad).__name__ == 'PartitionedValueGrad'
+        f = model.logp_dlogp_function()
+        theta = theta_points(b200.plan, 2, seed=9, scale=0.3)[1]
+        logp, grad = f(theta)
+        ref_logp, ref_grad = logp_dlogp(b200.plan, theta)
+        assert abs(logp - ref_logp) <= 1e-10 * abs(ref_logp) and np.allclose(grad, ref_grad, rtol=1e-9, atol=1e-9)
+    finally:
+        pymc_stub.uninstall()
